@@ -1,0 +1,197 @@
+"""Bit sources for the detector: the MVD-PHILOX-1 stream spec and the bitstream layout.
+
+The reference never defines where its random bits come from: the simulator it calls
+(``vm.simulate_markov_sequence``, Pd_plotter.py:149,212,219) is absent, only the idiom is
+visible elsewhere (uniform info bits, iid Bernoulli(p) flips, alpha_exponent.py:130-132).
+This module *defines* the two sources the CUDA kernels consume; the CPU oracle implements the
+same spec independently, so that even throughput-mode (on-device RNG) tallies are bit-exact.
+
+MVD-PHILOX-1
+------------
+* generator: Philox4x32-10 (Salmon et al., SC'11), key = (seed & 2^32-1, seed >> 32),
+  counter = (q, trial & 2^32-1, trial >> 32, stream); ``q`` counts the calls of one trial.
+* a trial of N steps is cut into superblocks of 128 steps = 4 blocks of 32 steps.
+  Per superblock: one call -> the four info words U[0..3] (bit b of U[w] is the info bit of
+  step 128*sb + 32*w + b).  Then, for every block that starts before N and every output
+  j = 0..n-1 in order, one *lazy Bernoulli word* E_j (bit b = flip of output j at that step).
+* lazy Bernoulli word for threshold T (P(flip) = T / 2^32), restricted to the valid lanes
+  ``vmask`` of the block: ``und = vmask, e = 0``; walk the threshold bits d = 31 .. ctz(T);
+  every 4th level starts with a fresh call (4 words = 4 levels) *if und != 0*, otherwise the
+  word is finished.  At level d with random word w: if bit d of T is set,
+  ``e |= und & ~w; und &= w`` else ``und &= ~w``.  Lanes still undecided at the end are 0.
+  This is exactly ``(32-bit uniform) < T`` evaluated MSB-first with early termination.
+
+Bitstream layout (verification mode, also the HBM-bound path)
+-------------------------------------------------------------
+``bits`` is an array of 128-bit words (4 x uint32, little-endian lanes x,y,z,w), indexed
+``[(sb * (1 + n) + c) * ntrials + trial]`` where c = 0 is the info stream and c = 1 + j the flip
+stream of output j: consecutive trials are adjacent, so a warp reads 512 contiguous bytes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Tuple
+
+import numpy as np
+
+PHILOX_M0 = 0xD2511F53
+PHILOX_M1 = 0xCD9E8D57
+PHILOX_W0 = 0x9E3779B9
+PHILOX_W1 = 0xBB67AE85
+MASK32 = 0xFFFFFFFF
+
+LEARN_STREAM = 0xFFFFFFFF      # stream tag of the learning chain (trial id 0)
+
+
+def philox4x32_10(ctr: Tuple[int, int, int, int], key: Tuple[int, int]) -> Tuple[int, int, int, int]:
+    """Scalar Philox4x32-10 on Python ints."""
+    c0, c1, c2, c3 = (int(c) & MASK32 for c in ctr)
+    k0, k1 = (int(k) & MASK32 for k in key)
+    for _ in range(10):
+        p0 = PHILOX_M0 * c0
+        p1 = PHILOX_M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK32, p1 & MASK32, ((p0 >> 32) ^ c3 ^ k1) & MASK32, p0 & MASK32
+        k0 = (k0 + PHILOX_W0) & MASK32
+        k1 = (k1 + PHILOX_W1) & MASK32
+    return c0, c1, c2, c3
+
+
+def philox4x32_10_np(c0, c1, c2, c3, seed: int) -> np.ndarray:
+    """Vectorised Philox4x32-10: arrays of counters -> uint32 [..., 4]."""
+    c0 = np.asarray(c0, dtype=np.uint64)
+    c1 = np.broadcast_to(np.asarray(c1, dtype=np.uint64), c0.shape).copy()
+    c2 = np.broadcast_to(np.asarray(c2, dtype=np.uint64), c0.shape).copy()
+    c3 = np.broadcast_to(np.asarray(c3, dtype=np.uint64), c0.shape).copy()
+    c0 = c0.copy()
+    k0 = np.uint64(seed & MASK32)
+    k1 = np.uint64((seed >> 32) & MASK32)
+    m32 = np.uint64(MASK32)
+    s32 = np.uint64(32)
+    for _ in range(10):
+        p0 = np.uint64(PHILOX_M0) * c0
+        p1 = np.uint64(PHILOX_M1) * c2
+        n0 = ((p1 >> s32) ^ c1 ^ k0) & m32
+        n2 = ((p0 >> s32) ^ c3 ^ k1) & m32
+        c1 = p1 & m32
+        c3 = p0 & m32
+        c0, c2 = n0, n2
+        k0 = (k0 + np.uint64(PHILOX_W0)) & m32
+        k1 = (k1 + np.uint64(PHILOX_W1)) & m32
+    return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)
+
+
+def bsc_threshold(p: float) -> int:
+    """32-bit flip threshold: P(flip) = T / 2^32, |T/2^32 - p| <= 2^-33 (clipped at 2^32 - 1)."""
+    if not (0.0 <= p <= 1.0):
+        raise ValueError("p must be in [0, 1]")
+    t = int(math.floor(p * 4294967296.0 + 0.5))
+    return min(t, MASK32)
+
+
+class TrialStream:
+    """Sequential word source of one (seed, stream, trial): the q-counter of MVD-PHILOX-1."""
+
+    def __init__(self, seed: int, stream: int, trial: int):
+        self.key = (seed & MASK32, (seed >> 32) & MASK32)
+        self.base = (trial & MASK32, (trial >> 32) & MASK32, stream & MASK32)
+        self.q = 0
+
+    def call(self) -> Tuple[int, int, int, int]:
+        out = philox4x32_10((self.q, *self.base), self.key)
+        self.q += 1
+        return out
+
+
+def lazy_bernoulli_word(src: TrialStream, T: int, vmask: int) -> int:
+    und = vmask & MASK32
+    e = 0
+    if T == 0:
+        return 0
+    dmin = (T & -T).bit_length() - 1
+    d = 31
+    while d >= dmin and und:
+        words = src.call()
+        for w in words:
+            if d < dmin:
+                break
+            if (T >> d) & 1:
+                e |= und & ~w & MASK32
+                und &= w
+            else:
+                und &= ~w & MASK32
+            d -= 1
+    return e
+
+
+def trial_words(seed: int, stream: int, trial: int, N: int, n: int, T: int) -> Tuple[np.ndarray, np.ndarray]:
+    """All info / flip words of one trial under MVD-PHILOX-1.
+
+    Returns ``U`` uint32 [nblk] and ``E`` uint32 [n, nblk] with nblk = ceil(N / 32).
+    """
+    src = TrialStream(seed, stream, trial)
+    nblk = (N + 31) // 32
+    U = np.zeros(nblk, dtype=np.uint32)
+    E = np.zeros((n, nblk), dtype=np.uint32)
+    for sb in range((N + 127) // 128):
+        uw = src.call()
+        for w in range(4):
+            blk = 4 * sb + w
+            t0 = 32 * blk
+            if t0 >= N:
+                break
+            U[blk] = uw[w]
+            valid = min(32, N - t0)
+            vmask = MASK32 if valid == 32 else (1 << valid) - 1
+            for j in range(n):
+                E[j, blk] = lazy_bernoulli_word(src, T, vmask)
+    return U, E
+
+
+def words_to_bits(words: np.ndarray, N: int) -> np.ndarray:
+    """uint32 [..., nblk] -> uint8 bits [..., N], LSB-first inside each word."""
+    w = np.ascontiguousarray(words, dtype="<u4")
+    bits = np.unpackbits(w.view(np.uint8), axis=-1, bitorder="little")
+    return bits[..., :N]
+
+
+def bits_to_words(bits: np.ndarray) -> np.ndarray:
+    """uint8 bits [..., N] -> uint32 words [..., ceil(N/128)*4], LSB-first, zero padded."""
+    bits = np.asarray(bits, dtype=np.uint8)
+    N = bits.shape[-1]
+    pad = (-N) % 128
+    if pad:
+        bits = np.concatenate([bits, np.zeros(bits.shape[:-1] + (pad,), dtype=np.uint8)], axis=-1)
+    by = np.packbits(bits, axis=-1, bitorder="little")
+    return np.ascontiguousarray(by).view("<u4")
+
+
+def pack_bitstreams(u_bits: np.ndarray, e_bits: np.ndarray) -> np.ndarray:
+    """Host bit arrays -> device layout.
+
+    ``u_bits`` uint8 [ntrials, N]; ``e_bits`` uint8 [ntrials, n, N].
+    Returns uint32 [nsb, 1 + n, ntrials, 4] (C-contiguous) == 128-bit words indexed
+    ``(sb * (1 + n) + c) * ntrials + trial``.
+    """
+    u_bits = np.asarray(u_bits, dtype=np.uint8)
+    e_bits = np.asarray(e_bits, dtype=np.uint8)
+    ntr, N = u_bits.shape
+    n = e_bits.shape[1]
+    assert e_bits.shape == (ntr, n, N)
+    uw = bits_to_words(u_bits)                      # [ntr, nsb*4]
+    ew = bits_to_words(e_bits)                      # [ntr, n, nsb*4]
+    nsb = uw.shape[-1] // 4
+    out = np.empty((nsb, 1 + n, ntr, 4), dtype=np.uint32)
+    out[:, 0] = uw.reshape(ntr, nsb, 4).transpose(1, 0, 2)
+    out[:, 1:] = ew.reshape(ntr, n, nsb, 4).transpose(2, 1, 0, 3)
+    return np.ascontiguousarray(out)
+
+
+def philox_bitstreams(seed: int, stream: int, trial_begin: int, ntrials: int, N: int, n: int, T: int):
+    """Materialise MVD-PHILOX-1 as host bit arrays (small cases; pure Python per trial)."""
+    u = np.zeros((ntrials, N), dtype=np.uint8)
+    e = np.zeros((ntrials, n, N), dtype=np.uint8)
+    for i in range(ntrials):
+        U, E = trial_words(seed, stream, trial_begin + i, N, n, T)
+        u[i] = words_to_bits(U, N)
+        e[i] = words_to_bits(E, N)
+    return u, e

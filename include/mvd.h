@@ -1,0 +1,150 @@
+/*
+ * mvd.h -- C ABI of libmvd.so, the B200 (sm_100a) implementation of the reference's
+ * Monte-Carlo hybrid-detector hot path.
+ *
+ * The reference (pure Python) has no FFI; the boundary this library sits behind is the Python
+ * function API of its two entry points.  Each entry point below names the reference interface
+ * it replaces (file:line into the reference repository); INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns MVD_OK (0) or a negative
+ * error code and never throws; mvd_last_error() gives the message; the library never frees or
+ * retains caller memory beyond the call; all device work of a context is ordered on one CUDA
+ * stream; one context per device (one process per GPU under torchrun).
+ *
+ * Tables are "edge-indexed": entry [i * R + r] belongs to Markov state i (BFS order,
+ * viterbi_markov.py:189-192) and received word r (index in itertools.product([0,1], repeat=n),
+ * viterbi_markov.py:175 -- first output bit is the MSB), R = 2^n.
+ */
+#ifndef MVD_H
+#define MVD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVD_ABI_VERSION 1
+#define MVD_MAX_N 4   /* outputs per step (R = 2^n <= 16)            */
+#define MVD_MAX_M 6   /* encoder memory  (2^m <= 64 trellis states)  */
+
+enum {
+    MVD_OK = 0,
+    MVD_E_INVALID = -1,       /* bad argument                                             */
+    MVD_E_CUDA = -2,          /* CUDA runtime error (no device, launch failure, ...)      */
+    MVD_E_UNSUPPORTED = -3,   /* outside the device envelope (k != 1, n > 4, m > 6, ...)  */
+    MVD_E_STATE = -4,         /* call order: tables not set                               */
+    MVD_E_NOMEM = -5,
+    MVD_E_UNKNOWN_STATE = -6  /* a metric vector was not in the state table: the KeyError of
+                                 Pd_plotter.py:112 / an 8-bit metric lane overflow          */
+};
+
+enum { MVD_SRC_PHILOX = 0, MVD_SRC_BITSTREAM = 1 };
+enum { MVD_ENGINE_AUTO = 0, MVD_ENGINE_ACS = 1, MVD_ENGINE_FSM = 2 };
+
+typedef struct mvd_ctx mvd_ctx;
+
+/* Where the info bits and BSC flips of a launch come from.
+ * PHILOX: generated on the device, stream spec MVD-PHILOX-1, key = seed.
+ * BITSTREAM: read from `bits`, an array of 128-bit words indexed
+ *   seg.bits_offset + (sb * (1 + n) + c) * ntrials + (trial - seg.trial_begin)
+ * (sb = step / 128, c = 0 info stream, c = 1 + j flips of output j, ntrials = trial_end - trial_begin;
+ * bit b of 32-bit lane w of a word is step 128*sb + 32*w + b). */
+typedef struct mvd_src {
+    int32_t mode;             /* MVD_SRC_*                                              */
+    int32_t bits_on_device;   /* BITSTREAM: 1 = `bits` is a device pointer, 0 = host    */
+    uint64_t seed;            /* PHILOX key                                             */
+    const void* bits;         /* BITSTREAM words                                        */
+    uint64_t bits_words;      /* BITSTREAM: number of 128-bit words in `bits`           */
+} mvd_src;
+
+/* One hypothesis of one (N, p) sweep point: the body of the trial loop Pd_plotter.py:210-223
+ * for `trial_end - trial_begin` iterations, or one learning chain (Pd_plotter.py:149-163). */
+typedef struct mvd_segment {
+    uint32_t N;                      /* trellis steps per trial / chain length            */
+    uint32_t threshold;              /* PHILOX: P(flip) = threshold / 2^32                */
+    uint32_t stream;                 /* PHILOX: stream tag (counter word 3)               */
+    uint32_t table;                  /* which log-likelihood table set scores this trial  */
+    uint32_t enc_taps[MVD_MAX_N];    /* encoder of this hypothesis: bit t of enc_taps[j] =
+                                        tap of output j on the input t steps ago          */
+    uint32_t decide;                 /* 0: success iff logp1 >  logp_ref (Pd_plotter.py:215)
+                                        1: success iff logp1 <= logp_ref (Pd_plotter.py:222) */
+    uint32_t random_input;           /* 1 = uniform info bits, 0 = all-zero input         */
+    uint64_t trial_begin, trial_end; /* global trial ids [begin, end)                     */
+    uint64_t bits_offset;            /* BITSTREAM: first word of this segment             */
+} mvd_segment;
+
+int mvd_abi_version(void);
+
+/* Create / destroy a context on CUDA device `device`.  Fails with MVD_E_CUDA when no usable
+ * device exists -- there is no CPU fallback. */
+int mvd_create(mvd_ctx** out, int device);
+int mvd_destroy(mvd_ctx* ctx);
+const char* mvd_last_error(const mvd_ctx* ctx);   /* ctx may be NULL: last create error */
+int mvd_set_stream(mvd_ctx* ctx, void* cuda_stream);
+int mvd_synchronize(mvd_ctx* ctx);
+
+/* Decoder code (always H1's generator, Pd_plotter.py:188): replaces build_trellis
+ * (viterbi_markov.py:118-132) + branch_output_and_next_state (:82-106) for k = 1.
+ * dec_taps[j] bit t = generator_matrix[j][0][t]. */
+int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps);
+
+/* Markov-state table: replaces the `states` list and the `state_index` dict
+ * (viterbi_markov.py:166-195, Pd_plotter.py:136-139).  metrics: S x 2^m bytes, next: S x 2^n. */
+int mvd_set_states(mvd_ctx* ctx, uint32_t S, const uint8_t* metrics, const uint32_t* next);
+
+/* Host-side (C++) breadth-first enumeration with the reference's discovery order; an
+ * accelerated enumerate_markov_states_allzero (viterbi_markov.py:166-195).  Installs the table
+ * like mvd_set_states.  mvd_get_states copies it out (either pointer may be NULL). */
+int mvd_enumerate_states(mvd_ctx* ctx, uint32_t max_states, uint32_t* S_out);
+int mvd_get_states(mvd_ctx* ctx, uint8_t* metrics, uint32_t* next);
+
+/* Log-likelihood tables: logP1[t][i*R + r] = log(max(P1_t[i, next[i][r]], 1e-300)) for table
+ * set t (one per distinct p; Pd_plotter.py:166-167 then :114-115), logTref likewise for
+ * T(p = 1/2) (Pd_plotter.py:193-194).  Host float64, computed by the caller with libm log. */
+int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const double* logTref);
+
+/* Transition counting: the loop Pd_plotter.py:158-163 for every segment (segment = one or more
+ * chains of N steps; only steps t >= burn are counted).  edge_counts: host, nsegs x S x R,
+ * edge_counts[s][i*R + r] = number of counted steps leaving state i on received word r. */
+int mvd_learn_counts(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
+                     uint32_t burn, int engine, uint64_t* edge_counts);
+
+/* Detection trials: Pd_plotter.py:210-223.  tallies: host, nsegs (successes per segment).
+ * logp (optional, host): 2 doubles (logp1, logp_ref) per trial, segments concatenated.
+ * d_tallies (optional, device uint64[nsegs]): also accumulate there, for a device-side
+ * allreduce; pass NULL otherwise. */
+int mvd_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
+               int engine, uint64_t* tallies, double* logp, void* d_tallies);
+
+/* Trajectory trace of one segment (verification): replaces simulate_markov_sequence(...)["metrics"]
+ * (call sites Pd_plotter.py:149,212,219).  state_idx: host, ntrials x (N+1) uint32;
+ * metrics (optional): host, ntrials x (N+1) x 2^m bytes (ACS engine: the registers themselves;
+ * FSM engine: gathered from the state table). */
+int mvd_trace(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, int engine,
+              uint32_t* state_idx, uint8_t* metrics);
+
+/* Eq. 4-5 recursion without a state table (memories whose Markov state set cannot be
+ * enumerated, m = 5, 6): per trial a 64-bit FNV-1a hash over the metric bytes of D_1..D_N and
+ * the final vector D_N.  hashes: host, ntrials; final_metrics (optional): ntrials x 2^m. */
+int mvd_acs_hash(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg,
+                 uint64_t* hashes, uint8_t* final_metrics);
+
+/* Timing of the last learn/detect/trace launch on the context's stream (CUDA events), and the
+ * number of kernels this library has launched since creation. */
+int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms);
+int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
+
+/* Integer-pipe roofline denominator, measured on this device: sustained 32-bit integer
+ * lane-ops/s of a dependent-free IADD3/LOP3 (+ IMAD) mix over all SMs. */
+int mvd_int_peak(mvd_ctx* ctx, double* alu_gops, double* alu_fma_gops);
+
+/* Device facts used by the host for sharding and reporting. */
+int mvd_device_info(mvd_ctx* ctx, int* sm_count, int* clock_khz, uint64_t* smem_per_block_optin,
+                    char* name, int name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVD_H */

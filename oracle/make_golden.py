@@ -1,0 +1,250 @@
+#!/usr/bin/env python3
+"""make_golden.py -- freeze golden vectors by EXECUTING THE REFERENCE'S OWN FUNCTIONS.
+
+Runs only in the build container (needs /root/reference, which does not exist on the GPU box);
+its output, tests/golden/*.json, is committed and is what pins the oracle and the CUDA path.
+
+What is executed unmodified from /root/reference:
+  viterbi_markov.{branch_output_and_next_state, build_trellis, viterbi_metric_step,
+                  enumerate_markov_states_allzero, build_symbolic_T}
+  Pd_plotter.{evaluate_symbolic_T, log_prob_sequence, learn_P1_empirical, run_experiment}
+What is injected: ``viterbi_markov.simulate_markov_sequence`` (absent from the reference, SURVEY
+F2) -- the driver in oracle/ref_port.py running on the reference's own branch/step/trellis
+functions, fed by the MVD-PHILOX-1 bit source, decoder fixed to gen1.
+matplotlib (not installed; imported but unused by Pd_plotter.py:58) is stubbed.
+
+Usage:  python oracle/make_golden.py [--ref /root/reference] [--out tests/golden]
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_port  # noqa: E402  (driver + bit source only; arithmetic comes from the reference)
+
+CODES = {
+    "c75": dict(k=1, n=2, m=2, gen=[[[1, 1, 1]], [[1, 0, 1]]]),               # Pd_plotter.py:247
+    "c65": dict(k=1, n=2, m=2, gen=[[[1, 1, 0]], [[1, 0, 1]]]),               # Pd_plotter.py:248
+    "m3a": dict(k=1, n=2, m=3, gen=[[[1, 1, 1, 1]], [[1, 0, 1, 1]]]),         # demo_script.py:49
+    "m3b": dict(k=1, n=2, m=3, gen=[[[1, 0, 1, 1]], [[1, 1, 1, 1]]]),         # demo_script.py:50
+    "r13": dict(k=1, n=3, m=2, gen=[[[1, 1, 1]], [[1, 0, 1]], [[1, 1, 0]]]),  # rate-1/3 edge case
+    "m1": dict(k=1, n=2, m=1, gen=[[[1, 1]], [[1, 0]]]),                      # smallest memory
+}
+
+
+def sha16(obj) -> str:
+    return hashlib.sha256(repr(obj).encode()).hexdigest()[:16]
+
+
+def load_reference(path):
+    sys.path.insert(0, path)
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import warnings
+    warnings.simplefilter("ignore")
+    import viterbi_markov as vm
+    import Pd_plotter as pdp
+    assert not hasattr(vm, "simulate_markov_sequence"), "reference now ships a simulator: re-survey"
+    return vm, pdp
+
+
+class Injected:
+    """The simulator injected into the reference; tracks which (point, hyp, trial) a call is."""
+
+    def __init__(self, vm, gen1, num_iter, trial_offset=0):
+        self.vm, self.gen1, self.num_iter, self.trial_offset = vm, gen1, num_iter, trial_offset
+        self.calls = 0
+        self.learn_calls = 0
+
+    def __call__(self, generator_matrix, m, k, n, length, p_val, random_input=True, seed=None):
+        vm = self.vm
+        kw = dict(step=vm.viterbi_metric_step, branch_fn=vm.branch_output_and_next_state,
+                  trellis_fn=vm.build_trellis, decoder_matrix=self.gen1)
+        if seed is not None:                                    # learn chain, Pd_plotter.py:149-155
+            self.learn_calls += 1
+            self.seed = seed
+            return ref_port.simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_input,
+                                                     seed, stream=ref_port.LEARN_STREAM, trial=0, **kw)
+        c = self.calls                                          # trial loop, Pd_plotter.py:212,219
+        self.calls += 1
+        point, within = divmod(c, 2 * self.num_iter)
+        trial, hyp = divmod(within, 2)
+        return ref_port.simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_input,
+                                                 self.seed, stream=2 * point + hyp,
+                                                 trial=self.trial_offset + trial, **kw)
+
+
+def kat_for_code(vm, pdp, name, spec, symbolic=True):
+    k, n, m, gen = spec["k"], spec["n"], spec["m"], spec["gen"]
+    states, trans, all_r = vm.enumerate_markov_states_allzero(gen, m, k, n)
+    index = {s: i for i, s in enumerate(states)}
+    trellis = vm.build_trellis(gen, m, k)
+    S = len(states)
+    nxt = [[index[vm.viterbi_metric_step(list(states[i]), trellis, r)] for r in all_r] for i in range(S)]
+    out = dict(k=k, n=n, m=m, gen=gen, S=S, max_metric=max(max(s) for s in states),
+               nnz=sum(len(trans[i]) for i in range(S)),
+               states_sha=sha16(states), next_sha=sha16(nxt),
+               all_r=[list(r) for r in all_r],
+               trellis={str(ns): [[ps, list(u), list(o)] for ps, u, o in lst] for ns, lst in trellis.items()},
+               branches=[[s, list(u), list(vm.branch_output_and_next_state(s, u, gen, m, k)[0]),
+                          vm.branch_output_and_next_state(s, u, gen, m, k)[1]]
+                         for s in range(1 << m) for u in ([(0,), (1,)] if k == 1 else [])])
+    if S <= 500:
+        out["states"] = [list(s) for s in states]
+        out["next"] = nxt
+        out["mult"] = [[len(trans[i][nxt[i][r]]) for r in range(len(all_r))] for i in range(S)]
+    # trajectory KAT: received words from a 32-bit LCG
+    x = 12345
+    cur = tuple([0] * (1 << m))
+    traj = []
+    for _ in range(10000):
+        x = (1664525 * x + 1013904223) % (1 << 32)
+        cur = vm.viterbi_metric_step(list(cur), trellis, all_r[x >> (32 - n)])
+        traj.append(index[cur])
+    out["lcg_traj_first"] = traj[:32]
+    out["lcg_traj_sum"] = sum(traj)
+    out["lcg_traj_sha"] = sha16(traj)
+    if symbolic:
+        t0 = time.time()
+        p_sym, T_sym = vm.build_symbolic_T(states, trans, all_r)
+        out["symbolic_seconds"] = round(time.time() - t0, 2)
+        tvals = {}
+        for pv in (0.5, 0.1, 0.3):
+            Tn = pdp.evaluate_symbolic_T(T_sym, p_sym, pv)
+            # edge form: T[i, next[i][r]]
+            tvals[repr(pv)] = [[float(Tn[i, nxt[i][r]]) for r in range(len(all_r))] for i in range(S)]
+            assert abs(Tn.sum(axis=1) - 1).max() < 1e-12
+        out["T_edge"] = tvals
+        if S <= 40:
+            out["T_sym_str"] = {f"{i},{j}": str(T_sym[i, j]) for i in range(S) for j in trans[i]}
+    return out
+
+
+def sim_kat(vm, name, spec, enc_spec, N, p, seed, stream, trial):
+    """Metric trajectory from the reference's branch + step functions under MVD-PHILOX-1."""
+    k, n, m = spec["k"], spec["n"], spec["m"]
+    sim = ref_port.simulate_markov_sequence(enc_spec["gen"], m, k, n, N, p, True, seed,
+                                            decoder_matrix=spec["gen"], stream=stream, trial=trial,
+                                            step=vm.viterbi_metric_step,
+                                            branch_fn=vm.branch_output_and_next_state,
+                                            trellis_fn=vm.build_trellis)
+    u, e = ref_port.philox_bits(seed, stream, trial, N, n, ref_port.threshold_of(p))
+    return dict(N=N, p=p, seed=seed, stream=stream, trial=trial, u_bits=u, e_bits=e,
+                metrics=[list(d) for d in sim["metrics"]], received=[list(r) for r in sim["received"]])
+
+
+def experiment_golden(vm, pdp, dec, enc2, num_iter, p_vec, N_list, seed, laplace=1.0, learn_len=None,
+                      learn_burn=200):
+    """Reference run_experiment + learn_P1_empirical, unmodified, with the injected simulator."""
+    k, n, m = dec["k"], dec["n"], dec["m"]
+    gen1, gen2 = dec["gen"], enc2["gen"]
+    inj = Injected(vm, gen1, num_iter)
+    vm.simulate_markov_sequence = inj
+    pdp.learn_P1_empirical.cache_clear()
+    saved = dict(pdp.N_SPECTRUM_BY_M)
+    pdp.N_SPECTRUM_BY_M[m] = list(N_list)            # configuration dict, Pd_plotter.py:78-83
+    logs = []
+    orig_lps = pdp.log_prob_sequence
+
+    def recording_lps(metrics, state_index, T):
+        v = orig_lps(metrics, state_index, T)
+        logs.append(v)
+        return v
+
+    pdp.log_prob_sequence = recording_lps
+    orig_tqdm = pdp.tqdm
+    pdp.tqdm = lambda it, **kw: it
+    try:
+        t0 = time.time()
+        df = pdp.run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, laplace, seed)
+        secs = time.time() - t0
+        # the learned matrices, straight from the reference's (cached) learner
+        states, trans, all_r = vm.enumerate_markov_states_allzero(gen1, m, k, n)
+        index = {s: i for i, s in enumerate(states)}
+        trellis = vm.build_trellis(gen1, m, k)
+        nxt = [[index[vm.viterbi_metric_step(list(s), trellis, r)] for r in all_r] for s in states]
+        P_edge = {}
+        for p in p_vec:
+            _, _, P = pdp.learn_P1_empirical(tuple(tuple(tuple(x) for x in row) for row in gen1),
+                                             k, n, m, p, learn_len, learn_burn, laplace, seed)
+            P_edge[repr(p)] = dict(
+                edge=[[float(P[i, nxt[i][r]]) for r in range(len(all_r))] for i in range(len(states))],
+                off_edge_min=float(P.min()), sha=hashlib.sha256(P.tobytes()).hexdigest()[:16])
+    finally:
+        pdp.log_prob_sequence = orig_lps
+        pdp.tqdm = orig_tqdm
+        pdp.N_SPECTRUM_BY_M.clear()
+        pdp.N_SPECTRUM_BY_M.update(saved)
+        del vm.simulate_markov_sequence
+    assert len(logs) == 4 * num_iter * len(p_vec) * len(N_list)
+    return dict(k=k, n=n, m=m, gen1=gen1, gen2=gen2, num_iter=num_iter, p_vec=p_vec, N_list=list(N_list),
+                seed=seed, laplace=laplace, learn_len=learn_len, learn_burn=learn_burn,
+                rows=df.to_dict(orient="records"), csv=df.to_csv(index=False),
+                logps=logs, P1_edge=P_edge, reference_seconds=round(secs, 2),
+                learn_calls=inj.learn_calls)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=os.path.join(HERE, "..", "tests", "golden"))
+    ap.add_argument("--skip-m3-symbolic", action="store_true")
+    args = ap.parse_args()
+    vm, pdp = load_reference(args.ref)
+    os.makedirs(args.out, exist_ok=True)
+
+    kats = {}
+    for name, spec in CODES.items():
+        sym = not (spec["m"] >= 3 and args.skip_m3_symbolic)
+        if name == "m3b":
+            sym = False                                   # 50 s of sympy for a mirrored pair: skip
+        t0 = time.time()
+        kats[name] = kat_for_code(vm, pdp, name, spec, symbolic=sym)
+        print(f"[kat] {name}: S={kats[name]['S']} ({time.time() - t0:.1f}s)", flush=True)
+    # step KATs quoted in SURVEY section 4 for (7,5)
+    tr = vm.build_trellis(CODES["c75"]["gen"], 2, 1)
+    kats["c75"]["step_kats"] = [[list(d), list(r), list(vm.viterbi_metric_step(list(d), tr, r))] for d, r in
+                                [((0, 0, 0, 0), (0, 0)), ((0, 0, 0, 0), (0, 1)), ((0, 0, 1, 1), (1, 1)),
+                                 ((2, 0, 1, 1), (1, 0)), ((0, 3, 2, 1), (0, 1))]]
+    with open(os.path.join(args.out, "code_kats.json"), "w") as f:
+        json.dump(kats, f, separators=(",", ":"))
+
+    sims = {
+        "c75_self": sim_kat(vm, "c75", CODES["c75"], CODES["c75"], 300, 0.1, 12345, 0, 7),
+        "c75_vs65": sim_kat(vm, "c75", CODES["c75"], CODES["c65"], 300, 0.1, 12345, 1, 7),
+        "c75_p001": sim_kat(vm, "c75", CODES["c75"], CODES["c75"], 200, 0.001, 99, 4, 0),
+        "c75_p05": sim_kat(vm, "c75", CODES["c75"], CODES["c75"], 129, 0.5, 1 << 40, 6, (1 << 33) + 5),
+        "m3_self": sim_kat(vm, "m3a", CODES["m3a"], CODES["m3a"], 260, 0.05, 123, 2, 1),
+        "m3_vs": sim_kat(vm, "m3a", CODES["m3a"], CODES["m3b"], 260, 0.2, 123, 3, 1),
+        "r13_self": sim_kat(vm, "r13", CODES["r13"], CODES["r13"], 100, 0.15, 5, 0, 3),
+        "m1_self": sim_kat(vm, "m1", CODES["m1"], CODES["m1"], 33, 0.25, 5, 0, 3),
+    }
+    with open(os.path.join(args.out, "sim_kats.json"), "w") as f:
+        json.dump(sims, f, separators=(",", ":"))
+    print("[sim] done", flush=True)
+
+    exps = {}
+    exps["c75_c65_small"] = experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=40,
+                                              p_vec=[0.01, 0.05, 0.1, 0.2, 0.3], N_list=[100, 500], seed=123)
+    print("[exp] c75_c65_small", exps["c75_c65_small"]["reference_seconds"], "s", flush=True)
+    exps["c75_c65_lap"] = experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=30,
+                                            p_vec=[0.1, 0.5], N_list=[64], seed=12345, laplace=0.1,
+                                            learn_len=3000, learn_burn=10)
+    print("[exp] c75_c65_lap", flush=True)
+    exps["m3_small"] = experiment_golden(vm, pdp, CODES["m3a"], CODES["m3b"], num_iter=12,
+                                         p_vec=[0.05, 0.2], N_list=[200], seed=123)
+    print("[exp] m3_small", exps["m3_small"]["reference_seconds"], "s", flush=True)
+    with open(os.path.join(args.out, "experiments.json"), "w") as f:
+        json.dump(exps, f, separators=(",", ":"))
+    print("golden vectors written to", os.path.abspath(args.out))
+
+
+if __name__ == "__main__":
+    main()
