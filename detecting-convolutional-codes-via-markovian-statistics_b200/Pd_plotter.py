@@ -1,0 +1,169 @@
+"""Pd_plotter -- drop-in for the reference's hybrid Markov detector driver, B200 edition.
+
+Same module-level names, signatures, defaults and CSV output as the reference's
+``Pd_plotter.py``: ``DEFAULTS``, ``N_SPECTRUM_BY_M``, ``evaluate_symbolic_T``,
+``log_prob_sequence``, ``learn_P1_empirical``, ``run_experiment`` and a ``__main__`` that writes
+``results_experiments/Pd_hybrid_results.csv`` (columns ``N,p,Pd,Pc``, N-major / p-minor rows).
+
+What changed is where the work happens.  The reference's triple loop (Pd_plotter.py:198-223)
+becomes: one GPU launch that walks the learning chains of all distinct p, a few hundred
+host float64 divisions (Laplace + row normalisation), and one GPU launch for every trial of every
+(N, p, hypothesis) of the sweep.  Trials shard across ranks under torchrun and the tallies are
+combined with a single allreduce (:mod:`mvd.dist`).
+
+Random bits: the reference never defines its simulator.  Here every chain is keyed --
+learning chain: (seed, LEARN_STREAM, trial 0); trial ``i`` of hypothesis ``h`` at sweep point
+``q`` (N-major, p-minor order): (seed, 2*q + h, i) -- so runs are reproducible and independent
+of the number of GPUs.
+"""
+from __future__ import annotations
+
+import math
+import os
+from functools import lru_cache
+
+import numpy as np
+
+import viterbi_markov as vm
+from mvd import bitsource, codes, dist
+from mvd.engine import Seg
+
+# Reference Pd_plotter.py:67-75
+DEFAULTS = {
+    "num_iter": 10000,
+    "p_vec": [0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5],
+    "seed": 12345,
+    "learn_len": None,
+    "learn_burn": 200,
+    "laplace": 1.0,
+    "save_dir": "results_experiments",
+}
+
+# Reference Pd_plotter.py:78-83
+N_SPECTRUM_BY_M = {
+    1: [5, 10, 20, 50, 100, 200],
+    2: [500],
+    3: [500],
+    4: [50, 100, 200, 300, 500],
+}
+
+
+def evaluate_symbolic_T(T_sym, p_sym, p_val):
+    """Numeric T(p_val) with rows renormalised (reference Pd_plotter.py:89-99)."""
+    import sympy as sp
+
+    S = T_sym.shape[0]
+    T_num = np.zeros((S, T_sym.shape[1]))
+    for i in range(S):
+        for j in range(T_sym.shape[1]):
+            x = T_sym[i, j]
+            if x != 0:
+                T_num[i, j] = float(sp.N(x.subs(p_sym, p_val)))
+    sums = T_num.sum(axis=1, keepdims=True)
+    sums[sums == 0] = 1.0
+    return T_num / sums
+
+
+def log_prob_sequence(metrics, state_index, T):
+    """log P(D_0..D_N) under transition matrix ``T`` (reference Pd_plotter.py:106-116): a
+    left-to-right float64 sum of ``log(max(T[i, j], 1e-300))``.  Host scalar kept for API
+    compatibility; inside ``run_experiment`` the same sums are formed on the GPU."""
+    total = 0.0
+    idx = [state_index[d] for d in metrics]
+    for a, b in zip(idx[:-1], idx[1:]):
+        total += math.log(max(T[a, b], 1e-300))
+    return total
+
+
+def _learn_len(S, learn_len):
+    return max(5000, 200 * S) if learn_len is None else int(learn_len)     # reference :143-146
+
+
+def _learn_edge_tables(det, p_list, learn_len, learn_burn, laplace, seed, engine="auto"):
+    """GPU learning chains for all p at once -> (edge counts, edge-form P1 tables)."""
+    L = _learn_len(det.S, learn_len)
+    segs = [Seg(N=L, threshold=bitsource.bsc_threshold(float(p)), stream=bitsource.LEARN_STREAM,
+                enc_taps=det.dec_taps, trial_begin=0, trial_end=1) for p in p_list]
+    counts = det.learn_counts(segs, burn=int(learn_burn), seed=int(seed), engine=engine)
+    tables = [codes.p1_from_edge_counts(det.table, counts[i], laplace) for i in range(len(p_list))]
+    return counts, tables
+
+
+@lru_cache(maxsize=128)
+def learn_P1_empirical(gens_tuple, k, n, m, p, learn_len, learn_burn, laplace, seed):
+    """Empirical P1 for hypothesis H1 (reference Pd_plotter.py:123-169).
+
+    Returns ``(states, state_index, P)`` with ``P`` the dense S x S float64 matrix for
+    S <= codes.DENSE_LIMIT (what the reference returns), else the edge table [S, 2^n]."""
+    det = vm._detector(codes.freeze_generator(gens_tuple), k, n, m)
+    counts, tables = _learn_edge_tables(det, [p], learn_len, learn_burn, laplace, seed)
+    states = det.table.state_tuples()
+    state_index = {s: i for i, s in enumerate(states)}
+    P = codes.p1_dense(det.table, counts[0], laplace) if det.S <= codes.DENSE_LIMIT else tables[0]
+    return states, state_index, P
+
+
+def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, laplace, seed, *,
+                   N_spectrum=None, engine="auto", device=None, trial_offset=0, details=None):
+    """Hybrid detector over all (N, p) points -> DataFrame[N, p, Pd, Pc]
+    (reference Pd_plotter.py:176-235; positional signature identical).
+
+    Extra keywords (all optional, reference behaviour when omitted): ``N_spectrum`` overrides
+    ``N_SPECTRUM_BY_M[m]``; ``engine`` in {"auto", "acs", "fsm"}; ``device`` the CUDA ordinal
+    (default LOCAL_RANK or 0); ``details`` a dict that receives tallies, tables and timings.
+    """
+    import pandas as pd
+
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", 0))
+    det = vm._detector(codes.freeze_generator(gen1), k, n, m, device)
+    taps1, taps2 = det.taps_of(gen1), det.taps_of(gen2)
+    spectrum = list(N_SPECTRUM_BY_M.get(m, [50, 100, 200])) if N_spectrum is None else list(N_spectrum)
+
+    # P1 for every distinct p (the reference's lru_cache, :123, learns once per p)
+    distinct = list(dict.fromkeys(float(p) for p in p_vec))
+    counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=engine)
+    det.set_models(tables)                              # T_ref = T(1/2) = mult / 2^n (reference :193-194)
+    tindex = {p: i for i, p in enumerate(distinct)}
+
+    rank, ws = dist.world()
+    begin, end = dist.shard_range(int(num_iter), rank, ws, offset=int(trial_offset))
+    segs, points = [], []
+    for N in spectrum:
+        for p in p_vec:
+            q = len(points)
+            T = bitsource.bsc_threshold(float(p))
+            segs.append(Seg(N=int(N), threshold=T, stream=2 * q, table=tindex[float(p)], enc_taps=taps1,
+                            decide=0, trial_begin=begin, trial_end=end))
+            segs.append(Seg(N=int(N), threshold=T, stream=2 * q + 1, table=tindex[float(p)], enc_taps=taps2,
+                            decide=1, trial_begin=begin, trial_end=end))
+            points.append((N, p))
+    tallies = det.detect(segs, seed=int(seed), engine=engine)
+    kernel_ms = det.last_kernel_ms()
+    tallies = dist.allreduce_sum(tallies.astype(np.int64))
+
+    rows = []
+    for q, (N, p) in enumerate(points):
+        s1, s2 = int(tallies[2 * q]), int(tallies[2 * q + 1])
+        rows.append({"N": N, "p": p, "Pd": s1 / num_iter, "Pc": (s1 + s2) / (2 * num_iter)})   # reference :225-226
+    if details is not None:
+        details.update(tallies=tallies, edge_counts=counts, p1_tables=tables, distinct_p=distinct,
+                       detect_kernel_ms=kernel_ms, steps=2 * sum(N for N, _ in points) * int(num_iter),
+                       learn_len=_learn_len(det.S, learn_len), S=det.S)
+    return pd.DataFrame(rows, columns=["N", "p", "Pd", "Pc"])
+
+
+if __name__ == "__main__":
+    print("Hybrid Markov-based detector (WCNC-2026) -- B200 build")
+
+    k, n, m = 1, 2, 2
+    gen1 = [[[1, 1, 1]], [[1, 0, 1]]]
+    gen2 = [[[1, 1, 0]], [[1, 0, 1]]]
+
+    df = run_experiment(k, n, m, gen1, gen2, DEFAULTS["num_iter"], DEFAULTS["p_vec"], DEFAULTS["learn_len"],
+                        DEFAULTS["learn_burn"], DEFAULTS["laplace"], DEFAULTS["seed"])
+
+    os.makedirs(DEFAULTS["save_dir"], exist_ok=True)
+    out_csv = os.path.join(DEFAULTS["save_dir"], "Pd_hybrid_results.csv")
+    df.to_csv(out_csv, index=False)
+    print("Saved results to", out_csv)

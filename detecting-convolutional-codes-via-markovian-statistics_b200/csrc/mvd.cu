@@ -1,0 +1,728 @@
+// mvd.cu -- C ABI (include/mvd.h) over the sm_100a kernels in mvd_kernels.cuh.
+//
+// Host responsibilities: validate arguments, turn the decoder code into branch-metric constants,
+// build the metric-vector hash table and the premultiplied NEXT table, stage segments, launch
+// one kernel per call (a whole sweep = one launch), read tallies / counts back.
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include "mvd_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct mvd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+
+    // code
+    bool have_code = false;
+    int k = 0, n = 0, m = 0;
+    uint32_t dec_taps[MVD_MAX_N] = {0, 0, 0, 0};
+    // states
+    bool have_states = false, acs_ok = false;
+    uint32_t S = 0;
+    std::vector<uint8_t> h_metrics;
+    std::vector<uint32_t> h_next;
+    uint32_t hcap = 0;
+    // loglik
+    uint32_t ntables = 0;
+
+    DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
+        d_hashes, d_final, d_err, d_bits, d_peak;
+};
+
+namespace {
+
+int fail(mvd_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(ctx, MVD_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline int label_of_branch(uint32_t ps, uint32_t u, const uint32_t* taps, int n) {
+    const uint32_t reg = (u & 1u) | (ps << 1);
+    int lab = 0;
+    for (int j = 0; j < n; ++j) lab = (lab << 1) | (__builtin_popcount(reg & taps[j]) & 1);
+    return lab;
+}
+
+// nibble-packed key of a metric vector (must match AcsCore<M>::key)
+inline bool pack_key(const uint8_t* met, int nstate, uint32_t* kw, int nkw) {
+    for (int i = 0; i < nkw; ++i) kw[i] = 0;
+    bool ok = true;
+    for (int s = 0; s < nstate; ++s) {
+        if (met[s] > 15) ok = false;
+        kw[s >> 3] |= (uint32_t)(met[s] & 15u) << (4 * (s & 7));
+    }
+    return ok;
+}
+
+inline uint32_t host_key_hash(const uint32_t* kw, int nkw) {
+    uint32_t h = 0x9E3779B1u;
+    for (int i = 0; i < nkw; ++i) {
+        h ^= kw[i];
+        h *= 0x85EBCA6Bu;
+        h ^= h >> 13;
+    }
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+
+int install_states(mvd_ctx* ctx) {
+    const int nstate = 1 << ctx->m, R = 1 << ctx->n;
+    const uint32_t S = ctx->S;
+    const size_t SR = (size_t)S * R;
+    if (SR >= 0xFFFFFFF0ull / (size_t)R) return fail(ctx, MVD_E_UNSUPPORTED, "state table too large (S=%u)", S);
+    std::vector<uint32_t> pre(SR);
+    for (size_t i = 0; i < SR; ++i) {
+        if (ctx->h_next[i] >= S) return fail(ctx, MVD_E_INVALID, "next[%zu]=%u out of range (S=%u)", i, ctx->h_next[i], S);
+        pre[i] = ctx->h_next[i] * (uint32_t)R;
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_nxt.reserve(SR * 4));
+    CK(cudaMemcpyAsync(ctx->d_nxt.p, pre.data(), SR * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // hash table: metric vector -> state * R
+    const int nkw = (nstate + 7) / 8;
+    uint32_t cap = 64;
+    while (cap < 2ull * S) cap <<= 1;
+    std::vector<uint32_t> keys((size_t)nkw * cap, 0u), vals(cap, MVD_EMPTY);
+    bool ok = true;
+    for (uint32_t i = 0; i < S && ok; ++i) {
+        uint32_t kw[8];
+        if (!pack_key(ctx->h_metrics.data() + (size_t)i * nstate, nstate, kw, nkw)) { ok = false; break; }
+        uint32_t slot = host_key_hash(kw, nkw) & (cap - 1);
+        while (vals[slot] != MVD_EMPTY) {
+            bool same = true;
+            for (int w = 0; w < nkw; ++w) same = same && keys[(size_t)w * cap + slot] == kw[w];
+            if (same) return fail(ctx, MVD_E_INVALID, "duplicate metric vector at state %u", i);
+            slot = (slot + 1) & (cap - 1);
+        }
+        vals[slot] = i * (uint32_t)R;
+        for (int w = 0; w < nkw; ++w) keys[(size_t)w * cap + slot] = kw[w];
+    }
+    ctx->acs_ok = ok;
+    ctx->hcap = cap;
+    CK(ctx->d_hkeys.reserve(keys.size() * 4));
+    CK(ctx->d_hvals.reserve(vals.size() * 4));
+    CK(cudaMemcpyAsync(ctx->d_hkeys.p, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hvals.p, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_states = true;
+    ctx->ntables = 0;
+    return MVD_OK;
+}
+
+struct LaunchOut {
+    uint64_t* tallies = nullptr;
+    double* logp = nullptr;
+    void* d_tallies = nullptr;
+    uint64_t* counts = nullptr;
+    uint32_t burn = 0;
+    uint32_t* trace_idx = nullptr;
+    uint8_t* trace_met = nullptr;
+    uint64_t* hashes = nullptr;
+    uint8_t* final_met = nullptr;
+};
+
+template <int MODE, int NOUT>
+cudaError_t launch_acs(int m, dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
+#define MVD_ACS_CASE(MM)                                                                              \
+    case MM: {                                                                                        \
+        auto kern = acs_kernel<MODE, NOUT, MM>;                                                       \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                               \
+        kern<<<grid, MVD_BLOCK, smem, st>>>(P);                                                       \
+        return cudaGetLastError();                                                                    \
+    }
+    switch (m) {
+        MVD_ACS_CASE(1)
+        MVD_ACS_CASE(2)
+        MVD_ACS_CASE(3)
+        MVD_ACS_CASE(4)
+        MVD_ACS_CASE(5)
+        MVD_ACS_CASE(6)
+        default: return cudaErrorInvalidValue;
+    }
+#undef MVD_ACS_CASE
+}
+
+template <int MODE, int NOUT, bool SMEM>
+cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
+    auto kern = fsm_kernel<MODE, NOUT, SMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, MVD_BLOCK, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
+        const LaunchOut& out) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!src || !segs || nsegs == 0) return fail(ctx, MVD_E_INVALID, "null source / segments");
+    if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code has not been called");
+    if (mode != MODE_HASH && !ctx->have_states) return fail(ctx, MVD_E_STATE, "no Markov state table (mvd_set_states)");
+    if (mode == MODE_DETECT && ctx->ntables == 0) return fail(ctx, MVD_E_STATE, "no log-likelihood tables (mvd_set_loglik)");
+    if (src->mode != MVD_SRC_PHILOX && src->mode != MVD_SRC_BITSTREAM) return fail(ctx, MVD_E_INVALID, "bad source mode");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n, m = ctx->m, R = 1 << n, nstate = 1 << m;
+    const uint32_t S = ctx->S;
+    const uint32_t SR = mode == MODE_HASH ? 0u : S * (uint32_t)R;
+
+    if (engine == MVD_ENGINE_AUTO) engine = (mode == MODE_HASH) ? MVD_ENGINE_ACS : MVD_ENGINE_FSM;
+    if (mode == MODE_HASH) engine = MVD_ENGINE_ACS;
+    if (engine != MVD_ENGINE_ACS && engine != MVD_ENGINE_FSM) return fail(ctx, MVD_E_INVALID, "bad engine %d", engine);
+    if (engine == MVD_ENGINE_ACS && mode != MODE_HASH && !ctx->acs_ok)
+        return fail(ctx, MVD_E_UNSUPPORTED, "ACS engine needs relative metrics <= 15");
+
+    // ---- segments
+    std::vector<DevSeg> ds(nsegs);
+    uint64_t blocks = 0, trials = 0, need_words = 0;
+    for (uint32_t i = 0; i < nsegs; ++i) {
+        const mvd_segment& s = segs[i];
+        if (s.trial_end < s.trial_begin) return fail(ctx, MVD_E_INVALID, "segment %u: trial_end < trial_begin", i);
+        if (mode == MODE_DETECT && s.table >= ctx->ntables) return fail(ctx, MVD_E_INVALID, "segment %u: table %u >= %u", i, s.table, ctx->ntables);
+        if (s.decide > 1) return fail(ctx, MVD_E_INVALID, "segment %u: decide must be 0 or 1", i);
+        DevSeg& d = ds[i];
+        d.N = s.N;
+        d.threshold = s.threshold;
+        d.stream = s.stream;
+        d.table = s.table;
+        for (int j = 0; j < MVD_MAX_N; ++j) {
+            d.enc_taps[j] = j < n ? s.enc_taps[j] : 0u;
+            if (j < n && (s.enc_taps[j] >> (m + 1))) return fail(ctx, MVD_E_INVALID, "segment %u: encoder tap beyond memory m=%d", i, m);
+        }
+        d.decide = s.decide;
+        d.random_input = s.random_input ? 1u : 0u;
+        d.dmin = s.threshold ? (uint32_t)__builtin_ctz(s.threshold) : 32u;
+        const uint64_t ntr = s.trial_end - s.trial_begin;
+        if (blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one call");
+        d.block_begin = (uint32_t)blocks;
+        d.trial_begin = s.trial_begin;
+        d.trial_end = s.trial_end;
+        d.bits_offset = s.bits_offset;
+        d.out_offset = trials;
+        blocks += (ntr + MVD_BLOCK - 1) / MVD_BLOCK;
+        trials += ntr;
+        if (src->mode == MVD_SRC_BITSTREAM) {
+            const uint64_t nsb = ((uint64_t)s.N + 127) / 128;
+            need_words = std::max<uint64_t>(need_words, s.bits_offset + nsb * (uint64_t)(1 + n) * ntr);
+        }
+    }
+    if (blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one call");
+    if ((mode == MODE_TRACE || mode == MODE_HASH) && nsegs != 1) return fail(ctx, MVD_E_INVALID, "trace/hash take exactly one segment");
+
+    Params P{};
+    P.n = n;
+    P.m = m;
+    P.R = R;
+    P.nstate = nstate;
+    P.S = S;
+    P.SR = SR;
+    P.src_mode = src->mode;
+    {
+        uint32_t k0 = (uint32_t)src->seed, k1 = (uint32_t)(src->seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            P.rk0[r] = k0;
+            P.rk1[r] = k1;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+    }
+    if (src->mode == MVD_SRC_BITSTREAM) {
+        if (!src->bits) return fail(ctx, MVD_E_INVALID, "bitstream source without bits");
+        if (src->bits_words < need_words) return fail(ctx, MVD_E_INVALID, "bitstream too short: %llu words, need %llu",
+                                                      (unsigned long long)src->bits_words, (unsigned long long)need_words);
+        if (src->bits_on_device) {
+            P.bits = reinterpret_cast<const uint4*>(src->bits);
+        } else {
+            CK(ctx->d_bits.reserve((size_t)need_words * 16));
+            CK(cudaMemcpyAsync(ctx->d_bits.p, src->bits, (size_t)need_words * 16, cudaMemcpyHostToDevice, ctx->stream));
+            P.bits = ctx->d_bits.as<uint4>();
+        }
+    }
+    CK(ctx->d_segs.reserve(sizeof(DevSeg) * nsegs));
+    CK(cudaMemcpyAsync(ctx->d_segs.p, ds.data(), sizeof(DevSeg) * nsegs, cudaMemcpyHostToDevice, ctx->stream));
+    P.segs = ctx->d_segs.as<DevSeg>();
+    P.nsegs = nsegs;
+    P.nxt = ctx->d_nxt.as<uint32_t>();
+    P.ll = ctx->d_ll.as<double2>();
+    P.bm = ctx->d_bm.as<uint32_t>();
+    P.hkeys = ctx->d_hkeys.as<uint32_t>();
+    P.hvals = ctx->d_hvals.as<uint32_t>();
+    P.hcap = ctx->hcap;
+    P.burn = out.burn;
+    CK(ctx->d_err.reserve(sizeof(int)));
+    CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
+    P.error_flag = ctx->d_err.as<int>();
+
+    // ---- outputs
+    if (mode == MODE_DETECT) {
+        CK(ctx->d_tallies.reserve(8 * (size_t)nsegs));
+        CK(cudaMemsetAsync(ctx->d_tallies.p, 0, 8 * (size_t)nsegs, ctx->stream));
+        P.tallies = ctx->d_tallies.as<unsigned long long>();
+        P.tallies2 = reinterpret_cast<unsigned long long*>(out.d_tallies);
+        if (out.logp) {
+            CK(ctx->d_logp.reserve(16 * (size_t)trials));
+            P.logp = ctx->d_logp.as<double>();
+        }
+    } else if (mode == MODE_LEARN) {
+        CK(ctx->d_counts.reserve(8 * (size_t)nsegs * SR));
+        CK(cudaMemsetAsync(ctx->d_counts.p, 0, 8 * (size_t)nsegs * SR, ctx->stream));
+        P.counts = ctx->d_counts.as<unsigned long long>();
+    } else if (mode == MODE_TRACE) {
+        const size_t cells = (size_t)trials * ((size_t)segs[0].N + 1);
+        CK(ctx->d_trace_idx.reserve(4 * cells));
+        P.trace_idx = ctx->d_trace_idx.as<uint32_t>();
+        if (out.trace_met && engine == MVD_ENGINE_ACS) {
+            CK(ctx->d_trace_met.reserve(cells * nstate));
+            P.trace_met = ctx->d_trace_met.as<uint8_t>();
+        }
+    } else if (mode == MODE_HASH) {
+        CK(ctx->d_hashes.reserve(8 * (size_t)trials));
+        P.hashes = ctx->d_hashes.as<unsigned long long>();
+        if (out.final_met) {
+            CK(ctx->d_final.reserve((size_t)trials * nstate));
+            P.final_met = ctx->d_final.as<uint8_t>();
+        }
+    }
+
+    // ---- shared memory plan
+    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
+    size_t smem = 0;
+    bool in_smem = false;
+    if (engine == MVD_ENGINE_FSM) {
+        size_t need = (size_t)SR * 2;
+        if (mode == MODE_DETECT) need += (size_t)SR * 16;
+        if (mode == MODE_LEARN) need += (size_t)SR * 4;
+        bool learn_fits32 = mode != MODE_LEARN || (uint64_t)MVD_BLOCK * (uint64_t)segs[0].N < 0xFFFFFFFFull;
+        for (uint32_t i = 0; i < nsegs && learn_fits32 && mode == MODE_LEARN; ++i)
+            learn_fits32 = (uint64_t)MVD_BLOCK * (uint64_t)segs[i].N < 0xFFFFFFFFull;
+        in_smem = (uint64_t)SR <= 65535ull && need + 64 <= smem_max && learn_fits32;
+        smem = in_smem ? need : 0;
+    } else {
+        const int NP = nstate / 2, KW = (nstate + 7) / 8;
+        size_t base = (((size_t)R * 2 * NP * 4) + 15) & ~(size_t)15;
+        size_t need = base;
+        if (mode == MODE_DETECT) need += (size_t)SR * 16;
+        if (mode == MODE_LEARN) need += (size_t)SR * 4;
+        need += (size_t)ctx->hcap * 4 * (1 + KW);
+        bool learn_fits32 = true;
+        for (uint32_t i = 0; i < nsegs && mode == MODE_LEARN; ++i)
+            learn_fits32 = learn_fits32 && (uint64_t)MVD_BLOCK * (uint64_t)segs[i].N < 0xFFFFFFFFull;
+        in_smem = mode != MODE_HASH && need + 64 <= smem_max && learn_fits32;
+        smem = in_smem ? need : base;
+    }
+    P.tables_in_smem = in_smem ? 1 : 0;
+
+    if (blocks == 0) {
+        if (out.tallies) memset(out.tallies, 0, 8 * (size_t)nsegs);
+        if (out.counts) memset(out.counts, 0, 8 * (size_t)nsegs * SR);
+        return MVD_OK;
+    }
+    const dim3 grid((unsigned)blocks);
+    const bool n2 = (n == 2);
+    cudaError_t le = cudaErrorInvalidValue;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (engine == MVD_ENGINE_FSM) {
+        if (mode == MODE_DETECT) {
+            if (in_smem) le = n2 ? launch_fsm<MODE_DETECT, 2, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, true>(grid, smem, ctx->stream, P);
+            else le = n2 ? launch_fsm<MODE_DETECT, 2, false>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, false>(grid, smem, ctx->stream, P);
+        } else if (mode == MODE_LEARN) {
+            le = in_smem ? launch_fsm<MODE_LEARN, 0, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_LEARN, 0, false>(grid, smem, ctx->stream, P);
+        } else {
+            le = in_smem ? launch_fsm<MODE_TRACE, 0, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_TRACE, 0, false>(grid, smem, ctx->stream, P);
+        }
+    } else {
+        if (mode == MODE_DETECT) le = n2 ? launch_acs<MODE_DETECT, 2>(m, grid, smem, ctx->stream, P) : launch_acs<MODE_DETECT, 0>(m, grid, smem, ctx->stream, P);
+        else if (mode == MODE_LEARN) le = launch_acs<MODE_LEARN, 0>(m, grid, smem, ctx->stream, P);
+        else if (mode == MODE_TRACE) le = launch_acs<MODE_TRACE, 0>(m, grid, smem, ctx->stream, P);
+        else le = n2 ? launch_acs<MODE_HASH, 2>(m, grid, smem, ctx->stream, P) : launch_acs<MODE_HASH, 0>(m, grid, smem, ctx->stream, P);
+    }
+    if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
+    ctx->launches += 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+
+    // ---- read back
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mode == MODE_DETECT) {
+        if (out.tallies) CK(cudaMemcpyAsync(out.tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out.logp) CK(cudaMemcpyAsync(out.logp, ctx->d_logp.p, 16 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (mode == MODE_LEARN) {
+        if (out.counts) CK(cudaMemcpyAsync(out.counts, ctx->d_counts.p, 8 * (size_t)nsegs * SR, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (mode == MODE_TRACE) {
+        const size_t cells = (size_t)trials * ((size_t)segs[0].N + 1);
+        CK(cudaMemcpyAsync(out.trace_idx, ctx->d_trace_idx.p, 4 * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out.trace_met && engine == MVD_ENGINE_ACS)
+            CK(cudaMemcpyAsync(out.trace_met, ctx->d_trace_met.p, cells * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(out.hashes, ctx->d_hashes.p, 8 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out.final_met) CK(cudaMemcpyAsync(out.final_met, ctx->d_final.p, (size_t)trials * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (mode == MODE_TRACE && out.trace_met && engine == MVD_ENGINE_FSM) {
+        // FSM engine: the metric vectors are a gather from the state table
+        const size_t cells = (size_t)trials * ((size_t)segs[0].N + 1);
+        for (size_t c = 0; c < cells; ++c)
+            memcpy(out.trace_met + c * nstate, ctx->h_metrics.data() + (size_t)out.trace_idx[c] * nstate, nstate);
+    }
+    if (herr & 1) return fail(ctx, MVD_E_UNKNOWN_STATE, "a relative-metric vector was not in the state table (KeyError)");
+    if (herr & 2) return fail(ctx, MVD_E_UNKNOWN_STATE, "relative metric exceeded 15 (hash key overflow)");
+    return MVD_OK;
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+int mvd_abi_version(void) { return MVD_ABI_VERSION; }
+
+int mvd_create(mvd_ctx** out, int device) {
+    mvd_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, MVD_E_INVALID, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MVD_E_CUDA, "no CUDA device available (%s); libmvd has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, MVD_E_INVALID, "device %d out of range (count %d)", device, count);
+    ctx = new mvd_ctx();
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&ctx->prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e != cudaSuccess) {
+        fail(nullptr, MVD_E_CUDA, "context creation failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return MVD_E_CUDA;
+    }
+    ctx->own_stream = true;
+    *out = ctx;
+    return MVD_OK;
+}
+
+int mvd_destroy(mvd_ctx* ctx) {
+    if (!ctx) return MVD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
+                      &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MVD_OK;
+}
+
+const char* mvd_last_error(const mvd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mvd_set_stream(mvd_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MVD_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return MVD_OK;
+}
+
+int mvd_synchronize(mvd_ctx* ctx) {
+    if (!ctx) return MVD_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVD_OK;
+}
+
+int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps) {
+    if (!ctx || !dec_taps) return ctx ? fail(ctx, MVD_E_INVALID, "null taps") : MVD_E_INVALID;
+    if (k != 1) return fail(ctx, MVD_E_UNSUPPORTED, "device path supports k = 1 codes only (got k=%d)", k);
+    if (n < 1 || n > MVD_MAX_N) return fail(ctx, MVD_E_UNSUPPORTED, "n=%d outside [1,%d]", n, MVD_MAX_N);
+    if (m < 1 || m > MVD_MAX_M) return fail(ctx, MVD_E_UNSUPPORTED, "m=%d outside [1,%d]", m, MVD_MAX_M);
+    for (int j = 0; j < n; ++j)
+        if (dec_taps[j] >> (m + 1)) return fail(ctx, MVD_E_INVALID, "decoder tap mask %d has bits beyond memory m=%d", j, m);
+    CK(cudaSetDevice(ctx->device));
+    ctx->k = k;
+    ctx->n = n;
+    ctx->m = m;
+    for (int j = 0; j < MVD_MAX_N; ++j) ctx->dec_taps[j] = j < n ? dec_taps[j] : 0u;
+    // branch metrics, 16x2 packed: low half = input 0 (ns = 2g), high half = input 1 (ns = 2g+1)
+    const int nstate = 1 << m, NP = nstate / 2, HALF = nstate / 2, R = 1 << n;
+    std::vector<uint32_t> bm((size_t)R * 2 * NP);
+    for (int r = 0; r < R; ++r)
+        for (int g = 0; g < NP; ++g) {
+            auto d = [&](uint32_t ps, uint32_t u) { return (uint32_t)__builtin_popcount((unsigned)(label_of_branch(ps, u, ctx->dec_taps, n) ^ r)); };
+            bm[((size_t)r * NP + g) * 2 + 0] = d(g, 0) | (d(g, 1) << 16);
+            bm[((size_t)r * NP + g) * 2 + 1] = d(g + HALF, 0) | (d(g + HALF, 1) << 16);
+        }
+    CK(ctx->d_bm.reserve(bm.size() * 4));
+    CK(cudaMemcpyAsync(ctx->d_bm.p, bm.data(), bm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_code = true;
+    ctx->have_states = false;
+    ctx->ntables = 0;
+    return MVD_OK;
+}
+
+int mvd_set_states(mvd_ctx* ctx, uint32_t S, const uint8_t* metrics, const uint32_t* next) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code first");
+    if (!metrics || !next || S == 0) return fail(ctx, MVD_E_INVALID, "null / empty state table");
+    const int nstate = 1 << ctx->m, R = 1 << ctx->n;
+    ctx->S = S;
+    ctx->h_metrics.assign(metrics, metrics + (size_t)S * nstate);
+    ctx->h_next.assign(next, next + (size_t)S * R);
+    return install_states(ctx);
+}
+
+int mvd_enumerate_states(mvd_ctx* ctx, uint32_t max_states, uint32_t* S_out) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code first");
+    if (max_states == 0) return fail(ctx, MVD_E_INVALID, "max_states = 0");
+    const int n = ctx->n, m = ctx->m, nstate = 1 << m, R = 1 << n, HALF = nstate / 2;
+    // branch labels of the butterfly
+    std::vector<int> lab0(nstate), lab1(nstate);   // label of branch into ns from ps0 / ps1
+    for (int ns = 0; ns < nstate; ++ns) {
+        lab0[ns] = label_of_branch((uint32_t)(ns >> 1), (uint32_t)(ns & 1), ctx->dec_taps, n);
+        lab1[ns] = label_of_branch((uint32_t)((ns >> 1) + HALF), (uint32_t)(ns & 1), ctx->dec_taps, n);
+    }
+    // discovery-ordered closure: the vector of states doubles as the BFS queue
+    std::vector<uint8_t>& met = ctx->h_metrics;
+    std::vector<uint32_t>& nxt = ctx->h_next;
+    met.assign(nstate, 0);
+    nxt.clear();
+    size_t cap = 1024;
+    std::vector<uint32_t> slots(cap, MVD_EMPTY);
+    auto vhash = [&](const uint8_t* v) {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < nstate; ++i) h = (h ^ v[i]) * 0xD6E8FEB86659FD93ull;
+        return (size_t)(h ^ (h >> 32));
+    };
+    auto insert_slot = [&](uint32_t idx) {
+        size_t h = vhash(met.data() + (size_t)idx * nstate) & (cap - 1);
+        while (slots[h] != MVD_EMPTY) h = (h + 1) & (cap - 1);
+        slots[h] = idx;
+    };
+    insert_slot(0);
+    uint32_t S = 1;
+    std::vector<uint8_t> cand(nstate);
+    for (uint32_t cur = 0; cur < S; ++cur) {
+        for (int r = 0; r < R; ++r) {
+            int lo = 1 << 30;
+            int tmp[64];
+            for (int ns = 0; ns < nstate; ++ns) {
+                const int a = met[(size_t)cur * nstate + (ns >> 1)] + __builtin_popcount((unsigned)(lab0[ns] ^ r));
+                const int b = met[(size_t)cur * nstate + (ns >> 1) + HALF] + __builtin_popcount((unsigned)(lab1[ns] ^ r));
+                tmp[ns] = a < b ? a : b;
+                lo = tmp[ns] < lo ? tmp[ns] : lo;
+            }
+            for (int ns = 0; ns < nstate; ++ns) {
+                const int v = tmp[ns] - lo;
+                if (v > 255) return fail(ctx, MVD_E_UNSUPPORTED, "relative metric exceeds 8 bits");
+                cand[ns] = (uint8_t)v;
+            }
+            size_t h = vhash(cand.data()) & (cap - 1);
+            uint32_t found = MVD_EMPTY;
+            while (slots[h] != MVD_EMPTY) {
+                if (memcmp(met.data() + (size_t)slots[h] * nstate, cand.data(), nstate) == 0) { found = slots[h]; break; }
+                h = (h + 1) & (cap - 1);
+            }
+            if (found == MVD_EMPTY) {
+                if (S >= max_states) {
+                    ctx->have_states = false;
+                    return fail(ctx, MVD_E_NOMEM, "more than %u Markov states", max_states);
+                }
+                met.insert(met.end(), cand.begin(), cand.end());
+                found = S++;
+                slots[h] = found;
+                if ((size_t)S * 2 > cap) {          // grow + rehash
+                    cap <<= 1;
+                    slots.assign(cap, MVD_EMPTY);
+                    for (uint32_t i = 0; i < S; ++i) insert_slot(i);
+                }
+            }
+            nxt.push_back(found);
+        }
+    }
+    ctx->S = S;
+    if (S_out) *S_out = S;
+    return install_states(ctx);
+}
+
+int mvd_get_states(mvd_ctx* ctx, uint8_t* metrics, uint32_t* next) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!ctx->have_states) return fail(ctx, MVD_E_STATE, "no state table");
+    if (metrics) memcpy(metrics, ctx->h_metrics.data(), ctx->h_metrics.size());
+    if (next) memcpy(next, ctx->h_next.data(), ctx->h_next.size() * 4);
+    return MVD_OK;
+}
+
+int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const double* logTref) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!ctx->have_states) return fail(ctx, MVD_E_STATE, "mvd_set_states first");
+    if (!logP1 || !logTref || ntables == 0) return fail(ctx, MVD_E_INVALID, "null / empty log-likelihood tables");
+    CK(cudaSetDevice(ctx->device));
+    const size_t SR = (size_t)ctx->S << ctx->n;
+    std::vector<double> inter(2 * SR * ntables);
+    for (uint32_t t = 0; t < ntables; ++t)
+        for (size_t e = 0; e < SR; ++e) {
+            inter[2 * (t * SR + e)] = logP1[t * SR + e];
+            inter[2 * (t * SR + e) + 1] = logTref[e];
+        }
+    CK(ctx->d_ll.reserve(inter.size() * 8));
+    CK(cudaMemcpyAsync(ctx->d_ll.p, inter.data(), inter.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ntables = ntables;
+    return MVD_OK;
+}
+
+int mvd_learn_counts(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs, uint32_t burn, int engine,
+                     uint64_t* edge_counts) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!edge_counts) return fail(ctx, MVD_E_INVALID, "null edge_counts");
+    LaunchOut o;
+    o.counts = edge_counts;
+    o.burn = burn;
+    return run(ctx, MODE_LEARN, engine, src, segs, nsegs, o);
+}
+
+int mvd_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs, int engine, uint64_t* tallies,
+               double* logp, void* d_tallies) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!tallies && !d_tallies) return fail(ctx, MVD_E_INVALID, "no tally destination");
+    LaunchOut o;
+    o.tallies = tallies;
+    o.logp = logp;
+    o.d_tallies = d_tallies;
+    return run(ctx, MODE_DETECT, engine, src, segs, nsegs, o);
+}
+
+int mvd_trace(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, int engine, uint32_t* state_idx, uint8_t* metrics) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!state_idx) return fail(ctx, MVD_E_INVALID, "null state_idx");
+    LaunchOut o;
+    o.trace_idx = state_idx;
+    o.trace_met = metrics;
+    return run(ctx, MODE_TRACE, engine, src, seg, 1, o);
+}
+
+int mvd_acs_hash(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint64_t* hashes, uint8_t* final_metrics) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!hashes) return fail(ctx, MVD_E_INVALID, "null hashes");
+    LaunchOut o;
+    o.hashes = hashes;
+    o.final_met = final_metrics;
+    return run(ctx, MODE_HASH, MVD_ENGINE_ACS, src, seg, 1, o);
+}
+
+int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return MVD_E_INVALID;
+    *ms = ctx->last_ms;
+    return MVD_OK;
+}
+
+int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches) {
+    if (!ctx || !launches) return MVD_E_INVALID;
+    *launches = ctx->launches;
+    return MVD_OK;
+}
+
+int mvd_int_peak(mvd_ctx* ctx, double* alu_gops, double* alu_fma_gops) {
+    if (!ctx) return MVD_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_peak.reserve(64));
+    CK(cudaMemsetAsync(ctx->d_peak.p, 0, 64, ctx->stream));
+    const int blocks = ctx->prop.multiProcessorCount * 8, iters = 4096;
+    double res[2] = {0, 0};
+    for (int mode = 0; mode < 2; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            int_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_peak.as<uint32_t>(), iters, mode);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            ctx->launches += 1;
+            if (rep > 0) best = std::min(best, ms);
+        }
+        const double ops = (double)blocks * 256.0 * iters * MVD_PEAK_OPS_PER_ITER;
+        res[mode] = ops / (best * 1e-3) * 1e-9;
+    }
+    if (alu_gops) *alu_gops = res[0];
+    if (alu_fma_gops) *alu_fma_gops = res[1];
+    return MVD_OK;
+}
+
+int mvd_device_info(mvd_ctx* ctx, int* sm_count, int* clock_khz, uint64_t* smem_per_block_optin, char* name, int name_len) {
+    if (!ctx) return MVD_E_INVALID;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *clock_khz = khz;
+    }
+    if (smem_per_block_optin) *smem_per_block_optin = ctx->prop.sharedMemPerBlockOptin;
+    if (name && name_len > 0) {
+        strncpy(name, ctx->prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return MVD_OK;
+}
+
+}  // extern "C"

@@ -297,34 +297,46 @@ def tref_half_table(tab: StateTable) -> np.ndarray:
     return tab.mult.astype(np.float64) / float(1 << tab.n)
 
 
-def p1_from_edge_counts(tab: StateTable, edge_counts: np.ndarray, laplace: float) -> np.ndarray:
-    """Edge form of the smoothed, row-normalised estimate (Pd_plotter.py:166-167).
+DENSE_LIMIT = 2048      # largest S for which the dense S x S replay of the reference is built
 
-    ``edge_counts[i, r]`` = number of counted steps that left state ``i`` on received word
-    ``r``.  The dense reference adds ``laplace`` to all S columns of row ``i`` and divides by
-    the row sum; on the edge ``(i, j = nxt[i, r])`` that is ``(c_ij + laplace) / rowsum`` with
-    ``c_ij`` summed over all r that reach j.  The row sum is accumulated exactly the way numpy
-    does it on the dense row (pairwise float64 add of S values) by building that row.
+
+def dense_counts_from_edges(tab: StateTable, edge_counts: np.ndarray) -> np.ndarray:
+    """The reference's ``counts`` matrix (Pd_plotter.py:158-163) from edge counts (small S)."""
+    S = tab.S
+    ec = np.asarray(edge_counts, dtype=np.float64).reshape(S, tab.R)
+    dense = np.zeros((S, S))
+    rows = np.repeat(np.arange(S), tab.R)
+    np.add.at(dense, (rows, tab.nxt.reshape(-1)), ec.reshape(-1))
+    return dense
+
+
+def p1_dense(tab: StateTable, edge_counts: np.ndarray, laplace: float) -> np.ndarray:
+    """Smoothed, row-normalised estimate with the reference's own two numpy statements
+    (Pd_plotter.py:166-167) on the dense matrix -- bit-identical by construction."""
+    P = dense_counts_from_edges(tab, edge_counts) + laplace
+    P /= P.sum(axis=1, keepdims=True)
+    return P
+
+
+def p1_from_edge_counts(tab: StateTable, edge_counts: np.ndarray, laplace: float) -> np.ndarray:
+    """Edge form ``P1[i, r] = P[i, nxt[i, r]]`` of Pd_plotter.py:166-167.
+
+    ``edge_counts[i, r]`` = counted steps that left state ``i`` on received word ``r``.  Up to
+    ``DENSE_LIMIT`` states the dense matrix is replayed exactly as the reference builds it and
+    gathered; above it (where the reference itself cannot allocate S x S) the closed form
+    ``(c_ij + laplace) / (row_i + laplace * S)`` is used, with ``c_ij`` summed over every r that
+    reaches j -- identical for dyadic ``laplace`` (1.0 is the only value the reference uses),
+    within 2 ulp otherwise.
     """
     S, R = tab.S, tab.R
     ec = np.asarray(edge_counts, dtype=np.float64).reshape(S, R)
-    nxt = tab.nxt
-    # c_ij gathered per edge: sum counts of all r' with the same successor
-    same = nxt[:, :, None] == nxt[:, None, :]
+    if S <= DENSE_LIMIT:
+        P = p1_dense(tab, ec, laplace)
+        return np.ascontiguousarray(P[np.arange(S)[:, None], tab.nxt])
+    same = tab.nxt[:, :, None] == tab.nxt[:, None, :]
     cij = (same * ec[:, None, :]).sum(axis=2)
-    out = np.empty((S, R), dtype=np.float64)
-    if S <= 4096:
-        # exact dense-row replay (numpy pairwise summation order matters in the last ulp)
-        row = np.empty(S, dtype=np.float64)
-        for i in range(S):
-            row[:] = 0.0
-            np.add.at(row, nxt[i], ec[i])
-            row += laplace
-            out[i] = (cij[i] + laplace) / row.sum()
-    else:
-        denom = ec.sum(axis=1) + laplace * S
-        out[:] = (cij + laplace) / denom[:, None]
-    return out
+    denom = ec.sum(axis=1) + laplace * S
+    return (cij + laplace) / denom[:, None]
 
 
 def dense_from_edges(tab: StateTable, edge_values: np.ndarray, fill: float = 0.0) -> np.ndarray:

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: trials shard across ranks, tallies combine with one allreduce.
+
+One process per GPU (torchrun).  Monte-Carlo trials are independent and every trial's bit stream
+is keyed by its *global* trial id, so rank r of W simply takes the contiguous id range
+``shard_range(total, r, W)`` of every sweep point and the summed tallies are bit-identical for
+any W.  The only data-path collective is a single ``all_reduce(SUM)`` of the int64 tally vector
+(NCCL over NVLink on GPUs; gloo in the CPU tests).  The reference has no equivalent: its trial
+loop is serial (Pd_plotter.py:198-223).
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import numpy as np
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) from torch.distributed if initialised, else from the torchrun env."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def shard_range(total: int, rank: int, world_size: int, offset: int = 0) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``[offset, offset + total)``; the first ``total % W`` ranks
+    get one extra trial."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(int(total), world_size)
+    begin = rank * base + min(rank, extra)
+    end = begin + base + (1 if rank < extra else 0)
+    return offset + begin, offset + end
+
+
+def allreduce_sum(values: np.ndarray, device: str | None = None) -> np.ndarray:
+    """Sum an integer vector over all ranks (no-op for a single process)."""
+    rank, ws = world()
+    arr = np.asarray(values)
+    if ws == 1:
+        return arr
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(arr.astype(np.int64))
+    backend = dist.get_backend()
+    if backend == "nccl":
+        dev = device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+        t = t.to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().astype(arr.dtype)
+
+
+def allreduce_sum_device(tensor):
+    """In-place SUM allreduce of a device tensor (used when tallies are left on the GPU)."""
+    _, ws = world()
+    if ws > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor

@@ -1,0 +1,248 @@
+"""High-level host driver over libmvd.so: one :class:`Detector` per (decoder code, GPU).
+
+Call order mirrors the reference's experiment (Pd_plotter.py:176-235):
+``Detector(gen1, ...)``  -> trellis + Markov state table (host) -> device tables;
+``learn_counts``         -> Pd_plotter.py:149-163 on the GPU;
+``set_models``           -> Pd_plotter.py:166-167 (host float64) + log tables to the GPU;
+``detect``               -> Pd_plotter.py:210-223 on the GPU, one launch for a whole sweep.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi, bitsource, codes
+
+
+@dataclass
+class Seg:
+    """One hypothesis of one sweep point (or one learning chain); see ``mvd_segment``."""
+    N: int
+    threshold: int = 0
+    stream: int = 0
+    table: int = 0
+    enc_taps: Sequence[int] = ()
+    decide: int = 0
+    random_input: bool = True
+    trial_begin: int = 0
+    trial_end: int = 1
+    bits_offset: int = 0
+
+    @property
+    def ntrials(self) -> int:
+        return self.trial_end - self.trial_begin
+
+
+def _log_table(values: np.ndarray) -> np.ndarray:
+    """Elementwise ``math.log(max(v, 1e-300))`` (Pd_plotter.py:114-115) with libm's log -- the
+    same function the reference calls per step, so device sums add bit-identical terms."""
+    flat = np.asarray(values, dtype=np.float64).ravel()
+    out = np.fromiter((math.log(v if v > 1e-300 else 1e-300) for v in flat.tolist()), dtype=np.float64, count=flat.size)
+    return out.reshape(np.shape(values))
+
+
+class Detector:
+    def __init__(self, gen1, k: int, n: int, m: int, device: int = 0, table: Optional[codes.StateTable] = None,
+                 enumerate_with: str = "python", max_states: int = 1 << 22):
+        self.lib = _capi.load()
+        self.gen1 = codes.freeze_generator(gen1)
+        self.k, self.n, self.m = int(k), int(n), int(m)
+        self.R = 1 << self.n
+        self.ctx = C.c_void_p()
+        rc = self.lib.mvd_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            _capi.check(self.lib, None, rc)
+        self.device = int(device)
+        if self.k != 1:
+            self.close()
+            raise _capi.MvdError(-3, "the device path supports k = 1 codes only")
+        self.dec_taps = codes.tap_masks(self.gen1, self.m, self.k)
+        taps = (C.c_uint32 * len(self.dec_taps))(*self.dec_taps)
+        self._ck(self.lib.mvd_set_code(self.ctx, self.k, self.n, self.m, taps))
+        if table is not None:
+            self.table = table
+            self._upload_states()
+        elif enumerate_with == "lib":
+            S = C.c_uint32()
+            self._ck(self.lib.mvd_enumerate_states(self.ctx, int(max_states), C.byref(S)))
+            met = np.empty((S.value, 1 << self.m), dtype=np.uint8)
+            nxt = np.empty((S.value, self.R), dtype=np.uint32)
+            self._ck(self.lib.mvd_get_states(self.ctx, met.ctypes.data, nxt.ctypes.data))
+            mult = (nxt[:, :, None] == nxt[:, None, :]).sum(axis=2).astype(np.uint8)
+            self.table = codes.StateTable(self.k, self.n, self.m, met, nxt, mult)
+        else:
+            self.table = codes.enumerate_states(self.gen1, self.m, self.k, self.n, max_states=max_states)
+            self._upload_states()
+        self.ntables = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc: int):
+        _capi.check(self.lib, self.ctx, rc)
+
+    def _upload_states(self):
+        met = np.ascontiguousarray(self.table.metrics, dtype=np.uint8)
+        nxt = np.ascontiguousarray(self.table.nxt, dtype=np.uint32)
+        self._ck(self.lib.mvd_set_states(self.ctx, self.table.S, met.ctypes.data, nxt.ctypes.data))
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.lib.mvd_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def S(self) -> int:
+        return self.table.S
+
+    def taps_of(self, gen) -> List[int]:
+        return codes.tap_masks(codes.freeze_generator(gen), self.m, self.k)
+
+    def _segments(self, segs: Sequence[Seg]):
+        arr = (_capi.Segment * len(segs))()
+        for a, s in zip(arr, segs):
+            a.N, a.threshold, a.stream, a.table = int(s.N), int(s.threshold), int(s.stream) & 0xFFFFFFFF, int(s.table)
+            taps = list(s.enc_taps) if len(s.enc_taps) else list(self.dec_taps)
+            for j in range(_capi.MAX_N):
+                a.enc_taps[j] = int(taps[j]) if j < len(taps) else 0
+            a.decide = int(s.decide)
+            a.random_input = 1 if s.random_input else 0
+            a.trial_begin, a.trial_end, a.bits_offset = int(s.trial_begin), int(s.trial_end), int(s.bits_offset)
+        return arr
+
+    @staticmethod
+    def _src(seed: Optional[int], bits, bits_device_ptr: Optional[int] = None, bits_words: int = 0):
+        src = _capi.Src()
+        if bits is None and bits_device_ptr is None:
+            src.mode = _capi.SRC_PHILOX
+            src.seed = int(seed or 0) & 0xFFFFFFFFFFFFFFFF
+            return src, None
+        src.mode = _capi.SRC_BITSTREAM
+        src.seed = 0
+        if bits_device_ptr is not None:
+            src.bits_on_device = 1
+            src.bits = int(bits_device_ptr)
+            src.bits_words = int(bits_words)
+            return src, None
+        keep = np.ascontiguousarray(bits, dtype=np.uint32)
+        src.bits_on_device = 0
+        src.bits = keep.ctypes.data
+        src.bits_words = keep.size // 4
+        return src, keep
+
+    # ------------------------------------------------------------------ hot path
+    def learn_counts(self, segs: Sequence[Seg], burn: int, seed: Optional[int] = None, bits=None,
+                     engine: str = "auto", bits_device_ptr=None, bits_words=0) -> np.ndarray:
+        """Edge counts uint64 [nsegs, S, R] of the steps t >= burn (Pd_plotter.py:158-163)."""
+        src, keep = self._src(seed, bits, bits_device_ptr, bits_words)
+        out = np.zeros((len(segs), self.S, self.R), dtype=np.uint64)
+        self._ck(self.lib.mvd_learn_counts(self.ctx, C.byref(src), self._segments(segs), len(segs), int(burn),
+                                           _capi.ENGINES[engine], out.ctypes.data))
+        del keep
+        return out
+
+    def set_models(self, p1_edge_tables: Iterable[np.ndarray], tref_edge: Optional[np.ndarray] = None):
+        """Upload ``log P1`` (one table per distinct p) and ``log T(1/2)``, edge-indexed [S, R]."""
+        tabs = [np.asarray(t, dtype=np.float64).reshape(self.S, self.R) for t in p1_edge_tables]
+        if tref_edge is None:
+            tref_edge = codes.tref_half_table(self.table)
+        self.logP1 = np.ascontiguousarray(np.stack([_log_table(t) for t in tabs]))
+        self.logTref = np.ascontiguousarray(_log_table(np.asarray(tref_edge, dtype=np.float64).reshape(self.S, self.R)))
+        self._ck(self.lib.mvd_set_loglik(self.ctx, len(tabs), self.logP1.ctypes.data, self.logTref.ctypes.data))
+        self.ntables = len(tabs)
+
+    def detect(self, segs: Sequence[Seg], seed: Optional[int] = None, bits=None, engine: str = "auto",
+               want_logp: bool = False, d_tallies_ptr: Optional[int] = None, bits_device_ptr=None, bits_words=0):
+        """Successes per segment (uint64 [nsegs]) and optionally (logp1, logp_ref) per trial."""
+        src, keep = self._src(seed, bits, bits_device_ptr, bits_words)
+        tallies = np.zeros(len(segs), dtype=np.uint64)
+        logp = None
+        if want_logp:
+            logp = np.zeros((sum(s.ntrials for s in segs), 2), dtype=np.float64)
+        self._ck(self.lib.mvd_detect(self.ctx, C.byref(src), self._segments(segs), len(segs), _capi.ENGINES[engine],
+                                     tallies.ctypes.data, logp.ctypes.data if want_logp else None,
+                                     C.c_void_p(d_tallies_ptr) if d_tallies_ptr else None))
+        del keep
+        return (tallies, logp) if want_logp else tallies
+
+    def trace(self, seg: Seg, seed: Optional[int] = None, bits=None, engine: str = "acs", want_metrics: bool = True):
+        """State indices uint32 [ntrials, N+1] and metric vectors uint8 [ntrials, N+1, 2^m]."""
+        src, keep = self._src(seed, bits)
+        idx = np.zeros((seg.ntrials, seg.N + 1), dtype=np.uint32)
+        met = np.zeros((seg.ntrials, seg.N + 1, 1 << self.m), dtype=np.uint8) if want_metrics else None
+        self._ck(self.lib.mvd_trace(self.ctx, C.byref(src), self._segments([seg]), _capi.ENGINES[engine],
+                                    idx.ctypes.data, met.ctypes.data if want_metrics else None))
+        del keep
+        return idx, met
+
+    def acs_hash(self, seg: Seg, seed: Optional[int] = None, bits=None, want_final: bool = True):
+        src, keep = self._src(seed, bits)
+        h = np.zeros(seg.ntrials, dtype=np.uint64)
+        fin = np.zeros((seg.ntrials, 1 << self.m), dtype=np.uint8) if want_final else None
+        self._ck(self.lib.mvd_acs_hash(self.ctx, C.byref(src), self._segments([seg]), h.ctypes.data,
+                                       fin.ctypes.data if want_final else None))
+        del keep
+        return h, fin
+
+    # ------------------------------------------------------------------ introspection
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.mvd_last_kernel_ms(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._ck(self.lib.mvd_launch_count(self.ctx, C.byref(v)))
+        return int(v.value)
+
+    def int_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.mvd_int_peak(self.ctx, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def device_info(self) -> dict:
+        sm, khz, smem = C.c_int(), C.c_int(), C.c_uint64()
+        name = C.create_string_buffer(128)
+        self._ck(self.lib.mvd_device_info(self.ctx, C.byref(sm), C.byref(khz), C.byref(smem), name, 128))
+        return dict(sm_count=sm.value, clock_khz=khz.value, smem_per_block_optin=int(smem.value), name=name.value.decode())
+
+
+class HashOnlyDetector(Detector):
+    """Decoder without a Markov state table (m = 5, 6): only :meth:`acs_hash` is usable."""
+
+    def __init__(self, gen1, k, n, m, device=0):
+        self.lib = _capi.load()
+        self.gen1 = codes.freeze_generator(gen1)
+        self.k, self.n, self.m = int(k), int(n), int(m)
+        self.R = 1 << self.n
+        self.ctx = C.c_void_p()
+        rc = self.lib.mvd_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            _capi.check(self.lib, None, rc)
+        self.dec_taps = codes.tap_masks(self.gen1, self.m, self.k)
+        taps = (C.c_uint32 * len(self.dec_taps))(*self.dec_taps)
+        self._ck(self.lib.mvd_set_code(self.ctx, self.k, self.n, self.m, taps))
+        self.table = None
+        self.ntables = 0
+
+    @property
+    def S(self):
+        return 0
+
+
+def philox_threshold(p: float) -> int:
+    return bitsource.bsc_threshold(p)

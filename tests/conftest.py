@@ -1,0 +1,44 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "detecting-convolutional-codes-via-markovian-statistics_b200")
+for p in (PKG, os.path.join(ROOT, "oracle"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CODES = {
+    "c75": dict(k=1, n=2, m=2, gen=[[[1, 1, 1]], [[1, 0, 1]]]),
+    "c65": dict(k=1, n=2, m=2, gen=[[[1, 1, 0]], [[1, 0, 1]]]),
+    "m3a": dict(k=1, n=2, m=3, gen=[[[1, 1, 1, 1]], [[1, 0, 1, 1]]]),
+    "m3b": dict(k=1, n=2, m=3, gen=[[[1, 0, 1, 1]], [[1, 1, 1, 1]]]),
+    "r13": dict(k=1, n=3, m=2, gen=[[[1, 1, 1]], [[1, 0, 1]], [[1, 1, 0]]]),
+    "m1": dict(k=1, n=2, m=1, gen=[[[1, 1]], [[1, 0]]]),
+    "m4a": dict(k=1, n=2, m=4, gen=[[[1, 1, 0, 0, 1]], [[1, 1, 0, 1, 1]]]),     # (31,33): S = 25 751
+    "m4b": dict(k=1, n=2, m=4, gen=[[[1, 1, 0, 1, 1]], [[1, 1, 0, 0, 1]]]),     # outputs swapped
+    "m5": dict(k=1, n=2, m=5, gen=[[[1, 0, 1, 0, 1, 1]], [[1, 1, 1, 1, 0, 1]]]),            # (53,75)
+    "m6": dict(k=1, n=2, m=6, gen=[[[1, 0, 1, 1, 0, 1, 1]], [[1, 1, 1, 1, 0, 0, 1]]]),      # (133,171)
+}
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    out = {}
+    for name in ("code_kats", "sim_kats", "experiments"):
+        with open(os.path.join(GOLDEN, name + ".json")) as f:
+            out[name] = json.load(f)
+    return out
+
+
+@pytest.fixture(scope="session")
+def codes_spec():
+    return CODES

@@ -1,0 +1,361 @@
+"""GPU parity tests: every CUDA path against golden vectors (from the reference's own functions)
+and against the CPU oracle on identical bit streams.  Integer results are compared bit-exactly;
+float64 log-likelihoods bit-exactly too (tolerance stated where it is looser).  All calls go through
+the C ABI (ctypes -> libmvd.so)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["acs", "fsm"]
+
+
+def _taps(spec):
+    from mvd import codes
+    return codes.tap_masks(codes.freeze_generator(spec["gen"]), spec["m"], spec["k"])
+
+
+@pytest.fixture(scope="module")
+def dets(codes_spec):
+    from mvd.engine import Detector
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            s = codes_spec[name]
+            cache[name] = Detector(s["gen"], s["k"], s["n"], s["m"])
+        return cache[name]
+
+    yield get
+    for d in cache.values():
+        d.close()
+
+
+SIM_CASES = [("c75_self", "c75", "c75"), ("c75_vs65", "c75", "c65"), ("c75_p001", "c75", "c75"),
+             ("c75_p05", "c75", "c75"), ("m3_self", "m3a", "m3a"), ("m3_vs", "m3a", "m3b"),
+             ("r13_self", "r13", "r13"), ("m1_self", "m1", "m1")]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case,dec,enc", SIM_CASES)
+def test_trace_bitstream_matches_reference(golden, codes_spec, dets, case, dec, enc, engine):
+    """Host-supplied bits -> relative metrics identical to the reference's step function."""
+    from mvd import bitsource
+    from mvd.engine import Seg
+    g = golden["sim_kats"][case]
+    det = dets(dec)
+    N, n = g["N"], codes_spec[dec]["n"]
+    u = np.array(g["u_bits"], dtype=np.uint8).reshape(1, N)
+    e = np.array(g["e_bits"], dtype=np.uint8).reshape(N, n).T.reshape(1, n, N)
+    seg = Seg(N=N, enc_taps=_taps(codes_spec[enc]), trial_begin=0, trial_end=1)
+    idx, met = det.trace(seg, bits=bitsource.pack_bitstreams(u, e), engine=engine)
+    want = np.array(g["metrics"], dtype=np.uint8)
+    assert np.array_equal(met[0], want)
+    states = {tuple(r): i for i, r in enumerate(det.table.metrics.tolist())}
+    assert idx[0].tolist() == [states[tuple(r)] for r in g["metrics"]]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case,dec,enc", SIM_CASES)
+def test_trace_philox_matches_reference(golden, codes_spec, dets, case, dec, enc, engine):
+    """On-device MVD-PHILOX-1 bits + encoder + BSC + recursion == golden trajectory."""
+    from mvd import bitsource
+    from mvd.engine import Seg
+    g = golden["sim_kats"][case]
+    det = dets(dec)
+    seg = Seg(N=g["N"], threshold=bitsource.bsc_threshold(g["p"]), stream=g["stream"], enc_taps=_taps(codes_spec[enc]),
+              trial_begin=g["trial"], trial_end=g["trial"] + 1)
+    idx, met = det.trace(seg, seed=g["seed"], engine=engine)
+    assert np.array_equal(met[0], np.array(g["metrics"], dtype=np.uint8))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 127, 128, 129, 300])
+def test_trace_lengths_vs_oracle(codes_spec, dets, engine, N):
+    """Ragged block / superblock boundaries, several trials per launch, vs the C oracle."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    T = bitsource.bsc_threshold(0.07)
+    tab = co.Table(det.table.metrics, 2)
+    seg = Seg(N=N, threshold=T, stream=9, enc_taps=_taps(codes_spec["c65"]), trial_begin=1000, trial_end=1000 + 300)
+    idx, met = det.trace(seg, seed=77, engine=engine)
+    for t in (0, 1, 255, 256, 299):
+        U, E = co.trial_words(77, 9, 1000 + t, N, 2, T)
+        oi, _, om = co.simulate(_taps(codes_spec["c75"]), _taps(codes_spec["c65"]), 2, 2, N, U, E, tab, True)
+        assert np.array_equal(idx[t], oi.astype(np.uint32))
+        assert np.array_equal(met[t], om)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["c75", "m3a", "r13"])
+def test_learn_counts_vs_oracle(codes_spec, dets, engine, name):
+    """Transition counts of a learning chain: bit-exact vs the oracle (Pd_plotter.py:158-163)."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    s = codes_spec[name]
+    det = dets(name)
+    tab = co.Table(det.table.metrics, s["m"])
+    taps = _taps(s)
+    L, burn = 20000, 200
+    ps = [0.01, 0.2]
+    segs = [Seg(N=L, threshold=bitsource.bsc_threshold(p), stream=bitsource.LEARN_STREAM, enc_taps=taps) for p in ps]
+    got = det.learn_counts(segs, burn=burn, seed=123, engine=engine)
+    for i, p in enumerate(ps):
+        want, _ = co.learn_chain(taps, taps, s["n"], s["m"], L, burn, bitsource.bsc_threshold(p), 123,
+                                 bitsource.LEARN_STREAM, 0, tab)
+        assert np.array_equal(got[i], want)
+        assert int(got[i].sum()) == L - burn
+
+
+def test_learn_counts_many_chains(codes_spec, dets):
+    """Several chains per segment aggregate into one histogram (shared-memory atomics)."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    tab = co.Table(det.table.metrics, 2)
+    taps = _taps(codes_spec["c75"])
+    T = bitsource.bsc_threshold(0.1)
+    seg = Seg(N=700, threshold=T, stream=3, enc_taps=taps, trial_begin=5, trial_end=5 + 600)
+    for engine in ENGINES:
+        got = det.learn_counts([seg], burn=100, seed=9, engine=engine)[0]
+        want = np.zeros_like(got)
+        for t in range(5, 605):
+            w, _ = co.learn_chain(taps, taps, 2, 2, 700, 100, T, 9, 3, t, tab)
+            want += w
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small"])
+def test_run_experiment_matches_reference(golden, exp, engine):
+    """Drop-in run_experiment == the reference's run_experiment (unmodified, injected simulator):
+    identical Pd / Pc, P1 and per-trial log-likelihoods."""
+    import Pd_plotter as pdp
+    from mvd import codes
+    g = golden["experiments"][exp]
+    details = {}
+    df = pdp.run_experiment(g["k"], g["n"], g["m"], g["gen1"], g["gen2"], g["num_iter"], g["p_vec"], g["learn_len"],
+                            g["learn_burn"], g["laplace"], g["seed"], N_spectrum=g["N_list"], engine=engine,
+                            details=details)
+    assert df.to_dict(orient="records") == g["rows"]
+    assert df.to_csv(index=False) == g["csv"]
+    for i, p in enumerate(details["distinct_p"]):
+        want = np.array(g["P1_edge"][repr(p)]["edge"])
+        got = details["p1_tables"][i]
+        if g["laplace"] == 1.0:
+            assert np.array_equal(got, want)                       # bit-exact
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-12)      # north star: 1e-6
+    # per-trial log-likelihood pairs, in the reference's call order (logp1, ref, logp2, ref)
+    import viterbi_markov as vm
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = vm._detector(codes.freeze_generator(g["gen1"]), g["k"], g["n"], g["m"], 0)
+    logs = np.array(g["logps"]).reshape(len(g["N_list"]) * len(g["p_vec"]), g["num_iter"], 2, 2)
+    q = 0
+    tindex = {p: i for i, p in enumerate(details["distinct_p"])}
+    for N in g["N_list"]:
+        for p in g["p_vec"]:
+            for h, gen in enumerate((g["gen1"], g["gen2"])):
+                seg = Seg(N=N, threshold=bitsource.bsc_threshold(p), stream=2 * q + h, table=tindex[p],
+                          enc_taps=det.taps_of(gen), decide=h, trial_begin=0, trial_end=g["num_iter"])
+                _, lp = det.detect([seg], seed=g["seed"], engine=engine, want_logp=True)
+                np.testing.assert_allclose(lp, logs[q, :, h, :], rtol=1e-6)     # north-star tolerance
+                assert np.array_equal(lp, logs[q, :, h, :])                      # and in fact bit-exact
+            q += 1
+
+
+def _oracle_models(det, spec, p, learn_len, seed):
+    import c_oracle as co
+    from mvd import bitsource, codes
+    taps = _taps(spec)
+    tab = co.Table(det.table.metrics, spec["m"])
+    edge, _ = co.learn_chain(taps, taps, spec["n"], spec["m"], learn_len, 200, bitsource.bsc_threshold(p), seed,
+                             bitsource.LEARN_STREAM, 0, tab)
+    P1 = codes.p1_from_edge_counts(det.table, edge, 1.0)
+    return tab, P1, codes.tref_half_table(det.table)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("dec,enc,N,p", [("c75", "c65", 500, 0.1), ("c75", "c75", 200, 0.3), ("m3a", "m3b", 333, 0.05),
+                                         ("r13", "r13", 97, 0.15), ("m1", "m1", 64, 0.2)])
+def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p):
+    """Tallies and per-trial float64 sums vs the oracle, 3000 trials, both decision rules."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec[dec]
+    det = dets(dec)
+    tab, P1, Tref = _oracle_models(det, spec, p, 8000, 5)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(p)
+    ntr = 3000
+    segs = [Seg(N=N, threshold=T, stream=10 + d, enc_taps=_taps(codes_spec[enc]), decide=d, trial_begin=17,
+                trial_end=17 + ntr) for d in (0, 1)]
+    tallies, lp = det.detect(segs, seed=2024, engine=engine, want_logp=True)
+    for d in (0, 1):
+        want, wlp = co.run_trials(_taps(spec), _taps(codes_spec[enc]), spec["n"], spec["m"], N, T, 2024, 10 + d, 17,
+                                  17 + ntr, tab, P1, Tref, d, want_logp=True)
+        assert int(tallies[d]) == want
+        assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
+
+
+def test_detect_rules_are_complementary(codes_spec, dets):
+    """On the *same* stream the H1 rule (>) and the H2 rule (<=) partition the trials."""
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    _, P1, _ = _oracle_models(det, codes_spec["c75"], 0.1, 6200, 123)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(0.1)
+    segs = [Seg(N=100, threshold=T, stream=4, decide=d, trial_begin=0, trial_end=5000) for d in (0, 1)]
+    for engine in ENGINES:
+        t = det.detect(segs, seed=1, engine=engine)
+        assert int(t[0]) + int(t[1]) == 5000
+
+
+def test_m4_global_tables_vs_oracle(codes_spec):
+    """m = 4 (S = 25 751): state / log tables leave shared memory (L2-resident path)."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Detector, Seg
+    spec = codes_spec["m4a"]
+    with Detector(spec["gen"], 1, 2, 4, enumerate_with="lib") as det:
+        assert det.S == 25751
+        om, on = co.enumerate_states(_taps(spec), 2, 4)
+        assert np.array_equal(det.table.metrics, om) and np.array_equal(det.table.nxt, on)
+        tab, P1, Tref = _oracle_models(det, spec, 0.05, 60000, 3)
+        det.set_models([P1])
+        T = bitsource.bsc_threshold(0.05)
+        taps2 = _taps(codes_spec["m4b"])
+        seg = Seg(N=150, threshold=T, stream=1, enc_taps=taps2, decide=1, trial_begin=0, trial_end=700)
+        want, wlp = co.run_trials(_taps(spec), taps2, 2, 4, 150, T, 8, 1, 0, 700, tab, P1, Tref, 1, want_logp=True)
+        for engine in ENGINES:
+            t, lp = det.detect([seg], seed=8, engine=engine, want_logp=True)
+            assert int(t[0]) == want
+            assert np.array_equal(lp, wlp)
+        # learning chain through the global-memory histogram
+        got = det.learn_counts([Seg(N=60000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=_taps(spec))],
+                               burn=200, seed=3)[0]
+        want_edge, _ = co.learn_chain(_taps(spec), _taps(spec), 2, 4, 60000, 200, T, 3, bitsource.LEARN_STREAM, 0, tab)
+        assert np.array_equal(got, want_edge)
+
+
+@pytest.mark.parametrize("name", ["m5", "m6", "m4a", "c75"])
+def test_acs_hash_large_memory(codes_spec, name):
+    """Eq. 4-5 recursion for memories without an enumerable state set: trajectory hash and
+    final metric vector vs the oracle."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import HashOnlyDetector, Seg
+    spec = codes_spec[name]
+    taps = _taps(spec)
+    T = bitsource.bsc_threshold(0.08)
+    with HashOnlyDetector(spec["gen"], 1, spec["n"], spec["m"]) as det:
+        seg = Seg(N=257, threshold=T, stream=2, enc_taps=taps, trial_begin=40, trial_end=40 + 300)
+        h, fin = det.acs_hash(seg, seed=31)
+        for t in (0, 1, 150, 299):
+            U, E = co.trial_words(31, 2, 40 + t, 257, spec["n"], T)
+            wh, wf = co.acs_hash(taps, taps, spec["n"], spec["m"], 257, U, E)
+            assert int(h[t]) == wh
+            assert np.array_equal(fin[t], wf)
+
+
+def test_engines_and_sources_agree_at_scale(codes_spec, dets):
+    """Size-independent properties at 2 x 10^5 trials x N = 500: ACS == FSM tallies, Philox ==
+    bitstream of the same bits (subset), and shard invariance (split ranges sum to the whole)."""
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    _, P1, _ = _oracle_models(det, codes_spec["c75"], 0.1, 6200, 123)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(0.1)
+    taps2 = _taps(codes_spec["c65"])
+    ntr = 200_000
+    whole = [Seg(N=500, threshold=T, stream=0, decide=0, trial_begin=0, trial_end=ntr),
+             Seg(N=500, threshold=T, stream=1, enc_taps=taps2, decide=1, trial_begin=0, trial_end=ntr)]
+    ta = det.detect(whole, seed=12345, engine="acs")
+    tf = det.detect(whole, seed=12345, engine="fsm")
+    assert np.array_equal(ta, tf)
+    cuts = [0, 1, 70_001, 133_337, ntr]
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        parts += [Seg(N=500, threshold=T, stream=0, decide=0, trial_begin=a, trial_end=b),
+                  Seg(N=500, threshold=T, stream=1, enc_taps=taps2, decide=1, trial_begin=a, trial_end=b)]
+    tp = det.detect(parts, seed=12345, engine="fsm")
+    assert int(tp[0::2].sum()) == int(tf[0]) and int(tp[1::2].sum()) == int(tf[1])
+    # bitstream of the same bits for the first 64 trials
+    u, e = bitsource.philox_bitstreams(12345, 1, 0, 64, 500, 2, T)
+    seg = Seg(N=500, enc_taps=taps2, decide=1, trial_begin=0, trial_end=64)
+    tb, lpb = det.detect([seg], bits=bitsource.pack_bitstreams(u, e), engine="fsm", want_logp=True)
+    seg_p = Seg(N=500, threshold=T, stream=1, enc_taps=taps2, decide=1, trial_begin=0, trial_end=64)
+    tq, lpq = det.detect([seg_p], seed=12345, engine="acs", want_logp=True)
+    assert int(tb[0]) == int(tq[0]) and np.array_equal(lpb, lpq)
+
+
+def test_edge_cases(codes_spec, dets):
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    _, P1, _ = _oracle_models(det, codes_spec["c75"], 0.1, 6200, 123)
+    det.set_models([P1])
+    # empty trial range, N = 0 (logp = 0: H1 rule fails, H2 rule succeeds), p = 0, p = 1
+    segs = [Seg(N=100, threshold=5, stream=0, decide=0, trial_begin=7, trial_end=7),
+            Seg(N=0, threshold=5, stream=0, decide=0, trial_begin=0, trial_end=10),
+            Seg(N=0, threshold=5, stream=0, decide=1, trial_begin=0, trial_end=10)]
+    for engine in ENGINES:
+        t = det.detect(segs, seed=1, engine=engine)
+        assert t.tolist() == [0, 0, 10]
+    # p = 0: noiseless all-zero-input chain stays in state 0 under its own decoder
+    seg = Seg(N=200, threshold=0, stream=0, random_input=False, trial_begin=0, trial_end=3)
+    for engine in ENGINES:
+        idx, met = det.trace(seg, seed=1, engine=engine)
+        # the all-zero codeword through a noiseless channel: metric of state 0 stays 0
+        assert (met[:, :, 0] == 0).all()
+    # p = 1 (threshold clipped to 2^32 - 1): every bit flips (up to the 2^-32 clip)
+    T1 = bitsource.bsc_threshold(1.0)
+    assert T1 == 0xFFFFFFFF
+    idx1, _ = det.trace(Seg(N=64, threshold=T1, stream=0, random_input=False, trial_begin=0, trial_end=2), seed=1, engine="fsm")
+    ones = np.ones((2, 2, 64), dtype=np.uint8)
+    idx2, _ = det.trace(Seg(N=64, random_input=False, trial_begin=0, trial_end=2),
+                        bits=bitsource.pack_bitstreams(np.zeros((2, 64), dtype=np.uint8), ones), engine="fsm")
+    assert np.array_equal(idx1, idx2)
+
+
+def test_unknown_state_is_an_error(codes_spec):
+    """A metric vector outside the table = the reference's KeyError (Pd_plotter.py:112)."""
+    from mvd import _capi, codes
+    from mvd.engine import Detector, Seg
+    s75, s65 = codes_spec["c75"], codes_spec["c65"]
+    wrong = codes.enumerate_states(codes.freeze_generator(s65["gen"]), 2, 1, 2)      # (6,5)'s 5 states
+    with Detector(s75["gen"], 1, 2, 2, table=wrong) as det:
+        with pytest.raises(_capi.UnknownStateError):
+            det.trace(Seg(N=200, threshold=1 << 30, trial_begin=0, trial_end=4), seed=3, engine="acs")
+        assert isinstance(_capi.UnknownStateError(-6, "x"), KeyError)
+
+
+def test_abi_argument_errors(codes_spec, dets):
+    from mvd import _capi
+    from mvd.engine import Detector, Seg
+    det = dets("c75")
+    with pytest.raises(_capi.MvdError):
+        det.detect([Seg(N=10, table=99, trial_begin=0, trial_end=1)], seed=1)           # table out of range
+    with pytest.raises(_capi.MvdError):
+        det.detect([Seg(N=10, trial_begin=5, trial_end=1)], seed=1)                     # end < begin
+    with pytest.raises(_capi.MvdError):
+        det.detect([Seg(N=300, trial_begin=0, trial_end=4)], bits=np.zeros((1, 3, 4, 4), dtype=np.uint32))  # short
+    with pytest.raises(_capi.MvdError):
+        Detector([[[1, 1, 1], [1, 0, 1]], [[1, 0, 1], [1, 1, 1]]], 2, 2, 2)              # k = 2 unsupported on device
+
+
+def test_int_peak_and_info(dets):
+    det = dets("c75")
+    info = det.device_info()
+    assert info["sm_count"] > 0
+    alu, mixed = det.int_peak()
+    assert alu > 1000 and mixed > 1000          # Gop/s
+    assert det.launch_count() > 0
