@@ -1,0 +1,114 @@
+"""CPU tests of the drop-in boundary: libmvd.so loads, exports every symbol include/mvd.h
+declares, its struct layouts match the ctypes mirror, and -- with no GPU -- refuses to compute
+(there is no CPU fallback).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mvd.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_boundary():
+    names = declared_functions()
+    for must in ("mvd_create", "mvd_destroy", "mvd_set_code", "mvd_set_states", "mvd_set_loglik", "mvd_learn_counts",
+                 "mvd_detect", "mvd_trace", "mvd_last_error"):
+        assert must in names
+    text = open(HEADER).read()
+    # every entry point cites the reference interface it replaces
+    for cite in ("Pd_plotter.py:210-223", "Pd_plotter.py:158-163", "viterbi_markov.py:166-195", "viterbi_markov.py:118-132",
+                 "Pd_plotter.py:149,212,219"):
+        assert cite in text
+
+
+def test_library_exports_every_declared_symbol():
+    from mvd import _capi
+    lib = _capi.load()
+    names = declared_functions()
+    assert set(names) == set(_capi.EXPORTS), "ctypes binding and header disagree"
+    for name in names:
+        assert getattr(lib, name) is not None
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _capi.LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (mvd_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert lib.mvd_abi_version() == 1
+
+
+def test_library_is_built_for_sm_100a():
+    from mvd import _capi
+    out = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+
+
+def test_library_does_not_link_the_oracle():
+    from mvd import _capi
+    out = subprocess.check_output(["ldd", _capi.LIB_PATH], text=True)
+    assert "oracle" not in out
+    syms = subprocess.check_output(["nm", "-D", _capi.LIB_PATH], text=True)
+    assert "mvdo_" not in syms
+
+
+def test_struct_layouts_match_header():
+    """Compile a tiny C program against include/mvd.h and compare sizeof/offsetof with ctypes."""
+    import tempfile
+    from mvd import _capi
+    fields_seg = ["N", "threshold", "stream", "table", "enc_taps", "decide", "random_input", "trial_begin", "trial_end",
+                  "bits_offset"]
+    fields_src = ["mode", "bits_on_device", "seed", "bits", "bits_words"]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "mvd.h"', "int main(void){",
+            'printf("%zu %zu\\n", sizeof(mvd_segment), sizeof(mvd_src));']
+    for f in fields_seg:
+        prog.append(f'printf("%zu\\n", offsetof(mvd_segment, {f}));')
+    for f in fields_src:
+        prog.append(f'printf("%zu\\n", offsetof(mvd_src, {f}));')
+    prog.append("return 0;}")
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.c")
+        open(src, "w").write("\n".join(prog))
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+        out = subprocess.check_output([exe], text=True).split()
+    vals = list(map(int, out))
+    assert vals[0] == C.sizeof(_capi.Segment) and vals[1] == C.sizeof(_capi.Src)
+    got_seg = [getattr(_capi.Segment, f).offset for f in fields_seg]
+    got_src = [getattr(_capi.Src, f).offset for f in fields_src]
+    assert vals[2:2 + len(fields_seg)] == got_seg
+    assert vals[2 + len(fields_seg):] == got_src
+
+
+def test_create_fails_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mvd import _capi
+    lib = _capi.load()
+    ctx = C.c_void_p()
+    rc = lib.mvd_create(C.byref(ctx), 0)
+    assert rc == -2 and not ctx.value                      # MVD_E_CUDA
+    msg = lib.mvd_last_error(None).decode()
+    assert "no CPU fallback" in msg
+    # NULL contexts are rejected, not dereferenced
+    assert lib.mvd_destroy(None) == 0
+    assert lib.mvd_synchronize(None) == -1
+    f = C.c_float()
+    assert lib.mvd_last_kernel_ms(None, C.byref(f)) == -1
+
+
+def test_missing_library_is_an_import_error(monkeypatch):
+    from mvd import _capi
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libmvd.so")
+    with pytest.raises(ImportError) as ei:
+        _capi.load()
+    assert "no CPU fallback" in str(ei.value)
