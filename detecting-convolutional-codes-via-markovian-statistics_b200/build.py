@@ -10,7 +10,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = [os.path.join(PKG, "csrc", "mvd.cu")]
-DEPS = SRC + [os.path.join(PKG, "csrc", "mvd_kernels.cuh"), os.path.join(ROOT, "include", "mvd.h")]
+DEPS = SRC + [os.path.join(PKG, "csrc", "mvd_kernels.cuh"), os.path.join(PKG, "csrc", "mvd_detect2.cuh"), os.path.join(ROOT, "include", "mvd.h")]
 OUT = os.path.join(PKG, "libmvd.so")
 
 

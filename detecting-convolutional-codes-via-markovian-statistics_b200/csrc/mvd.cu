@@ -5,6 +5,7 @@
 // one kernel per call (a whole sweep = one launch), read tallies / counts back.
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include "mvd_kernels.cuh"
+#include "mvd_detect2.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -49,6 +50,8 @@ struct mvd_ctx {
     std::string err;
     uint64_t launches = 0;
     float last_ms = 0.f;
+    int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
+    bool force_generic = false;
 
     // code
     bool have_code = false;
@@ -56,6 +59,9 @@ struct mvd_ctx {
     uint32_t dec_taps[MVD_MAX_N] = {0, 0, 0, 0};
     // states
     bool have_states = false, acs_ok = false;
+    bool closed = false;            // every successor of every state is in the table (fast kernels)
+    int max_metric = 0;
+    uint32_t nkeys = 0;             // direct metric-vector -> state table (m <= 2), 0 = none
     uint32_t S = 0;
     std::vector<uint8_t> h_metrics;
     std::vector<uint32_t> h_next;
@@ -64,7 +70,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate;
 };
 
 namespace {
@@ -154,6 +160,56 @@ int install_states(mvd_ctx* ctx) {
     CK(ctx->d_hvals.reserve(vals.size() * 4));
     CK(cudaMemcpyAsync(ctx->d_hkeys.p, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_hvals.p, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // ---- closure: metrics[next[i][r]] == Eq.4-5(metrics[i], r) for every (i, r), state 0 = all-zero.
+    // Only closed tables may take the fast kernels, which do not check for unknown vectors.
+    {
+        const int HALF = nstate / 2;
+        std::vector<int> lab0(nstate), lab1(nstate);
+        for (int ns = 0; ns < nstate; ++ns) {
+            lab0[ns] = label_of_branch((uint32_t)(ns >> 1), (uint32_t)(ns & 1), ctx->dec_taps, ctx->n);
+            lab1[ns] = label_of_branch((uint32_t)((ns >> 1) + HALF), (uint32_t)(ns & 1), ctx->dec_taps, ctx->n);
+        }
+        bool closed = true;
+        int mx = 0;
+        for (int s = 0; s < nstate; ++s) closed = closed && ctx->h_metrics[s] == 0;
+        for (uint32_t i = 0; i < S && closed; ++i) {
+            const uint8_t* cur = ctx->h_metrics.data() + (size_t)i * nstate;
+            for (int r = 0; r < R && closed; ++r) {
+                int tmp[64], lo = 1 << 30;
+                for (int ns = 0; ns < nstate; ++ns) {
+                    const int a = cur[ns >> 1] + __builtin_popcount((unsigned)(lab0[ns] ^ r));
+                    const int b = cur[(ns >> 1) + HALF] + __builtin_popcount((unsigned)(lab1[ns] ^ r));
+                    tmp[ns] = a < b ? a : b;
+                    lo = tmp[ns] < lo ? tmp[ns] : lo;
+                }
+                const uint8_t* nx = ctx->h_metrics.data() + (size_t)ctx->h_next[(size_t)i * R + r] * nstate;
+                for (int ns = 0; ns < nstate; ++ns) closed = closed && (tmp[ns] - lo) == (int)nx[ns];
+            }
+        }
+        for (size_t i = 0; i < ctx->h_metrics.size(); ++i) mx = std::max(mx, (int)ctx->h_metrics[i]);
+        ctx->closed = closed;
+        ctx->max_metric = mx;
+    }
+    // ---- direct table for m <= 2: key = hi + (lo << b), lo = s0 | s2 << 2b, hi = s1 | s3 << 2b
+    // (must match Acs2Engine::step), b = 4 (m = 1) or 2 (m = 2)
+    ctx->nkeys = 0;
+    if (ctx->closed && ((ctx->m == 1 && ctx->max_metric <= 15) || (ctx->m == 2 && ctx->max_metric <= 3))) {
+        const int b = ctx->m == 1 ? 4 : 2;
+        const uint32_t nkeys = 256;
+        std::vector<uint16_t> dst(nkeys, (uint16_t)0xFFFF);
+        for (uint32_t i = 0; i < S; ++i) {
+            const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
+            uint32_t lo = v[0], hi = v[1];
+            if (ctx->m == 2) {
+                lo |= (uint32_t)v[2] << (2 * b);
+                hi |= (uint32_t)v[3] << (2 * b);
+            }
+            dst[hi + (lo << b)] = (uint16_t)i;
+        }
+        CK(ctx->d_dstate.reserve(nkeys * 2));
+        CK(cudaMemcpyAsync(ctx->d_dstate.p, dst.data(), nkeys * 2, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->nkeys = S <= 0xFFFE ? nkeys : 0;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_states = true;
     ctx->ntables = 0;
@@ -203,6 +259,69 @@ cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P)
     return cudaGetLastError();
 }
 
+template <int LK, int M>
+cudaError_t launch_det2(int lls, dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
+#define MVD_DET2_CASE(L)                                                                              \
+    case L: {                                                                                         \
+        auto kern = detect2_kernel<LK, M, L>;                                                         \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                               \
+        kern<<<grid, DET2_BLOCK, smem, st>>>(P);                                                      \
+        return cudaGetLastError();                                                                    \
+    }
+    switch (lls) {
+        MVD_DET2_CASE(4)
+        MVD_DET2_CASE(5)
+        MVD_DET2_CASE(6)
+        MVD_DET2_CASE(7)
+        default: return cudaErrorInvalidValue;
+    }
+#undef MVD_DET2_CASE
+}
+
+// Shared-memory plan of the fast detection kernels; returns false if they do not apply.
+bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPlan* fp, size_t* smem_out) {
+    if (ctx->n != 2 || !ctx->closed) return false;
+    const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 4;
+    const size_t SR = (size_t)ctx->S * R;
+    int lk;
+    if (engine == MVD_ENGINE_FSM) lk = LK_FSM;
+    else if (ctx->nkeys) lk = LK_DIRECT;
+    else if ((m == 2 || m == 3) && ctx->acs_ok) lk = LK_HASH;
+    else return false;
+    const size_t budget2 = 110 * 1024, smem_max = ctx->prop.sharedMemPerBlockOptin;   // 2 blocks / SM if possible
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int lls = 7; lls >= 4; --lls) {
+            size_t off = 0, st_bytes;
+            fp->off_bm = 0;
+            if (lk != LK_FSM) {
+                const size_t row = 8 * (size_t)NP, stride = std::max(row, (size_t)1 << lls);
+                off = R * stride;
+            }
+            off = (off + 15) & ~(size_t)15;
+            fp->off_st = (uint32_t)off;
+            if (lk == LK_FSM) st_bytes = lls == 7 ? SR * 128 : SR * 4;
+            else if (lk == LK_DIRECT) st_bytes = (size_t)ctx->nkeys * 128;
+            else st_bytes = (size_t)ctx->hcap * 4 * (1 + (nstate + 7) / 8);
+            off = (off + st_bytes + 15) & ~(size_t)15;
+            fp->off_ll = (uint32_t)off;
+            off += SR << lls;
+            if (lk == LK_DIRECT && fp->off_st + ((size_t)ctx->nkeys << 7) + 128 >= 65536) continue;
+            if (off + 64 <= (pass == 0 ? budget2 : smem_max)) {
+                const int b = m == 1 ? 4 : 2;
+                fp->key_mul = ((1u << (16 + b)) + 1u) << 7;
+                fp->nkeys = ctx->nkeys;
+                fp->dstate = ctx->d_dstate.as<uint16_t>();
+                *lk_out = lk;
+                *lls_out = lls;
+                *smem_out = off;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
 int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
         const LaunchOut& out) {
     if (!ctx) return MVD_E_INVALID;
@@ -221,6 +340,13 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     if (engine != MVD_ENGINE_ACS && engine != MVD_ENGINE_FSM) return fail(ctx, MVD_E_INVALID, "bad engine %d", engine);
     if (engine == MVD_ENGINE_ACS && mode != MODE_HASH && !ctx->acs_ok)
         return fail(ctx, MVD_E_UNSUPPORTED, "ACS engine needs relative metrics <= 15");
+
+    // ---- kernel choice: the fast detection kernels when they apply, else the generic ones
+    FastPlan fplan{};
+    int det2_lk = -1, det2_lls = 0;
+    size_t det2_smem = 0;
+    const bool fast = mode == MODE_DETECT && !ctx->force_generic && plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem);
+    const uint32_t block = fast ? DET2_BLOCK : MVD_BLOCK;
 
     // ---- segments
     std::vector<DevSeg> ds(nsegs);
@@ -249,7 +375,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         d.trial_end = s.trial_end;
         d.bits_offset = s.bits_offset;
         d.out_offset = trials;
-        blocks += (ntr + MVD_BLOCK - 1) / MVD_BLOCK;
+        blocks += (ntr + block - 1) / block;
         trials += ntr;
         if (src->mode == MVD_SRC_BITSTREAM) {
             const uint64_t nsb = ((uint64_t)s.N + 127) / 128;
@@ -302,6 +428,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     CK(ctx->d_err.reserve(sizeof(int)));
     CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
     P.error_flag = ctx->d_err.as<int>();
+    P.fp = fplan;
 
     // ---- outputs
     if (mode == MODE_DETECT) {
@@ -371,7 +498,14 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool n2 = (n == 2);
     cudaError_t le = cudaErrorInvalidValue;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (engine == MVD_ENGINE_FSM) {
+    if (fast) {
+        if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, grid, det2_smem, ctx->stream, P);
+        else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, grid, det2_smem, ctx->stream, P)
+                                                   : launch_det2<LK_DIRECT, 2>(det2_lls, grid, det2_smem, ctx->stream, P);
+        else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, grid, det2_smem, ctx->stream, P)
+                         : launch_det2<LK_HASH, 3>(det2_lls, grid, det2_smem, ctx->stream, P);
+        ctx->last_fast = 1 + det2_lk + 16 * det2_lls;
+    } else if (engine == MVD_ENGINE_FSM) {
         if (mode == MODE_DETECT) {
             if (in_smem) le = n2 ? launch_fsm<MODE_DETECT, 2, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, true>(grid, smem, ctx->stream, P);
             else le = n2 ? launch_fsm<MODE_DETECT, 2, false>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, false>(grid, smem, ctx->stream, P);
@@ -386,6 +520,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         else if (mode == MODE_TRACE) le = launch_acs<MODE_TRACE, 0>(m, grid, smem, ctx->stream, P);
         else le = n2 ? launch_acs<MODE_HASH, 2>(m, grid, smem, ctx->stream, P) : launch_acs<MODE_HASH, 0>(m, grid, smem, ctx->stream, P);
     }
+    if (!fast) ctx->last_fast = 0;
     if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -460,7 +595,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak};
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -678,6 +813,21 @@ int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms) {
 int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches) {
     if (!ctx || !launches) return MVD_E_INVALID;
     *launches = ctx->launches;
+    return MVD_OK;
+}
+
+int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return MVD_E_INVALID;
+    if (option == MVD_OPT_FORCE_GENERIC) {
+        ctx->force_generic = value != 0;
+        return MVD_OK;
+    }
+    return fail(ctx, MVD_E_INVALID, "unknown option %d", option);
+}
+
+int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind) {
+    if (!ctx || !kind) return MVD_E_INVALID;
+    *kind = ctx->last_fast;
     return MVD_OK;
 }
 

@@ -1,0 +1,315 @@
+// mvd_detect2.cuh -- the throughput kernels of the detection trial loop (Pd_plotter.py:210-223)
+// for rate-1/n codes with n = 2 whose tables fit shared memory (every code of BASELINE configs 1-3
+// and 5).  Same arithmetic and the same per-trial results as the generic kernels in
+// mvd_kernels.cuh; what changes is how the work is laid out for the SM:
+//
+//   * every table access is an LDS on a *bank-conflict-free replica*: the {log P1, log Tref} pair
+//     of an edge is replicated 2^(LLS-4) times (one copy per lane of a quarter warp, the unit an
+//     LDS.128 is served in), the metric-vector -> Markov-state table (ACS) / the NEXT table (FSM)
+//     32 times (one copy per lane = per bank).  A warp's step costs 4 + 4 + 1 shared-memory
+//     wavefronts (ACS: log pair, branch metrics, state) instead of ~21 with plain tables;
+//   * the received word of a step is never materialised as an index: the two received-bit words
+//     of 32 steps are bit-interleaved once (r_t = bits 2t+1, 2t) and a step takes
+//     ((w >> (2j - LLS)) & (3 << LLS)) = r * stride directly as the byte offset of both the
+//     branch-metric row and the log-likelihood row;
+//   * m <= 2: the normalised metric vector packs into 8 bits, so the state_index dict of
+//     Pd_plotter.py:139 is a direct 256-entry table; two IMADs turn the two 16x2 metric registers
+//     into the byte address of this lane's copy (see direct_addr);
+//   * the step loop is unrolled 8-fold, not 32-fold: the whole kernel is ~1/8 of the instruction
+//     footprint of the generic kernel, which was instruction-cache bound.
+//
+// The kernels assume a *closed* state table (every successor of every state is in the table --
+// verified on the host in install_states); anything else takes the generic, checked path.
+#pragma once
+#include "mvd_kernels.cuh"
+
+#define DET2_BLOCK 512
+
+enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2 };
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {      // bit i -> bit 2i  (x < 2^16)
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// r * 2^LLS for step J of a 16-bit (8-step) chunk of the interleaved received word
+template <int LLS, int J>
+__device__ __forceinline__ uint32_t roff(uint32_t w) {
+    constexpr int sh = 2 * J - LLS;
+    return (sh >= 0 ? (w >> (sh >= 0 ? sh : 0)) : (w << (sh < 0 ? -sh : 0))) & (3u << LLS);
+}
+
+// ------------------------------------------------------------------------------------------ driver (n = 2)
+template <int LLS, class Eng>
+__device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, bool active, unsigned long long trial,
+                                             unsigned long long tl, unsigned long long ntr, Eng& eng) {
+    const int m = P.m;
+    const uint32_t N = sg.N;
+    const uint32_t T = sg.threshold;
+    const int dmin = (int)sg.dmin;
+    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
+    const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
+    uint32_t q = 0, prevU = 0;
+    const uint32_t nsb = (N + 127u) >> 7;
+    for (uint32_t sb = 0; sb < nsb; ++sb) {
+        uint4 Uw = make_uint4(0, 0, 0, 0), E0 = Uw, E1 = Uw;
+        if (philox) {
+            Uw = philox10(q, c1, c2, c3, P);
+            q += 1u;
+        } else if (active) {
+            const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 3ull * ntr + tl;
+            Uw = __ldg(base);
+            E0 = __ldg(base + ntr);
+            E1 = __ldg(base + 2ull * ntr);
+        }
+        if (!sg.random_input) Uw = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t0 = sb * 128u + (uint32_t)w * 32u;
+            if (t0 >= N) break;
+            const uint32_t valid = min(32u, N - t0);
+            const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+            const uint32_t U = pick(Uw, w);
+            uint32_t e0, e1;
+            if (philox) {
+                e0 = lazy_bernoulli(q, c1, c2, c3, T, dmin, active ? vmask : 0u, P);
+                e1 = lazy_bernoulli(q, c1, c2, c3, T, dmin, active ? vmask : 0u, P);
+            } else {
+                e0 = pick(E0, w);
+                e1 = pick(E1, w);
+            }
+            // bit-parallel encoder (viterbi_markov.py:82-106 for k = 1): 32 steps per XOR
+            uint32_t o0 = (taps0 & 1u) ? U : 0u, o1 = (taps1 & 1u) ? U : 0u;
+#pragma unroll
+            for (int i = 1; i <= MVD_MAX_M; ++i) {
+                if (i <= m) {
+                    const uint32_t sh = __funnelshift_l(prevU, U, i);
+                    if ((taps0 >> i) & 1u) o0 ^= sh;
+                    if ((taps1 >> i) & 1u) o1 ^= sh;
+                }
+            }
+            prevU = U;
+            const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;            // BSC
+            // received word of step t = bits (2t+1, 2t) of (whi:wlo); first output is the MSB
+            const uint32_t wlo = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
+            const uint32_t whi = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+#pragma unroll 1
+            for (uint32_t c = 0; c < valid; c += 8u) {
+                const uint32_t wsel = (c & 16u) ? whi : wlo;
+                const uint32_t wv = wsel >> ((c & 8u) << 1);
+                if (c + 8u <= valid) {
+                    eng.step(roff<LLS, 0>(wv));
+                    eng.step(roff<LLS, 1>(wv));
+                    eng.step(roff<LLS, 2>(wv));
+                    eng.step(roff<LLS, 3>(wv));
+                    eng.step(roff<LLS, 4>(wv));
+                    eng.step(roff<LLS, 5>(wv));
+                    eng.step(roff<LLS, 6>(wv));
+                    eng.step(roff<LLS, 7>(wv));
+                } else {
+                    for (uint32_t j = 0; j < valid - c; ++j) eng.step(((wv >> (2u * j)) & 3u) << LLS);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ engines
+// ACS: Eq. 4-5 in registers (AcsCore), then metric vector -> Markov state.
+//   sx = shared-memory byte address of this lane's copy of the log-likelihood row of the current state.
+template <int LK, int M, int LLS>
+struct Acs2Engine {
+    static constexpr int NP = AcsCore<M>::NP;
+    static constexpr int BMROW = 8 * NP;                          // bytes of one branch-metric row
+    static constexpr int BMSTRIDE = BMROW > (1 << LLS) ? BMROW : (1 << LLS);
+    AcsCore<M> core;
+    const unsigned char* sm;
+    uint32_t sx, bm_base;
+    uint32_t key_mul, key_add;       // DIRECT
+    uint32_t ll_lane, st_base, hmask;   // HASH
+    double a1, a0;
+
+    __device__ __forceinline__ void step(uint32_t r_off) {
+        const double2 v = *reinterpret_cast<const double2*>(sm + sx + r_off);     // edge (state, r)
+        a1 += v.x;                                                                // Pd_plotter.py:114-115,
+        a0 += v.y;                                                                // in step order
+        uint32_t bm[2 * NP];
+        const uint32_t boff = bm_base + (BMSTRIDE == (1 << LLS) ? r_off : (r_off >> LLS) * (uint32_t)BMSTRIDE);
+        if (NP == 1) {
+            const uint2 b = *reinterpret_cast<const uint2*>(sm + boff);
+            bm[0] = b.x;
+            bm[1] = b.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP / 2; ++i) {
+                const uint4 b = *reinterpret_cast<const uint4*>(sm + boff + 16 * i);
+                bm[4 * i] = b.x;
+                bm[4 * i + 1] = b.y;
+                bm[4 * i + 2] = b.z;
+                bm[4 * i + 3] = b.w;
+            }
+        }
+        core.step(bm);                                                            // Eq. 4 + Eq. 5
+        if (LK == LK_DIRECT) {
+            // D[0] = s0 | s1 << 16, D[1] = s2 | s3 << 16, every metric < 2^b (b = 2 for m = 2, 4 for m = 1):
+            //   t  = s0 | s2 << 2b  |  (s1 | s3 << 2b) << 16
+            //   t * ((2^(16+b) + 1) << 7): bits 31..16 = (lo * 2^b + hi) << 7 = key << 7
+            // + key_add = (table base + 4 * lane) << 16, so the upper half is the byte address of this
+            // lane's copy of entry `key`.
+            constexpr int B = (M == 1) ? 4 : 2;
+            uint32_t t = core.D[0];
+            if (NP > 1) t += core.D[1] << (2 * B);
+            const uint32_t u = t * key_mul + key_add;
+            sx = *reinterpret_cast<const uint32_t*>(sm + (u >> 16));
+        } else {
+            uint32_t kw[AcsCore<M>::KW];
+            core.key(kw);
+            uint32_t slot = key_hash(kw, AcsCore<M>::KW) & hmask;
+            const uint32_t* hk = reinterpret_cast<const uint32_t*>(sm + st_base + 4u * (hmask + 1u));
+            for (uint32_t probe = 0; probe <= hmask; ++probe) {
+                bool same = true;
+#pragma unroll
+                for (int i = 0; i < AcsCore<M>::KW; ++i) same = same && (hk[(size_t)i * (hmask + 1u) + slot] == kw[i]);
+                if (same) break;
+                slot = (slot + 1u) & hmask;
+            }
+            const uint32_t val = *reinterpret_cast<const uint32_t*>(sm + st_base + 4u * slot);   // state * R
+            sx = ll_lane + (val << LLS);
+        }
+    }
+};
+
+// FSM: the same chain walked through NEXT[state][r].
+//   LLS == 7: sx = byte address of this lane's copy of the current state's log-likelihood row, the
+//             NEXT table is lane-replicated with the same 128-byte entry stride and stores such addresses;
+//   else    : sx = state * R and NEXT is a plain table.
+template <int LLS>
+struct Fsm2Engine {
+    const unsigned char* sm;
+    uint32_t sx, ll_lane, nx_lane;
+    double a1, a0;
+
+    __device__ __forceinline__ void step(uint32_t r_off) {
+        if (LLS == 7) {
+            const uint32_t a = sx + r_off;
+            const double2 v = *reinterpret_cast<const double2*>(sm + a);
+            a1 += v.x;
+            a0 += v.y;
+            sx = *reinterpret_cast<const uint32_t*>(sm + a + nx_lane);      // nx_lane = NEXT copy - log copy
+        } else {
+            const uint32_t e = sx + (r_off >> LLS);
+            const double2 v = *reinterpret_cast<const double2*>(sm + ll_lane + (e << LLS));
+            a1 += v.x;
+            a0 += v.y;
+            sx = *reinterpret_cast<const uint32_t*>(sm + nx_lane + (e << 2));
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------ kernel
+// grid: one block per (segment, chunk of DET2_BLOCK trials); one thread = one trial.
+// dynamic shared memory (byte offsets in P.fp): [bm rows][state table][log-likelihood replicas]
+template <int LK, int M, int LLS>
+__global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int REP = 1 << (LLS - 4);
+    const uint32_t seg = find_segment(P, blockIdx.x);
+    const DevSeg sg = P.segs[seg];
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    const unsigned long long tl = (unsigned long long)(blockIdx.x - sg.block_begin) * DET2_BLOCK + threadIdx.x;
+    const bool active = tl < ntr;
+    const unsigned long long trial = sg.trial_begin + tl;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t SR = P.SR;
+    const uint32_t ll_lane = P.fp.off_ll + ((lane & (uint32_t)(REP - 1)) << 4);
+
+    // ---- stage the tables of this segment's p
+    {
+        const double2* llg = P.ll + (size_t)sg.table * SR;
+        for (uint32_t i = threadIdx.x; i < SR * REP; i += DET2_BLOCK) {
+            const uint32_t e = i >> (LLS - 4), c = i & (uint32_t)(REP - 1);
+            *reinterpret_cast<double2*>(smem_raw + P.fp.off_ll + (e << LLS) + (c << 4)) = __ldg(llg + e);
+        }
+    }
+    if (LK == LK_FSM) {
+        if (LLS == 7) {
+            for (uint32_t i = threadIdx.x; i < SR * 32u; i += DET2_BLOCK)
+                *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) =
+                    P.fp.off_ll + (__ldg(P.nxt + (i >> 5)) << 7) + (((i & 31u) & 7u) << 4);
+        } else {
+            for (uint32_t i = threadIdx.x; i < SR; i += DET2_BLOCK)
+                *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) = __ldg(P.nxt + i);
+        }
+    } else {
+        constexpr int NP = AcsCore<M>::NP;
+        constexpr int BMSTRIDE = Acs2Engine<LK, M, LLS>::BMSTRIDE;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)P.R * 2u * NP; i += DET2_BLOCK) {
+            const uint32_t r = i / (2u * NP), w = i % (2u * NP);
+            *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_bm + r * BMSTRIDE + 4u * w) = P.bm[i];
+        }
+        if (LK == LK_DIRECT) {
+            for (uint32_t i = threadIdx.x; i < P.fp.nkeys * 32u; i += DET2_BLOCK) {
+                const uint32_t st = P.fp.dstate[i >> 5];          // 0xFFFF: not a state (never looked up)
+                const uint32_t row = st == 0xFFFFu ? 0u : st * (uint32_t)P.R;
+                *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) =
+                    P.fp.off_ll + (row << LLS) + (((i & 31u) & (uint32_t)(REP - 1)) << 4);
+            }
+        } else {
+            constexpr int KW = AcsCore<M>::KW;
+            for (uint32_t i = threadIdx.x; i < P.hcap; i += DET2_BLOCK) {
+                const uint32_t v = P.hvals[i];
+                *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) = v == MVD_EMPTY ? 0u : v;
+#pragma unroll
+                for (int w = 0; w < KW; ++w)
+                    *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * (P.hcap * (1u + w) + i)) =
+                        v == MVD_EMPTY ? 0xFFFFFFFFu : P.hkeys[(size_t)w * P.hcap + i];
+            }
+        }
+    }
+    __syncthreads();
+
+    double a1, a0;
+    if (LK == LK_FSM) {
+        Fsm2Engine<LLS> eng;
+        eng.sm = smem_raw;
+        eng.sx = LLS == 7 ? ll_lane : 0u;
+        eng.ll_lane = ll_lane;
+        eng.nx_lane = LLS == 7 ? (P.fp.off_st + lane * 4u) - ll_lane : P.fp.off_st;
+        eng.a1 = 0.0;
+        eng.a0 = 0.0;
+        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, eng);
+        a1 = eng.a1;
+        a0 = eng.a0;
+    } else {
+        Acs2Engine<LK, M, LLS> eng;
+        eng.core.reset();
+        eng.sm = smem_raw;
+        eng.sx = ll_lane;                                         // state 0 = the all-zero vector (viterbi_markov.py:177)
+        eng.bm_base = P.fp.off_bm;
+        eng.key_mul = P.fp.key_mul;
+        eng.key_add = (P.fp.off_st + lane * 4u) << 16;
+        eng.ll_lane = ll_lane;
+        eng.st_base = P.fp.off_st;
+        eng.hmask = P.hcap - 1u;
+        eng.a1 = 0.0;
+        eng.a0 = 0.0;
+        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, eng);
+        a1 = eng.a1;
+        a0 = eng.a0;
+    }
+
+    const bool win = active && (sg.decide == 0 ? (a1 > a0) : (a1 <= a0));          // Pd_plotter.py:215 / :222
+    const int c = __syncthreads_count(win ? 1 : 0);
+    if (threadIdx.x == 0 && c) {
+        atomicAdd(P.tallies + seg, (unsigned long long)c);
+        if (P.tallies2) atomicAdd(P.tallies2 + seg, (unsigned long long)c);
+    }
+    if (P.logp && active) {
+        double2* o = reinterpret_cast<double2*>(P.logp) + sg.out_offset + tl;
+        *o = make_double2(a1, a0);
+    }
+}

@@ -31,6 +31,13 @@ struct DevSeg {
     unsigned long long trial_begin, trial_end, bits_offset, out_offset;
 };
 
+// shared-memory plan of the fast detection kernels (mvd_detect2.cuh)
+struct FastPlan {
+    uint32_t off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
+    uint32_t key_mul, nkeys;           // direct metric-vector -> state table (m <= 2)
+    const uint16_t* dstate;            // [nkeys] state index or 0xFFFF
+};
+
 struct Params {
     int n, m, R, nstate;
     uint32_t S, SR;                 // SR = S * R
@@ -59,6 +66,7 @@ struct Params {
     unsigned long long* hashes;
     uint8_t* final_met;
     int* error_flag;
+    FastPlan fp;
 };
 
 // ------------------------------------------------------------------------------------------ Philox

@@ -17,6 +17,7 @@ ENGINE_AUTO, ENGINE_ACS, ENGINE_FSM = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "acs": ENGINE_ACS, "fsm": ENGINE_FSM}
 
 E_UNKNOWN_STATE = -6
+OPT_FORCE_GENERIC = 1
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 
@@ -24,7 +25,7 @@ EXPORTS = (
     "mvd_abi_version", "mvd_create", "mvd_destroy", "mvd_last_error", "mvd_set_stream", "mvd_synchronize",
     "mvd_set_code", "mvd_set_states", "mvd_enumerate_states", "mvd_get_states", "mvd_set_loglik",
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
-    "mvd_int_peak", "mvd_device_info",
+    "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind",
 )
 
 
@@ -83,6 +84,8 @@ def load():
     lib.mvd_last_kernel_ms.argtypes = [vp, P(C.c_float)]
     lib.mvd_launch_count.argtypes = [vp, P(u64)]
     lib.mvd_int_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
+    lib.mvd_set_option.argtypes = [vp, i32, C.c_int64]
+    lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]
     lib.mvd_device_info.argtypes = [vp, P(i32), P(i32), P(u64), C.c_char_p, i32]
     for name in EXPORTS:
         getattr(lib, name)            # AttributeError here = header / library mismatch

@@ -209,6 +209,16 @@ class Detector:
         self._ck(self.lib.mvd_launch_count(self.ctx, C.byref(v)))
         return int(v.value)
 
+    def force_generic(self, on: bool = True):
+        """Route detection through the generic (checked) kernels instead of the fast ones."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_FORCE_GENERIC, 1 if on else 0))
+
+    def last_kernel_kind(self) -> int:
+        """0 = generic kernel; else 1 + lookup kind (0 direct, 1 hash, 2 NEXT walk) + 16 * log2(row stride)."""
+        v = C.c_int()
+        self._ck(self.lib.mvd_last_kernel_kind(self.ctx, C.byref(v)))
+        return int(v.value)
+
     def int_peak(self):
         a, b = C.c_double(), C.c_double()
         self._ck(self.lib.mvd_int_peak(self.ctx, C.byref(a), C.byref(b)))

@@ -136,6 +136,14 @@ int mvd_acs_hash(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg,
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms);
 int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
 
+/* Options.  MVD_OPT_FORCE_GENERIC (value 0/1): 1 = never take the fast detection kernels
+ * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.
+ * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
+ * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry). */
+enum { MVD_OPT_FORCE_GENERIC = 1 };
+int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
+int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
+
 /* Integer-pipe roofline denominator, measured on this device: sustained 32-bit integer
  * lane-ops/s of a dependent-free IADD3/LOP3 (+ IMAD) mix over all SMs. */
 int mvd_int_peak(mvd_ctx* ctx, double* alu_gops, double* alu_fma_gops);

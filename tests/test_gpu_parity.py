@@ -180,11 +180,14 @@ def _oracle_models(det, spec, p, learn_len, seed):
     return tab, P1, codes.tref_half_table(det.table)
 
 
+@pytest.mark.parametrize("path", ["fast", "generic"])
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("dec,enc,N,p", [("c75", "c65", 500, 0.1), ("c75", "c75", 200, 0.3), ("m3a", "m3b", 333, 0.05),
-                                         ("r13", "r13", 97, 0.15), ("m1", "m1", 64, 0.2)])
-def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p):
-    """Tallies and per-trial float64 sums vs the oracle, 3000 trials, both decision rules."""
+                                         ("r13", "r13", 97, 0.15), ("m1", "m1", 64, 0.2), ("c75", "c65", 7, 0.4),
+                                         ("c75", "c65", 129, 0.001), ("m3a", "m3a", 40, 0.5)])
+def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
+    """Tallies and per-trial float64 sums vs the oracle, 3000 trials, both decision rules; through
+    the fast kernels (mvd_detect2.cuh: n = 2 codes with shared-memory tables) and the generic ones."""
     import c_oracle as co
     from mvd import bitsource
     from mvd.engine import Seg
@@ -196,12 +199,57 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p):
     ntr = 3000
     segs = [Seg(N=N, threshold=T, stream=10 + d, enc_taps=_taps(codes_spec[enc]), decide=d, trial_begin=17,
                 trial_end=17 + ntr) for d in (0, 1)]
-    tallies, lp = det.detect(segs, seed=2024, engine=engine, want_logp=True)
+    det.force_generic(path == "generic")
+    try:
+        tallies, lp = det.detect(segs, seed=2024, engine=engine, want_logp=True)
+        kind = det.last_kernel_kind()
+    finally:
+        det.force_generic(False)
+    if path == "generic" or spec["n"] != 2:
+        assert kind == 0
+    else:
+        want_lookup = 2 if engine == "fsm" else (0 if spec["m"] <= 2 else 1)
+        assert kind != 0 and (kind - 1) % 16 == want_lookup
     for d in (0, 1):
         want, wlp = co.run_trials(_taps(spec), _taps(codes_spec[enc]), spec["n"], spec["m"], N, T, 2024, 10 + d, 17,
                                   17 + ntr, tab, P1, Tref, d, want_logp=True)
         assert int(tallies[d]) == want
         assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
+    """Host-supplied bit streams through the fast kernels == generic kernels == oracle sums."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    spec = codes_spec["c75"]
+    tab, P1, Tref = _oracle_models(det, spec, 0.1, 6200, 123)
+    det.set_models([P1])
+    rng = np.random.default_rng(11)
+    ntr, N = 777, 301
+    u = rng.integers(0, 2, (ntr, N), dtype=np.uint8)
+    e = (rng.random((ntr, 2, N)) < 0.12).astype(np.uint8)
+    bits = bitsource.pack_bitstreams(u, e)
+    taps2 = _taps(codes_spec["c65"])
+    seg = Seg(N=N, enc_taps=taps2, decide=1, trial_begin=0, trial_end=ntr)
+    t_fast, lp_fast = det.detect([seg], bits=bits, engine=engine, want_logp=True)
+    assert det.last_kernel_kind() != 0
+    det.force_generic(True)
+    try:
+        t_gen, lp_gen = det.detect([seg], bits=bits, engine=engine, want_logp=True)
+        assert det.last_kernel_kind() == 0
+    finally:
+        det.force_generic(False)
+    assert int(t_fast[0]) == int(t_gen[0]) and np.array_equal(lp_fast, lp_gen)
+    # oracle on the same bits (first 40 trials)
+    for t in range(40):
+        U = bitsource.bits_to_words(u[t])[:(N + 31) // 32]
+        E = bitsource.bits_to_words(e[t])[:, :(N + 31) // 32]
+        idx, rseq, _ = co.simulate(_taps(spec), taps2, 2, 2, N, U, E, tab)
+        assert co.log_prob(idx, rseq, N, 2, P1) == lp_fast[t, 0]
+        assert co.log_prob(idx, rseq, N, 2, Tref) == lp_fast[t, 1]
 
 
 def test_detect_rules_are_complementary(codes_spec, dets):
