@@ -260,13 +260,13 @@ cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P)
 }
 
 template <int LK, int M>
-cudaError_t launch_det2(int lls, dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
+cudaError_t launch_det2(int lls, dim3 grid, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
 #define MVD_DET2_CASE(L)                                                                              \
     case L: {                                                                                         \
         auto kern = detect2_kernel<LK, M, L>;                                                         \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
-        kern<<<grid, DET2_BLOCK, smem, st>>>(P);                                                      \
+        kern<<<grid, DET2_BLOCK, smem, st>>>(P, B);                                                   \
         return cudaGetLastError();                                                                    \
     }
     switch (lls) {
@@ -292,12 +292,10 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
     const size_t budget2 = 110 * 1024, smem_max = ctx->prop.sharedMemPerBlockOptin;   // 2 blocks / SM if possible
     for (int pass = 0; pass < 2; ++pass) {
         for (int lls = 7; lls >= 4; --lls) {
-            size_t off = 0, st_bytes;
-            fp->off_bm = 0;
-            if (lk != LK_FSM) {
-                const size_t row = 8 * (size_t)NP, stride = std::max(row, (size_t)1 << lls);
-                off = R * stride;
-            }
+            size_t off = 128, st_bytes;                 // 32 threshold-bit masks
+            fp->off_tb = 0;
+            fp->off_bm = 128;
+            if (lk != LK_FSM) off += (size_t)(NP >= 2 ? NP / 2 : 1) * ((size_t)R << lls);   // planes x rows x copies
             off = (off + 15) & ~(size_t)15;
             fp->off_st = (uint32_t)off;
             if (lk == LK_FSM) st_bytes = lls == 7 ? SR * 128 : SR * 4;
@@ -499,12 +497,29 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     cudaError_t le = cudaErrorInvalidValue;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (fast) {
-        if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, grid, det2_smem, ctx->stream, P);
-        else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, grid, det2_smem, ctx->stream, P)
-                                                   : launch_det2<LK_DIRECT, 2>(det2_lls, grid, det2_smem, ctx->stream, P);
-        else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, grid, det2_smem, ctx->stream, P)
-                         : launch_det2<LK_HASH, 3>(det2_lls, grid, det2_smem, ctx->stream, P);
+        // segments travel as kernel parameters, DET2_MAXSEG per launch; grid.y = segment
+        le = cudaSuccess;
+        uint32_t extra_launches = 0;
+        for (uint32_t base = 0; base < nsegs && le == cudaSuccess; base += DET2_MAXSEG) {
+            const uint32_t cnt = std::min<uint32_t>(DET2_MAXSEG, nsegs - base);
+            SegBatch B{};
+            uint64_t maxblocks = 0;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                B.s[i] = ds[base + i];
+                B.s[i].block_begin = base + i;                       // global segment index (tally slot)
+                maxblocks = std::max<uint64_t>(maxblocks, (ds[base + i].trial_end - ds[base + i].trial_begin + DET2_BLOCK - 1) / DET2_BLOCK);
+            }
+            if (maxblocks == 0) continue;
+            const dim3 g2((unsigned)maxblocks, cnt);
+            if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B);
+            else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B)
+                                                       : launch_det2<LK_DIRECT, 2>(det2_lls, g2, det2_smem, ctx->stream, P, B);
+            else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, g2, det2_smem, ctx->stream, P, B)
+                             : launch_det2<LK_HASH, 3>(det2_lls, g2, det2_smem, ctx->stream, P, B);
+            extra_launches += 1;
+        }
         ctx->last_fast = 1 + det2_lk + 16 * det2_lls;
+        if (extra_launches > 1) ctx->launches += extra_launches - 1;  // the common increment below counts one
     } else if (engine == MVD_ENGINE_FSM) {
         if (mode == MODE_DETECT) {
             if (in_smem) le = n2 ? launch_fsm<MODE_DETECT, 2, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, true>(grid, smem, ctx->stream, P);

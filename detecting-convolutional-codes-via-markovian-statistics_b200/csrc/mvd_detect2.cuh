@@ -24,6 +24,11 @@
 #include "mvd_kernels.cuh"
 
 #define DET2_BLOCK 512
+#define DET2_MAXSEG 96          // segments per launch: they travel in the kernel parameters (uniform registers)
+
+struct SegBatch {
+    DevSeg s[DET2_MAXSEG];
+};
 
 enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2 };
 
@@ -42,14 +47,38 @@ __device__ __forceinline__ uint32_t roff(uint32_t w) {
     return (sh >= 0 ? (w >> (sh >= 0 ? sh : 0)) : (w << (sh < 0 ? -sh : 0))) & (3u << LLS);
 }
 
+// 32 Bernoulli(T / 2^32) lanes (MVD-PHILOX-1, same stream as lazy_bernoulli) for a block-uniform
+// threshold.  tbm[k] (shared memory, staged once per block) is all-ones if bit 31-k of T is set: the
+// bits of T steer LOP3 masks instead of branches.  Levels below ctz(T) inside the last call have
+// T-bit 0 and can only retire undecided lanes, never set a flip, so running all four levels of a
+// call gives the same word as the level-exact loop of lazy_bernoulli.
+__device__ __forceinline__ uint32_t lazy_bernoulli_s(uint32_t& q, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     const uint4* tbm, int ncalls, uint32_t vmask, const Params& P) {
+    uint32_t und = vmask, e = 0;
+    for (int k = 0; k < ncalls; ++k) {
+        if (!__any_sync(0xFFFFFFFFu, und != 0u)) break;
+        const uint4 w = philox10(q, c1, c2, c3, P);
+        q += (und != 0u) ? 1u : 0u;
+        const uint4 tb = tbm[k];
+        e |= und & ~w.x & tb.x;
+        und &= ~(w.x ^ tb.x);
+        e |= und & ~w.y & tb.y;
+        und &= ~(w.y ^ tb.y);
+        e |= und & ~w.z & tb.z;
+        und &= ~(w.z ^ tb.z);
+        e |= und & ~w.w & tb.w;
+        und &= ~(w.w ^ tb.w);
+    }
+    return e;
+}
+
 // ------------------------------------------------------------------------------------------ driver (n = 2)
 template <int LLS, class Eng>
 __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, bool active, unsigned long long trial,
-                                             unsigned long long tl, unsigned long long ntr, Eng& eng) {
+                                             unsigned long long tl, unsigned long long ntr, const uint4* tbm, Eng& eng) {
     const int m = P.m;
     const uint32_t N = sg.N;
-    const uint32_t T = sg.threshold;
-    const int dmin = (int)sg.dmin;
+    const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);      // Philox calls per flip word, at most
     const bool philox = P.src_mode == MVD_SRC_PHILOX;
     const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
@@ -76,8 +105,8 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
             const uint32_t U = pick(Uw, w);
             uint32_t e0, e1;
             if (philox) {
-                e0 = lazy_bernoulli(q, c1, c2, c3, T, dmin, active ? vmask : 0u, P);
-                e1 = lazy_bernoulli(q, c1, c2, c3, T, dmin, active ? vmask : 0u, P);
+                e0 = lazy_bernoulli_s(q, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
+                e1 = lazy_bernoulli_s(q, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
             } else {
                 e0 = pick(E0, w);
                 e1 = pick(E1, w);
@@ -102,14 +131,15 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
                 const uint32_t wsel = (c & 16u) ? whi : wlo;
                 const uint32_t wv = wsel >> ((c & 8u) << 1);
                 if (c + 8u <= valid) {
+                    const uint32_t wu = wv >> 8;                     // steps 4..7: left shifts only (FMA pipe)
                     eng.step(roff<LLS, 0>(wv));
                     eng.step(roff<LLS, 1>(wv));
                     eng.step(roff<LLS, 2>(wv));
                     eng.step(roff<LLS, 3>(wv));
-                    eng.step(roff<LLS, 4>(wv));
-                    eng.step(roff<LLS, 5>(wv));
-                    eng.step(roff<LLS, 6>(wv));
-                    eng.step(roff<LLS, 7>(wv));
+                    eng.step(roff<LLS, 0>(wu));
+                    eng.step(roff<LLS, 1>(wu));
+                    eng.step(roff<LLS, 2>(wu));
+                    eng.step(roff<LLS, 3>(wu));
                 } else {
                     for (uint32_t j = 0; j < valid - c; ++j) eng.step(((wv >> (2u * j)) & 3u) << LLS);
                 }
@@ -124,8 +154,10 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
 template <int LK, int M, int LLS>
 struct Acs2Engine {
     static constexpr int NP = AcsCore<M>::NP;
-    static constexpr int BMROW = 8 * NP;                          // bytes of one branch-metric row
-    static constexpr int BMSTRIDE = BMROW > (1 << LLS) ? BMROW : (1 << LLS);
+    // branch metrics: row r = 2 * NP words, stored as NV 16-byte (8-byte for m = 1) planes; plane i of
+    // row r, copy c lives at bm_base + i * (4 << LLS) + (r << LLS) + 16 c -- the layout of the log rows,
+    // so lanes of a quarter warp never meet in a bank whatever their r.
+    static constexpr int NV = NP >= 2 ? NP / 2 : 1;
     AcsCore<M> core;
     const unsigned char* sm;
     uint32_t sx, bm_base;
@@ -138,15 +170,15 @@ struct Acs2Engine {
         a1 += v.x;                                                                // Pd_plotter.py:114-115,
         a0 += v.y;                                                                // in step order
         uint32_t bm[2 * NP];
-        const uint32_t boff = bm_base + (BMSTRIDE == (1 << LLS) ? r_off : (r_off >> LLS) * (uint32_t)BMSTRIDE);
+        const uint32_t boff = bm_base + r_off;                                    // bm_base includes the lane copy
         if (NP == 1) {
             const uint2 b = *reinterpret_cast<const uint2*>(sm + boff);
             bm[0] = b.x;
             bm[1] = b.y;
         } else {
 #pragma unroll
-            for (int i = 0; i < NP / 2; ++i) {
-                const uint4 b = *reinterpret_cast<const uint4*>(sm + boff + 16 * i);
+            for (int i = 0; i < NV; ++i) {
+                const uint4 b = *reinterpret_cast<const uint4*>(sm + boff + i * (4 << LLS));
                 bm[4 * i] = b.x;
                 bm[4 * i + 1] = b.y;
                 bm[4 * i + 2] = b.z;
@@ -211,23 +243,31 @@ struct Fsm2Engine {
 };
 
 // ------------------------------------------------------------------------------------------ kernel
-// grid: one block per (segment, chunk of DET2_BLOCK trials); one thread = one trial.
-// dynamic shared memory (byte offsets in P.fp): [bm rows][state table][log-likelihood replicas]
+// grid: (chunks of DET2_BLOCK trials, segments of this launch); one thread = one trial.  The segment
+// descriptors are kernel parameters, so everything derived from them (N, threshold, taps, decision
+// rule) is warp-uniform and lives on the uniform datapath.
+// dynamic shared memory (byte offsets in P.fp): [threshold masks][branch-metric replicas][state table][log-likelihood replicas]
 template <int LK, int M, int LLS>
-__global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_constant__ Params P,
+                                                                const __grid_constant__ SegBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REP = 1 << (LLS - 4);
-    const uint32_t seg = find_segment(P, blockIdx.x);
-    const DevSeg sg = P.segs[seg];
+    const DevSeg& sg = B.s[blockIdx.y];
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
-    const unsigned long long tl = (unsigned long long)(blockIdx.x - sg.block_begin) * DET2_BLOCK + threadIdx.x;
+    if ((unsigned long long)blockIdx.x * DET2_BLOCK >= ntr) return;          // uniform: shorter segment
+    const uint32_t seg = sg.block_begin;                                     // global segment index
+    const unsigned long long tl = (unsigned long long)blockIdx.x * DET2_BLOCK + threadIdx.x;
     const bool active = tl < ntr;
     const unsigned long long trial = sg.trial_begin + tl;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t SR = P.SR;
-    const uint32_t ll_lane = P.fp.off_ll + ((lane & (uint32_t)(REP - 1)) << 4);
+    const uint32_t copy = (lane & (uint32_t)(REP - 1)) << 4;
+    const uint32_t ll_lane = P.fp.off_ll + copy;
 
     // ---- stage the tables of this segment's p
+    if (threadIdx.x < 32u)
+        *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
+    const uint4* tbm = reinterpret_cast<const uint4*>(smem_raw + P.fp.off_tb);
     {
         const double2* llg = P.ll + (size_t)sg.table * SR;
         for (uint32_t i = threadIdx.x; i < SR * REP; i += DET2_BLOCK) {
@@ -246,15 +286,19 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         }
     } else {
         constexpr int NP = AcsCore<M>::NP;
-        constexpr int BMSTRIDE = Acs2Engine<LK, M, LLS>::BMSTRIDE;
-        for (uint32_t i = threadIdx.x; i < (uint32_t)P.R * 2u * NP; i += DET2_BLOCK) {
-            const uint32_t r = i / (2u * NP), w = i % (2u * NP);
-            *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_bm + r * BMSTRIDE + 4u * w) = P.bm[i];
+        constexpr int NV = Acs2Engine<LK, M, LLS>::NV;
+        constexpr int WPV = NP >= 2 ? 4 : 2;                                 // words per plane vector
+        // word w of row r -> plane w / WPV, every copy c
+        for (uint32_t i = threadIdx.x; i < 4u * 2u * NP * REP; i += DET2_BLOCK) {
+            const uint32_t c = i % REP, rw = i / REP, r = rw / (2u * NP), w = rw % (2u * NP);
+            *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_bm + (w / WPV) * (4u << LLS) + (r << LLS) + (c << 4) +
+                                         4u * (w % WPV)) = P.bm[rw];
         }
+        (void)NV;
         if (LK == LK_DIRECT) {
             for (uint32_t i = threadIdx.x; i < P.fp.nkeys * 32u; i += DET2_BLOCK) {
                 const uint32_t st = P.fp.dstate[i >> 5];          // 0xFFFF: not a state (never looked up)
-                const uint32_t row = st == 0xFFFFu ? 0u : st * (uint32_t)P.R;
+                const uint32_t row = st == 0xFFFFu ? 0u : st * 4u;
                 *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) =
                     P.fp.off_ll + (row << LLS) + (((i & 31u) & (uint32_t)(REP - 1)) << 4);
             }
@@ -281,7 +325,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         eng.nx_lane = LLS == 7 ? (P.fp.off_st + lane * 4u) - ll_lane : P.fp.off_st;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, eng);
+        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     } else {
@@ -289,7 +333,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         eng.core.reset();
         eng.sm = smem_raw;
         eng.sx = ll_lane;                                         // state 0 = the all-zero vector (viterbi_markov.py:177)
-        eng.bm_base = P.fp.off_bm;
+        eng.bm_base = P.fp.off_bm + copy;
         eng.key_mul = P.fp.key_mul;
         eng.key_add = (P.fp.off_st + lane * 4u) << 16;
         eng.ll_lane = ll_lane;
@@ -297,7 +341,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         eng.hmask = P.hcap - 1u;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, eng);
+        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     }

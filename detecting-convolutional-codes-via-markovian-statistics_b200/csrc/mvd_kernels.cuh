@@ -33,7 +33,7 @@ struct DevSeg {
 
 // shared-memory plan of the fast detection kernels (mvd_detect2.cuh)
 struct FastPlan {
-    uint32_t off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
+    uint32_t off_tb, off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
     uint32_t key_mul, nkeys;           // direct metric-vector -> state table (m <= 2)
     const uint16_t* dstate;            // [nkeys] state index or 0xFFFF
 };
