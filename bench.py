@@ -42,7 +42,8 @@ N_BLOCK = 500                               # Pd_plotter.py:80
 SEED = 12345                                # Pd_plotter.py:70
 K, NOUT, M = 1, 2, 2
 OPS_CORE = 5 * (1 << M) + 11                # 31 int-ops / step at m = 2
-OPS_RNG = 41                                # naive Philox + threshold-compare estimate
+OPS_RNG = 41                                # naive Philox + threshold-compare estimate (the lazy
+                                            # bit-sliced Bernoulli actually spends ~13 instructions/step)
 METRIC = "trellis-steps/sec (whole box) for Pd-vs-p Monte-Carlo sweep"
 
 
@@ -210,7 +211,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=120))
 
     import Pd_plotter as pdp
     import viterbi_markov as vm
@@ -315,19 +318,31 @@ def main():
                 peaks = json.load(f)
         except Exception:
             pass
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.engine}_detect")
+        except Exception:
+            pass
+        ach = OPS_CORE * rate_kernel * 1e-9
         line["roofline"] = {
             "bound": "int_alu", "unit": "Gop/s",
-            "achieved": OPS_CORE * rate_kernel * 1e-9, "peak": alu_gops, "frac": OPS_CORE * rate_kernel * 1e-9 / alu_gops,
+            "achieved": ach, "peak": mixed_gops, "frac": ach / mixed_gops,
+            "peak_alu_pipe_only": alu_gops, "frac_alu_pipe_only": ach / alu_gops,
             "achieved_core_plus_rng": (OPS_CORE + OPS_RNG) * rate_kernel * 1e-9,
-            "frac_core_plus_rng": (OPS_CORE + OPS_RNG) * rate_kernel * 1e-9 / alu_gops,
-            "peak_alu_plus_fma_pipe": mixed_gops,
+            "frac_core_plus_rng": (OPS_CORE + OPS_RNG) * rate_kernel * 1e-9 / mixed_gops,
             "ops_per_step": {"core": OPS_CORE, "rng_estimate": OPS_RNG},
-            "peak_source": "libmvd mvd_int_peak(): dependent-free IADD/LOP3 chains on all SMs, measured in this run "
-                           "(MEASURED_PEAKS.json has no integer figure)",
-            "kernel": f"{args.engine}_kernel<DETECT,2>", "kernel_ms": kernel_ms, "steps_per_launch": steps_per_pass_rank,
-            "traffic": None, "hbm_bytes_per_step_algorithmic": 0.0,
+            "peak_source": "libmvd mvd_int_peak(), measured in this run on this GPU: `peak` = alternating LOP3/IMAD chains "
+                           "(ALU + FMA pipes = warp-instruction issue rate, the most any integer code can retire); "
+                           "`peak_alu_pipe_only` = LOP3-only chains (min/shift/logic/permute can only issue there). "
+                           "MEASURED_PEAKS.json has no integer figure; the path moves ~0 HBM bytes (bits are generated in "
+                           "registers), so the HBM roofline does not bind it -- see roofline_hbm_bitstream for the HBM view",
+            "kernel": ("detect2_kernel<%s>" % ("DIRECT,2,7" if args.engine == "acs" else "FSM,7")),
+            "kernel_ms": kernel_ms, "steps_per_launch": steps_per_pass_rank,
+            "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
+            "hbm_bytes_per_step_algorithmic": 0.0,
         }
-        if not args.no_extras:
+        if not args.no_extras and world == 1:       # single-GPU legs only: nothing below may enter a collective
             other = "fsm" if args.engine == "acs" else "acs"
             dto, kmo, _ = timed(lambda: device_pass(other), max(3, args.steps // 2), 3)
             line["alt_engine"] = {"engine": other, "value": steps_per_pass * max(3, args.steps // 2) / dto,

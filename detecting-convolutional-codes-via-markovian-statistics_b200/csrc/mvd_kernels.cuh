@@ -549,22 +549,26 @@ __global__ void __launch_bounds__(MVD_BLOCK) acs_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------ integer peak
-// Dependent chains on 8 independent accumulators per thread; mode 0: LOP3/IADD3 only (ALU pipe),
-// mode 1: alternating IMAD (FMA pipe) and LOP3 (ALU pipe).  OPS_PER_ITER instructions per loop.
+// Dependent chains on 8 independent accumulators per thread.
+//   mode 0: LOP3 only -- the ALU pipe alone (LOP3/SHF/PRMT/VIMNMX/IADD3 issue there, 16 lanes/clk/SMSP);
+//   mode 1: alternating IMAD (FMA pipe) and LOP3 (ALU pipe) -- both integer-capable pipes, i.e. the
+//           issue-rate bound of 1 warp instruction / clk / SMSP.
+// OPS_PER_ITER instructions per loop.
 #define MVD_PEAK_OPS_PER_ITER 64
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, int mode) {
     uint32_t a[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 2654435761u + i + blockIdx.x;
-    const uint32_t c = out[0] | 1u;           // runtime value, prevents constant folding
+    const uint32_t c = out[0] | 1u;           // runtime values, prevent constant folding
+    const uint32_t d = out[2] | 0x10u;
     if (mode == 0) {
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int u = 0; u < MVD_PEAK_OPS_PER_ITER / 8; ++u) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (u & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
-                    else asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
+                    if (u & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(c), "r"(d));   // xor3
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(c), "r"(d));        // majority
                 }
             }
         }
@@ -574,8 +578,8 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters,
             for (int u = 0; u < MVD_PEAK_OPS_PER_ITER / 8; ++u) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(a[i]) : "r"(c));
-                    else asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
+                    if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(c), "r"(d));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(c), "r"(d));
                 }
             }
         }

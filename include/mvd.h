@@ -144,8 +144,9 @@ enum { MVD_OPT_FORCE_GENERIC = 1 };
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 
-/* Integer-pipe roofline denominator, measured on this device: sustained 32-bit integer
- * lane-ops/s of a dependent-free IADD3/LOP3 (+ IMAD) mix over all SMs. */
+/* Integer roofline denominators, measured on this device (32-bit lane-ops/s over all SMs):
+ * alu_gops     -- dependent-free LOP3 chains: the ALU pipe alone (min/shift/logic/permute issue only there);
+ * alu_fma_gops -- alternating LOP3 / IMAD: ALU + FMA pipes together = the warp-instruction issue rate. */
 int mvd_int_peak(mvd_ctx* ctx, double* alu_gops, double* alu_fma_gops);
 
 /* Device facts used by the host for sharding and reporting. */
