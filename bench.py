@@ -174,7 +174,7 @@ def workload_config(args, per_gpu_trials):
     return {"workload": "Pd_plotter.py paper sweep (BASELINE configs[1]): (7,5) vs (6,5), k=1 n=2 m=2, S=31 Markov states, "
                         f"N={N_BLOCK}, p_vec={P_VEC}, both hypotheses, learn_len=6200 burn=200 laplace=1",
             "trials_per_point_per_gpu": per_gpu_trials, "engine": args.engine,
-            "bit_source": "on-device Philox4x32-10 (MVD-PHILOX-1)",
+            "bit_source": "on-device Philox4x32-10 (MVD-PHILOX-2)",
             "l2_policy": "no input stream to cache: bits are generated in registers, tables (<4 KB) live in shared "
                          "memory; the bit-stream variant reads > 2 GB per step (>> 126 MB L2)",
             "parallelism": f"trial-sharded x{args.gpus}"}

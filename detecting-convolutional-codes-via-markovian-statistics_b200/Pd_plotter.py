@@ -104,12 +104,14 @@ def learn_P1_empirical(gens_tuple, k, n, m, p, learn_len, learn_burn, laplace, s
 
 
 def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, laplace, seed, *,
-                   N_spectrum=None, engine="auto", device=None, trial_offset=0, details=None):
+                   N_spectrum=None, engine="auto", learn_engine="auto", device=None, trial_offset=0, details=None):
     """Hybrid detector over all (N, p) points -> DataFrame[N, p, Pd, Pc]
     (reference Pd_plotter.py:176-235; positional signature identical).
 
     Extra keywords (all optional, reference behaviour when omitted): ``N_spectrum`` overrides
-    ``N_SPECTRUM_BY_M[m]``; ``engine`` in {"auto", "acs", "fsm"}; ``device`` the CUDA ordinal
+    ``N_SPECTRUM_BY_M[m]``; ``engine`` in {"auto", "acs", "fsm"} for the detection trials and
+    ``learn_engine`` for the learning chains (0.1 % of the steps; "auto" walks them through the
+    NEXT table, identical counts); ``device`` the CUDA ordinal
     (default LOCAL_RANK or 0); ``details`` a dict that receives tallies, tables and timings.
     """
     import pandas as pd
@@ -122,7 +124,7 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
 
     # P1 for every distinct p (the reference's lru_cache, :123, learns once per p)
     distinct = list(dict.fromkeys(float(p) for p in p_vec))
-    counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=engine)
+    counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=learn_engine)
     det.set_models(tables)                              # T_ref = T(1/2) = mult / 2^n (reference :193-194)
     tindex = {p: i for i, p in enumerate(distinct)}
 

@@ -47,18 +47,17 @@ __device__ __forceinline__ uint32_t roff(uint32_t w) {
     return (sh >= 0 ? (w >> (sh >= 0 ? sh : 0)) : (w << (sh < 0 ? -sh : 0))) & (3u << LLS);
 }
 
-// 32 Bernoulli(T / 2^32) lanes (MVD-PHILOX-1, same stream as lazy_bernoulli) for a block-uniform
+// 32 Bernoulli(T / 2^32) lanes (MVD-PHILOX-2, same words as lazy_bernoulli) for a block-uniform
 // threshold.  tbm[k] (shared memory, staged once per block) is all-ones if bit 31-k of T is set: the
 // bits of T steer LOP3 masks instead of branches.  Levels below ctz(T) inside the last call have
 // T-bit 0 and can only retire undecided lanes, never set a flip, so running all four levels of a
 // call gives the same word as the level-exact loop of lazy_bernoulli.
-__device__ __forceinline__ uint32_t lazy_bernoulli_s(uint32_t& q, uint32_t c1, uint32_t c2, uint32_t c3,
+__device__ __forceinline__ uint32_t lazy_bernoulli_s(uint32_t c0base, uint32_t c1, uint32_t c2, uint32_t c3,
                                                      const uint4* tbm, int ncalls, uint32_t vmask, const Params& P) {
     uint32_t und = vmask, e = 0;
     for (int k = 0; k < ncalls; ++k) {
         if (!__any_sync(0xFFFFFFFFu, und != 0u)) break;
-        const uint4 w = philox10(q, c1, c2, c3, P);
-        q += (und != 0u) ? 1u : 0u;
+        const uint4 w = philox10(c0base + (uint32_t)k, c1, c2, c3, P);
         const uint4 tb = tbm[k];
         e |= und & ~w.x & tb.x;
         und &= ~(w.x ^ tb.x);
@@ -82,13 +81,12 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
     const bool philox = P.src_mode == MVD_SRC_PHILOX;
     const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
-    uint32_t q = 0, prevU = 0;
+    uint32_t prevU = 0;
     const uint32_t nsb = (N + 127u) >> 7;
     for (uint32_t sb = 0; sb < nsb; ++sb) {
         uint4 Uw = make_uint4(0, 0, 0, 0), E0 = Uw, E1 = Uw;
         if (philox) {
-            Uw = philox10(q, c1, c2, c3, P);
-            q += 1u;
+            Uw = philox10(((4u * sb) << 6) | 32u, c1, c2, c3, P);
         } else if (active) {
             const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 3ull * ntr + tl;
             Uw = __ldg(base);
@@ -105,8 +103,9 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
             const uint32_t U = pick(Uw, w);
             uint32_t e0, e1;
             if (philox) {
-                e0 = lazy_bernoulli_s(q, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
-                e1 = lazy_bernoulli_s(q, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
+                const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
+                e0 = lazy_bernoulli_s(cb, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
+                e1 = lazy_bernoulli_s(cb | 8u, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
             } else {
                 e0 = pick(E0, w);
                 e1 = pick(E1, w);

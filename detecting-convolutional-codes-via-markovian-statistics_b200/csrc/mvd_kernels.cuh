@@ -1,7 +1,7 @@
 // mvd_kernels.cuh -- sm_100a kernels of the hybrid-detector hot path.
 //
 // One thread = one Monte-Carlo trial (or one learning chain).  Per 32 trellis steps a thread
-//   1. obtains 32 info bits and n x 32 BSC flips  (on-device Philox4x32-10, lazily evaluated
+//   1. obtains 32 info bits and n x 32 BSC flips  (on-device Philox4x32-10 "MVD-PHILOX-2", lazily evaluated
 //      32-lane Bernoulli words -- or coalesced 128-bit loads of host-supplied bitstreams),
 //   2. encodes the 32 steps bit-parallel (XOR of funnel-shifted info words = GF(2) convolution,
 //      the bit-sliced form of viterbi_markov.py:82-106 for k = 1),
@@ -85,17 +85,19 @@ __device__ __forceinline__ uint4 philox10(uint32_t c0, uint32_t c1, uint32_t c2,
     return make_uint4(c0, c1, c2, c3);
 }
 
-// 32 Bernoulli(T / 2^32) lanes at once: MSB-first comparison of a lazily drawn uniform with T.
-// The loop is warp-uniform (vote), the call counter q advances only for threads that still had
-// undecided lanes, so the stream of a trial does not depend on which trials share its warp.
-__device__ __forceinline__ uint32_t lazy_bernoulli(uint32_t& q, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t T,
+// 32 Bernoulli(T / 2^32) lanes at once: MSB-first comparison of a lazily drawn uniform with T
+// (MVD-PHILOX-2: call k of output j of 32-step block b has counter word c0 = (b << 6) | (8 j + k)).
+// The loop is warp-uniform (vote); calls are addressed by position, so skipping one for a warp whose
+// lanes are all decided changes nothing else.
+__device__ __forceinline__ uint32_t lazy_bernoulli(uint32_t c0base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t T,
                                                    int dmin, uint32_t vmask, const Params& P) {
     uint32_t und = vmask, e = 0;
     int d = 31;
+    uint32_t k = 0;
     while (d >= dmin) {
         if (!__any_sync(0xFFFFFFFFu, und != 0u)) break;
-        const uint4 w = philox10(q, c1, c2, c3, P);
-        q += (und != 0u) ? 1u : 0u;
+        const uint4 w = philox10(c0base + k, c1, c2, c3, P);
+        ++k;
         const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -139,7 +141,7 @@ __device__ __forceinline__ void run_trial(const Params& P, const DevSeg& sg, boo
     const int dmin = (int)sg.dmin;
     const bool philox = P.src_mode == MVD_SRC_PHILOX;
     const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
-    uint32_t q = 0, prevU = 0;
+    uint32_t prevU = 0;
     const uint32_t nsb = (N + 127u) >> 7;
     for (uint32_t sb = 0; sb < nsb; ++sb) {
         uint4 Uw = make_uint4(0, 0, 0, 0);
@@ -147,8 +149,7 @@ __device__ __forceinline__ void run_trial(const Params& P, const DevSeg& sg, boo
 #pragma unroll
         for (int j = 0; j < MVD_MAX_N; ++j) Ew[j] = make_uint4(0, 0, 0, 0);
         if (philox) {
-            Uw = philox10(q, c1, c2, c3, P);
-            q += 1u;
+            Uw = philox10(((4u * sb) << 6) | 32u, c1, c2, c3, P);
         } else if (active) {
             const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * (unsigned)(1 + n) * ntr + tl;
             Uw = __ldg(base);
@@ -170,7 +171,8 @@ __device__ __forceinline__ void run_trial(const Params& P, const DevSeg& sg, boo
                 Rw[j] = 0;
                 if (j < n) {
                     uint32_t E;
-                    if (philox) E = lazy_bernoulli(q, c1, c2, c3, T, dmin, active ? vmask : 0u, P);
+                    if (philox) E = lazy_bernoulli(((4u * sb + (uint32_t)w) << 6) | (8u * (uint32_t)j), c1, c2, c3, T, dmin,
+                                                   active ? vmask : 0u, P);
                     else E = pick(Ew[j], w);
                     const uint32_t taps = sg.enc_taps[j];
                     uint32_t o = (taps & 1u) ? U : 0u;

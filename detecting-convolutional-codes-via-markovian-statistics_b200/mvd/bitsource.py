@@ -1,4 +1,4 @@
-"""Bit sources for the detector: the MVD-PHILOX-1 stream spec and the bitstream layout.
+"""Bit sources for the detector: the MVD-PHILOX-2 stream spec and the bitstream layout.
 
 The reference never defines where its random bits come from: the simulator it calls
 (``vm.simulate_markov_sequence``, Pd_plotter.py:149,212,219) is absent, only the idiom is
@@ -6,20 +6,27 @@ visible elsewhere (uniform info bits, iid Bernoulli(p) flips, alpha_exponent.py:
 This module *defines* the two sources the CUDA kernels consume; the CPU oracle implements the
 same spec independently, so that even throughput-mode (on-device RNG) tallies are bit-exact.
 
-MVD-PHILOX-1
+MVD-PHILOX-2
 ------------
 * generator: Philox4x32-10 (Salmon et al., SC'11), key = (seed & 2^32-1, seed >> 32),
-  counter = (q, trial & 2^32-1, trial >> 32, stream); ``q`` counts the calls of one trial.
-* a trial of N steps is cut into superblocks of 128 steps = 4 blocks of 32 steps.
-  Per superblock: one call -> the four info words U[0..3] (bit b of U[w] is the info bit of
-  step 128*sb + 32*w + b).  Then, for every block that starts before N and every output
-  j = 0..n-1 in order, one *lazy Bernoulli word* E_j (bit b = flip of output j at that step).
+  counter = (c0, trial & 2^32-1, trial >> 32, stream).  Every call is addressed by *position*:
+  ``c0 = (b << 6) | slot`` with ``b`` the index of a block of 32 trellis steps (b < 2^26), so any
+  block of any trial can be generated independently (chunk-parallel learning chains, several
+  threads per long trial) and skipping a call never moves the rest of the stream.
+* info bits: the four info words of the superblock of blocks 4s..4s+3 come from ONE call with
+  ``b = 4s, slot = 32``; bit t of word w is the info bit of step 128 s + 32 w + t.
+* BSC flips: for block b and output j (0 <= j < n <= 4) a *lazy Bernoulli word* E_j (bit t = flip of
+  output j at step 32 b + t), whose k-th call (k = 0..7) has ``slot = 8 j + k``.
 * lazy Bernoulli word for threshold T (P(flip) = T / 2^32), restricted to the valid lanes
-  ``vmask`` of the block: ``und = vmask, e = 0``; walk the threshold bits d = 31 .. ctz(T);
-  every 4th level starts with a fresh call (4 words = 4 levels) *if und != 0*, otherwise the
-  word is finished.  At level d with random word w: if bit d of T is set,
-  ``e |= und & ~w; und &= w`` else ``und &= ~w``.  Lanes still undecided at the end are 0.
-  This is exactly ``(32-bit uniform) < T`` evaluated MSB-first with early termination.
+  ``vmask`` of the block: ``und = vmask, e = 0``; walk the threshold bits d = 31 .. ctz(T); call k
+  supplies the 4 words of levels d = 31 - 4k .. 28 - 4k and is made only while ``und != 0``.
+  At level d with random word w: if bit d of T is set, ``e |= und & ~w; und &= w`` else
+  ``und &= ~w``.  Lanes still undecided at the end are 0.  This is exactly
+  ``(32-bit uniform) < T`` evaluated MSB-first with early termination (expected 6.3 levels for 32
+  lanes instead of 32 uniform words).
+
+(MVD-PHILOX-2, the first draft, numbered calls sequentially per trial; the data-dependent number
+of lazy calls made every block's position depend on all earlier blocks.)
 
 Bitstream layout (verification mode, also the HBM-bound path)
 -------------------------------------------------------------
@@ -88,29 +95,27 @@ def bsc_threshold(p: float) -> int:
     return min(t, MASK32)
 
 
-class TrialStream:
-    """Sequential word source of one (seed, stream, trial): the q-counter of MVD-PHILOX-1."""
-
-    def __init__(self, seed: int, stream: int, trial: int):
-        self.key = (seed & MASK32, (seed >> 32) & MASK32)
-        self.base = (trial & MASK32, (trial >> 32) & MASK32, stream & MASK32)
-        self.q = 0
-
-    def call(self) -> Tuple[int, int, int, int]:
-        out = philox4x32_10((self.q, *self.base), self.key)
-        self.q += 1
-        return out
+def stream_call(seed: int, stream: int, trial: int, block: int, slot: int) -> Tuple[int, int, int, int]:
+    """The Philox call at position (block, slot) of the stream (seed, stream, trial)."""
+    key = (seed & MASK32, (seed >> 32) & MASK32)
+    c0 = ((block << 6) | slot) & MASK32
+    return philox4x32_10((c0, trial & MASK32, (trial >> 32) & MASK32, stream & MASK32), key)
 
 
-def lazy_bernoulli_word(src: TrialStream, T: int, vmask: int) -> int:
+INFO_SLOT = 32
+
+
+def lazy_bernoulli_word(seed: int, stream: int, trial: int, block: int, j: int, T: int, vmask: int) -> int:
     und = vmask & MASK32
     e = 0
     if T == 0:
         return 0
     dmin = (T & -T).bit_length() - 1
     d = 31
+    k = 0
     while d >= dmin and und:
-        words = src.call()
+        words = stream_call(seed, stream, trial, block, 8 * j + k)
+        k += 1
         for w in words:
             if d < dmin:
                 break
@@ -124,16 +129,15 @@ def lazy_bernoulli_word(src: TrialStream, T: int, vmask: int) -> int:
 
 
 def trial_words(seed: int, stream: int, trial: int, N: int, n: int, T: int) -> Tuple[np.ndarray, np.ndarray]:
-    """All info / flip words of one trial under MVD-PHILOX-1.
+    """All info / flip words of one trial under MVD-PHILOX-2.
 
     Returns ``U`` uint32 [nblk] and ``E`` uint32 [n, nblk] with nblk = ceil(N / 32).
     """
-    src = TrialStream(seed, stream, trial)
     nblk = (N + 31) // 32
     U = np.zeros(nblk, dtype=np.uint32)
     E = np.zeros((n, nblk), dtype=np.uint32)
     for sb in range((N + 127) // 128):
-        uw = src.call()
+        uw = stream_call(seed, stream, trial, 4 * sb, INFO_SLOT)
         for w in range(4):
             blk = 4 * sb + w
             t0 = 32 * blk
@@ -143,7 +147,7 @@ def trial_words(seed: int, stream: int, trial: int, N: int, n: int, T: int) -> T
             valid = min(32, N - t0)
             vmask = MASK32 if valid == 32 else (1 << valid) - 1
             for j in range(n):
-                E[j, blk] = lazy_bernoulli_word(src, T, vmask)
+                E[j, blk] = lazy_bernoulli_word(seed, stream, trial, blk, j, T, vmask)
     return U, E
 
 
@@ -187,7 +191,7 @@ def pack_bitstreams(u_bits: np.ndarray, e_bits: np.ndarray) -> np.ndarray:
 
 
 def philox_bitstreams(seed: int, stream: int, trial_begin: int, ntrials: int, N: int, n: int, T: int):
-    """Materialise MVD-PHILOX-1 as host bit arrays (small cases; pure Python per trial)."""
+    """Materialise MVD-PHILOX-2 as host bit arrays (small cases; pure Python per trial)."""
     u = np.zeros((ntrials, N), dtype=np.uint8)
     e = np.zeros((ntrials, n, N), dtype=np.uint8)
     for i in range(ntrials):

@@ -101,7 +101,7 @@ def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_in
     Returns ``{"metrics": [D_0, ..., D_length], "states": indices}``; D_0 is all-zero.
 
     Bits: ``u_bits`` [length] / ``e_bits`` [length][n] if given (verification mode), otherwise the
-    on-device MVD-PHILOX-1 stream keyed by ``(seed, stream, trial)``; ``seed=None`` draws a fresh
+    on-device MVD-PHILOX-2 stream keyed by ``(seed, stream, trial)``; ``seed=None`` draws a fresh
     64-bit key from numpy's global generator (the reference idiom: no reseed,
     alpha_exponent.py:105-106).
     """

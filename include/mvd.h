@@ -46,7 +46,7 @@ enum { MVD_ENGINE_AUTO = 0, MVD_ENGINE_ACS = 1, MVD_ENGINE_FSM = 2 };
 typedef struct mvd_ctx mvd_ctx;
 
 /* Where the info bits and BSC flips of a launch come from.
- * PHILOX: generated on the device, stream spec MVD-PHILOX-1, key = seed.
+ * PHILOX: generated on the device, stream spec MVD-PHILOX-2 (mvd/bitsource.py), key = seed.
  * BITSTREAM: read from `bits`, an array of 128-bit words indexed
  *   seg.bits_offset + (sb * (1 + n) + c) * ntrials + (trial - seg.trial_begin)
  * (sb = step / 128, c = 0 info stream, c = 1 + j flips of output j, ntrials = trial_end - trial_begin;

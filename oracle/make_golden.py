@@ -10,7 +10,7 @@ What is executed unmodified from /root/reference:
   Pd_plotter.{evaluate_symbolic_T, log_prob_sequence, learn_P1_empirical, run_experiment}
 What is injected: ``viterbi_markov.simulate_markov_sequence`` (absent from the reference, SURVEY
 F2) -- the driver in oracle/ref_port.py running on the reference's own branch/step/trellis
-functions, fed by the MVD-PHILOX-1 bit source, decoder fixed to gen1.
+functions, fed by the MVD-PHILOX-2 bit source, decoder fixed to gen1.
 matplotlib (not installed; imported but unused by Pd_plotter.py:58) is stubbed.
 
 Usage:  python oracle/make_golden.py [--ref /root/reference] [--out tests/golden]
@@ -128,7 +128,7 @@ def kat_for_code(vm, pdp, name, spec, symbolic=True):
 
 
 def sim_kat(vm, name, spec, enc_spec, N, p, seed, stream, trial):
-    """Metric trajectory from the reference's branch + step functions under MVD-PHILOX-1."""
+    """Metric trajectory from the reference's branch + step functions under MVD-PHILOX-2."""
     k, n, m = spec["k"], spec["n"], spec["m"]
     sim = ref_port.simulate_markov_sequence(enc_spec["gen"], m, k, n, N, p, True, seed,
                                             decoder_matrix=spec["gen"], stream=stream, trial=trial,

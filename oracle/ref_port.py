@@ -11,7 +11,7 @@ Each function cites the lines of /root/reference it follows.
 Parity status: pinned against the reference's own functions executed in the build container
 (oracle/make_golden.py -> tests/golden/*.json).  Unpinned: the random-bit source -- the
 reference calls ``vm.simulate_markov_sequence`` (Pd_plotter.py:149,212,219) but does not ship it;
-``simulate_markov_sequence`` below restates the call contract with the MVD-PHILOX-1 source.
+``simulate_markov_sequence`` below restates the call contract with the MVD-PHILOX-2 source.
 """
 from __future__ import annotations
 
@@ -124,23 +124,21 @@ def threshold_of(p):
 
 
 def philox_bits(seed, stream, trial, N, n, T):
-    """MVD-PHILOX-1: info bits u[N] and flips e[N][n] of one trial."""
+    """MVD-PHILOX-2 (mvd/bitsource.py docstring): info bits u[N] and flips e[N][n] of one trial.
+    Every Philox call is addressed by position: c0 = (block << 6) | slot."""
     key = (seed & M32, (seed >> 32) & M32)
-    q = [0]
 
-    def call():
-        w = _philox((q[0], trial & M32, (trial >> 32) & M32, stream & M32), key)
-        q[0] += 1
-        return w
+    def call(block, slot):
+        return _philox((((block << 6) | slot) & M32, trial & M32, (trial >> 32) & M32, stream & M32), key)
 
-    def lazy(vmask):
+    def lazy(block, j, vmask):
         und, e = vmask, 0
         if T == 0:
             return 0
         dmin = (T & -T).bit_length() - 1
-        d = 31
+        d, k = 31, 0
         while d >= dmin and und:
-            for w in call():
+            for w in call(block, 8 * j + k):
                 if d < dmin:
                     break
                 if (T >> d) & 1:
@@ -149,19 +147,20 @@ def philox_bits(seed, stream, trial, N, n, T):
                 else:
                     und &= ~w & M32
                 d -= 1
+            k += 1
         return e
 
     u = [0] * N
     e = [[0] * n for _ in range(N)]
     for sb in range((N + 127) // 128):
-        uw = call()
+        uw = call(4 * sb, 32)
         for w in range(4):
             t0 = 128 * sb + 32 * w
             if t0 >= N:
                 break
             valid = min(32, N - t0)
             vmask = M32 if valid == 32 else (1 << valid) - 1
-            ew = [lazy(vmask) for _ in range(n)]
+            ew = [lazy(4 * sb + w, j, vmask) for j in range(n)]
             for b in range(valid):
                 u[t0 + b] = (uw[w] >> b) & 1
                 for j in range(n):
@@ -177,7 +176,7 @@ def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_in
     212,219): returns ``{"metrics": [D_0 .. D_length]}``; D_0 all-zero (viterbi_markov.py:177),
     encoder state 0 (alpha_exponent.py:123), k = 1 info bits uniform, flips iid Bernoulli(p),
     recursion on the *decoder* trellis (H1).  Bits come from ``u_bits``/``e_bits`` when
-    given, else from MVD-PHILOX-1 keyed by (seed, stream, trial).
+    given, else from MVD-PHILOX-2 keyed by (seed, stream, trial).
 
     ``step``/``branch_fn``/``trellis_fn`` let make_golden.py run this driver on the reference's
     own functions.
@@ -186,7 +185,7 @@ def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_in
     trellis = trellis_fn(dec, m, k)
     if u_bits is None or e_bits is None:
         if k != 1:
-            raise NotImplementedError("MVD-PHILOX-1 is defined for k = 1")
+            raise NotImplementedError("MVD-PHILOX-2 is defined for k = 1")
         gu, ge = philox_bits(0 if seed is None else int(seed), stream, trial, length, n, threshold_of(p_val))
         u_bits = gu if u_bits is None else u_bits
         e_bits = ge if e_bits is None else e_bits

@@ -58,7 +58,7 @@ def test_trace_bitstream_matches_reference(golden, codes_spec, dets, case, dec, 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("case,dec,enc", SIM_CASES)
 def test_trace_philox_matches_reference(golden, codes_spec, dets, case, dec, enc, engine):
-    """On-device MVD-PHILOX-1 bits + encoder + BSC + recursion == golden trajectory."""
+    """On-device MVD-PHILOX-2 bits + encoder + BSC + recursion == golden trajectory."""
     from mvd import bitsource
     from mvd.engine import Seg
     g = golden["sim_kats"][case]

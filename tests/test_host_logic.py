@@ -201,7 +201,7 @@ def test_bitsource_philox_matches_oracle():
 
 @pytest.mark.parametrize("N,p", [(1, 0.1), (32, 0.5), (33, 0.001), (129, 0.25), (500, 0.1), (257, 1.0), (64, 0.0)])
 def test_bitsource_trial_words_match_oracle(N, p):
-    """MVD-PHILOX-1 in the product's host module == the C oracle's independent implementation."""
+    """MVD-PHILOX-2 in the product's host module == the C oracle's independent implementation."""
     import c_oracle as co
     from mvd import bitsource
     T = bitsource.bsc_threshold(p)
