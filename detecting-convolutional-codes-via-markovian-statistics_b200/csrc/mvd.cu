@@ -51,7 +51,7 @@ struct mvd_ctx {
     uint64_t launches = 0;
     float last_ms = 0.f;
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
-    bool force_generic = false;
+    bool force_generic = false, no_pair = false;
 
     // code
     bool have_code = false;
@@ -344,7 +344,10 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     int det2_lk = -1, det2_lls = 0;
     size_t det2_smem = 0;
     const bool fast = mode == MODE_DETECT && !ctx->force_generic && plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem);
-    const uint32_t block = fast ? DET2_BLOCK : MVD_BLOCK;
+    // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
+    const size_t pair_smem = 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 128 + 32768;
+    const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && pair_smem <= 72 * 1024;
+    const uint32_t block = pair ? 2 * DET2P_BLOCK : (fast ? DET2_BLOCK : MVD_BLOCK);
 
     // ---- segments
     std::vector<DevSeg> ds(nsegs);
@@ -507,18 +510,25 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             for (uint32_t i = 0; i < cnt; ++i) {
                 B.s[i] = ds[base + i];
                 B.s[i].block_begin = base + i;                       // global segment index (tally slot)
-                maxblocks = std::max<uint64_t>(maxblocks, (ds[base + i].trial_end - ds[base + i].trial_begin + DET2_BLOCK - 1) / DET2_BLOCK);
+                maxblocks = std::max<uint64_t>(maxblocks, (ds[base + i].trial_end - ds[base + i].trial_begin + block - 1) / block);
             }
             if (maxblocks == 0) continue;
             const dim3 g2((unsigned)maxblocks, cnt);
-            if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B);
+            if (pair) {
+                auto kern = detect2p_kernel<0>;
+                le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem);
+                if (le == cudaSuccess) {
+                    kern<<<g2, DET2P_BLOCK, pair_smem, ctx->stream>>>(P, B);
+                    le = cudaGetLastError();
+                }
+            } else if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B);
             else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B)
                                                        : launch_det2<LK_DIRECT, 2>(det2_lls, g2, det2_smem, ctx->stream, P, B);
             else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, g2, det2_smem, ctx->stream, P, B)
                              : launch_det2<LK_HASH, 3>(det2_lls, g2, det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }
-        ctx->last_fast = 1 + det2_lk + 16 * det2_lls;
+        ctx->last_fast = 1 + det2_lk + 16 * det2_lls + (pair ? 256 : 0);
         if (extra_launches > 1) ctx->launches += extra_launches - 1;  // the common increment below counts one
     } else if (engine == MVD_ENGINE_FSM) {
         if (mode == MODE_DETECT) {
@@ -835,6 +845,10 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
     if (!ctx) return MVD_E_INVALID;
     if (option == MVD_OPT_FORCE_GENERIC) {
         ctx->force_generic = value != 0;
+        return MVD_OK;
+    }
+    if (option == MVD_OPT_NO_PAIR) {
+        ctx->no_pair = value != 0;
         return MVD_OK;
     }
     return fail(ctx, MVD_E_INVALID, "unknown option %d", option);

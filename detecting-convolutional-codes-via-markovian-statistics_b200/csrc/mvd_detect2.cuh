@@ -356,3 +356,220 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         *o = make_double2(a1, a0);
     }
 }
+
+// =========================================================================================== pair kernel
+// m = 2, n = 2, direct state table: TWO trials per thread, the 16x2 SIMD lanes run ACROSS the two
+// trials instead of across trellis states.  Q[s] = (D_A[s], D_B[s]); one VIADDMNMX.U16x2 per new
+// state does Eq. 4 for both trials, so the four PRMT broadcasts and the PRMT of the global minimum of
+// the state-packed layout disappear (ALU pipe: 6.5 instead of 14 instructions per trellis step; the ALU
+// pipe is what bounds this kernel).  Branch metrics come as (metric for r_A, metric for r_B) pairs
+// from a 16-row table indexed by (r_A, r_B).
+//
+// All table reads use absolute shared-memory addresses (ld.shared) whose alignment lets a single
+// LOP3 build them: log rows are 512-byte aligned (address = row | r * 128), the branch-metric planes
+// 2048-byte aligned (address = plane | r_A * 128 | r_B * 512 | copy * 16).
+#define DET2P_BLOCK 256
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+struct PairEngine {
+    uint32_t Q0, Q1, Q2, Q3;          // (trial A, trial B) metrics of trellis states 0..3
+    uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
+    uint32_t kbm, kst;                // branch-metric plane 0 | copy * 16 ; state table + lane * 4
+    double a1A, a0A, a1B, a0B;
+
+    // sA, sB7: r_A, r_B at bits 7..8; sB: r_B at bits 9..10 (other bits arbitrary)
+    __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7) {
+        const uint32_t rA = sA & 0x180u;
+        const double2 vA = lds_d2(sxA | rA);
+        const double2 vB = lds_d2(sxB | (sB7 & 0x180u));
+        a1A += vA.x;
+        a0A += vA.y;
+        a1B += vB.x;
+        a0B += vB.y;
+        const uint32_t boff = kbm | rA | (sB & 0x600u);
+        const uint4 b0 = lds_v4(boff);                 // ns 0: (pred 0, pred 2), ns 1: (pred 0, pred 2)
+        const uint4 b1 = lds_v4(boff + 2048u);         // ns 2: (pred 1, pred 3), ns 3: (pred 1, pred 3)
+        const uint32_t n0 = __viaddmin_u16x2(Q0, b0.x, Q2 + b0.y);          // Eq. 4, both trials
+        const uint32_t n1 = __viaddmin_u16x2(Q0, b0.z, Q2 + b0.w);
+        const uint32_t n2 = __viaddmin_u16x2(Q1, b1.x, Q3 + b1.y);
+        const uint32_t n3 = __viaddmin_u16x2(Q1, b1.z, Q3 + b1.w);
+        const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);       // per-trial minimum
+        Q0 = n0 - mn;                                                       // Eq. 5 (no borrow: every lane >= its minimum)
+        Q1 = n1 - mn;
+        Q2 = n2 - mn;
+        Q3 = n3 - mn;
+        // key = s1 | s0 << 2 | s3 << 4 | s2 << 6 per trial (the direct table's index), times 128
+        const uint32_t t7 = Q1 * 128u + Q0 * 512u + Q3 * 2048u + Q2 * 8192u;
+        sxA = lds_u32((t7 & 0xFFFFu) + kst);
+        sxB = lds_u32((t7 >> 16) + kst);
+    }
+};
+
+template <int DUMMY>
+__global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_constant__ Params P,
+                                                                  const __grid_constant__ SegBatch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevSeg& sg = B.s[blockIdx.y];
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    const unsigned long long blk0 = (unsigned long long)blockIdx.x * (2u * DET2P_BLOCK);
+    if (blk0 >= ntr) return;
+    const uint32_t seg = sg.block_begin;
+    const unsigned long long tlA = blk0 + threadIdx.x, tlB = tlA + DET2P_BLOCK;
+    const bool actA = tlA < ntr, actB = tlB < ntr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t SR = P.SR;
+    // absolute shared addresses: [bm plane 0 (2 KB)][bm plane 1 (2 KB)][log rows SR x 128][masks 128][state 256 x 128]
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t a_bm = (sbase + 2047u) & ~2047u;
+    const uint32_t a_ll = a_bm + 4096u;
+    const uint32_t a_tb = a_ll + (SR << 7);
+    const uint32_t a_st = a_tb + 128u;
+    unsigned char* g = smem_raw - sbase;                      // generic pointer of shared address 0
+
+    if (threadIdx.x < 32u)
+        *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
+    {
+        const double2* llg = P.ll + (size_t)sg.table * SR;
+        for (uint32_t i = threadIdx.x; i < SR * 8u; i += DET2P_BLOCK)
+            *reinterpret_cast<double2*>(g + a_ll + ((i >> 3) << 7) + ((i & 7u) << 4)) = __ldg(llg + (i >> 3));
+    }
+    // pair branch metrics: row (rA | rB << 2), word (ns, b): lo = d(pred_b -> ns | rA), hi = ... | rB
+    // P.bm[r][2 g + b] = (d(pred -> 2g), d(pred -> 2g+1)) for pred = g + 2 b
+    for (uint32_t i = threadIdx.x; i < 16u * 8u * 8u; i += DET2P_BLOCK) {
+        const uint32_t c = i & 7u, wd = (i >> 3) & 7u, row = i >> 6;
+        const uint32_t rA = row & 3u, rB = row >> 2, ns = wd >> 1, b = wd & 1u, gg = ns >> 1, h = ns & 1u;
+        const uint32_t wa = P.bm[rA * 4u + 2u * gg + b], wb = P.bm[rB * 4u + 2u * gg + b];
+        const uint32_t da = h ? (wa >> 16) : (wa & 0xFFFFu), db = h ? (wb >> 16) : (wb & 0xFFFFu);
+        *reinterpret_cast<uint32_t*>(g + a_bm + (wd >> 2) * 2048u + (rA << 7) + (rB << 9) + (c << 4) + 4u * (wd & 3u)) =
+            da | (db << 16);
+    }
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += DET2P_BLOCK) {
+        const uint32_t st = P.fp.dstate[i >> 5];
+        const uint32_t row = st == 0xFFFFu ? 0u : st * 4u;
+        *reinterpret_cast<uint32_t*>(g + a_st + 4u * i) = a_ll + (row << 7) + (((i & 31u) & 7u) << 4);
+    }
+    __syncthreads();
+
+    const uint4* tbm = reinterpret_cast<const uint4*>(g + a_tb);
+    PairEngine eng;
+    eng.Q0 = eng.Q1 = eng.Q2 = eng.Q3 = 0u;
+    eng.sxA = eng.sxB = a_ll + ((lane & 7u) << 4);            // state 0 = the all-zero vector
+    eng.kbm = a_bm + ((lane & 7u) << 4);
+    eng.kst = a_st + lane * 4u;
+    eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
+
+    const int m = P.m;
+    const uint32_t N = sg.N;
+    const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
+    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
+    const uint32_t c3 = sg.stream;
+    const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
+    uint32_t prevUA = 0, prevUB = 0;
+    const uint32_t nsb = (N + 127u) >> 7;
+    for (uint32_t sb = 0; sb < nsb; ++sb) {
+        uint4 UA = make_uint4(0, 0, 0, 0), UB = UA, EA0 = UA, EA1 = UA, EB0 = UA, EB1 = UA;
+        if (philox) {
+            UA = philox10(((4u * sb) << 6) | 32u, (uint32_t)trA, (uint32_t)(trA >> 32), c3, P);
+            UB = philox10(((4u * sb) << 6) | 32u, (uint32_t)trB, (uint32_t)(trB >> 32), c3, P);
+        } else {
+            const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 3ull * ntr;
+            if (actA) {
+                UA = __ldg(base + tlA);
+                EA0 = __ldg(base + ntr + tlA);
+                EA1 = __ldg(base + 2ull * ntr + tlA);
+            }
+            if (actB) {
+                UB = __ldg(base + tlB);
+                EB0 = __ldg(base + ntr + tlB);
+                EB1 = __ldg(base + 2ull * ntr + tlB);
+            }
+        }
+        if (!sg.random_input) UA = UB = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t0 = sb * 128u + (uint32_t)w * 32u;
+            if (t0 >= N) break;
+            const uint32_t valid = min(32u, N - t0);
+            const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+            uint32_t wlo[2], whi[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const uint32_t U = pick(x ? UB : UA, w);
+                const bool act = x ? actB : actA;
+                const unsigned long long tr = x ? trB : trA;
+                uint32_t e0, e1;
+                if (philox) {
+                    const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
+                    e0 = lazy_bernoulli_s(cb, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
+                    e1 = lazy_bernoulli_s(cb | 8u, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
+                } else {
+                    e0 = pick(x ? EB0 : EA0, w);
+                    e1 = pick(x ? EB1 : EA1, w);
+                }
+                const uint32_t pu = x ? prevUB : prevUA;
+                uint32_t o0 = (taps0 & 1u) ? U : 0u, o1 = (taps1 & 1u) ? U : 0u;
+#pragma unroll
+                for (int i = 1; i <= 2; ++i) {
+                    if (i <= m) {
+                        const uint32_t sh = __funnelshift_l(pu, U, i);
+                        if ((taps0 >> i) & 1u) o0 ^= sh;
+                        if ((taps1 >> i) & 1u) o1 ^= sh;
+                    }
+                }
+                if (x) prevUB = U; else prevUA = U;
+                const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
+                wlo[x] = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
+                whi[x] = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+            }
+#pragma unroll 1
+            for (uint32_t c = 0; c < valid; c += 8u) {
+                const uint32_t sh = (c & 8u) << 1;
+                const uint32_t wa = ((c & 16u) ? whi[0] : wlo[0]) >> sh;      // 8 steps = bits 0..15
+                const uint32_t wb = ((c & 16u) ? whi[1] : wlo[1]) >> sh;
+                if (c + 8u <= valid) {
+                    const uint32_t wa2 = wa >> 8, wb2 = wb >> 8;
+                    eng.step(wa << 7, wb << 9, wb << 7);
+                    eng.step(wa << 5, wb << 7, wb << 5);
+                    eng.step(wa << 3, wb << 5, wb << 3);
+                    eng.step(wa << 1, wb << 3, wb << 1);
+                    eng.step(wa2 << 7, wb2 << 9, wb2 << 7);
+                    eng.step(wa2 << 5, wb2 << 7, wb2 << 5);
+                    eng.step(wa2 << 3, wb2 << 5, wb2 << 3);
+                    eng.step(wa2 << 1, wb2 << 3, wb2 << 1);
+                } else {
+                    for (uint32_t j = 0; j < valid - c; ++j)
+                        eng.step((wa >> (2u * j)) << 7, (wb >> (2u * j)) << 9, (wb >> (2u * j)) << 7);
+                }
+            }
+        }
+    }
+
+    const bool winA = actA && (sg.decide == 0 ? (eng.a1A > eng.a0A) : (eng.a1A <= eng.a0A));
+    const bool winB = actB && (sg.decide == 0 ? (eng.a1B > eng.a0B) : (eng.a1B <= eng.a0B));
+    const int cnt = __syncthreads_count(winA ? 1 : 0) + __syncthreads_count(winB ? 1 : 0);
+    if (threadIdx.x == 0 && cnt) {
+        atomicAdd(P.tallies + seg, (unsigned long long)cnt);
+        if (P.tallies2) atomicAdd(P.tallies2 + seg, (unsigned long long)cnt);
+    }
+    if (P.logp) {
+        double2* o = reinterpret_cast<double2*>(P.logp) + sg.out_offset;
+        if (actA) o[tlA] = make_double2(eng.a1A, eng.a0A);
+        if (actB) o[tlB] = make_double2(eng.a1B, eng.a0B);
+    }
+}

@@ -18,6 +18,7 @@ ENGINES = {"auto": ENGINE_AUTO, "acs": ENGINE_ACS, "fsm": ENGINE_FSM}
 
 E_UNKNOWN_STATE = -6
 OPT_FORCE_GENERIC = 1
+OPT_NO_PAIR = 2
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 

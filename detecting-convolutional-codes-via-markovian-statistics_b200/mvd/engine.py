@@ -213,8 +213,13 @@ class Detector:
         """Route detection through the generic (checked) kernels instead of the fast ones."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_FORCE_GENERIC, 1 if on else 0))
 
+    def no_pair(self, on: bool = True):
+        """Fast kernels with one trial per thread instead of two (m = 2 only has the choice)."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_PAIR, 1 if on else 0))
+
     def last_kernel_kind(self) -> int:
-        """0 = generic kernel; else 1 + lookup kind (0 direct, 1 hash, 2 NEXT walk) + 16 * log2(row stride)."""
+        """0 = generic kernel; else 1 + lookup kind (0 direct, 1 hash, 2 NEXT walk) + 16 * log2(row stride)
+        (+ 256 for the two-trials-per-thread kernel)."""
         v = C.c_int()
         self._ck(self.lib.mvd_last_kernel_kind(self.ctx, C.byref(v)))
         return int(v.value)

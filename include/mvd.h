@@ -139,8 +139,9 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
 /* Options.  MVD_OPT_FORCE_GENERIC (value 0/1): 1 = never take the fast detection kernels
  * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
- * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry). */
-enum { MVD_OPT_FORCE_GENERIC = 1 };
+ * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
+ * + 256 if the two-trials-per-thread kernel ran. */
+enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2 };   /* NO_PAIR: fast kernels, but one trial per thread */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 

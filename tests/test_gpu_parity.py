@@ -180,7 +180,7 @@ def _oracle_models(det, spec, p, learn_len, seed):
     return tab, P1, codes.tref_half_table(det.table)
 
 
-@pytest.mark.parametrize("path", ["fast", "generic"])
+@pytest.mark.parametrize("path", ["fast", "fast1", "generic"])
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("dec,enc,N,p", [("c75", "c65", 500, 0.1), ("c75", "c75", 200, 0.3), ("m3a", "m3b", 333, 0.05),
                                          ("r13", "r13", 97, 0.15), ("m1", "m1", 64, 0.2), ("c75", "c65", 7, 0.4),
@@ -200,16 +200,19 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
     segs = [Seg(N=N, threshold=T, stream=10 + d, enc_taps=_taps(codes_spec[enc]), decide=d, trial_begin=17,
                 trial_end=17 + ntr) for d in (0, 1)]
     det.force_generic(path == "generic")
+    det.no_pair(path == "fast1")
     try:
         tallies, lp = det.detect(segs, seed=2024, engine=engine, want_logp=True)
         kind = det.last_kernel_kind()
     finally:
         det.force_generic(False)
+        det.no_pair(False)
     if path == "generic" or spec["n"] != 2:
         assert kind == 0
     else:
         want_lookup = 2 if engine == "fsm" else (0 if spec["m"] <= 2 else 1)
         assert kind != 0 and (kind - 1) % 16 == want_lookup
+        assert (kind >= 256) == (path == "fast" and engine == "acs" and spec["m"] == 2)
     for d in (0, 1):
         want, wlp = co.run_trials(_taps(spec), _taps(codes_spec[enc]), spec["n"], spec["m"], N, T, 2024, 10 + d, 17,
                                   17 + ntr, tab, P1, Tref, d, want_logp=True)
