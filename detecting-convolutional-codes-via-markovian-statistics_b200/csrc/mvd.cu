@@ -6,6 +6,7 @@
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include "mvd_kernels.cuh"
 #include "mvd_detect2.cuh"
+#include "mvd_learn2.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -52,6 +53,8 @@ struct mvd_ctx {
     float last_ms = 0.f;
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
     bool force_generic = false, no_pair = false;
+    uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
+    uint32_t learn_warm = LEARN_WARM;
 
     // code
     bool have_code = false;
@@ -70,7 +73,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty;
 };
 
 namespace {
@@ -499,7 +502,45 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool n2 = (n == 2);
     cudaError_t le = cudaErrorInvalidValue;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (fast) {
+    bool plearn = mode == MODE_LEARN && engine == MVD_ENGINE_FSM && !ctx->force_generic && src->mode == MVD_SRC_PHILOX;
+    uint32_t maxL = 0;
+    for (uint32_t i = 0; i < nsegs && plearn; ++i) {
+        plearn = (segs[i].trial_end - segs[i].trial_begin) == 1;
+        maxL = std::max(maxL, segs[i].N);
+    }
+    if (plearn && maxL > 0) {
+        // chunk-parallel learning chains (mvd_learn2.cuh): speculate, check, fix
+        LearnParams LP{};
+        LP.nchunks = (maxL + LEARN_CH - 1) / LEARN_CH;
+        LP.warm = ctx->learn_warm;
+        const size_t cells = (size_t)nsegs * LP.nchunks;
+        CK(ctx->d_lspec.reserve(cells * 4));
+        CK(ctx->d_lend.reserve(cells * 4));
+        CK(ctx->d_ldirty.reserve((size_t)nsegs * 4));
+        CK(cudaMemsetAsync(ctx->d_ldirty.p, 0, (size_t)nsegs * 4, ctx->stream));
+        LP.spec_start = ctx->d_lspec.as<uint32_t>();
+        LP.end = ctx->d_lend.as<uint32_t>();
+        LP.ndirty = ctx->d_ldirty.as<uint32_t>();
+        const size_t lsmem = (size_t)SR * 8;
+        const bool lin = lsmem <= 96 * 1024;
+        LP.nxt_in_smem = lin ? 1 : 0;
+        const dim3 g1((LP.nchunks + LEARN_BLOCK - 1) / LEARN_BLOCK, nsegs);
+        if (lin) {
+            auto kern = learn_spec_kernel<true>;
+            le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            if (le == cudaSuccess) kern<<<g1, LEARN_BLOCK, lsmem, ctx->stream>>>(P, LP);
+        } else {
+            learn_spec_kernel<false><<<g1, LEARN_BLOCK, 0, ctx->stream>>>(P, LP);
+        }
+        le = cudaGetLastError();
+        if (le == cudaSuccess) {
+            learn_check_kernel<<<dim3((LP.nchunks + 255) / 256, nsegs), 256, 0, ctx->stream>>>(P, LP);
+            learn_fix_kernel<<<nsegs, 1024, 0, ctx->stream>>>(P, LP);
+            le = cudaGetLastError();
+            ctx->launches += 2;
+        }
+        ctx->last_fast = 1024;
+    } else if (fast) {
         // segments travel as kernel parameters, DET2_MAXSEG per launch; grid.y = segment
         le = cudaSuccess;
         uint32_t extra_launches = 0;
@@ -545,19 +586,24 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         else if (mode == MODE_TRACE) le = launch_acs<MODE_TRACE, 0>(m, grid, smem, ctx->stream, P);
         else le = n2 ? launch_acs<MODE_HASH, 2>(m, grid, smem, ctx->stream, P) : launch_acs<MODE_HASH, 0>(m, grid, smem, ctx->stream, P);
     }
-    if (!fast) ctx->last_fast = 0;
+    if (!fast && !(plearn && maxL > 0)) ctx->last_fast = 0;
     if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
 
     // ---- read back
     int herr = 0;
+    std::vector<uint32_t> hdirty;
     CK(cudaMemcpyAsync(&herr, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (mode == MODE_DETECT) {
         if (out.tallies) CK(cudaMemcpyAsync(out.tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
         if (out.logp) CK(cudaMemcpyAsync(out.logp, ctx->d_logp.p, 16 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
     } else if (mode == MODE_LEARN) {
         if (out.counts) CK(cudaMemcpyAsync(out.counts, ctx->d_counts.p, 8 * (size_t)nsegs * SR, cudaMemcpyDeviceToHost, ctx->stream));
+        if (plearn && maxL > 0) {
+            hdirty.assign(nsegs, 0u);
+            CK(cudaMemcpyAsync(hdirty.data(), ctx->d_ldirty.p, 4 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
+        }
     } else if (mode == MODE_TRACE) {
         const size_t cells = (size_t)trials * ((size_t)segs[0].N + 1);
         CK(cudaMemcpyAsync(out.trace_idx, ctx->d_trace_idx.p, 4 * cells, cudaMemcpyDeviceToHost, ctx->stream));
@@ -569,6 +615,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->last_dirty = 0;
+    for (uint32_t v : hdirty) ctx->last_dirty += v;
     if (mode == MODE_TRACE && out.trace_met && engine == MVD_ENGINE_FSM) {
         // FSM engine: the metric vectors are a gather from the state table
         const size_t cells = (size_t)trials * ((size_t)segs[0].N + 1);
@@ -620,7 +668,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate};
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -851,12 +899,23 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
         ctx->no_pair = value != 0;
         return MVD_OK;
     }
+    if (option == MVD_OPT_LEARN_WARM) {
+        if (value < 0 || value > (1 << 20) || (value & 31)) return fail(ctx, MVD_E_INVALID, "warm-up must be a multiple of 32 in [0, 2^20]");
+        ctx->learn_warm = (uint32_t)value;
+        return MVD_OK;
+    }
     return fail(ctx, MVD_E_INVALID, "unknown option %d", option);
 }
 
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind) {
     if (!ctx || !kind) return MVD_E_INVALID;
     *kind = ctx->last_fast;
+    return MVD_OK;
+}
+
+int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks) {
+    if (!ctx || !dirty_chunks) return MVD_E_INVALID;
+    *dirty_chunks = ctx->last_dirty;
     return MVD_OK;
 }
 

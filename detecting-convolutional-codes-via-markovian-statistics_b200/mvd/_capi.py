@@ -19,6 +19,7 @@ ENGINES = {"auto": ENGINE_AUTO, "acs": ENGINE_ACS, "fsm": ENGINE_FSM}
 E_UNKNOWN_STATE = -6
 OPT_FORCE_GENERIC = 1
 OPT_NO_PAIR = 2
+OPT_LEARN_WARM = 3
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 
@@ -26,7 +27,7 @@ EXPORTS = (
     "mvd_abi_version", "mvd_create", "mvd_destroy", "mvd_last_error", "mvd_set_stream", "mvd_synchronize",
     "mvd_set_code", "mvd_set_states", "mvd_enumerate_states", "mvd_get_states", "mvd_set_loglik",
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
-    "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind",
+    "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
 )
 
 
@@ -87,6 +88,7 @@ def load():
     lib.mvd_int_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
     lib.mvd_set_option.argtypes = [vp, i32, C.c_int64]
     lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]
+    lib.mvd_learn_stats.argtypes = [vp, P(u32)]
     lib.mvd_device_info.argtypes = [vp, P(i32), P(i32), P(u64), C.c_char_p, i32]
     for name in EXPORTS:
         getattr(lib, name)            # AttributeError here = header / library mismatch

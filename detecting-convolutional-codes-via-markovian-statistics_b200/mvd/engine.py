@@ -217,6 +217,16 @@ class Detector:
         """Fast kernels with one trial per thread instead of two (m = 2 only has the choice)."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_PAIR, 1 if on else 0))
 
+    def learn_warm(self, steps: int = 128):
+        """Warm-up steps of the chunk-parallel learning chains (0 = speculate cold: every chunk is
+        repaired by the fix-up pass; results are identical)."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_LEARN_WARM, int(steps)))
+
+    def learn_dirty_chunks(self) -> int:
+        v = C.c_uint32()
+        self._ck(self.lib.mvd_learn_stats(self.ctx, C.byref(v)))
+        return int(v.value)
+
     def last_kernel_kind(self) -> int:
         """0 = generic kernel; else 1 + lookup kind (0 direct, 1 hash, 2 NEXT walk) + 16 * log2(row stride)
         (+ 256 for the two-trials-per-thread kernel)."""

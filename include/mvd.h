@@ -106,7 +106,8 @@ int mvd_get_states(mvd_ctx* ctx, uint8_t* metrics, uint32_t* next);
 int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const double* logTref);
 
 /* Transition counting: the loop Pd_plotter.py:158-163 for every segment (segment = one or more
- * chains of N steps; only steps t >= burn are counted).  edge_counts: host, nsegs x S x R,
+ * chains of N steps; only steps t >= burn are counted).  Single-chain segments on the on-device
+ * bit source with engine AUTO/FSM are walked chunk-parallel (exact; see csrc/mvd_learn2.cuh).  edge_counts: host, nsegs x S x R,
  * edge_counts[s][i*R + r] = number of counted steps leaving state i on received word r. */
 int mvd_learn_counts(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
                      uint32_t burn, int engine, uint64_t* edge_counts);
@@ -140,10 +141,14 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
- * + 256 if the two-trials-per-thread kernel ran. */
-enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2 };   /* NO_PAIR: fast kernels, but one trial per thread */
+ * + 256 if the two-trials-per-thread kernel ran; 1024 = chunk-parallel learning chain.
+ * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
+ * wrong and had to be repaired (results are exact either way; this is a performance counter). */
+enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: fast kernels, but one trial per thread */
+       MVD_OPT_LEARN_WARM = 3 };   /* warm-up steps of the chunk-parallel learning chains (default 128) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
+int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);
 
 /* Integer roofline denominators, measured on this device (32-bit lane-ops/s over all SMs):
  * alu_gops     -- dependent-free LOP3 chains: the ALU pipe alone (min/shift/logic/permute issue only there);

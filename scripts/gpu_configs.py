@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Throughput / wall time of the other BASELINE configs (not the bench line): m = 3 demo pair, m = 4,
+the paper sweep at the reference's own num_iter, and the N sweep.  Prints one JSON per case."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "detecting-convolutional-codes-via-markovian-statistics_b200"))
+import numpy as np
+import Pd_plotter as pdp
+import viterbi_markov as vm
+from mvd import bitsource, codes
+from mvd.engine import Detector, Seg
+
+def timed_detect(det, segs, engine, reps=3):
+    det.detect(segs, seed=1, engine=engine)
+    ms = []
+    for _ in range(reps):
+        det.detect(segs, seed=1, engine=engine)
+        ms.append(det.last_kernel_ms())
+    return float(np.median(ms)), det.last_kernel_kind()
+
+def case_code(name, gen1, gen2, m, N, trials, ps, learn_len=None, enumerate_with="python"):
+    t0 = time.perf_counter()
+    det = Detector(gen1, 1, 2, m, enumerate_with=enumerate_with)
+    t_enum = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    counts, tables = pdp._learn_edge_tables(det, ps, learn_len, 200, 1.0, 12345)
+    t_learn = time.perf_counter() - t0
+    learn_ms = det.last_kernel_ms()
+    det.set_models(tables)
+    t1, t2 = det.taps_of(gen1), det.taps_of(gen2)
+    segs = []
+    for q, p in enumerate(ps):
+        T = bitsource.bsc_threshold(p)
+        segs.append(Seg(N=N, threshold=T, stream=2 * q, table=q, enc_taps=t1, decide=0, trial_begin=0, trial_end=trials))
+        segs.append(Seg(N=N, threshold=T, stream=2 * q + 1, table=q, enc_taps=t2, decide=1, trial_begin=0, trial_end=trials))
+    steps = 2 * N * trials * len(ps)
+    out = dict(case=name, S=det.S, m=m, N=N, trials=trials, points=len(ps), steps=steps, enum_s=round(t_enum, 3),
+               learn_wall_s=round(t_learn, 4), learn_kernel_ms=round(learn_ms, 3), learn_len=pdp._learn_len(det.S, learn_len))
+    for eng in ("acs", "fsm"):
+        try:
+            ms, kind = timed_detect(det, segs, eng)
+            out[eng] = dict(kernel_ms=round(ms, 3), steps_per_s=steps / (ms * 1e-3), kind=kind)
+        except Exception as exc:
+            out[eng] = dict(error=str(exc)[:200])
+    det.close()
+    print(json.dumps(out), flush=True)
+
+P7 = [0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5]
+which = sys.argv[1:] or ["m2", "m3", "m4", "paper", "nsweep"]
+if "m2" in which:
+    case_code("m2 (7,5)/(6,5) paper", [[[1,1,1]],[[1,0,1]]], [[[1,1,0]],[[1,0,1]]], 2, 500, 200000, P7)
+if "m3" in which:
+    case_code("m3 demo pair", [[[1,1,1,1]],[[1,0,1,1]]], [[[1,0,1,1]],[[1,1,1,1]]], 3, 500, 200000, [0.01, 0.05, 0.1, 0.2, 0.3])
+if "m4" in which:
+    case_code("m4 (31,33)", [[[1,1,0,0,1]],[[1,1,0,1,1]]], [[[1,1,0,1,1]],[[1,1,0,0,1]]], 4, 500, 100000, [0.05, 0.1], learn_len=200000, enumerate_with="lib")
+if "nsweep" in which:
+    for N in (100, 1000, 10000, 100000):
+        case_code(f"N sweep N={N}", [[[1,1,1]],[[1,0,1]]], [[[1,1,0]],[[1,0,1]]], 2, N, max(2000, 20000000 // N), [0.1])
+if "paper" in which:
+    # python Pd_plotter.py as shipped: num_iter = 10^4 (reference default), wall time through the public API
+    for it in (10000, 1000000):
+        pdp.run_experiment(1, 2, 2, [[[1,1,1]],[[1,0,1]]], [[[1,1,0]],[[1,0,1]]], it, P7, None, 200, 1.0, 12345)
+        t0 = time.perf_counter()
+        d = {}
+        df = pdp.run_experiment(1, 2, 2, [[[1,1,1]],[[1,0,1]]], [[[1,1,0]],[[1,0,1]]], it, P7, None, 200, 1.0, 12345, details=d)
+        wall = time.perf_counter() - t0
+        print(json.dumps(dict(case=f"paper sweep run_experiment num_iter={it}", wall_ms=round(1e3 * wall, 3), detect_kernel_ms=round(d["detect_kernel_ms"], 3),
+                              steps=d["steps"], steps_per_s=d["steps"] / wall, Pd=df["Pd"].tolist())), flush=True)

@@ -110,6 +110,43 @@ def test_learn_counts_vs_oracle(codes_spec, dets, engine, name):
         assert int(got[i].sum()) == L - burn
 
 
+@pytest.mark.parametrize("name,L,burn,p", [("c75", 6200, 200, 0.1), ("c75", 6200, 200, 0.5), ("c75", 100, 0, 0.3),
+                                           ("c75", 129, 200, 0.3), ("c75", 4097, 33, 0.001), ("m3a", 87000, 200, 0.05),
+                                           ("r13", 5000, 100, 0.2), ("m1", 777, 7, 0.4), ("c65", 3000, 0, 0.0)])
+@pytest.mark.parametrize("warm", [128, 0, 32])
+def test_learn_chunk_parallel_vs_oracle(codes_spec, dets, name, L, burn, p, warm):
+    """Chunk-parallel learning chain (speculate / check / fix) == the sequential chain of the oracle,
+    bit-exact, with the default warm-up, with none (every chunk repaired) and with a short one."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    s = codes_spec[name]
+    det = dets(name)
+    tab = co.Table(det.table.metrics, s["m"])
+    taps = _taps(s)
+    T = bitsource.bsc_threshold(p)
+    seg = Seg(N=L, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=taps)
+    want, _ = co.learn_chain(taps, taps, s["n"], s["m"], L, burn, T, 321, bitsource.LEARN_STREAM, 0, tab)
+    det.learn_warm(warm)
+    try:
+        got = det.learn_counts([seg, seg], burn=burn, seed=321, engine="fsm")
+        assert det.last_kernel_kind() == 1024
+        dirty = det.learn_dirty_chunks()
+    finally:
+        det.learn_warm(128)
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
+    assert int(got[0].sum()) == max(0, L - burn)
+    if warm == 128 and name != "m3a":
+        assert dirty == 0
+    det.force_generic(True)
+    try:
+        ser = det.learn_counts([seg], burn=burn, seed=321, engine="fsm")[0]
+        assert det.last_kernel_kind() == 0
+    finally:
+        det.force_generic(False)
+    assert np.array_equal(ser, want)
+
+
 def test_learn_counts_many_chains(codes_spec, dets):
     """Several chains per segment aggregate into one histogram (shared-memory atomics)."""
     import c_oracle as co
