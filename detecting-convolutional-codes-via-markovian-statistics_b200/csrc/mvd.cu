@@ -9,6 +9,7 @@
 #include "mvd_learn2.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -52,7 +53,9 @@ struct mvd_ctx {
     uint64_t launches = 0;
     float last_ms = 0.f;
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
-    bool force_generic = false, no_pair = false;
+    bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false;
+    bool tref_packed = false;       // log Tref = c * unit with c in {0, 2^j}: one-load NEXT walk possible
+    double tref_unit = 0.0;
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
     uint32_t learn_warm = LEARN_WARM;
 
@@ -73,7 +76,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode;
 };
 
 namespace {
@@ -263,13 +266,13 @@ cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P)
 }
 
 template <int LK, int M>
-cudaError_t launch_det2(int lls, dim3 grid, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
+cudaError_t launch_det2(int lls, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
 #define MVD_DET2_CASE(L)                                                                              \
     case L: {                                                                                         \
         auto kern = detect2_kernel<LK, M, L>;                                                         \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
-        kern<<<grid, DET2_BLOCK, smem, st>>>(P, B);                                                   \
+        kern<<<grid, threads, smem, st>>>(P, B);                                                      \
         return cudaGetLastError();                                                                    \
     }
     switch (lls) {
@@ -288,6 +291,21 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
     const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 4;
     const size_t SR = (size_t)ctx->S * R;
     int lk;
+    if (engine == MVD_ENGINE_FSM && ctx->tref_packed && !ctx->no_fsm1 && 128 + (SR << 7) + 64 <= ctx->prop.sharedMemPerBlockOptin) {
+        // one-load NEXT walk: [masks][S*R entries x 8 copies x 16 B]
+        fp->off_tb = 0;
+        fp->off_bm = fp->off_st = 128;
+        fp->off_ll = 128;
+        fp->key_mul = 0;
+        fp->nkeys = 0;
+        fp->dstate = nullptr;
+        fp->tcode = ctx->d_tcode.as<uint32_t>();
+        fp->tref_unit = ctx->tref_unit;
+        *lk_out = LK_FSM1;
+        *lls_out = 7;
+        *smem_out = 128 + (SR << 7);
+        return true;
+    }
     if (engine == MVD_ENGINE_FSM) lk = LK_FSM;
     else if (ctx->nkeys) lk = LK_DIRECT;
     else if ((m == 2 || m == 3) && ctx->acs_ok) lk = LK_HASH;
@@ -349,8 +367,19 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool fast = mode == MODE_DETECT && !ctx->force_generic && plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
     const size_t pair_smem = 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 128 + 32768;
-    const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && pair_smem <= 72 * 1024;
-    const uint32_t block = pair ? 2 * DET2P_BLOCK : (fast ? DET2_BLOCK : MVD_BLOCK);
+    uint64_t all_trials = 0;
+    for (uint32_t i = 0; i < nsegs; ++i) all_trials += segs[i].trial_end >= segs[i].trial_begin ? segs[i].trial_end - segs[i].trial_begin : 0;
+    const uint64_t sms = (uint64_t)ctx->prop.multiProcessorCount;
+    // pairing halves the thread count: only when the GPU stays full (3 blocks of 256 pair-threads per SM)
+    const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && pair_smem <= 72 * 1024 &&
+                      (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
+    // few trials: smaller blocks so that every SM gets work (the kernels read blockDim.x)
+    uint32_t threads = pair ? DET2P_BLOCK : DET2_BLOCK;
+    if (fast) {
+        const uint64_t per_thread = pair ? 2 : 1;
+        while (threads > 64 && (all_trials + threads * per_thread - 1) / (threads * per_thread) < 4 * sms) threads >>= 1;
+    }
+    const uint32_t block = fast ? threads * (pair ? 2u : 1u) : MVD_BLOCK;
 
     // ---- segments
     std::vector<DevSeg> ds(nsegs);
@@ -559,14 +588,21 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
                 auto kern = detect2p_kernel<0>;
                 le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem);
                 if (le == cudaSuccess) {
-                    kern<<<g2, DET2P_BLOCK, pair_smem, ctx->stream>>>(P, B);
+                    kern<<<g2, threads, pair_smem, ctx->stream>>>(P, B);
                     le = cudaGetLastError();
                 }
-            } else if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B);
-            else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, g2, det2_smem, ctx->stream, P, B)
-                                                       : launch_det2<LK_DIRECT, 2>(det2_lls, g2, det2_smem, ctx->stream, P, B);
-            else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, g2, det2_smem, ctx->stream, P, B)
-                             : launch_det2<LK_HASH, 3>(det2_lls, g2, det2_smem, ctx->stream, P, B);
+            } else if (det2_lk == LK_FSM1) {
+                auto kern = detect2_kernel<LK_FSM1, 1, 7>;
+                le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det2_smem);
+                if (le == cudaSuccess) {
+                    kern<<<g2, threads, det2_smem, ctx->stream>>>(P, B);
+                    le = cudaGetLastError();
+                }
+            } else if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B);
+            else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B)
+                                                       : launch_det2<LK_DIRECT, 2>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B);
+            else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B)
+                             : launch_det2<LK_HASH, 3>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }
         ctx->last_fast = 1 + det2_lk + 16 * det2_lls + (pair ? 256 : 0);
@@ -668,7 +704,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty};
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -833,6 +869,32 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
         }
     CK(ctx->d_ll.reserve(inter.size() * 8));
     CK(cudaMemcpyAsync(ctx->d_ll.p, inter.data(), inter.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // log Tref[e] == c[e] * unit exactly, c = 0 or a power of two?  (unit = the non-zero value of least magnitude)
+    {
+        double unit = 0.0;
+        for (size_t e = 0; e < SR; ++e)
+            if (logTref[e] != 0.0 && (unit == 0.0 || std::fabs(logTref[e]) < std::fabs(unit))) unit = logTref[e];
+        bool ok = true;
+        std::vector<uint32_t> code(SR, 0u);
+        for (size_t e = 0; e < SR && ok; ++e) {
+            double c = 0.0;
+            if (logTref[e] != 0.0) {
+                c = logTref[e] / unit;
+                int ex = 0;
+                ok = std::frexp(c, &ex) == 0.5 && c >= 1.0 && c <= 1048576.0 && c * unit == logTref[e];
+            }
+            uint64_t bits;
+            memcpy(&bits, &c, 8);
+            ok = ok && (uint32_t)bits == 0u;
+            code[e] = (uint32_t)(bits >> 32);
+        }
+        ctx->tref_packed = ok;
+        ctx->tref_unit = unit;
+        if (ok) {
+            CK(ctx->d_tcode.reserve(SR * 4));
+            CK(cudaMemcpyAsync(ctx->d_tcode.p, code.data(), SR * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ntables = ntables;
     return MVD_OK;
@@ -896,7 +958,12 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
         return MVD_OK;
     }
     if (option == MVD_OPT_NO_PAIR) {
-        ctx->no_pair = value != 0;
+        ctx->no_pair = value == 1;
+        ctx->force_pair = value == 2;
+        return MVD_OK;
+    }
+    if (option == MVD_OPT_NO_FSM1) {
+        ctx->no_fsm1 = value != 0;
         return MVD_OK;
     }
     if (option == MVD_OPT_LEARN_WARM) {

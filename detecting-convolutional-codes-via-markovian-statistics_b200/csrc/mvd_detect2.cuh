@@ -30,7 +30,7 @@ struct SegBatch {
     DevSeg s[DET2_MAXSEG];
 };
 
-enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2 };
+enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2, LK_FSM1 = 3 };
 
 __device__ __forceinline__ uint32_t spread16(uint32_t x) {      // bit i -> bit 2i  (x < 2^16)
     x = (x | (x << 8)) & 0x00FF00FFu;
@@ -241,8 +241,26 @@ struct Fsm2Engine {
     }
 };
 
+// FSM, one LDS.128 per step: the 16-byte entry of edge (state, r) is {log P1 (f64), address of the next
+// state's row, high word of the double c} with log Tref = c * unit exactly (c = 0 or a power of two: for
+// rate-1/2 codes T(1/2) entries are 1/4, 1/2, 1 and their logs 2u, u, 0 with u = log(1/2)).  The
+// reference's a0 += log Tref becomes a0 = fma(c, unit, a0): c * unit is exact, so the rounding -- and
+// every bit of the running sum -- is the same.
+struct Fsm1Engine {
+    const unsigned char* sm;
+    uint32_t sx;
+    double unit, a1, a0;
+
+    __device__ __forceinline__ void step(uint32_t r_off) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sm + sx + r_off);
+        a1 += __hiloint2double((int)v.y, (int)v.x);
+        a0 = fma(__hiloint2double((int)v.w, 0), unit, a0);
+        sx = v.z;
+    }
+};
+
 // ------------------------------------------------------------------------------------------ kernel
-// grid: (chunks of DET2_BLOCK trials, segments of this launch); one thread = one trial.  The segment
+// grid: (chunks of blockDim.x trials, segments of this launch); one thread = one trial.  The segment
 // descriptors are kernel parameters, so everything derived from them (N, threshold, taps, decision
 // rule) is warp-uniform and lives on the uniform datapath.
 // dynamic shared memory (byte offsets in P.fp): [threshold masks][branch-metric replicas][state table][log-likelihood replicas]
@@ -252,10 +270,11 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REP = 1 << (LLS - 4);
     const DevSeg& sg = B.s[blockIdx.y];
+    const uint32_t BS = blockDim.x;                                          // <= DET2_BLOCK, chosen by the host
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
-    if ((unsigned long long)blockIdx.x * DET2_BLOCK >= ntr) return;          // uniform: shorter segment
+    if ((unsigned long long)blockIdx.x * BS >= ntr) return;                  // uniform: shorter segment
     const uint32_t seg = sg.block_begin;                                     // global segment index
-    const unsigned long long tl = (unsigned long long)blockIdx.x * DET2_BLOCK + threadIdx.x;
+    const unsigned long long tl = (unsigned long long)blockIdx.x * BS + threadIdx.x;
     const bool active = tl < ntr;
     const unsigned long long trial = sg.trial_begin + tl;
     const uint32_t lane = threadIdx.x & 31u;
@@ -267,20 +286,30 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
     if (threadIdx.x < 32u)
         *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
     const uint4* tbm = reinterpret_cast<const uint4*>(smem_raw + P.fp.off_tb);
-    {
+    if (LK == LK_FSM1) {
         const double2* llg = P.ll + (size_t)sg.table * SR;
-        for (uint32_t i = threadIdx.x; i < SR * REP; i += DET2_BLOCK) {
+        for (uint32_t i = threadIdx.x; i < SR * REP; i += BS) {
+            const uint32_t e = i >> (LLS - 4), c = i & (uint32_t)(REP - 1);
+            const double lp = __ldg(llg + e).x;
+            *reinterpret_cast<uint4*>(smem_raw + P.fp.off_ll + (e << LLS) + (c << 4)) =
+                make_uint4((uint32_t)__double2loint(lp), (uint32_t)__double2hiint(lp),
+                           P.fp.off_ll + (__ldg(P.nxt + e) << LLS) + (c << 4), __ldg(P.fp.tcode + e));
+        }
+    } else {
+        const double2* llg = P.ll + (size_t)sg.table * SR;
+        for (uint32_t i = threadIdx.x; i < SR * REP; i += BS) {
             const uint32_t e = i >> (LLS - 4), c = i & (uint32_t)(REP - 1);
             *reinterpret_cast<double2*>(smem_raw + P.fp.off_ll + (e << LLS) + (c << 4)) = __ldg(llg + e);
         }
     }
-    if (LK == LK_FSM) {
+    if (LK == LK_FSM1) {
+    } else if (LK == LK_FSM) {
         if (LLS == 7) {
-            for (uint32_t i = threadIdx.x; i < SR * 32u; i += DET2_BLOCK)
+            for (uint32_t i = threadIdx.x; i < SR * 32u; i += BS)
                 *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) =
                     P.fp.off_ll + (__ldg(P.nxt + (i >> 5)) << 7) + (((i & 31u) & 7u) << 4);
         } else {
-            for (uint32_t i = threadIdx.x; i < SR; i += DET2_BLOCK)
+            for (uint32_t i = threadIdx.x; i < SR; i += BS)
                 *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) = __ldg(P.nxt + i);
         }
     } else {
@@ -288,14 +317,14 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         constexpr int NV = Acs2Engine<LK, M, LLS>::NV;
         constexpr int WPV = NP >= 2 ? 4 : 2;                                 // words per plane vector
         // word w of row r -> plane w / WPV, every copy c
-        for (uint32_t i = threadIdx.x; i < 4u * 2u * NP * REP; i += DET2_BLOCK) {
+        for (uint32_t i = threadIdx.x; i < 4u * 2u * NP * REP; i += BS) {
             const uint32_t c = i % REP, rw = i / REP, r = rw / (2u * NP), w = rw % (2u * NP);
             *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_bm + (w / WPV) * (4u << LLS) + (r << LLS) + (c << 4) +
                                          4u * (w % WPV)) = P.bm[rw];
         }
         (void)NV;
         if (LK == LK_DIRECT) {
-            for (uint32_t i = threadIdx.x; i < P.fp.nkeys * 32u; i += DET2_BLOCK) {
+            for (uint32_t i = threadIdx.x; i < P.fp.nkeys * 32u; i += BS) {
                 const uint32_t st = P.fp.dstate[i >> 5];          // 0xFFFF: not a state (never looked up)
                 const uint32_t row = st == 0xFFFFu ? 0u : st * 4u;
                 *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) =
@@ -303,7 +332,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
             }
         } else {
             constexpr int KW = AcsCore<M>::KW;
-            for (uint32_t i = threadIdx.x; i < P.hcap; i += DET2_BLOCK) {
+            for (uint32_t i = threadIdx.x; i < P.hcap; i += BS) {
                 const uint32_t v = P.hvals[i];
                 *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_st + 4u * i) = v == MVD_EMPTY ? 0u : v;
 #pragma unroll
@@ -316,7 +345,17 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
     __syncthreads();
 
     double a1, a0;
-    if (LK == LK_FSM) {
+    if (LK == LK_FSM1) {
+        Fsm1Engine eng;
+        eng.sm = smem_raw;
+        eng.sx = ll_lane;
+        eng.unit = P.fp.tref_unit;
+        eng.a1 = 0.0;
+        eng.a0 = 0.0;
+        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
+        a1 = eng.a1;
+        a0 = eng.a0;
+    } else if (LK == LK_FSM) {
         Fsm2Engine<LLS> eng;
         eng.sm = smem_raw;
         eng.sx = LLS == 7 ? ll_lane : 0u;
@@ -426,10 +465,11 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevSeg& sg = B.s[blockIdx.y];
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
-    const unsigned long long blk0 = (unsigned long long)blockIdx.x * (2u * DET2P_BLOCK);
+    const uint32_t BS = blockDim.x;
+    const unsigned long long blk0 = (unsigned long long)blockIdx.x * (2u * BS);
     if (blk0 >= ntr) return;
     const uint32_t seg = sg.block_begin;
-    const unsigned long long tlA = blk0 + threadIdx.x, tlB = tlA + DET2P_BLOCK;
+    const unsigned long long tlA = blk0 + threadIdx.x, tlB = tlA + BS;
     const bool actA = tlA < ntr, actB = tlB < ntr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t SR = P.SR;
@@ -445,12 +485,12 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
         *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
     {
         const double2* llg = P.ll + (size_t)sg.table * SR;
-        for (uint32_t i = threadIdx.x; i < SR * 8u; i += DET2P_BLOCK)
+        for (uint32_t i = threadIdx.x; i < SR * 8u; i += BS)
             *reinterpret_cast<double2*>(g + a_ll + ((i >> 3) << 7) + ((i & 7u) << 4)) = __ldg(llg + (i >> 3));
     }
     // pair branch metrics: row (rA | rB << 2), word (ns, b): lo = d(pred_b -> ns | rA), hi = ... | rB
     // P.bm[r][2 g + b] = (d(pred -> 2g), d(pred -> 2g+1)) for pred = g + 2 b
-    for (uint32_t i = threadIdx.x; i < 16u * 8u * 8u; i += DET2P_BLOCK) {
+    for (uint32_t i = threadIdx.x; i < 16u * 8u * 8u; i += BS) {
         const uint32_t c = i & 7u, wd = (i >> 3) & 7u, row = i >> 6;
         const uint32_t rA = row & 3u, rB = row >> 2, ns = wd >> 1, b = wd & 1u, gg = ns >> 1, h = ns & 1u;
         const uint32_t wa = P.bm[rA * 4u + 2u * gg + b], wb = P.bm[rB * 4u + 2u * gg + b];
@@ -458,7 +498,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
         *reinterpret_cast<uint32_t*>(g + a_bm + (wd >> 2) * 2048u + (rA << 7) + (rB << 9) + (c << 4) + 4u * (wd & 3u)) =
             da | (db << 16);
     }
-    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += DET2P_BLOCK) {
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += BS) {
         const uint32_t st = P.fp.dstate[i >> 5];
         const uint32_t row = st == 0xFFFFu ? 0u : st * 4u;
         *reinterpret_cast<uint32_t*>(g + a_st + 4u * i) = a_ll + (row << 7) + (((i & 31u) & 7u) << 4);

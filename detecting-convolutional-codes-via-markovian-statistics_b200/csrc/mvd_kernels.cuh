@@ -36,6 +36,8 @@ struct FastPlan {
     uint32_t off_tb, off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
     uint32_t key_mul, nkeys;           // direct metric-vector -> state table (m <= 2)
     const uint16_t* dstate;            // [nkeys] state index or 0xFFFF
+    const uint32_t* tcode;             // packed NEXT walk: high word of the double c with log Tref[e] = c * tref_unit
+    double tref_unit;
 };
 
 struct Params {

@@ -20,6 +20,7 @@ E_UNKNOWN_STATE = -6
 OPT_FORCE_GENERIC = 1
 OPT_NO_PAIR = 2
 OPT_LEARN_WARM = 3
+OPT_NO_FSM1 = 4
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 

@@ -213,9 +213,14 @@ class Detector:
         """Route detection through the generic (checked) kernels instead of the fast ones."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_FORCE_GENERIC, 1 if on else 0))
 
-    def no_pair(self, on: bool = True):
-        """Fast kernels with one trial per thread instead of two (m = 2 only has the choice)."""
-        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_PAIR, 1 if on else 0))
+    def no_pair(self, on=True):
+        """Fast kernels with one trial per thread (True / 1), two per thread even for few trials (2),
+        or the automatic choice (False / 0).  Only m = 2 has the choice."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_PAIR, int(on)))
+
+    def no_fsm1(self, on: bool = True):
+        """NEXT-table walk with separate log-likelihood and NEXT tables instead of the one-load entry."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_FSM1, 1 if on else 0))
 
     def learn_warm(self, steps: int = 128):
         """Warm-up steps of the chunk-parallel learning chains (0 = speculate cold: every chunk is

@@ -140,12 +140,14 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
 /* Options.  MVD_OPT_FORCE_GENERIC (value 0/1): 1 = never take the fast detection kernels
  * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
- * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
+ * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
  * + 256 if the two-trials-per-thread kernel ran; 1024 = chunk-parallel learning chain.
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
-enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: fast kernels, but one trial per thread */
-       MVD_OPT_LEARN_WARM = 3 };   /* warm-up steps of the chunk-parallel learning chains (default 128) */
+enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread
+                                                               even for few trials, 0 = automatic              */
+       MVD_OPT_LEARN_WARM = 3,     /* warm-up steps of the chunk-parallel learning chains (default 128) */
+       MVD_OPT_NO_FSM1 = 4 };      /* 1 = NEXT-table walk with separate log / NEXT tables (two loads per step) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);

@@ -237,17 +237,19 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
     segs = [Seg(N=N, threshold=T, stream=10 + d, enc_taps=_taps(codes_spec[enc]), decide=d, trial_begin=17,
                 trial_end=17 + ntr) for d in (0, 1)]
     det.force_generic(path == "generic")
-    det.no_pair(path == "fast1")
+    det.no_pair(1 if path == "fast1" else 2)
+    det.no_fsm1(path == "fast1")
     try:
         tallies, lp = det.detect(segs, seed=2024, engine=engine, want_logp=True)
         kind = det.last_kernel_kind()
     finally:
         det.force_generic(False)
         det.no_pair(False)
+        det.no_fsm1(False)
     if path == "generic" or spec["n"] != 2:
         assert kind == 0
     else:
-        want_lookup = 2 if engine == "fsm" else (0 if spec["m"] <= 2 else 1)
+        want_lookup = (2 if path == "fast1" else 3) if engine == "fsm" else (0 if spec["m"] <= 2 else 1)
         assert kind != 0 and (kind - 1) % 16 == want_lookup
         assert (kind >= 256) == (path == "fast" and engine == "acs" and spec["m"] == 2)
     for d in (0, 1):
