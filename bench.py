@@ -42,8 +42,6 @@ N_BLOCK = 500                               # Pd_plotter.py:80
 SEED = 12345                                # Pd_plotter.py:70
 K, NOUT, M = 1, 2, 2
 OPS_CORE = 5 * (1 << M) + 11                # 31 int-ops / step at m = 2
-OPS_RNG = 41                                # naive Philox + threshold-compare estimate (the lazy
-                                            # bit-sliced Bernoulli actually spends ~13 instructions/step)
 METRIC = "trellis-steps/sec (whole box) for Pd-vs-p Monte-Carlo sweep"
 
 
@@ -174,7 +172,7 @@ def workload_config(args, per_gpu_trials):
     return {"workload": "Pd_plotter.py paper sweep (BASELINE configs[1]): (7,5) vs (6,5), k=1 n=2 m=2, S=31 Markov states, "
                         f"N={N_BLOCK}, p_vec={P_VEC}, both hypotheses, learn_len=6200 burn=200 laplace=1",
             "trials_per_point_per_gpu": per_gpu_trials, "engine": args.engine,
-            "bit_source": "on-device Philox4x32-10 (MVD-PHILOX-2)",
+            "bit_source": "on-device Philox4x32-10, position-addressed (MVD-PHILOX-2)",
             "l2_policy": "no input stream to cache: bits are generated in registers, tables (<4 KB) live in shared "
                          "memory; the bit-stream variant reads > 2 GB per step (>> 126 MB L2)",
             "parallelism": f"trial-sharded x{args.gpus}"}
@@ -329,15 +327,16 @@ def main():
             "bound": "int_alu", "unit": "Gop/s",
             "achieved": ach, "peak": mixed_gops, "frac": ach / mixed_gops,
             "peak_alu_pipe_only": alu_gops, "frac_alu_pipe_only": ach / alu_gops,
-            "achieved_core_plus_rng": (OPS_CORE + OPS_RNG) * rate_kernel * 1e-9,
-            "frac_core_plus_rng": (OPS_CORE + OPS_RNG) * rate_kernel * 1e-9 / mixed_gops,
-            "ops_per_step": {"core": OPS_CORE, "rng_estimate": OPS_RNG},
+            "ops_per_step": {"core": OPS_CORE, "f64_adds": 2,
+                             "note": "SURVEY 8(d): 2^(m+k+1) + 2^m + 3n + 5 at m=2, k=1, n=2; bit generation is not "
+                                     "counted (ncu: 38.6 warp-instructions issued per trellis step, ~20 of them Philox + "
+                                     "lazy Bernoulli + interleave, profiles/r01d_*)"},
             "peak_source": "libmvd mvd_int_peak(), measured in this run on this GPU: `peak` = alternating LOP3/IMAD chains "
                            "(ALU + FMA pipes = warp-instruction issue rate, the most any integer code can retire); "
                            "`peak_alu_pipe_only` = LOP3-only chains (min/shift/logic/permute can only issue there). "
                            "MEASURED_PEAKS.json has no integer figure; the path moves ~0 HBM bytes (bits are generated in "
                            "registers), so the HBM roofline does not bind it -- see roofline_hbm_bitstream for the HBM view",
-            "kernel": ("detect2_kernel<%s>" % ("DIRECT,2,7" if args.engine == "acs" else "FSM,7")),
+            "kernel": ("detect2p_kernel (two trials/thread ACS)" if args.engine == "acs" else "detect2_kernel<FSM1> (one-load NEXT walk)"),
             "kernel_ms": kernel_ms, "steps_per_launch": steps_per_pass_rank,
             "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
             "hbm_bytes_per_step_algorithmic": 0.0,
@@ -369,7 +368,7 @@ def main():
             line["roofline_hbm_bitstream"] = {
                 "bound": "hbm", "unit": "GB/s", "achieved": bbytes / (bms * 1e-3) * 1e-9,
                 "peak": peaks.get("hbm_gbs"), "frac": (bbytes / (bms * 1e-3) * 1e-9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                "bytes_per_step": bbytes / bsteps, "steps_per_s": bsteps / (bms * 1e-3), "kernel": "fsm_kernel<DETECT,2> bitstream",
+                "bytes_per_step": bbytes / bsteps, "steps_per_s": bsteps / (bms * 1e-3), "kernel": "detect2_kernel<FSM1> bitstream (host-supplied bits resident in HBM, no RNG)",
                 "note": "inputs 3 bits/step >> L2; this path is integer/LSU-bound, not HBM-bound"}
             del bits
         if not args.no_cpu_baseline and world == 1:

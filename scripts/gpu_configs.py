@@ -56,6 +56,24 @@ if "m4" in which:
 if "nsweep" in which:
     for N in (100, 1000, 10000, 100000):
         case_code(f"N sweep N={N}", [[[1,1,1]],[[1,0,1]]], [[[1,1,0]],[[1,0,1]]], 2, N, max(2000, 20000000 // N), [0.1])
+if "m56" in which:
+    from mvd.engine import HashOnlyDetector
+    for name, gen, m in (("m4 (23,35) recursion only", [[[1,0,0,1,1]],[[1,1,1,0,1]]], 4),
+                         ("m5 (53,75) recursion only", [[[1,0,1,0,1,1]],[[1,1,1,1,0,1]]], 5),
+                         ("m6 (133,171) recursion only", [[[1,0,1,1,0,1,1]],[[1,1,1,1,0,0,1]]], 6)):
+        det = HashOnlyDetector(gen, 1, 2, m)
+        taps = det.dec_taps
+        N, trials = 500, 400000
+        seg = Seg(N=N, threshold=bitsource.bsc_threshold(0.05), stream=1, enc_taps=taps, trial_begin=0, trial_end=trials)
+        det.acs_hash(seg, seed=3, want_final=False)
+        ms = []
+        for _ in range(3):
+            det.acs_hash(seg, seed=3, want_final=False)
+            ms.append(det.last_kernel_ms())
+        ms = float(np.median(ms))
+        print(json.dumps(dict(case=name, m=m, N=N, trials=trials, kernel_ms=round(ms, 3), steps_per_s=N * trials / (ms * 1e-3),
+                              int_ops_per_s=(5 * 2 ** m + 11) * N * trials / (ms * 1e-3))), flush=True)
+        det.close()
 if "paper" in which:
     # python Pd_plotter.py as shipped: num_iter = 10^4 (reference default), wall time through the public API
     for it in (10000, 1000000):
