@@ -4,9 +4,7 @@
 // build the metric-vector hash table and the premultiplied NEXT table, stage segments, launch
 // one kernel per call (a whole sweep = one launch), read tallies / counts back.
 // There is no CPU fallback: every compute entry point needs a CUDA device.
-#include "mvd_kernels.cuh"
-#include "mvd_detect2.cuh"
-#include "mvd_learn2.cuh"
+#include "mvd_launch.h"
 
 #include <algorithm>
 #include <cmath>
@@ -54,6 +52,7 @@ struct mvd_ctx {
     float last_ms = 0.f;
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
     bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false;
+    bool have_gfsm1 = false;
     bool tref_packed = false;       // log Tref = c * unit with c in {0, 2^j}: one-load NEXT walk possible
     double tref_unit = 0.0;
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
@@ -76,7 +75,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1;
 };
 
 namespace {
@@ -145,7 +144,8 @@ int install_states(mvd_ctx* ctx) {
     const int nkw = (nstate + 7) / 8;
     uint32_t cap = 64;
     while (cap < 2ull * S) cap <<= 1;
-    std::vector<uint32_t> keys((size_t)nkw * cap, 0u), vals(cap, MVD_EMPTY);
+    // empty slots carry the key 0xFFFFFFFF.. (no metric vector packs to it: min-normalised vectors contain a 0)
+    std::vector<uint32_t> keys((size_t)nkw * cap, 0xFFFFFFFFu), vals(cap, MVD_EMPTY);
     bool ok = true;
     for (uint32_t i = 0; i < S && ok; ++i) {
         uint32_t kw[8];
@@ -234,59 +234,9 @@ struct LaunchOut {
     uint8_t* final_met = nullptr;
 };
 
-template <int MODE, int NOUT>
-cudaError_t launch_acs(int m, dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
-#define MVD_ACS_CASE(MM)                                                                              \
-    case MM: {                                                                                        \
-        auto kern = acs_kernel<MODE, NOUT, MM>;                                                       \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                               \
-        kern<<<grid, MVD_BLOCK, smem, st>>>(P);                                                       \
-        return cudaGetLastError();                                                                    \
-    }
-    switch (m) {
-        MVD_ACS_CASE(1)
-        MVD_ACS_CASE(2)
-        MVD_ACS_CASE(3)
-        MVD_ACS_CASE(4)
-        MVD_ACS_CASE(5)
-        MVD_ACS_CASE(6)
-        default: return cudaErrorInvalidValue;
-    }
-#undef MVD_ACS_CASE
-}
-
-template <int MODE, int NOUT, bool SMEM>
-cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
-    auto kern = fsm_kernel<MODE, NOUT, SMEM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, MVD_BLOCK, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-template <int LK, int M>
-cudaError_t launch_det2(int lls, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
-#define MVD_DET2_CASE(L)                                                                              \
-    case L: {                                                                                         \
-        auto kern = detect2_kernel<LK, M, L>;                                                         \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                               \
-        kern<<<grid, threads, smem, st>>>(P, B);                                                      \
-        return cudaGetLastError();                                                                    \
-    }
-    switch (lls) {
-        MVD_DET2_CASE(4)
-        MVD_DET2_CASE(5)
-        MVD_DET2_CASE(6)
-        MVD_DET2_CASE(7)
-        default: return cudaErrorInvalidValue;
-    }
-#undef MVD_DET2_CASE
-}
-
 // Shared-memory plan of the fast detection kernels; returns false if they do not apply.
-bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPlan* fp, size_t* smem_out) {
+bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPlan* fp, size_t* smem_out, bool* gt_out) {
+    *gt_out = false;
     if (ctx->n != 2 || !ctx->closed) return false;
     const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 4;
     const size_t SR = (size_t)ctx->S * R;
@@ -309,9 +259,9 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
     if (engine == MVD_ENGINE_FSM) lk = LK_FSM;
     else if (ctx->nkeys) lk = LK_DIRECT;
     else if ((m == 2 || m == 3) && ctx->acs_ok) lk = LK_HASH;
-    else return false;
+    else lk = -1;                                   // no shared-memory variant: maybe the global-table one below
     const size_t budget2 = 110 * 1024, smem_max = ctx->prop.sharedMemPerBlockOptin;   // 2 blocks / SM if possible
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < 2 && lk >= 0; ++pass) {
         for (int lls = 7; lls >= 4; --lls) {
             size_t off = 128, st_bytes;                 // 32 threshold-bit masks
             fp->off_tb = 0;
@@ -337,6 +287,29 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
                 return true;
             }
         }
+    }
+    // tables too large for shared memory: leave them in global memory (L2), stage only masks + branch metrics
+    fp->off_tb = 0;
+    fp->off_bm = fp->off_st = fp->off_ll = 128;
+    fp->key_mul = 0;
+    fp->nkeys = 0;
+    fp->dstate = nullptr;
+    fp->tcode = ctx->d_tcode.as<uint32_t>();
+    fp->tref_unit = ctx->tref_unit;
+    fp->gfsm1 = ctx->d_gfsm1.as<uint4>();
+    if (engine == MVD_ENGINE_FSM && ctx->have_gfsm1) {
+        *lk_out = LK_FSM1;
+        *lls_out = 4;
+        *smem_out = 128;
+        *gt_out = true;
+        return true;
+    }
+    if (engine == MVD_ENGINE_ACS && (m == 3 || m == 4) && ctx->acs_ok) {
+        *lk_out = LK_HASH;
+        *lls_out = 4;
+        *smem_out = 128 + (size_t)(NP / 2) * ((size_t)R << 4);
+        *gt_out = true;
+        return true;
     }
     return false;
 }
@@ -364,7 +337,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     FastPlan fplan{};
     int det2_lk = -1, det2_lls = 0;
     size_t det2_smem = 0;
-    const bool fast = mode == MODE_DETECT && !ctx->force_generic && plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem);
+    bool det2_gt = false;
+    const bool fast = mode == MODE_DETECT && !ctx->force_generic &&
+                      plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
     const size_t pair_smem = 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 128 + 32768;
     uint64_t all_trials = 0;
@@ -553,21 +528,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         const size_t lsmem = (size_t)SR * 8;
         const bool lin = lsmem <= 96 * 1024;
         LP.nxt_in_smem = lin ? 1 : 0;
-        const dim3 g1((LP.nchunks + LEARN_BLOCK - 1) / LEARN_BLOCK, nsegs);
-        if (lin) {
-            auto kern = learn_spec_kernel<true>;
-            le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-            if (le == cudaSuccess) kern<<<g1, LEARN_BLOCK, lsmem, ctx->stream>>>(P, LP);
-        } else {
-            learn_spec_kernel<false><<<g1, LEARN_BLOCK, 0, ctx->stream>>>(P, LP);
-        }
-        le = cudaGetLastError();
-        if (le == cudaSuccess) {
-            learn_check_kernel<<<dim3((LP.nchunks + 255) / 256, nsegs), 256, 0, ctx->stream>>>(P, LP);
-            learn_fix_kernel<<<nsegs, 1024, 0, ctx->stream>>>(P, LP);
-            le = cudaGetLastError();
-            ctx->launches += 2;
-        }
+        le = mvd_launch_learn(lin, lsmem, nsegs, ctx->stream, P, LP);
+        ctx->launches += 2;
         ctx->last_fast = 1024;
     } else if (fast) {
         // segments travel as kernel parameters, DET2_MAXSEG per launch; grid.y = segment
@@ -584,43 +546,13 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             }
             if (maxblocks == 0) continue;
             const dim3 g2((unsigned)maxblocks, cnt);
-            if (pair) {
-                auto kern = detect2p_kernel<0>;
-                le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem);
-                if (le == cudaSuccess) {
-                    kern<<<g2, threads, pair_smem, ctx->stream>>>(P, B);
-                    le = cudaGetLastError();
-                }
-            } else if (det2_lk == LK_FSM1) {
-                auto kern = detect2_kernel<LK_FSM1, 1, 7>;
-                le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det2_smem);
-                if (le == cudaSuccess) {
-                    kern<<<g2, threads, det2_smem, ctx->stream>>>(P, B);
-                    le = cudaGetLastError();
-                }
-            } else if (det2_lk == LK_FSM) le = launch_det2<LK_FSM, 1>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B);
-            else if (det2_lk == LK_DIRECT) le = m == 1 ? launch_det2<LK_DIRECT, 1>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B)
-                                                       : launch_det2<LK_DIRECT, 2>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B);
-            else le = m == 2 ? launch_det2<LK_HASH, 2>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B)
-                             : launch_det2<LK_HASH, 3>(det2_lls, g2, threads, det2_smem, ctx->stream, P, B);
+            le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }
-        ctx->last_fast = 1 + det2_lk + 16 * det2_lls + (pair ? 256 : 0);
+        ctx->last_fast = 1 + det2_lk + 16 * det2_lls + (pair ? 256 : 0) + (det2_gt ? 512 : 0);
         if (extra_launches > 1) ctx->launches += extra_launches - 1;  // the common increment below counts one
-    } else if (engine == MVD_ENGINE_FSM) {
-        if (mode == MODE_DETECT) {
-            if (in_smem) le = n2 ? launch_fsm<MODE_DETECT, 2, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, true>(grid, smem, ctx->stream, P);
-            else le = n2 ? launch_fsm<MODE_DETECT, 2, false>(grid, smem, ctx->stream, P) : launch_fsm<MODE_DETECT, 0, false>(grid, smem, ctx->stream, P);
-        } else if (mode == MODE_LEARN) {
-            le = in_smem ? launch_fsm<MODE_LEARN, 0, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_LEARN, 0, false>(grid, smem, ctx->stream, P);
-        } else {
-            le = in_smem ? launch_fsm<MODE_TRACE, 0, true>(grid, smem, ctx->stream, P) : launch_fsm<MODE_TRACE, 0, false>(grid, smem, ctx->stream, P);
-        }
     } else {
-        if (mode == MODE_DETECT) le = n2 ? launch_acs<MODE_DETECT, 2>(m, grid, smem, ctx->stream, P) : launch_acs<MODE_DETECT, 0>(m, grid, smem, ctx->stream, P);
-        else if (mode == MODE_LEARN) le = launch_acs<MODE_LEARN, 0>(m, grid, smem, ctx->stream, P);
-        else if (mode == MODE_TRACE) le = launch_acs<MODE_TRACE, 0>(m, grid, smem, ctx->stream, P);
-        else le = n2 ? launch_acs<MODE_HASH, 2>(m, grid, smem, ctx->stream, P) : launch_acs<MODE_HASH, 0>(m, grid, smem, ctx->stream, P);
+        le = mvd_launch_generic(engine, mode, n2, m, in_smem, grid, smem, ctx->stream, P);
     }
     if (!fast && !(plearn && maxL > 0)) ctx->last_fast = 0;
     if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
@@ -704,7 +636,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode};
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -890,9 +822,28 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
         }
         ctx->tref_packed = ok;
         ctx->tref_unit = unit;
+        ctx->have_gfsm1 = false;
         if (ok) {
             CK(ctx->d_tcode.reserve(SR * 4));
             CK(cudaMemcpyAsync(ctx->d_tcode.p, code.data(), SR * 4, cudaMemcpyHostToDevice, ctx->stream));
+            if (128 + (SR << 7) + 64 > ctx->prop.sharedMemPerBlockOptin && SR < (1ull << 28)) {
+                // large S: packed NEXT-walk entries {log P1, next row byte offset, c} stay in global memory
+                std::vector<uint32_t> pk(4 * SR * ntables);
+                for (uint32_t t = 0; t < ntables; ++t)
+                    for (size_t e = 0; e < SR; ++e) {
+                        uint64_t bits;
+                        memcpy(&bits, &logP1[t * SR + e], 8);
+                        uint32_t* o = pk.data() + 4 * (t * SR + e);
+                        o[0] = (uint32_t)bits;
+                        o[1] = (uint32_t)(bits >> 32);
+                        o[2] = (ctx->h_next[e] << ctx->n) << 4;
+                        o[3] = code[e];
+                    }
+                CK(ctx->d_gfsm1.reserve(pk.size() * 4));
+                CK(cudaMemcpyAsync(ctx->d_gfsm1.p, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                ctx->have_gfsm1 = true;
+            }
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -997,8 +948,7 @@ int mvd_int_peak(mvd_ctx* ctx, double* alu_gops, double* alu_fma_gops) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
             CK(cudaEventRecord(ctx->ev0, ctx->stream));
-            int_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_peak.as<uint32_t>(), iters, mode);
-            CK(cudaGetLastError());
+            CK(mvd_launch_int_peak(blocks, ctx->stream, ctx->d_peak.as<uint32_t>(), iters, mode));
             CK(cudaEventRecord(ctx->ev1, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             float ms = 0;

@@ -23,14 +23,6 @@
 #pragma once
 #include "mvd_kernels.cuh"
 
-#define DET2_BLOCK 512
-#define DET2_MAXSEG 96          // segments per launch: they travel in the kernel parameters (uniform registers)
-
-struct SegBatch {
-    DevSeg s[DET2_MAXSEG];
-};
-
-enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2, LK_FSM1 = 3 };
 
 __device__ __forceinline__ uint32_t spread16(uint32_t x) {      // bit i -> bit 2i  (x < 2^16)
     x = (x | (x << 8)) & 0x00FF00FFu;
@@ -150,7 +142,7 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
 // ------------------------------------------------------------------------------------------ engines
 // ACS: Eq. 4-5 in registers (AcsCore), then metric vector -> Markov state.
 //   sx = shared-memory byte address of this lane's copy of the log-likelihood row of the current state.
-template <int LK, int M, int LLS>
+template <int LK, int M, int LLS, bool GT = false>
 struct Acs2Engine {
     static constexpr int NP = AcsCore<M>::NP;
     // branch metrics: row r = 2 * NP words, stored as NV 16-byte (8-byte for m = 1) planes; plane i of
@@ -158,14 +150,18 @@ struct Acs2Engine {
     // so lanes of a quarter warp never meet in a bank whatever their r.
     static constexpr int NV = NP >= 2 ? NP / 2 : 1;
     AcsCore<M> core;
-    const unsigned char* sm;
+    const unsigned char* sm;         // shared memory: branch metrics and (GT = false) every table
+    const unsigned char* tbg;        // GT: log-likelihood rows in global memory (L2)
+    const uint32_t* hvg;             // GT: hash values (state * R) and keys in global memory
+    const uint32_t* hkg;
     uint32_t sx, bm_base;
     uint32_t key_mul, key_add;       // DIRECT
     uint32_t ll_lane, st_base, hmask;   // HASH
     double a1, a0;
 
     __device__ __forceinline__ void step(uint32_t r_off) {
-        const double2 v = *reinterpret_cast<const double2*>(sm + sx + r_off);     // edge (state, r)
+        const double2 v = GT ? __ldg(reinterpret_cast<const double2*>(tbg + sx + r_off))
+                             : *reinterpret_cast<const double2*>(sm + sx + r_off);   // edge (state, r)
         a1 += v.x;                                                                // Pd_plotter.py:114-115,
         a0 += v.y;                                                                // in step order
         uint32_t bm[2 * NP];
@@ -200,7 +196,8 @@ struct Acs2Engine {
             uint32_t kw[AcsCore<M>::KW];
             core.key(kw);
             uint32_t slot = key_hash(kw, AcsCore<M>::KW) & hmask;
-            const uint32_t* hk = reinterpret_cast<const uint32_t*>(sm + st_base + 4u * (hmask + 1u));
+            const uint32_t* hv = GT ? hvg : reinterpret_cast<const uint32_t*>(sm + st_base);
+            const uint32_t* hk = GT ? hkg : reinterpret_cast<const uint32_t*>(sm + st_base) + (hmask + 1u);
             for (uint32_t probe = 0; probe <= hmask; ++probe) {
                 bool same = true;
 #pragma unroll
@@ -208,7 +205,7 @@ struct Acs2Engine {
                 if (same) break;
                 slot = (slot + 1u) & hmask;
             }
-            const uint32_t val = *reinterpret_cast<const uint32_t*>(sm + st_base + 4u * slot);   // state * R
+            const uint32_t val = hv[slot];                                        // state * R
             sx = ll_lane + (val << LLS);
         }
     }
@@ -246,13 +243,15 @@ struct Fsm2Engine {
 // rate-1/2 codes T(1/2) entries are 1/4, 1/2, 1 and their logs 2u, u, 0 with u = log(1/2)).  The
 // reference's a0 += log Tref becomes a0 = fma(c, unit, a0): c * unit is exact, so the rounding -- and
 // every bit of the running sum -- is the same.
+template <bool GT>
 struct Fsm1Engine {
-    const unsigned char* sm;
+    const unsigned char* sm;         // shared memory, or (GT) the packed table in global memory
     uint32_t sx;
     double unit, a1, a0;
 
     __device__ __forceinline__ void step(uint32_t r_off) {
-        const uint4 v = *reinterpret_cast<const uint4*>(sm + sx + r_off);
+        const uint4 v = GT ? __ldg(reinterpret_cast<const uint4*>(sm + sx + r_off))
+                           : *reinterpret_cast<const uint4*>(sm + sx + r_off);
         a1 += __hiloint2double((int)v.y, (int)v.x);
         a0 = fma(__hiloint2double((int)v.w, 0), unit, a0);
         sx = v.z;
@@ -264,7 +263,10 @@ struct Fsm1Engine {
 // descriptors are kernel parameters, so everything derived from them (N, threshold, taps, decision
 // rule) is warp-uniform and lives on the uniform datapath.
 // dynamic shared memory (byte offsets in P.fp): [threshold masks][branch-metric replicas][state table][log-likelihood replicas]
-template <int LK, int M, int LLS>
+// GT = true: the state / log-likelihood tables stay in global memory (L2-resident; S too large for
+// shared memory, e.g. m = 4 with S = 25 751 ... 232 567): nothing but the threshold masks and the
+// branch metrics is staged, LLS = 4 (no replicas).
+template <int LK, int M, int LLS, bool GT = false>
 __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_constant__ Params P,
                                                                 const __grid_constant__ SegBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,7 +288,8 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
     if (threadIdx.x < 32u)
         *reinterpret_cast<uint32_t*>(smem_raw + P.fp.off_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
     const uint4* tbm = reinterpret_cast<const uint4*>(smem_raw + P.fp.off_tb);
-    if (LK == LK_FSM1) {
+    if (GT) {
+    } else if (LK == LK_FSM1) {
         const double2* llg = P.ll + (size_t)sg.table * SR;
         for (uint32_t i = threadIdx.x; i < SR * REP; i += BS) {
             const uint32_t e = i >> (LLS - 4), c = i & (uint32_t)(REP - 1);
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         }
     } else {
         constexpr int NP = AcsCore<M>::NP;
-        constexpr int NV = Acs2Engine<LK, M, LLS>::NV;
+        constexpr int NV = Acs2Engine<LK, M, LLS, GT>::NV;
         constexpr int WPV = NP >= 2 ? 4 : 2;                                 // words per plane vector
         // word w of row r -> plane w / WPV, every copy c
         for (uint32_t i = threadIdx.x; i < 4u * 2u * NP * REP; i += BS) {
@@ -323,7 +326,8 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
                                          4u * (w % WPV)) = P.bm[rw];
         }
         (void)NV;
-        if (LK == LK_DIRECT) {
+        if (GT) {
+        } else if (LK == LK_DIRECT) {
             for (uint32_t i = threadIdx.x; i < P.fp.nkeys * 32u; i += BS) {
                 const uint32_t st = P.fp.dstate[i >> 5];          // 0xFFFF: not a state (never looked up)
                 const uint32_t row = st == 0xFFFFu ? 0u : st * 4u;
@@ -346,9 +350,9 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
 
     double a1, a0;
     if (LK == LK_FSM1) {
-        Fsm1Engine eng;
-        eng.sm = smem_raw;
-        eng.sx = ll_lane;
+        Fsm1Engine<GT> eng;
+        eng.sm = GT ? reinterpret_cast<const unsigned char*>(P.fp.gfsm1) + (size_t)sg.table * SR * 16u : smem_raw;
+        eng.sx = GT ? 0u : ll_lane;
         eng.unit = P.fp.tref_unit;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
@@ -367,15 +371,18 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         a1 = eng.a1;
         a0 = eng.a0;
     } else {
-        Acs2Engine<LK, M, LLS> eng;
+        Acs2Engine<LK, M, LLS, GT> eng;
         eng.core.reset();
         eng.sm = smem_raw;
-        eng.sx = ll_lane;                                         // state 0 = the all-zero vector (viterbi_markov.py:177)
+        eng.tbg = reinterpret_cast<const unsigned char*>(P.ll + (size_t)sg.table * SR);
+        eng.hvg = P.hvals;
+        eng.hkg = P.hkeys;
+        eng.st_base = P.fp.off_st;
+        eng.sx = GT ? 0u : ll_lane;                               // state 0 = the all-zero vector (viterbi_markov.py:177)
         eng.bm_base = P.fp.off_bm + copy;
         eng.key_mul = P.fp.key_mul;
         eng.key_add = (P.fp.off_st + lane * 4u) << 16;
-        eng.ll_lane = ll_lane;
-        eng.st_base = P.fp.off_st;
+        eng.ll_lane = GT ? 0u : ll_lane;
         eng.hmask = P.hcap - 1u;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
@@ -407,7 +414,6 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
 // All table reads use absolute shared-memory addresses (ld.shared) whose alignment lets a single
 // LOP3 build them: log rows are 512-byte aligned (address = row | r * 128), the branch-metric planes
 // 2048-byte aligned (address = plane | r_A * 128 | r_B * 512 | copy * 16).
-#define DET2P_BLOCK 256
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;

@@ -18,58 +18,7 @@
 #include <stdint.h>
 
 #include "mvd.h"
-
-#define MVD_BLOCK 256
-#define MVD_EMPTY 0xFFFFFFFFu
-
-enum { MODE_DETECT = 0, MODE_LEARN = 1, MODE_TRACE = 2, MODE_HASH = 3 };
-
-struct DevSeg {
-    uint32_t N, threshold, stream, table;
-    uint32_t enc_taps[MVD_MAX_N];
-    uint32_t decide, random_input, dmin, block_begin;
-    unsigned long long trial_begin, trial_end, bits_offset, out_offset;
-};
-
-// shared-memory plan of the fast detection kernels (mvd_detect2.cuh)
-struct FastPlan {
-    uint32_t off_tb, off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
-    uint32_t key_mul, nkeys;           // direct metric-vector -> state table (m <= 2)
-    const uint16_t* dstate;            // [nkeys] state index or 0xFFFF
-    const uint32_t* tcode;             // packed NEXT walk: high word of the double c with log Tref[e] = c * tref_unit
-    double tref_unit;
-};
-
-struct Params {
-    int n, m, R, nstate;
-    uint32_t S, SR;                 // SR = S * R
-    int src_mode;
-    uint32_t rk0[10], rk1[10];      // Philox round keys (key + r * Weyl), shared by every thread
-    const uint4* bits;
-    const DevSeg* segs;
-    uint32_t nsegs;
-    // state machine / log-likelihood tables (global memory masters)
-    const uint32_t* nxt;            // [SR]  next_state * R
-    const double2* ll;              // [ntables][SR]  {log P1, log Tref}
-    // ACS constants
-    const uint32_t* bm;             // [R][2 * NP] branch metrics, 16x2 packed
-    const uint32_t* hkeys;          // [KW][hcap] nibble-packed metric keys
-    const uint32_t* hvals;          // [hcap] state * R, or MVD_EMPTY
-    uint32_t hcap;                  // power of two
-    int tables_in_smem;             // FSM: NX/LL staged in shared memory; ACS: hash + LL staged
-    // outputs
-    unsigned long long* tallies;
-    unsigned long long* tallies2;
-    double* logp;
-    unsigned long long* counts;     // [nsegs][SR]
-    uint32_t burn;
-    uint32_t* trace_idx;
-    uint8_t* trace_met;
-    unsigned long long* hashes;
-    uint8_t* final_met;
-    int* error_flag;
-    FastPlan fp;
-};
+#include "mvd_types.h"
 
 // ------------------------------------------------------------------------------------------ Philox
 __device__ __forceinline__ uint4 philox10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const Params& P) {
@@ -552,44 +501,3 @@ __global__ void __launch_bounds__(MVD_BLOCK) acs_kernel(const __grid_constant__ 
     }
 }
 
-// ------------------------------------------------------------------------------------------ integer peak
-// Dependent chains on 8 independent accumulators per thread.
-//   mode 0: LOP3 only -- the ALU pipe alone (LOP3/SHF/PRMT/VIMNMX/IADD3 issue there, 16 lanes/clk/SMSP);
-//   mode 1: alternating IMAD (FMA pipe) and LOP3 (ALU pipe) -- both integer-capable pipes, i.e. the
-//           issue-rate bound of 1 warp instruction / clk / SMSP.
-// OPS_PER_ITER instructions per loop.
-#define MVD_PEAK_OPS_PER_ITER 64
-__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, int mode) {
-    uint32_t a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 2654435761u + i + blockIdx.x;
-    const uint32_t c = out[0] | 1u;           // runtime values, prevent constant folding
-    const uint32_t d = out[2] | 0x10u;
-    if (mode == 0) {
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int u = 0; u < MVD_PEAK_OPS_PER_ITER / 8; ++u) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (u & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(c), "r"(d));   // xor3
-                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(c), "r"(d));        // majority
-                }
-            }
-        }
-    } else {
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int u = 0; u < MVD_PEAK_OPS_PER_ITER / 8; ++u) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(c), "r"(d));
-                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(c), "r"(d));
-                }
-            }
-        }
-    }
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s ^= a[i];
-    if (s == 0x12345678u) out[1] = s;          // practically never true: keeps the chains alive
-}

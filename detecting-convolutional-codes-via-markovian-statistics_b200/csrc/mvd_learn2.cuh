@@ -22,9 +22,6 @@
 #pragma once
 #include "mvd_kernels.cuh"
 
-#define LEARN_CH 128u       // steps per chunk (one info-word call)
-#define LEARN_WARM 128u     // default warm-up steps (LearnParams.warm; multiples of 32)
-#define LEARN_BLOCK 128
 
 // thread-local lazy Bernoulli word (no warp vote: chunks of a warp have different block counts)
 __device__ __forceinline__ uint32_t lazy_bernoulli_t(uint32_t c0base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t T,
@@ -52,14 +49,6 @@ __device__ __forceinline__ uint32_t lazy_bernoulli_t(uint32_t c0base, uint32_t c
     return e;
 }
 
-struct LearnParams {
-    uint32_t nchunks;                 // per segment
-    uint32_t warm;                    // warm-up steps before a chunk (multiple of 32)
-    uint32_t* spec_start;             // [nsegs][nchunks]  state * R at the chunk start (speculated)
-    uint32_t* end;                    // [nsegs][nchunks]  state * R at the chunk end
-    uint32_t* ndirty;                 // [nsegs]
-    int nxt_in_smem;
-};
 
 // received words of the 32-step block b of the chain of segment sg -> Rw[j] (bit t = received bit of output j)
 __device__ __forceinline__ void learn_block_words(const Params& P, const DevSeg& sg, uint32_t b, uint32_t valid,

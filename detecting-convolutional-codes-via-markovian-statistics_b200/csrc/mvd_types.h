@@ -1,0 +1,87 @@
+// mvd_types.h -- types and constants shared by the host side (mvd.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mvd.h"
+
+#define MVD_BLOCK 256
+#define MVD_EMPTY 0xFFFFFFFFu
+
+enum { MODE_DETECT = 0, MODE_LEARN = 1, MODE_TRACE = 2, MODE_HASH = 3 };
+
+struct DevSeg {
+    uint32_t N, threshold, stream, table;
+    uint32_t enc_taps[MVD_MAX_N];
+    uint32_t decide, random_input, dmin, block_begin;
+    unsigned long long trial_begin, trial_end, bits_offset, out_offset;
+};
+
+// shared-memory plan of the fast detection kernels (mvd_detect2.cuh)
+struct FastPlan {
+    uint32_t off_tb, off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
+    uint32_t key_mul, nkeys;           // direct metric-vector -> state table (m <= 2)
+    const uint16_t* dstate;            // [nkeys] state index or 0xFFFF
+    const uint32_t* tcode;             // packed NEXT walk: high word of the double c with log Tref[e] = c * tref_unit
+    double tref_unit;
+    const uint4* gfsm1;                // [ntables][S*R] packed NEXT-walk entries in global memory (large S)
+};
+
+struct Params {
+    int n, m, R, nstate;
+    uint32_t S, SR;                 // SR = S * R
+    int src_mode;
+    uint32_t rk0[10], rk1[10];      // Philox round keys (key + r * Weyl), shared by every thread
+    const uint4* bits;
+    const DevSeg* segs;
+    uint32_t nsegs;
+    // state machine / log-likelihood tables (global memory masters)
+    const uint32_t* nxt;            // [SR]  next_state * R
+    const double2* ll;              // [ntables][SR]  {log P1, log Tref}
+    // ACS constants
+    const uint32_t* bm;             // [R][2 * NP] branch metrics, 16x2 packed
+    const uint32_t* hkeys;          // [KW][hcap] nibble-packed metric keys
+    const uint32_t* hvals;          // [hcap] state * R, or MVD_EMPTY
+    uint32_t hcap;                  // power of two
+    int tables_in_smem;             // FSM: NX/LL staged in shared memory; ACS: hash + LL staged
+    // outputs
+    unsigned long long* tallies;
+    unsigned long long* tallies2;
+    double* logp;
+    unsigned long long* counts;     // [nsegs][SR]
+    uint32_t burn;
+    uint32_t* trace_idx;
+    uint8_t* trace_met;
+    unsigned long long* hashes;
+    uint8_t* final_met;
+    int* error_flag;
+    FastPlan fp;
+};
+
+
+// ---- fast detection kernels (mvd_detect2.cuh)
+#define DET2_BLOCK 512
+#define DET2P_BLOCK 256
+#define DET2_MAXSEG 96          // segments per launch: they travel in the kernel parameters (uniform registers)
+
+struct SegBatch {
+    DevSeg s[DET2_MAXSEG];
+};
+
+enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2, LK_FSM1 = 3 };
+
+// ---- chunk-parallel learning chains (mvd_learn2.cuh)
+#define LEARN_CH 128u       // steps per chunk (one info-word call)
+#define LEARN_WARM 128u     // default warm-up steps (LearnParams.warm; multiples of 32)
+#define LEARN_BLOCK 128
+
+struct LearnParams {
+    uint32_t nchunks;                 // per segment
+    uint32_t warm;                    // warm-up steps before a chunk (multiple of 32)
+    uint32_t* spec_start;             // [nsegs][nchunks]  state * R at the chunk start (speculated)
+    uint32_t* end;                    // [nsegs][nchunks]  state * R at the chunk end
+    uint32_t* ndirty;                 // [nsegs]
+    int nxt_in_smem;
+};
+
+#define MVD_PEAK_OPS_PER_ITER 64

@@ -141,7 +141,8 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
- * + 256 if the two-trials-per-thread kernel ran; 1024 = chunk-parallel learning chain.
+ * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
+ * 1024 = chunk-parallel learning chain.
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread

@@ -325,9 +325,16 @@ def test_m4_global_tables_vs_oracle(codes_spec):
         seg = Seg(N=150, threshold=T, stream=1, enc_taps=taps2, decide=1, trial_begin=0, trial_end=700)
         want, wlp = co.run_trials(_taps(spec), taps2, 2, 4, 150, T, 8, 1, 0, 700, tab, P1, Tref, 1, want_logp=True)
         for engine in ENGINES:
-            t, lp = det.detect([seg], seed=8, engine=engine, want_logp=True)
-            assert int(t[0]) == want
-            assert np.array_equal(lp, wlp)
+            for generic in (False, True):
+                det.force_generic(generic)
+                try:
+                    t, lp = det.detect([seg], seed=8, engine=engine, want_logp=True)
+                    kind = det.last_kernel_kind()
+                finally:
+                    det.force_generic(False)
+                assert (kind == 0) == generic and (generic or kind & 512)      # fast path with tables in global memory
+                assert int(t[0]) == want
+                assert np.array_equal(lp, wlp)
         # learning chain through the global-memory histogram
         got = det.learn_counts([Seg(N=60000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=_taps(spec))],
                                burn=200, seed=3)[0]
