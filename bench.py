@@ -375,6 +375,8 @@ def main():
             cores = os.cpu_count() or 1
             base = cpu_port_throughput(args.ref_iters, cores)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            one = cpu_port_throughput(max(20, args.ref_iters // 3), 1)      # as shipped: the reference is single-process
+            line["cpu_baseline_1core"] = {k: one[k] for k in ("value", "unit", "cores", "kind", "sample")}
             try:
                 line["cpu_baseline_c_oracle"] = c_oracle_throughput()
             except Exception as exc:     # the C oracle is optional for the bench

@@ -456,3 +456,82 @@ def test_int_peak_and_info(dets):
     alu, mixed = det.int_peak()
     assert alu > 1000 and mixed > 1000          # Gop/s
     assert det.launch_count() > 0
+
+
+# ------------------------------------------------------------------ entry points, as a user runs them
+def _run_script(args, stdin_text, cwd):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "detecting-convolutional-codes-via-markovian-statistics_b200")
+    env = dict(os.environ, PYTHONPATH=pkg)
+    return subprocess.run([sys.executable] + [os.path.join(pkg, args[0])] + args[1:], input=stdin_text, text=True,
+                          capture_output=True, cwd=cwd, env=env, timeout=600)
+
+
+def test_pd_plotter_main_writes_the_reference_csv(tmp_path):
+    """`python Pd_plotter.py` (reference Pd_plotter.py:242-264): results_experiments/Pd_hybrid_results.csv
+    with header N,p,Pd,Pc, 7 rows (N = 500, the reference's p grid), 10^4 iterations per point."""
+    import csv
+    out = _run_script(["Pd_plotter.py"], "", str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    path = tmp_path / "results_experiments" / "Pd_hybrid_results.csv"
+    rows = list(csv.reader(open(path)))
+    assert rows[0] == ["N", "p", "Pd", "Pc"]
+    assert [r[0] for r in rows[1:]] == ["500"] * 7
+    assert [float(r[1]) for r in rows[1:]] == [0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5]
+    pd_, pc_ = [float(r[2]) for r in rows[1:]], [float(r[3]) for r in rows[1:]]
+    assert pd_[0] == 1.0 and pc_[0] == 1.0                     # clean channel: perfect detection
+    assert all(0.0 <= v <= 1.0 for v in pd_ + pc_)
+    assert abs(pc_[-1] - 0.5) < 0.02                           # p = 1/2: the channel carries nothing
+    assert all(round(v * 10000) == pytest.approx(v * 10000, abs=1e-6) for v in pd_)     # multiples of 1 / num_iter
+
+
+def test_demo_script_predefined_pair(tmp_path):
+    """`python demo_script.py`, option 1 / example 1 (reference demo_script.py:82-131): runs, prints a
+    5-row table (matplotlib is absent here), same numbers as run_experiment with the demo's arguments."""
+    import Pd_plotter as pdp
+    out = _run_script(["demo_script.py"], "1\n1\n", str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    df = pdp.run_experiment(k=1, n=2, m=2, gen1=[[[1, 1, 1]], [[1, 0, 1]]], gen2=[[[1, 1, 0]], [[1, 0, 1]]], num_iter=2000,
+                            p_vec=[0.01, 0.05, 0.1, 0.2, 0.3], learn_len=None, learn_burn=200, laplace=1.0, seed=123)
+    assert len(df) == 5 and df["N"].tolist() == [500] * 5
+    if "matplotlib is not installed" in out.stdout:
+        table = [ln.split() for ln in out.stdout.splitlines() if ln.strip().startswith("500")]
+        assert len(table) == 5
+        assert [float(r[2]) for r in table] == pytest.approx(df["Pd"].tolist(), abs=1e-6)
+        assert [float(r[3]) for r in table] == pytest.approx(df["Pc"].tolist(), abs=1e-6)
+
+
+def test_simulate_markov_sequence_contract(golden):
+    """The function the reference calls but does not ship: positional call as at Pd_plotter.py:212,
+    keyword call as at :149-155; returns length+1 hashable metric tuples starting at all-zero."""
+    import viterbi_markov as vm
+    gen1 = [[[1, 1, 1]], [[1, 0, 1]]]
+    a = vm.simulate_markov_sequence(gen1, 2, 1, 2, 300, 0.1, True)
+    assert len(a["metrics"]) == 301 and a["metrics"][0] == (0, 0, 0, 0)
+    assert all(isinstance(d, tuple) and min(d) == 0 for d in a["metrics"])
+    b = vm.simulate_markov_sequence(gen1, 2, 1, 2, 300, p_val=0.1, random_input=True, seed=12345)
+    c = vm.simulate_markov_sequence(gen1, 2, 1, 2, 300, p_val=0.1, random_input=True, seed=12345)
+    assert b["metrics"] == c["metrics"]                        # seeded: reproducible
+    g = golden["sim_kats"]["c75_self"]
+    d = vm.simulate_markov_sequence(gen1, 2, 1, 2, g["N"], g["p"], True, g["seed"], stream=g["stream"], trial=g["trial"])
+    assert [list(x) for x in d["metrics"]] == g["metrics"]
+    e = vm.simulate_markov_sequence(gen1, 2, 1, 2, g["N"], g["p"], True, None, u_bits=g["u_bits"], e_bits=g["e_bits"])
+    assert [list(x) for x in e["metrics"]] == g["metrics"]
+
+
+def test_learn_P1_empirical_contract(golden):
+    """learn_P1_empirical(gens_tuple, k, n, m, p, learn_len, learn_burn, laplace, seed) -> (states,
+    state_index, P) like the reference (Pd_plotter.py:123-169): dense row-stochastic P, cached."""
+    import Pd_plotter as pdp
+    g = golden["experiments"]["c75_c65_small"]
+    gens = tuple(tuple(tuple(t) for t in row) for row in g["gen1"])
+    states, index, P = pdp.learn_P1_empirical(gens, 1, 2, 2, 0.1, None, 200, 1.0, 123)
+    assert len(states) == 31 and index[(0, 0, 0, 0)] == 0 and P.shape == (31, 31)
+    np.testing.assert_allclose(P.sum(axis=1), 1.0, rtol=1e-12)
+    want = np.array(g["P1_edge"]["0.1"]["edge"])
+    tab = __import__("viterbi_markov").state_table(g["gen1"], 2, 1, 2)
+    assert np.array_equal(P[np.arange(31)[:, None], tab.nxt], want)
+    assert pdp.learn_P1_empirical(gens, 1, 2, 2, 0.1, None, 200, 1.0, 123)[2] is P      # lru_cache, Pd_plotter.py:123
