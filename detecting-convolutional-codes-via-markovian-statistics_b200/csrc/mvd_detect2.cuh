@@ -64,10 +64,11 @@ __device__ __forceinline__ uint32_t lazy_bernoulli_s(uint32_t c0base, uint32_t c
 }
 
 // ------------------------------------------------------------------------------------------ driver (n = 2)
-template <int LLS, class Eng>
+// MM = encoder memory when known at compile time (ACS kernels), 0 = read it from the parameters
+template <int LLS, int MM, class Eng>
 __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, bool active, unsigned long long trial,
                                              unsigned long long tl, unsigned long long ntr, const uint4* tbm, Eng& eng) {
-    const int m = P.m;
+    const int m = MM ? MM : P.m;
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);      // Philox calls per flip word, at most
     const bool philox = P.src_mode == MVD_SRC_PHILOX;
@@ -103,13 +104,20 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
                 e1 = pick(E1, w);
             }
             // bit-parallel encoder (viterbi_markov.py:82-106 for k = 1): 32 steps per XOR
-            uint32_t o0 = (taps0 & 1u) ? U : 0u, o1 = (taps1 & 1u) ? U : 0u;
+            uint32_t o0 = U & (0u - (taps0 & 1u)), o1 = U & (0u - (taps1 & 1u));
+            if (MM) {
 #pragma unroll
-            for (int i = 1; i <= MVD_MAX_M; ++i) {
-                if (i <= m) {
+                for (int i = 1; i <= (MM ? MM : 1); ++i) {
                     const uint32_t sh = __funnelshift_l(prevU, U, i);
-                    if ((taps0 >> i) & 1u) o0 ^= sh;
-                    if ((taps1 >> i) & 1u) o1 ^= sh;
+                    o0 ^= sh & (0u - ((taps0 >> i) & 1u));
+                    o1 ^= sh & (0u - ((taps1 >> i) & 1u));
+                }
+            } else {
+#pragma unroll 1
+                for (int i = 1; i <= m; ++i) {
+                    const uint32_t sh = __funnelshift_l(prevU, U, i);
+                    o0 ^= sh & (0u - ((taps0 >> i) & 1u));
+                    o1 ^= sh & (0u - ((taps1 >> i) & 1u));
                 }
             }
             prevU = U;
@@ -267,7 +275,7 @@ struct Fsm1Engine {
 // shared memory, e.g. m = 4 with S = 25 751 ... 232 567): nothing but the threshold masks and the
 // branch metrics is staged, LLS = 4 (no replicas).
 template <int LK, int M, int LLS, bool GT = false>
-__global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(DET2_BLOCK, (LK == LK_FSM1 || LK == LK_FSM) ? 3 : 2) detect2_kernel(const __grid_constant__ Params P,
                                                                 const __grid_constant__ SegBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REP = 1 << (LLS - 4);
@@ -356,7 +364,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         eng.unit = P.fp.tref_unit;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
+        run_trial_n2<LLS, 0>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     } else if (LK == LK_FSM) {
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         eng.nx_lane = LLS == 7 ? (P.fp.off_st + lane * 4u) - ll_lane : P.fp.off_st;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
+        run_trial_n2<LLS, 0>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     } else {
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(DET2_BLOCK, 2) detect2_kernel(const __grid_con
         eng.hmask = P.hcap - 1u;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
+        run_trial_n2<LLS, M>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     }
@@ -519,13 +527,14 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     eng.kst = a_st + lane * 4u;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
 
-    const int m = P.m;
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
     const bool philox = P.src_mode == MVD_SRC_PHILOX;
     const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
     const uint32_t c3 = sg.stream;
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
+    const uint32_t tm00 = 0u - (taps0 & 1u), tm01 = 0u - ((taps0 >> 1) & 1u), tm02 = 0u - ((taps0 >> 2) & 1u);
+    const uint32_t tm10 = 0u - (taps1 & 1u), tm11 = 0u - ((taps1 >> 1) & 1u), tm12 = 0u - ((taps1 >> 2) & 1u);
     uint32_t prevUA = 0, prevUB = 0;
     const uint32_t nsb = (N + 127u) >> 7;
     for (uint32_t sb = 0; sb < nsb; ++sb) {
@@ -556,7 +565,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             uint32_t wlo[2], whi[2];
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-                const uint32_t U = pick(x ? UB : UA, w);
+                const uint32_t U = x ? UB.x : UA.x;                      // word w: the vectors rotate below
                 const bool act = x ? actB : actA;
                 const unsigned long long tr = x ? trB : trA;
                 uint32_t e0, e1;
@@ -569,20 +578,17 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
                     e1 = pick(x ? EB1 : EA1, w);
                 }
                 const uint32_t pu = x ? prevUB : prevUA;
-                uint32_t o0 = (taps0 & 1u) ? U : 0u, o1 = (taps1 & 1u) ? U : 0u;
-#pragma unroll
-                for (int i = 1; i <= 2; ++i) {
-                    if (i <= m) {
-                        const uint32_t sh = __funnelshift_l(pu, U, i);
-                        if ((taps0 >> i) & 1u) o0 ^= sh;
-                        if ((taps1 >> i) & 1u) o1 ^= sh;
-                    }
-                }
+                uint32_t o0 = U & tm00, o1 = U & tm10;                  // m = 2: three tap masks per output
+                const uint32_t sh1 = __funnelshift_l(pu, U, 1), sh2 = __funnelshift_l(pu, U, 2);
+                o0 ^= (sh1 & tm01) ^ (sh2 & tm02);
+                o1 ^= (sh1 & tm11) ^ (sh2 & tm12);
                 if (x) prevUB = U; else prevUA = U;
                 const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
                 wlo[x] = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
                 whi[x] = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
             }
+            UA = make_uint4(UA.y, UA.z, UA.w, 0u);
+            UB = make_uint4(UB.y, UB.z, UB.w, 0u);
 #pragma unroll 1
             for (uint32_t c = 0; c < valid; c += 8u) {
                 const uint32_t sh = (c & 8u) << 1;
