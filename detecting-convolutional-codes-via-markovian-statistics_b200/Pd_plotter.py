@@ -104,7 +104,8 @@ def learn_P1_empirical(gens_tuple, k, n, m, p, learn_len, learn_burn, laplace, s
 
 
 def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, laplace, seed, *,
-                   N_spectrum=None, engine="auto", learn_engine="auto", device=None, trial_offset=0, details=None):
+                   N_spectrum=None, engine="auto", learn_engine="auto", device=None, trial_offset=0, details=None,
+                   ref_p=0.5):
     """Hybrid detector over all (N, p) points -> DataFrame[N, p, Pd, Pc]
     (reference Pd_plotter.py:176-235; positional signature identical).
 
@@ -112,7 +113,9 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     ``N_SPECTRUM_BY_M[m]``; ``engine`` in {"auto", "acs", "fsm"} for the detection trials and
     ``learn_engine`` for the learning chains (0.1 % of the steps; "auto" walks them through the
     NEXT table, identical counts); ``device`` the CUDA ordinal
-    (default LOCAL_RANK or 0); ``details`` a dict that receives tallies, tables and timings.
+    (default LOCAL_RANK or 0); ``ref_p`` the crossover of the theoretical reference chain T(ref_p)
+    the sequences are scored against (the reference hard-codes 1/2, :193-194; other values use the
+    sympy-free numeric T(p) of :func:`mvd.codes.t_edge_table`); ``details`` a dict that receives tallies, tables and timings.
     """
     import pandas as pd
 
@@ -125,7 +128,8 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     # P1 for every distinct p (the reference's lru_cache, :123, learns once per p)
     distinct = list(dict.fromkeys(float(p) for p in p_vec))
     counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=learn_engine)
-    det.set_models(tables)                              # T_ref = T(1/2) = mult / 2^n (reference :193-194)
+    # T_ref = T(1/2) = mult / 2^n (reference :193-194)
+    det.set_models(tables, None if float(ref_p) == 0.5 else codes.t_edge_table(det.table, float(ref_p)))
     tindex = {p: i for i, p in enumerate(distinct)}
 
     rank, ws = dist.world()

@@ -297,6 +297,29 @@ def tref_half_table(tab: StateTable) -> np.ndarray:
     return tab.mult.astype(np.float64) / float(1 << tab.n)
 
 
+def t_edge_table(tab: StateTable, p: float) -> np.ndarray:
+    """Edge form of the theoretical transition matrix ``T(p)`` (Eq. 6) for any crossover ``p``,
+    without sympy: ``T[i, nxt[i, r]] = sum over the received words r' that lead i to the same
+    state of p^w(r') (1-p)^(n-w(r'))``, rows renormalised as Pd_plotter.py:97-99 does.
+
+    Same numbers as ``evaluate_symbolic_T(*build_symbolic_T(...)[::-1], p)`` (viterbi_markov.py:
+    202-230 + Pd_plotter.py:89-99) on the edges, to float64 rounding; O(S 2^n) instead of the
+    S x S sympy matrix, so it also works at S = 10^5 (m = 4) where the reference cannot run.
+    """
+    n, R = tab.n, tab.R
+    w = np.array([bin(r).count("1") for r in range(R)])
+    weight = np.array([float(p) ** int(wr) * (1.0 - float(p)) ** int(n - wr) for wr in w])
+    same = tab.nxt[:, :, None] == tab.nxt[:, None, :]                    # [S, r, r']
+    edge = (same * weight[None, None, :]).sum(axis=2)
+    # row sum over *distinct* successors: each successor counted once
+    first = np.ones((tab.S, R), dtype=bool)
+    for r in range(1, R):
+        first[:, r] = ~(tab.nxt[:, :r] == tab.nxt[:, r:r + 1]).any(axis=1)
+    rows = (edge * first).sum(axis=1, keepdims=True)
+    rows[rows == 0] = 1.0
+    return edge / rows
+
+
 DENSE_LIMIT = 2048      # largest S for which the dense S x S replay of the reference is built
 
 

@@ -91,6 +91,16 @@ def build_symbolic_T(states, transitions, all_r, normalize=True):
     return p, T
 
 
+def numeric_T(states, transitions, all_r, p_val):
+    """Numeric T(p_val) as a dense S x S float64 matrix, straight from ``transitions`` -- what
+    ``evaluate_symbolic_T(T, p, p_val)`` (reference Pd_plotter.py:89-99) returns for the matrix of
+    ``build_symbolic_T`` (reference viterbi_markov.py:202-230), without the sympy round trip
+    (44 s at S = 435, infeasible at S >= 10^4).  The GPU consumes the edge form,
+    :func:`mvd.codes.t_edge_table`."""
+    tab = codes.table_from_transitions(states, transitions, len(all_r[0]))
+    return codes.dense_from_edges(tab, codes.t_edge_table(tab, float(p_val)))
+
+
 def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_input=True, seed=None, *,
                              decoder_matrix=None, u_bits=None, e_bits=None, stream=0, trial=0,
                              engine="acs", device=0):

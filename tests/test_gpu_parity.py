@@ -260,6 +260,32 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("dec,enc", [("c75", "c65"), ("m3a", "m3b")])
+def test_detect_against_numeric_T_of_any_p(codes_spec, dets, engine, dec, enc):
+    """scoring against T(p_ref) for p_ref != 1/2 (sympy-free numeric T(p); log T is no
+    longer a multiple of log 1/2, so the NEXT walk takes its two-load form) -- bit-exact vs the oracle."""
+    import c_oracle as co
+    from mvd import bitsource, codes
+    from mvd.engine import Seg
+    spec = codes_spec[dec]
+    det = dets(dec)
+    tab, P1, _ = _oracle_models(det, spec, 0.1, 8000, 5)
+    Tref = codes.t_edge_table(det.table, 0.3)
+    assert not np.array_equal(Tref, codes.tref_half_table(det.table))
+    det.set_models([P1], Tref)
+    T = bitsource.bsc_threshold(0.1)
+    ntr = 2000
+    segs = [Seg(N=211, threshold=T, stream=20 + d, enc_taps=_taps(codes_spec[enc]), decide=d, trial_begin=0,
+                trial_end=ntr) for d in (0, 1)]
+    tallies, lp = det.detect(segs, seed=99, engine=engine, want_logp=True)
+    for d in (0, 1):
+        want, wlp = co.run_trials(_taps(spec), _taps(codes_spec[enc]), spec["n"], spec["m"], 211, T, 99, 20 + d, 0,
+                                  ntr, tab, P1, Tref, d, want_logp=True)
+        assert int(tallies[d]) == want
+        assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
     """Host-supplied bit streams through the fast kernels == generic kernels == oracle sums."""
     import c_oracle as co

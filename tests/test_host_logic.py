@@ -121,6 +121,28 @@ def test_tref_half_table(golden, name):
     assert np.array_equal(codes.tref_half_table(tab), np.array(g["T_edge"]["0.5"]))
 
 
+@pytest.mark.parametrize("name", ["c75", "c65", "m3a", "r13", "m1"])
+@pytest.mark.parametrize("pv", [0.5, 0.1, 0.3])
+def test_numeric_T_edges_match_reference_symbolic(golden, name, pv):
+    """the sympy-free T(p) (codes.t_edge_table / vm.numeric_T) equals the reference's
+    evaluate_symbolic_T(build_symbolic_T(...), p) on every edge (golden, generated by the reference)."""
+    import viterbi_markov as vm
+    from mvd import codes
+    g = golden["code_kats"][name]
+    tab = vm.state_table(g["gen"], g["m"], g["k"], g["n"])
+    got = codes.t_edge_table(tab, pv)
+    np.testing.assert_allclose(got, np.array(g["T_edge"][repr(pv)]), rtol=1e-13, atol=0)
+    if pv == 0.5:
+        assert np.array_equal(got, codes.tref_half_table(tab))
+    if g["S"] <= 100:
+        states, trans, all_r = vm.enumerate_markov_states_allzero(g["gen"], g["m"], g["k"], g["n"])
+        dense = vm.numeric_T(states, trans, all_r, pv)
+        assert dense.shape == (g["S"], g["S"])
+        np.testing.assert_allclose(dense.sum(axis=1), 1.0, rtol=1e-13)
+        assert np.count_nonzero(dense) == g["nnz"] or pv in (0.0, 1.0)
+        np.testing.assert_allclose(dense[np.arange(g["S"])[:, None], tab.nxt], got, rtol=0, atol=0)
+
+
 def test_log_prob_sequence_host(golden):
     """Host log_prob_sequence (Pd_plotter.py:106-116) reproduces the reference's per-trial sums."""
     import Pd_plotter as pdp
