@@ -55,6 +55,7 @@ struct mvd_ctx {
     bool have_gfsm1 = false;
     bool tref_packed = false;       // log Tref = c * unit with c in {0, 2^j}: one-load NEXT walk possible
     double tref_unit = 0.0;
+    std::vector<uint32_t> bfs_levels;   // level sizes of the last GPU enumeration
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
     uint32_t learn_warm = LEARN_WARM;
 
@@ -777,6 +778,54 @@ int mvd_enumerate_states(mvd_ctx* ctx, uint32_t max_states, uint32_t* S_out) {
     ctx->S = S;
     if (S_out) *S_out = S;
     return install_states(ctx);
+}
+
+int mvd_enumerate_states_gpu(mvd_ctx* ctx, uint32_t max_states, uint32_t flags, uint32_t chunk_parents, mvd_bfs_stats* stats) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code first");
+    if ((flags & MVD_BFS_INSTALL) && (flags & MVD_BFS_COUNT_ONLY)) return fail(ctx, MVD_E_INVALID, "INSTALL and COUNT_ONLY exclude each other");
+    CK(cudaSetDevice(ctx->device));
+    MvdBfsConfig cfg;
+    cfg.n = ctx->n;
+    cfg.m = ctx->m;
+    for (int j = 0; j < MVD_MAX_N; ++j) cfg.dec_taps[j] = ctx->dec_taps[j];
+    cfg.max_states = max_states;
+    cfg.chunk_parents = chunk_parents;
+    cfg.keep_next = !(flags & MVD_BFS_COUNT_ONLY);
+    cfg.copy_out = (flags & MVD_BFS_INSTALL) != 0;
+    MvdBfsResult res;
+    const int rc = mvd_bfs_run(cfg, ctx->stream, res);
+    ctx->launches += res.launches;
+    ctx->last_ms = res.ms;
+    ctx->last_fast = 2048;
+    ctx->bfs_levels = res.levels;
+    if (stats) {
+        stats->S = res.S;
+        stats->frontier = res.frontier;
+        stats->iterations = res.iterations;
+        stats->launches = res.launches;
+        stats->candidates = res.candidates;
+        stats->closed = res.closed ? 1 : 0;
+        stats->max_metric = res.max_metric;
+        stats->ms = res.ms;
+        stats->reserved = 0;
+    }
+    if (rc != MVD_OK) return fail(ctx, rc, "%s", res.error);
+    if (flags & MVD_BFS_INSTALL) {
+        ctx->S = res.S;
+        ctx->h_metrics.swap(res.metrics);
+        ctx->h_next.swap(res.next);
+        return install_states(ctx);
+    }
+    return MVD_OK;
+}
+
+int mvd_bfs_levels(mvd_ctx* ctx, uint32_t* sizes, uint32_t cap, uint32_t* nlevels) {
+    if (!ctx) return MVD_E_INVALID;
+    if (nlevels) *nlevels = (uint32_t)ctx->bfs_levels.size();
+    if (sizes)
+        for (uint32_t i = 0; i < cap && i < ctx->bfs_levels.size(); ++i) sizes[i] = ctx->bfs_levels[i];
+    return MVD_OK;
 }
 
 int mvd_get_states(mvd_ctx* ctx, uint8_t* metrics, uint32_t* next) {

@@ -3,6 +3,8 @@
 #pragma once
 #include "mvd_types.h"
 
+#include <vector>
+
 cudaError_t mvd_launch_generic(int engine, int mode, bool n2, int m, bool in_smem, dim3 grid, size_t smem, cudaStream_t st,
                                const Params& P);
 cudaError_t mvd_launch_generic_acs(int mode, bool n2, int m, dim3 grid, size_t smem, cudaStream_t st, const Params& P);
@@ -17,3 +19,26 @@ cudaError_t mvd_launch_det2_pair(dim3 grid, unsigned threads, size_t smem, cudaS
 cudaError_t mvd_launch_learn(bool smem_tables, size_t lsmem, uint32_t nsegs, cudaStream_t st, const Params& P,
                              const LearnParams& LP);
 cudaError_t mvd_launch_int_peak(int blocks, cudaStream_t st, uint32_t* out, int iters, int mode);
+
+// GPU breadth-first enumeration of the Markov states (mvd_tu_bfs.cu)
+struct MvdBfsConfig {
+    int n = 0, m = 0;
+    uint32_t dec_taps[MVD_MAX_N] = {0, 0, 0, 0};
+    uint32_t max_states = 0;
+    uint32_t chunk_parents = 0;     // queue entries expanded per pass (0 = default 2^22)
+    bool keep_next = true;          // false: count only (no NEXT table)
+    bool copy_out = true;           // copy metrics / NEXT to the host vectors of the result
+};
+struct MvdBfsResult {
+    uint32_t S = 0, frontier = 0, iterations = 0, launches = 0;
+    uint64_t candidates = 0;
+    bool closed = false;
+    int max_metric = 0;
+    float ms = 0.f;
+    char error[256] = {0};
+    std::vector<uint8_t> metrics;
+    std::vector<uint32_t> next;
+    std::vector<uint32_t> levels;   // states first reached at BFS depth d (complete levels only)
+};
+#define MVD_BFS_MAX_STATES 1610612736u   /* 3/4 of the 2^31 slots a 32-bit slot word can address */
+int mvd_bfs_run(const MvdBfsConfig& cfg, cudaStream_t st, MvdBfsResult& res);

@@ -29,6 +29,7 @@ EXPORTS = (
     "mvd_set_code", "mvd_set_states", "mvd_enumerate_states", "mvd_get_states", "mvd_set_loglik",
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
+    "mvd_enumerate_states_gpu", "mvd_bfs_levels",
 )
 
 
@@ -54,6 +55,14 @@ class Segment(C.Structure):
                 ("trial_begin", C.c_uint64), ("trial_end", C.c_uint64), ("bits_offset", C.c_uint64)]
 
 
+class BfsStats(C.Structure):
+    _fields_ = [("S", C.c_uint32), ("frontier", C.c_uint32), ("iterations", C.c_uint32), ("launches", C.c_uint32),
+                ("candidates", C.c_uint64), ("closed", C.c_int32), ("max_metric", C.c_int32), ("ms", C.c_float),
+                ("reserved", C.c_uint32)]
+
+
+BFS_INSTALL, BFS_COUNT_ONLY = 1, 2
+
 _lib = None
 
 
@@ -78,6 +87,8 @@ def load():
     lib.mvd_set_code.argtypes = [vp, i32, i32, i32, P(u32)]
     lib.mvd_set_states.argtypes = [vp, u32, vp, vp]
     lib.mvd_enumerate_states.argtypes = [vp, u32, P(u32)]
+    lib.mvd_enumerate_states_gpu.argtypes = [vp, u32, u32, u32, P(BfsStats)]
+    lib.mvd_bfs_levels.argtypes = [vp, vp, u32, P(u32)]
     lib.mvd_get_states.argtypes = [vp, vp, vp]
     lib.mvd_set_loglik.argtypes = [vp, u32, vp, vp]
     lib.mvd_learn_counts.argtypes = [vp, P(Src), P(Segment), u32, u32, i32, vp]

@@ -66,6 +66,9 @@ class Detector:
         if table is not None:
             self.table = table
             self._upload_states()
+        elif enumerate_with == "gpu":
+            self.bfs_stats = self._enumerate_gpu(int(max_states), install=True)
+            self.table = self._fetch_states(self.bfs_stats["S"])
         elif enumerate_with == "lib":
             S = C.c_uint32()
             self._ck(self.lib.mvd_enumerate_states(self.ctx, int(max_states), C.byref(S)))
@@ -87,6 +90,34 @@ class Detector:
         met = np.ascontiguousarray(self.table.metrics, dtype=np.uint8)
         nxt = np.ascontiguousarray(self.table.nxt, dtype=np.uint32)
         self._ck(self.lib.mvd_set_states(self.ctx, self.table.S, met.ctypes.data, nxt.ctypes.data))
+
+    def _fetch_states(self, S: int) -> codes.StateTable:
+        met = np.empty((S, 1 << self.m), dtype=np.uint8)
+        nxt = np.empty((S, self.R), dtype=np.uint32)
+        self._ck(self.lib.mvd_get_states(self.ctx, met.ctypes.data, nxt.ctypes.data))
+        if S * self.R * self.R <= 1 << 26:
+            mult = (nxt[:, :, None] == nxt[:, None, :]).sum(axis=2).astype(np.uint8)
+        else:
+            mult = np.zeros_like(nxt, dtype=np.uint8)
+            for r in range(self.R):
+                mult += (nxt == nxt[:, r:r + 1]).astype(np.uint8)
+        return codes.StateTable(self.k, self.n, self.m, met, nxt, mult)
+
+    def _enumerate_gpu(self, max_states: int, install: bool = True, count_only: bool = False, chunk_parents: int = 0,
+                       allow_partial: bool = False) -> dict:
+        """enumerate_markov_states_allzero (viterbi_markov.py:166-195) on the GPU; see mvd_enumerate_states_gpu."""
+        st = _capi.BfsStats()
+        flags = (_capi.BFS_INSTALL if install else 0) | (_capi.BFS_COUNT_ONLY if count_only else 0)
+        rc = self.lib.mvd_enumerate_states_gpu(self.ctx, int(max_states), flags, int(chunk_parents), C.byref(st))
+        if rc != 0 and not (allow_partial and rc == -5 and st.S > 0):
+            self._ck(rc)
+        nl = C.c_uint32()
+        self.lib.mvd_bfs_levels(self.ctx, None, 0, C.byref(nl))
+        lev = np.zeros(nl.value, dtype=np.uint32)
+        self.lib.mvd_bfs_levels(self.ctx, lev.ctypes.data, nl.value, C.byref(nl))
+        return dict(S=int(st.S), frontier=int(st.frontier), iterations=int(st.iterations), launches=int(st.launches),
+                    candidates=int(st.candidates), closed=bool(st.closed), max_metric=int(st.max_metric), ms=float(st.ms),
+                    levels=lev.tolist())
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx:

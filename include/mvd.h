@@ -100,6 +100,32 @@ int mvd_set_states(mvd_ctx* ctx, uint32_t S, const uint8_t* metrics, const uint3
 int mvd_enumerate_states(mvd_ctx* ctx, uint32_t max_states, uint32_t* S_out);
 int mvd_get_states(mvd_ctx* ctx, uint8_t* metrics, uint32_t* next);
 
+/* The same enumeration on the GPU (csrc/mvd_bfs.cuh): the queue of viterbi_markov.py:183-193 is
+ * expanded chunk-parallel, duplicates meet in an open-addressing table in HBM and ties are broken
+ * by candidate rank (parent index, received word), so state indices and NEXT are identical to the
+ * reference's discovery order.  flags: MVD_BFS_INSTALL = install the table like mvd_set_states
+ * (then mvd_get_states works); MVD_BFS_COUNT_ONLY = keep no NEXT table (memories whose state set
+ * is too large to use, m = 5, 6: how many states are there?).  chunk_parents: queue entries
+ * expanded per pass, 0 = default.  When max_states (<= 1 610 612 736) is exceeded the call returns
+ * MVD_E_NOMEM and stats->S is the number enumerated so far (a lower bound), stats->closed = 0. */
+enum { MVD_BFS_INSTALL = 1, MVD_BFS_COUNT_ONLY = 2 };
+typedef struct mvd_bfs_stats {
+    uint32_t S;             /* states enumerated                                      */
+    uint32_t frontier;      /* queue position reached (== S when closed)              */
+    uint32_t iterations;    /* chunk passes                                           */
+    uint32_t launches;      /* kernels launched                                       */
+    uint64_t candidates;    /* (state, received word) pairs expanded                  */
+    int32_t closed;         /* 1 = the queue ran empty: S is the size of the state set */
+    int32_t max_metric;     /* largest relative metric seen                           */
+    float ms;               /* device time of the whole enumeration (CUDA events)     */
+    uint32_t reserved;
+} mvd_bfs_stats;
+int mvd_enumerate_states_gpu(mvd_ctx* ctx, uint32_t max_states, uint32_t flags, uint32_t chunk_parents,
+                             mvd_bfs_stats* stats);
+/* Sizes of the BFS levels the last mvd_enumerate_states_gpu completed (sizes[d] = states first
+ * reached after d received words; sizes may be NULL to query *nlevels). */
+int mvd_bfs_levels(mvd_ctx* ctx, uint32_t* sizes, uint32_t cap, uint32_t* nlevels);
+
 /* Log-likelihood tables: logP1[t][i*R + r] = log(max(P1_t[i, next[i][r]], 1e-300)) for table
  * set t (one per distinct p; Pd_plotter.py:166-167 then :114-115), logTref likewise for
  * T(p = 1/2) (Pd_plotter.py:193-194).  Host float64, computed by the caller with libm log. */
@@ -142,7 +168,7 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
  * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
- * 1024 = chunk-parallel learning chain.
+ * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration.
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread

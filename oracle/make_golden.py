@@ -39,6 +39,12 @@ CODES = {
 }
 
 
+M4_CODES = {
+    "m4a": dict(k=1, n=2, m=4, gen=[[[1, 1, 0, 0, 1]], [[1, 1, 0, 1, 1]]]),   # (31,33)
+    "m4c": dict(k=1, n=2, m=4, gen=[[[1, 0, 0, 1, 1]], [[1, 1, 1, 0, 1]]]),   # (23,35)
+}
+
+
 def sha16(obj) -> str:
     return hashlib.sha256(repr(obj).encode()).hexdigest()[:16]
 
@@ -196,9 +202,23 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(HERE, "..", "tests", "golden"))
     ap.add_argument("--skip-m3-symbolic", action="store_true")
+    ap.add_argument("--m4-only", action="store_true", help="only (re)write m4_kats.json")
     args = ap.parse_args()
     vm, pdp = load_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
+
+    # m = 4: the reference's own BFS (5 s and 28 s of CPython); hashes of the state list / NEXT table and
+    # the LCG trajectory pin the oracle's and the GPU's enumeration at the largest fully checkable memory
+    m4 = {}
+    for name, spec in M4_CODES.items():
+        t0 = time.time()
+        m4[name] = kat_for_code(vm, pdp, name, spec, symbolic=False)
+        m4[name]["reference_bfs_seconds"] = round(time.time() - t0, 1)
+        print(f"[kat] {name}: S={m4[name]['S']} ({time.time() - t0:.1f}s)", flush=True)
+    with open(os.path.join(args.out, "m4_kats.json"), "w") as f:
+        json.dump(m4, f, separators=(",", ":"))
+    if args.m4_only:
+        return
 
     kats = {}
     for name, spec in CODES.items():

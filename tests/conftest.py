@@ -21,6 +21,7 @@ CODES = {
     "m1": dict(k=1, n=2, m=1, gen=[[[1, 1]], [[1, 0]]]),
     "m4a": dict(k=1, n=2, m=4, gen=[[[1, 1, 0, 0, 1]], [[1, 1, 0, 1, 1]]]),     # (31,33): S = 25 751
     "m4b": dict(k=1, n=2, m=4, gen=[[[1, 1, 0, 1, 1]], [[1, 1, 0, 0, 1]]]),     # outputs swapped
+    "m4c": dict(k=1, n=2, m=4, gen=[[[1, 0, 0, 1, 1]], [[1, 1, 1, 0, 1]]]),     # (23,35): S = 150 743
     "m5": dict(k=1, n=2, m=5, gen=[[[1, 0, 1, 0, 1, 1]], [[1, 1, 1, 1, 0, 1]]]),            # (53,75)
     "m6": dict(k=1, n=2, m=6, gen=[[[1, 0, 1, 1, 0, 1, 1]], [[1, 1, 1, 1, 0, 0, 1]]]),      # (133,171)
 }
@@ -33,7 +34,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     out = {}
-    for name in ("code_kats", "sim_kats", "experiments"):
+    for name in ("code_kats", "sim_kats", "experiments", "m4_kats"):
         with open(os.path.join(GOLDEN, name + ".json")) as f:
             out[name] = json.load(f)
     return out

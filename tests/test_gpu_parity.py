@@ -368,6 +368,70 @@ def test_m4_global_tables_vs_oracle(codes_spec):
         assert np.array_equal(got, want_edge)
 
 
+@pytest.mark.parametrize("chunk", [0, 1, 7, 64])
+@pytest.mark.parametrize("name", ["c75", "c65", "m3a", "m3b", "r13", "m1"])
+def test_gpu_bfs_matches_reference_order(golden, codes_spec, name, chunk):
+    """enumerate_markov_states_allzero on the GPU -- state set, BFS *index order* and NEXT
+    identical to the reference's (golden sha256 of repr(states) / repr(NEXT) from the reference run),
+    for the default chunk and for tiny chunks that split BFS levels and force cross-chunk duplicates."""
+    import hashlib
+    from mvd.engine import Detector
+    s, g = codes_spec[name], golden["code_kats"][name]
+    with Detector(s["gen"], s["k"], s["n"], s["m"], enumerate_with="lib") as det:
+        st = det._enumerate_gpu(1 << 12, install=True, chunk_parents=chunk)
+        tab = det._fetch_states(st["S"])
+        assert st["closed"] and st["S"] == g["S"] == st["frontier"]
+        assert st["max_metric"] == g["max_metric"] == tab.max_metric
+        assert st["candidates"] == g["S"] * (1 << s["n"])
+        assert sum(st["levels"]) == g["S"] and st["levels"][0] == 1 and st["levels"][1] <= 1 << s["n"]
+        states = [tuple(int(v) for v in row) for row in tab.metrics]
+        assert hashlib.sha256(repr(states).encode()).hexdigest()[:16] == g["states_sha"]
+        assert hashlib.sha256(repr(tab.nxt.tolist()).encode()).hexdigest()[:16] == g["next_sha"]
+        assert np.array_equal(tab.mult, np.array(g["mult"], dtype=np.uint8))
+        assert det.last_kernel_kind() == 2048
+
+
+@pytest.mark.parametrize("name,S", [("m4a", 25751), ("m4c", 150743)])
+def test_gpu_bfs_m4_vs_host_bfs(golden, codes_spec, name, S):
+    """m = 4 (S = 25 751 and 150 743): GPU enumeration == the reference's own BFS (golden hashes of its
+    state list and NEXT table) and == the C oracle's sequential BFS, index for index."""
+    import hashlib
+    import c_oracle as co
+    from mvd.engine import Detector
+    spec, g = codes_spec[name], golden["m4_kats"][name]
+    om, on = co.enumerate_states(_taps(spec), 2, 4)
+    assert om.shape[0] == S == g["S"]
+    assert hashlib.sha256(repr([tuple(r) for r in om.tolist()]).encode()).hexdigest()[:16] == g["states_sha"]
+    assert hashlib.sha256(repr(on.tolist()).encode()).hexdigest()[:16] == g["next_sha"]
+    for chunk in (0, 1000):
+        with Detector(spec["gen"], 1, 2, 4, enumerate_with="gpu", max_states=1 << 18) as det:
+            if chunk:
+                st = det._enumerate_gpu(1 << 18, install=True, chunk_parents=chunk)
+                det.table = det._fetch_states(st["S"])
+            assert det.S == S
+            assert np.array_equal(det.table.metrics, om) and np.array_equal(det.table.nxt, on)
+
+
+def test_gpu_bfs_limits_and_count_only(codes_spec):
+    """max_states exhausted -> MVD_E_NOMEM with a usable lower bound; count-only mode keeps no NEXT table;
+    the recursion of m = 5 is enumerated up to a budget (its closure is far larger, SURVEY 8 a5 note)."""
+    from mvd import _capi
+    from mvd.engine import Detector, HashOnlyDetector
+    s = codes_spec["m3a"]
+    with Detector(s["gen"], 1, 2, 3, enumerate_with="lib") as det:
+        with pytest.raises(_capi.MvdError) as ei:
+            det._enumerate_gpu(100, install=False)
+        assert ei.value.code == -5
+        st = det._enumerate_gpu(100, install=False, allow_partial=True)
+        assert not st["closed"] and 0 < st["S"] <= 100 and st["frontier"] < st["S"]
+        st = det._enumerate_gpu(1 << 10, install=False, count_only=True)
+        assert st["closed"] and st["S"] == 435
+    s = codes_spec["m5"]
+    with HashOnlyDetector(s["gen"], 1, 2, 5) as det:
+        st = det._enumerate_gpu(1 << 21, install=False, count_only=True, allow_partial=True)
+        assert not st["closed"] and st["S"] > 1 << 20 and st["max_metric"] <= 15
+
+
 @pytest.mark.parametrize("name", ["m5", "m6", "m4a", "c75"])
 def test_acs_hash_large_memory(codes_spec, name):
     """Eq. 4-5 recursion for memories without an enumerable state set: trajectory hash and

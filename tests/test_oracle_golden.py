@@ -78,6 +78,24 @@ def test_c_oracle_enumeration(golden, name):
     assert sum(len(set(row)) for row in nxt.tolist()) == g["nnz"]
 
 
+@pytest.mark.parametrize("name", ["m4a", "m4c"])
+def test_c_oracle_enumeration_m4(golden, name):
+    """m = 4 (S = 25 751 / 150 743), the largest memory the reference's own BFS finishes: the oracle's
+    state list, index order, NEXT table and LCG trajectory == the reference's (hashes in m4_kats.json)."""
+    import c_oracle as co
+    g = golden["m4_kats"][name]
+    met, nxt = co.enumerate_states(_taps(g), g["n"], g["m"], max_states=1 << 18)
+    assert met.shape[0] == g["S"] and int(met.max()) == g["max_metric"]
+    assert sha16([tuple(r) for r in met.tolist()]) == g["states_sha"]
+    assert sha16(nxt.tolist()) == g["next_sha"]
+    x, cur, traj = 12345, 0, []
+    for _ in range(10000):
+        x = (1664525 * x + 1013904223) % (1 << 32)
+        cur = int(nxt[cur, x >> 30])
+        traj.append(cur)
+    assert traj[:32] == g["lcg_traj_first"] and sum(traj) == g["lcg_traj_sum"] and sha16(traj) == g["lcg_traj_sha"]
+
+
 @pytest.mark.parametrize("name", ["c75", "c65", "m1", "r13"])
 def test_ref_port_enumeration(golden, name):
     import ref_port
