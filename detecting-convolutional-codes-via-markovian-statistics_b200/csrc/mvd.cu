@@ -939,6 +939,130 @@ int mvd_acs_hash(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint6
     return run(ctx, MODE_HASH, MVD_ENGINE_ACS, src, seg, 1, o);
 }
 
+int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next, const double* lp1, const double* lp2,
+                     const double* lb1, const double* lb2, const double* u_vals, uint32_t nu, double tol, uint32_t max_iter,
+                     double* rho, uint32_t* iters) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!next || !lp1 || !lp2 || !lb1 || !lb2 || !u_vals || !rho) return fail(ctx, MVD_E_INVALID, "null argument");
+    if (K == 0 || R == 0 || nu == 0 || max_iter == 0) return fail(ctx, MVD_E_INVALID, "empty problem");
+    const size_t KR = (size_t)K * R;
+    for (size_t e = 0; e < KR; ++e)
+        if (next[e] >= K) return fail(ctx, MVD_E_INVALID, "next[%zu]=%u out of range (K=%u)", e, next[e], K);
+    CK(cudaSetDevice(ctx->device));
+    const size_t per_u = (KR + 3 * (size_t)K) * 8;
+    uint32_t ub = (uint32_t)std::max<size_t>(1, std::min<size_t>(nu, ((size_t)8 << 30) / per_u));
+    DevBuf d_in, d_scr, d_out;
+    const size_t in_bytes = KR * 4 + 2 * KR * 8 + 2 * (size_t)K * 8 + (size_t)nu * 8;
+    CK(d_in.reserve(in_bytes + 64));
+    CK(d_scr.reserve((size_t)ub * per_u));
+    CK(d_out.reserve((size_t)nu * 12));
+    unsigned char* base = d_in.as<unsigned char>();
+    double* g_lp1 = reinterpret_cast<double*>(base);
+    double* g_lp2 = g_lp1 + KR;
+    double* g_lb1 = g_lp2 + KR;
+    double* g_lb2 = g_lb1 + K;
+    double* g_u = g_lb2 + K;
+    uint32_t* g_nxt = reinterpret_cast<uint32_t*>(g_u + nu);
+    CK(cudaMemcpyAsync(g_lp1, lp1, KR * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_lp2, lp2, KR * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_lb1, lb1, (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_lb2, lb2, (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_u, u_vals, (size_t)nu * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_nxt, next, KR * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ChernoffParams P;
+    P.K = K;
+    P.R = R;
+    P.max_iter = max_iter;
+    P.nxt = g_nxt;
+    P.lp1 = g_lp1;
+    P.lp2 = g_lp2;
+    P.lb1 = g_lb1;
+    P.lb2 = g_lb2;
+    P.tol = tol;
+    P.wd = d_scr.as<double>();
+    P.bgR = P.wd + (size_t)ub * KR;
+    P.xa = P.bgR + (size_t)ub * K;
+    P.xb = P.xa + (size_t)ub * K;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (uint32_t u0 = 0; u0 < nu; u0 += ub) {
+        P.nu = std::min(ub, nu - u0);
+        P.u_vals = g_u + u0;
+        P.rho = d_out.as<double>() + u0;
+        P.iters = reinterpret_cast<uint32_t*>(d_out.as<double>() + nu) + u0;
+        CK(mvd_launch_chernoff(P, ctx->stream));
+        ctx->launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(rho, d_out.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> it(nu);
+    CK(cudaMemcpyAsync(it.data(), d_out.as<double>() + nu, (size_t)nu * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->last_fast = 4096;
+    if (iters) memcpy(iters, it.data(), (size_t)nu * 4);
+    d_in.release();
+    d_scr.release();
+    d_out.release();
+    return MVD_OK;
+}
+
+int mvd_chernoff_rho_dense(mvd_ctx* ctx, uint32_t K, uint32_t R, const double* logP1, const double* logP2, const double* u_vals,
+                           uint32_t nu, double tol, uint32_t max_iter, double* rho, uint32_t* iters) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!logP1 || !logP2 || !u_vals || !rho) return fail(ctx, MVD_E_INVALID, "null argument");
+    if (K == 0 || R == 0 || nu == 0 || max_iter == 0) return fail(ctx, MVD_E_INVALID, "empty problem");
+    CK(cudaSetDevice(ctx->device));
+    const size_t KKR = (size_t)K * K * R;
+    const size_t per_u = ((size_t)K * K + 2 * (size_t)K) * 8;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (2 * KKR * 8 + per_u + ((size_t)1 << 30) > free_b)
+        return fail(ctx, MVD_E_NOMEM, "dense tensors of K=%u need %.1f GB; use the edge form (mvd_chernoff_rho)", K, 2 * KKR * 8 / 1e9);
+    uint32_t ub = (uint32_t)std::max<size_t>(1, std::min<size_t>(nu, ((size_t)8 << 30) / per_u));
+    DevBuf d_in, d_scr, d_out;
+    CK(d_in.reserve(2 * KKR * 8 + (size_t)nu * 8));
+    CK(d_scr.reserve((size_t)ub * per_u));
+    CK(d_out.reserve((size_t)nu * 12));
+    double* g_lp1 = d_in.as<double>();
+    double* g_lp2 = g_lp1 + KKR;
+    double* g_u = g_lp2 + KKR;
+    CK(cudaMemcpyAsync(g_lp1, logP1, KKR * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_lp2, logP2, KKR * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g_u, u_vals, (size_t)nu * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ChernoffParams P;
+    memset(&P, 0, sizeof P);
+    P.K = K;
+    P.R = R;
+    P.max_iter = max_iter;
+    P.lp1 = g_lp1;
+    P.lp2 = g_lp2;
+    P.tol = tol;
+    P.wd = d_scr.as<double>();
+    P.xa = P.wd + (size_t)ub * K * K;
+    P.xb = P.xa + (size_t)ub * K;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (uint32_t u0 = 0; u0 < nu; u0 += ub) {
+        P.nu = std::min(ub, nu - u0);
+        P.u_vals = g_u + u0;
+        P.rho = d_out.as<double>() + u0;
+        P.iters = reinterpret_cast<uint32_t*>(d_out.as<double>() + nu) + u0;
+        CK(mvd_launch_chernoff_dense(P, ctx->stream));
+        ctx->launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(rho, d_out.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> it(nu);
+    CK(cudaMemcpyAsync(it.data(), d_out.as<double>() + nu, (size_t)nu * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->last_fast = 4097;
+    if (iters) memcpy(iters, it.data(), (size_t)nu * 4);
+    d_in.release();
+    d_scr.release();
+    d_out.release();
+    return MVD_OK;
+}
+
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms) {
     if (!ctx || !ms) return MVD_E_INVALID;
     *ms = ctx->last_ms;

@@ -42,3 +42,27 @@ struct MvdBfsResult {
 };
 #define MVD_BFS_MAX_STATES 1610612736u   /* 3/4 of the 2^31 slots a 32-bit slot word can address */
 int mvd_bfs_run(const MvdBfsConfig& cfg, cudaStream_t st, MvdBfsResult& res);
+
+// Chernoff spectral radius (mvd_tu_chernoff.cu, mvd_chernoff.cuh)
+#define CHERNOFF_BLOCK 512
+
+struct ChernoffParams {
+    uint32_t K, R, nu, max_iter;
+    const uint32_t* nxt;       // [K * R] next state index
+    const double* lp1;         // [K * R] log P1 on the edges
+    const double* lp2;
+    const double* lb1;         // [K] log background of row i under P1
+    const double* lb2;
+    const double* u_vals;      // [nu]
+    double tol;
+    double* wd;                // scratch [nu][K * R]   w - bg
+    double* bgR;               // scratch [nu][K]       R * bg
+    double* xa;                // scratch [nu][K]
+    double* xb;                // scratch [nu][K]
+    double* rho;               // [nu]
+    uint32_t* iters;           // [nu]
+};
+
+cudaError_t mvd_launch_chernoff(const ChernoffParams& P, cudaStream_t st);
+cudaError_t mvd_launch_chernoff(const ChernoffParams& P, cudaStream_t st);
+cudaError_t mvd_launch_chernoff_dense(const ChernoffParams& P, cudaStream_t st);

@@ -48,6 +48,7 @@ PHILOX_W1 = 0xBB67AE85
 MASK32 = 0xFFFFFFFF
 
 LEARN_STREAM = 0xFFFFFFFF      # stream tag of the learning chain (trial id 0)
+ALPHA_STREAM = 0xFFFFFFFE      # stream tag of the joint-tensor chains of alpha_exponent.py (trial id 0)
 
 
 def philox4x32_10(ctr: Tuple[int, int, int, int], key: Tuple[int, int]) -> Tuple[int, int, int, int]:

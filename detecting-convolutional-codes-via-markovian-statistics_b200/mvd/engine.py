@@ -229,6 +229,33 @@ class Detector:
         del keep
         return h, fin
 
+    # ------------------------------------------------------------------ error exponent (alpha_exponent.py)
+    def chernoff_rho_edges(self, nxt, lp1, lp2, lb1, lb2, u_vals, tol: float = 1e-14, max_iter: int = 100000):
+        """rho(M(u)) for every u (Eq. 7) from edge-form log tensors; see ``mvd_chernoff_rho``."""
+        nxt = np.ascontiguousarray(nxt, dtype=np.uint32)
+        K, R = nxt.shape
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (lp1, lp2, lb1, lb2, u_vals)]
+        assert arrs[0].shape == (K, R) and arrs[1].shape == (K, R) and arrs[2].shape == (K,) and arrs[3].shape == (K,)
+        nu = arrs[4].size
+        rho = np.zeros(nu, dtype=np.float64)
+        iters = np.zeros(nu, dtype=np.uint32)
+        self._ck(self.lib.mvd_chernoff_rho(self.ctx, K, R, nxt.ctypes.data, *(a.ctypes.data for a in arrs), nu, float(tol),
+                                           int(max_iter), rho.ctypes.data, iters.ctypes.data))
+        return rho, iters
+
+    def chernoff_rho_dense(self, logP1, logP2, u_vals, tol: float = 1e-14, max_iter: int = 100000):
+        """rho(M(u)) for dense K x K x R log tensors; see ``mvd_chernoff_rho_dense``."""
+        a = np.ascontiguousarray(logP1, dtype=np.float64)
+        b = np.ascontiguousarray(logP2, dtype=np.float64)
+        K, K2, R = a.shape
+        assert K == K2 and b.shape == a.shape
+        u = np.ascontiguousarray(u_vals, dtype=np.float64)
+        rho = np.zeros(u.size, dtype=np.float64)
+        iters = np.zeros(u.size, dtype=np.uint32)
+        self._ck(self.lib.mvd_chernoff_rho_dense(self.ctx, K, R, a.ctypes.data, b.ctypes.data, u.ctypes.data, u.size,
+                                                 float(tol), int(max_iter), rho.ctypes.data, iters.ctypes.data))
+        return rho, iters
+
     # ------------------------------------------------------------------ introspection
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
@@ -303,6 +330,20 @@ class HashOnlyDetector(Detector):
     @property
     def S(self):
         return 0
+
+
+class BareContext(Detector):
+    """A device context without a code: entry points that need no trellis (Chernoff spectral radius)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _capi.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.mvd_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            _capi.check(self.lib, None, rc)
+        self.device = int(device)
+        self.table = None
+        self.ntables = 0
 
 
 def philox_threshold(p: float) -> int:

@@ -5,7 +5,7 @@ Same public names and argument orders as the reference's ``viterbi_markov.py`` s
 
     state_bits_from_int, bits_to_int, branch_output_and_next_state, hamming_distance,
     build_trellis, viterbi_metric_step, enumerate_markov_states_allzero, build_symbolic_T,
-    simulate_markov_sequence
+    simulate_markov_sequence, octal_to_taps (the last two are imported by the reference but never defined)
 
 Host-side by design (north star): trellis construction, Markov-state enumeration and the symbolic
 T(p) stay on the CPU; they are thin views over :mod:`mvd.codes`.  ``simulate_markov_sequence`` --
@@ -20,6 +20,21 @@ from functools import lru_cache
 import numpy as np
 
 from mvd import bitsource, codes
+
+
+def octal_to_taps(octal, m=None):
+    """Octal generator -> tap list, coefficient of D^0 first.  ``alpha_exponent.py:58`` imports this name from
+    ``viterbi_markov`` but the reference never defines it; the convention here is the one of the only octal
+    parser the reference ships, ``parity_eqn_check.parse_poly_token`` (:80-83, LSB-first), padded to ``m + 1``
+    taps when ``m`` is given.  (Pd_plotter.py:247-248 writes its tap lists MSB-first -- "6" there is [1,1,0] --
+    so always check which convention a tap list came from; the tap lists themselves are authoritative.)"""
+    val = int(str(octal), 8)
+    taps = [(val >> i) & 1 for i in range(max(val.bit_length(), 1))]
+    if m is not None:
+        if len(taps) > m + 1:
+            raise ValueError(f"octal {octal} needs more than m + 1 = {m + 1} taps")
+        taps += [0] * (m + 1 - len(taps))
+    return taps
 
 
 def state_bits_from_int(state_int, m):

@@ -158,6 +158,24 @@ int mvd_trace(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, int engi
 int mvd_acs_hash(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg,
                  uint64_t* hashes, uint8_t* final_metrics);
 
+/* Error exponent, Eq. 7: rho[q] = spectral radius of M(u_q), M(u)[i,j] = sum_r P1(i->j,r)^u P2(i->j,r)^(1-u)
+ * -- the eigenvalue loop of compute_error_exponent (alpha_exponent.py:155-184) for two Laplace-smoothed
+ * joint tensors of the same decoder (learn_transition_tensor, alpha_exponent.py:83-149), given in edge
+ * form: lp_h[i*R + r] = log P_h(i -> next[i*R + r], r) and lb_h[i] = log of row i's background entry
+ * (lambda / d_i; every (j, r) that is not an edge).  Power iteration on the sparse + rank-one form, one
+ * thread block per u; stops when the estimate moves by <= tol * rho or after max_iter products.
+ * next: K x R state indices (host); rho: nu doubles; iters (optional): products taken per u.
+ * Needs no code / state table in the context. */
+int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next, const double* lp1, const double* lp2,
+                     const double* lb1, const double* lb2, const double* u_vals, uint32_t nu, double tol,
+                     uint32_t max_iter, double* rho, uint32_t* iters);
+
+/* The same for dense K x K x R tensors (the objects alpha_exponent.py:155-184 takes):
+ * logP_h[(i*K + j)*R + r] = log(clip(P_h[i,j,r], 1e-300, 1)) (alpha_exponent.py:167-168). */
+int mvd_chernoff_rho_dense(mvd_ctx* ctx, uint32_t K, uint32_t R, const double* logP1, const double* logP2,
+                           const double* u_vals, uint32_t nu, double tol, uint32_t max_iter, double* rho,
+                           uint32_t* iters);
+
 /* Timing of the last learn/detect/trace launch on the context's stream (CUDA events), and the
  * number of kernels this library has launched since creation. */
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms);
@@ -168,7 +186,7 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
  * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
- * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration.
+ * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius.
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread

@@ -197,20 +197,139 @@ def experiment_golden(vm, pdp, dec, enc2, num_iter, p_vec, N_list, seed, laplace
                 learn_calls=inj.learn_calls)
 
 
+class _RandomFromBits:
+    """Stands in for ``np.random`` inside the reference's alpha_exponent module: hands out the MVD-PHILOX-2
+    bits in the order the module draws them (one randint per step, then one binomial per output bit)."""
+
+    def __init__(self, u_bits, e_bits):
+        self.u, self.e, self.t, self.j = u_bits, e_bits, -1, 0
+
+    def seed(self, _):
+        pass
+
+    def randint(self, lo, hi):
+        assert (lo, hi) == (0, 2)
+        self.t += 1
+        self.j = 0
+        return int(self.u[self.t])
+
+    def binomial(self, one, p):
+        assert one == 1
+        v = int(self.e[self.t][self.j])
+        self.j += 1
+        return v
+
+
+class _NumpyProxy:
+    def __init__(self, real, rnd):
+        self._real, self.random = real, rnd
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+def load_alpha_exponent(vm, ref_path):
+    """Import the reference's alpha_exponent.py.  Two names it imports from viterbi_markov do not exist
+    (alpha_exponent.py:58,62): they are stubbed for the import only (never called by the functions used here)."""
+    import importlib
+    vm.octal_to_taps = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("absent from the reference"))
+    had_sim = hasattr(vm, "simulate_markov_sequence")
+    if not had_sim:
+        vm.simulate_markov_sequence = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("absent"))
+    try:
+        ae = importlib.import_module("alpha_exponent")
+    finally:
+        del vm.octal_to_taps
+        if not had_sim:
+            del vm.simulate_markov_sequence
+    # the two stale call sites (:109, :116) adapted to the shipped signatures (k = 1, n = number of tap lists)
+    ae.enumerate_markov_states_allzero = lambda taps, m: vm.enumerate_markov_states_allzero([[list(g)] for g in taps], m, 1, len(taps))
+    ae.build_trellis = lambda taps, m: vm.build_trellis([[list(g)] for g in taps], m, 1)
+    return ae
+
+
+def alpha_golden(vm, ae, dec, enc1, enc2, m, p, length, burn_in, laplace, seed, u_grid):
+    """learn_transition_tensor + compute_error_exponent of the reference, run on MVD-PHILOX-2 bits."""
+    import numpy as real_np
+    n = len(dec)
+    out = dict(dec=dec, enc1=enc1, enc2=enc2, m=m, p=p, length=length, burn_in=burn_in, laplace=laplace, seed=seed,
+               u_grid=u_grid, tensors=[])
+    Cs = []
+    for hyp, enc in enumerate((enc1, enc2)):
+        trial = hyp
+        u, e = ref_port.philox_bits(seed, ref_port.ALPHA_STREAM, trial, burn_in + length, n, ref_port.threshold_of(p))
+        ae.np = _NumpyProxy(real_np, _RandomFromBits(u, e))
+        try:
+            t0 = time.time()
+            C, states, sidx, all_r = ae.learn_transition_tensor(enc, dec, m, p, length=length, burn_in=burn_in,
+                                                                laplace=laplace, seed=seed)
+            secs = time.time() - t0
+        finally:
+            ae.np = real_np
+        K, R = len(states), len(all_r)
+        trellis = vm.build_trellis([[list(g)] for g in dec], m, 1)
+        nxt = [[sidx[vm.viterbi_metric_step(list(s), trellis, r)] for r in all_r] for s in states]
+        edge = [[float(C[i, nxt[i][r], r]) for r in range(R)] for i in range(K)]
+        mask = real_np.ones((K, K, R), dtype=bool)
+        for i in range(K):
+            for r in range(R):
+                mask[i, nxt[i][r], r] = False
+        bg = [float(C[i][mask[i]].max()) for i in range(K)]
+        assert all(float(C[i][mask[i]].min()) == bg[i] for i in range(K))
+        out["tensors"].append(dict(trial=trial, K=K, R=R, edge=edge, background=bg,
+                                   sha=hashlib.sha256(real_np.ascontiguousarray(C).tobytes()).hexdigest()[:16],
+                                   reference_seconds=round(secs, 2)))
+        Cs.append(C)
+    t0 = time.time()
+    I_err, best_u = ae.compute_error_exponent(Cs[0], Cs[1], u_grid=u_grid)
+    out["I_err"], out["best_u"] = I_err, best_u
+    out["exponent_seconds"] = round(time.time() - t0, 2)
+    P1 = real_np.clip(Cs[0], 1e-300, 1.0)
+    P2 = real_np.clip(Cs[1], 1e-300, 1.0)
+    out["rho"] = {repr(u): ae.spectral_radius(real_np.sum((P1 ** u) * (P2 ** (1.0 - u)), axis=2))
+                  for u in (0.0, 0.25, 0.5, 0.75, 1.0)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(HERE, "..", "tests", "golden"))
     ap.add_argument("--skip-m3-symbolic", action="store_true")
     ap.add_argument("--m4-only", action="store_true", help="only (re)write m4_kats.json")
+    ap.add_argument("--alpha-only", action="store_true", help="only (re)write alpha_kats.json")
     args = ap.parse_args()
     vm, pdp = load_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
 
+    # alpha_exponent.py (Eq. 7): the reference's learn_transition_tensor / compute_error_exponent / fit_error_exponent
+    if not args.m4_only:
+        ae = load_alpha_exponent(vm, args.ref)
+        alpha = {}
+        alpha["c75_vs_c65"] = alpha_golden(vm, ae, [[1, 1, 1], [1, 0, 1]], [[1, 1, 1], [1, 0, 1]], [[1, 1, 0], [1, 0, 1]],
+                                           2, 0.1, 20000, 1000, 1.0, 5, 101)
+        print("[alpha] c75_vs_c65", alpha["c75_vs_c65"]["I_err"], alpha["c75_vs_c65"]["best_u"], flush=True)
+        alpha["c75_lap"] = alpha_golden(vm, ae, [[1, 1, 1], [1, 0, 1]], [[1, 1, 1], [1, 0, 1]], [[1, 0, 1], [1, 1, 1]],
+                                        2, 0.05, 4000, 100, 0.25, 77, 41)
+        print("[alpha] c75_lap", alpha["c75_lap"]["I_err"], flush=True)
+        alpha["m3"] = alpha_golden(vm, ae, [[1, 1, 1, 1], [1, 0, 1, 1]], [[1, 1, 1, 1], [1, 0, 1, 1]],
+                                   [[1, 0, 1, 1], [1, 1, 1, 1]], 3, 0.05, 30000, 1000, 1.0, 9, 11)
+        print("[alpha] m3", alpha["m3"]["I_err"], alpha["m3"]["exponent_seconds"], "s", flush=True)
+        Nv = [50, 100, 150, 200, 250, 300, 400]
+        Pe = [0.31, 0.12, 0.05, 0.021, 0.0085, 0.0036, 0.0]
+        alpha["fit"] = dict(N=Nv, Pe=Pe, result=list(ae.fit_error_exponent(Nv, Pe)),
+                            few=list(ae.fit_error_exponent([10, 20], [0.1, 0.05])))
+        alpha["encoder_steps"] = [[s, u, list(ae._encoder_step(s, u, [[1, 1, 0, 1], [1, 0, 1, 1]], 3)[0]),
+                                   ae._encoder_step(s, u, [[1, 1, 0, 1], [1, 0, 1, 1]], 3)[1]] for s in range(8) for u in (0, 1)]
+        with open(os.path.join(args.out, "alpha_kats.json"), "w") as f:
+            json.dump(alpha, f, separators=(",", ":"))
+        if args.alpha_only:
+            return
+
     # m = 4: the reference's own BFS (5 s and 28 s of CPython); hashes of the state list / NEXT table and
     # the LCG trajectory pin the oracle's and the GPU's enumeration at the largest fully checkable memory
     m4 = {}
-    for name, spec in M4_CODES.items():
+    for name, spec in (M4_CODES.items() if not args.alpha_only else []):
         t0 = time.time()
         m4[name] = kat_for_code(vm, pdp, name, spec, symbolic=False)
         m4[name]["reference_bfs_seconds"] = round(time.time() - t0, 1)

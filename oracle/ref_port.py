@@ -265,6 +265,72 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     return rows
 
 
+# ----------------------------------------------------------------------------- alpha_exponent.py (Eq. 7)
+ALPHA_STREAM = 0xFFFFFFFE
+
+
+def alpha_encoder_step(state, u, taps, m):
+    """alpha_exponent.py:220-234, literally: x = [u, s_0..s_{m-1}], next = (u << (m-1)) | (state >> 1)."""
+    x = [u] + [(state >> i) & 1 for i in range(m)]
+    y = tuple(sum(g[i] & x[i] for i in range(len(g))) % 2 for g in taps)
+    return y, (((u << (m - 1)) | (state >> 1)) if m > 0 else 0)
+
+
+def learn_transition_tensor(encoder_taps, decoder_taps, m, p, length=300_000, burn_in=5_000, laplace=1.0,
+                            seed=0, stream=ALPHA_STREAM, trial=0):
+    """alpha_exponent.py:83-149 with its two stale calls adapted to the shipped signatures
+    (enumerate_markov_states_allzero(decoder_taps, m) -> (G, m, 1, n); build_trellis(decoder_taps, m) ->
+    (G, m, 1)) and np.random replaced by the MVD-PHILOX-2 bits of (seed, stream, trial): per step one info
+    bit (:130,:138) then one flip per output in order (:132,:140).  Returns (C, states, sidx, all_r, counts)."""
+    n = len(decoder_taps)
+    G = [[list(g)] for g in decoder_taps]
+    states, _, all_r = enumerate_states(G, m, 1, n)                 # :109
+    sidx = {s: i for i, s in enumerate(states)}
+    K, R = len(states), len(all_r)
+    r_index = {r: i for i, r in enumerate(all_r)}
+    trellis = trellis_of(G, m, 1)                                   # :116
+    u_bits, e_bits = philox_bits(seed, stream, trial, burn_in + length, n, threshold_of(p))
+    cur = tuple([0] * (1 << m))                                     # :119
+    cur_i = sidx[cur]
+    enc = 0                                                         # :123
+    C = np.zeros((K, K, R))
+    for t in range(burn_in):                                        # :129-135
+        y, enc = alpha_encoder_step(enc, u_bits[t], encoder_taps, m)
+        r = tuple(b ^ f for b, f in zip(y, e_bits[t]))
+        cur = metric_step(list(cur), trellis, r)
+        cur_i = sidx.get(cur, cur_i)
+    for t in range(burn_in, burn_in + length):                      # :137-149
+        y, enc = alpha_encoder_step(enc, u_bits[t], encoder_taps, m)
+        r = tuple(b ^ f for b, f in zip(y, e_bits[t]))
+        nxt = metric_step(list(cur), trellis, r)
+        nxt_i = sidx.get(nxt, None)
+        if nxt_i is not None:
+            C[cur_i, nxt_i, r_index[r]] += 1.0
+            cur, cur_i = nxt, nxt_i
+    counts = C.copy()
+    C += laplace                                                    # :144-145
+    C /= np.maximum(C.sum(axis=(1, 2), keepdims=True), 1.0)
+    return C, states, sidx, all_r, counts
+
+
+def chernoff_matrix(P1_ijr, P2_ijr, u):
+    """M(u) of Eq. 7 as alpha_exponent.py:167-171 forms it."""
+    P1 = np.clip(P1_ijr, 1e-300, 1.0)
+    P2 = np.clip(P2_ijr, 1e-300, 1.0)
+    return np.sum((P1 ** u) * (P2 ** (1.0 - u)), axis=2)
+
+
+def compute_error_exponent(P1_ijr, P2_ijr, u_grid=401):
+    """alpha_exponent.py:155-184: grid search of -log rho(M(u)) with LAPACK eigenvalues; also returns rho(u)."""
+    best, best_u, rhos = None, None, []
+    for u in np.linspace(0.0, 1.0, u_grid):
+        rho = max(float(np.max(np.abs(np.linalg.eigvals(chernoff_matrix(P1_ijr, P2_ijr, u))))), 1e-300)
+        rhos.append(rho)
+        if best is None or rho < best:
+            best, best_u = rho, u
+    return float(-np.log(best)), float(best_u), rhos
+
+
 def timed_steps(gen1, gen2, m, k, n, N, p, num_iter, seed, trial_offset=0):
     """bench helper: run ``num_iter`` iterations of the trial loop (Pd_plotter.py:210-223) of one
     point with a fixed small learned P1; returns (steps done, tallies)."""
