@@ -1063,6 +1063,108 @@ int mvd_chernoff_rho_dense(mvd_ctx* ctx, uint32_t K, uint32_t R, const double* l
     return MVD_OK;
 }
 
+int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment* segs, uint32_t nsegs, uint64_t* tallies,
+                      uint32_t* satisfied) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!src || !segs || nsegs == 0 || !tallies) return fail(ctx, MVD_E_INVALID, "null source / segments / tallies");
+    if (src->mode != MVD_SRC_PHILOX && src->mode != MVD_SRC_BITSTREAM) return fail(ctx, MVD_E_INVALID, "bad source mode");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<ParitySeg> ps(nsegs);
+    uint64_t trials = 0, need_words = 0, max_blocks = 0;
+    for (uint32_t i = 0; i < nsegs; ++i) {
+        const mvd_parity_segment& s = segs[i];
+        if (s.n < 1 || s.n > MVD_MAX_N) return fail(ctx, MVD_E_UNSUPPORTED, "segment %u: n=%u outside [1,%d]", i, s.n, MVD_MAX_N);
+        if (s.m > 31) return fail(ctx, MVD_E_UNSUPPORTED, "segment %u: m=%u > 31", i, s.m);
+        if (s.trial_end < s.trial_begin) return fail(ctx, MVD_E_INVALID, "segment %u: trial_end < trial_begin", i);
+        if (s.decide > 1) return fail(ctx, MVD_E_INVALID, "segment %u: decide must be 0 or 1", i);
+        if ((uint64_t)s.N + s.m > 0xFFFFFF00ull) return fail(ctx, MVD_E_INVALID, "segment %u: N too large", i);
+        ParitySeg& d = ps[i];
+        memset(&d, 0, sizeof d);
+        d.N = s.N;
+        d.m = s.m;
+        d.n = s.n;
+        d.threshold = s.threshold;
+        d.stream = s.stream;
+        d.dmin = s.threshold ? (uint32_t)__builtin_ctz(s.threshold) : 32u;
+        d.decide = s.decide;
+        uint32_t any = 0;
+        for (uint32_t j = 0; j < s.n; ++j) {
+            if (s.m < 31 && (s.enc_taps[j] >> (s.m + 1))) return fail(ctx, MVD_E_INVALID, "segment %u: encoder tap beyond memory m=%u", i, s.m);
+            d.enc_taps[j] = s.enc_taps[j];
+            d.tmpl[j] = s.tmpl[j];
+            any |= s.tmpl[j];
+        }
+        if (!any) return fail(ctx, MVD_E_INVALID, "segment %u: empty parity template", i);
+        d.max_delay = 31u - (uint32_t)__builtin_clz(any);                         // comp_parity.py:101
+        d.gamma = s.gamma;
+        d.trial_begin = s.trial_begin;
+        d.trial_end = s.trial_end;
+        d.bits_offset = s.bits_offset;
+        d.out_offset = trials;
+        d.seg_index = i;
+        const uint64_t ntr = s.trial_end - s.trial_begin;
+        trials += ntr;
+        max_blocks = std::max<uint64_t>(max_blocks, (ntr + PARITY_BLOCK - 1) / PARITY_BLOCK);
+        if (src->mode == MVD_SRC_BITSTREAM) {
+            const uint64_t nsb = ((uint64_t)s.N + s.m + 127) / 128;
+            need_words = std::max<uint64_t>(need_words, s.bits_offset + nsb * (uint64_t)(1 + s.n) * ntr);
+        }
+    }
+    if (max_blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one segment");
+    Params P{};
+    P.src_mode = src->mode;
+    {
+        uint32_t k0 = (uint32_t)src->seed, k1 = (uint32_t)(src->seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            P.rk0[r] = k0;
+            P.rk1[r] = k1;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+    }
+    if (src->mode == MVD_SRC_BITSTREAM) {
+        if (!src->bits) return fail(ctx, MVD_E_INVALID, "bitstream source without bits");
+        if (src->bits_words < need_words) return fail(ctx, MVD_E_INVALID, "bitstream too short: %llu words, need %llu",
+                                                      (unsigned long long)src->bits_words, (unsigned long long)need_words);
+        if (src->bits_on_device) {
+            P.bits = reinterpret_cast<const uint4*>(src->bits);
+        } else {
+            CK(ctx->d_bits.reserve((size_t)need_words * 16));
+            CK(cudaMemcpyAsync(ctx->d_bits.p, src->bits, (size_t)need_words * 16, cudaMemcpyHostToDevice, ctx->stream));
+            P.bits = ctx->d_bits.as<uint4>();
+        }
+    }
+    CK(ctx->d_tallies.reserve(8 * (size_t)nsegs));
+    CK(cudaMemsetAsync(ctx->d_tallies.p, 0, 8 * (size_t)nsegs, ctx->stream));
+    P.tallies = ctx->d_tallies.as<unsigned long long>();
+    uint32_t* d_sat = nullptr;
+    if (satisfied) {
+        CK(ctx->d_trace_idx.reserve(4 * (size_t)std::max<uint64_t>(trials, 1)));
+        d_sat = ctx->d_trace_idx.as<uint32_t>();
+    }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (uint32_t s0 = 0; s0 < nsegs; s0 += PARITY_MAXSEG) {
+        const uint32_t cnt = std::min<uint32_t>(PARITY_MAXSEG, nsegs - s0);
+        ParityBatch B;
+        memset(&B, 0, sizeof B);
+        uint64_t mb = 0;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            B.s[i] = ps[s0 + i];
+            mb = std::max<uint64_t>(mb, (ps[s0 + i].trial_end - ps[s0 + i].trial_begin + PARITY_BLOCK - 1) / PARITY_BLOCK);
+        }
+        if (mb == 0) continue;
+        CK(mvd_launch_parity(dim3((unsigned)mb, cnt), ctx->stream, P, B, d_sat));
+        ctx->launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (satisfied && trials) CK(cudaMemcpyAsync(satisfied, d_sat, 4 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->last_fast = 8192;
+    return MVD_OK;
+}
+
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms) {
     if (!ctx || !ms) return MVD_E_INVALID;
     *ms = ctx->last_ms;

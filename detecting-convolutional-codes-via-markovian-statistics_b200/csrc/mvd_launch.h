@@ -66,3 +66,6 @@ struct ChernoffParams {
 cudaError_t mvd_launch_chernoff(const ChernoffParams& P, cudaStream_t st);
 cudaError_t mvd_launch_chernoff(const ChernoffParams& P, cudaStream_t st);
 cudaError_t mvd_launch_chernoff_dense(const ChernoffParams& P, cudaStream_t st);
+
+// parity-template baseline (mvd_tu_parity.cu, mvd_parity.cuh)
+cudaError_t mvd_launch_parity(dim3 grid, cudaStream_t st, const Params& P, const ParityBatch& B, uint32_t* satisfied);

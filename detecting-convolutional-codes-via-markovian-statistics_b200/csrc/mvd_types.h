@@ -84,4 +84,21 @@ struct LearnParams {
     int nxt_in_smem;
 };
 
+// ---- parity-template baseline trials (mvd_parity.cuh)
+#define PARITY_BLOCK 256
+#define PARITY_MAXSEG 64
+
+struct ParitySeg {
+    uint32_t N, m, n, threshold, stream, dmin, decide, max_delay;
+    uint32_t enc_taps[MVD_MAX_N];
+    uint32_t tmpl[MVD_MAX_N];        // bit s of tmpl[j]: term (j, s) of the template
+    double gamma;
+    unsigned long long trial_begin, trial_end, bits_offset, out_offset;
+    uint32_t seg_index, pad;
+};
+
+struct ParityBatch {
+    ParitySeg s[PARITY_MAXSEG];
+};
+
 #define MVD_PEAK_OPS_PER_ITER 64

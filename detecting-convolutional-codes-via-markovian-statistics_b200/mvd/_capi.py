@@ -29,7 +29,7 @@ EXPORTS = (
     "mvd_set_code", "mvd_set_states", "mvd_enumerate_states", "mvd_get_states", "mvd_set_loglik",
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
-    "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense",
+    "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect",
 )
 
 
@@ -52,6 +52,12 @@ class Src(C.Structure):
 class Segment(C.Structure):
     _fields_ = [("N", C.c_uint32), ("threshold", C.c_uint32), ("stream", C.c_uint32), ("table", C.c_uint32),
                 ("enc_taps", C.c_uint32 * MAX_N), ("decide", C.c_uint32), ("random_input", C.c_uint32),
+                ("trial_begin", C.c_uint64), ("trial_end", C.c_uint64), ("bits_offset", C.c_uint64)]
+
+
+class ParitySegment(C.Structure):
+    _fields_ = [("N", C.c_uint32), ("m", C.c_uint32), ("n", C.c_uint32), ("threshold", C.c_uint32), ("stream", C.c_uint32),
+                ("decide", C.c_uint32), ("enc_taps", C.c_uint32 * MAX_N), ("tmpl", C.c_uint32 * MAX_N), ("gamma", C.c_double),
                 ("trial_begin", C.c_uint64), ("trial_end", C.c_uint64), ("bits_offset", C.c_uint64)]
 
 
@@ -89,6 +95,7 @@ def load():
     lib.mvd_enumerate_states.argtypes = [vp, u32, P(u32)]
     lib.mvd_enumerate_states_gpu.argtypes = [vp, u32, u32, u32, P(BfsStats)]
     lib.mvd_bfs_levels.argtypes = [vp, vp, u32, P(u32)]
+    lib.mvd_parity_detect.argtypes = [vp, P(Src), P(ParitySegment), u32, vp, vp]
     lib.mvd_chernoff_rho_dense.argtypes = [vp, u32, u32, vp, vp, vp, u32, C.c_double, u32, vp, vp]
     lib.mvd_chernoff_rho.argtypes = [vp, u32, u32, vp, vp, vp, vp, vp, vp, u32, C.c_double, u32, vp, vp]
     lib.mvd_get_states.argtypes = [vp, vp, vp]

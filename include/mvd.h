@@ -176,6 +176,29 @@ int mvd_chernoff_rho_dense(mvd_ctx* ctx, uint32_t K, uint32_t R, const double* l
                            const double* u_vals, uint32_t nu, double tol, uint32_t max_iter, double* rho,
                            uint32_t* iters);
 
+/* Parity-template baseline detector (paper section IV): the Monte-Carlo loop of comp_parity.py:165-176.
+ * One trial = N info bits -> encode_convolutional (comp_parity.py:65-86: n streams of N + m bits, zero
+ * tail) -> BSC -> parity_satisfaction_fraction over t in [max_delay, N + m) (:93-116) -> decide H1 iff the
+ * fraction >= gamma (parity_detector, :123-132).  Bit sources as for mvd_detect; in BITSTREAM mode a trial
+ * supplies (1 + n) streams of N + m bits in the layout of mvd_src (info bits beyond N are ignored).
+ * tallies: host, nsegs (successes per segment); satisfied (optional, host): satisfied positions per trial,
+ * segments concatenated.  Needs no code / state table in the context. */
+typedef struct mvd_parity_segment {
+    uint32_t N;                      /* info bits per trial                                        */
+    uint32_t m;                      /* encoder memory = length of the zero tail                   */
+    uint32_t n;                      /* output streams                                             */
+    uint32_t threshold;              /* PHILOX: P(flip) = threshold / 2^32                         */
+    uint32_t stream;                 /* PHILOX: stream tag                                         */
+    uint32_t decide;                 /* 0: success iff decided H1 (fraction >= gamma), 1: iff H2   */
+    uint32_t enc_taps[MVD_MAX_N];    /* bit t = tap of output j on the input t steps ago           */
+    uint32_t tmpl[MVD_MAX_N];        /* bit s of tmpl[j] = template term (j, s): y_j[t - s]        */
+    double gamma;                    /* decision threshold (comp_parity.py:161)                    */
+    uint64_t trial_begin, trial_end; /* global trial ids [begin, end)                              */
+    uint64_t bits_offset;            /* BITSTREAM: first word of this segment                      */
+} mvd_parity_segment;
+int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment* segs, uint32_t nsegs,
+                      uint64_t* tallies, uint32_t* satisfied);
+
 /* Timing of the last learn/detect/trace launch on the context's stream (CUDA events), and the
  * number of kernels this library has launched since creation. */
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms);
@@ -186,7 +209,7 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
  * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
- * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius.
+ * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius, 8192 = parity-template trials.
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread

@@ -291,6 +291,48 @@ def alpha_golden(vm, ae, dec, enc1, enc2, m, p, length, burn_in, laplace, seed, 
     return out
 
 
+def parity_golden(ref_path):
+    """parity_eqn_check.py + comp_parity.py of the reference, executed unmodified: parity-check bases and
+    per-trial parity_detector outputs on MVD-PHILOX-2 bits (the reference draws from Python's `random`)."""
+    import importlib
+    pec = importlib.import_module("parity_eqn_check")
+    cp = importlib.import_module("comp_parity")
+    out = dict(bases={}, trials={})
+    for name, toks, deg in (("c75", ("7", "5"), 5), ("m3", ("17", "13"), 6), ("m4", ("23", "35"), 7), ("r13", ("7", "5", "6"), 4)):
+        gens = [[pec.parse_poly_token(t)] for t in toks]
+        A = pec.build_parity_system(gens, deg)
+        basis = pec.nullspace_mod2(A)
+        eqs = [pec.parity_vector_to_equation([row[j * (deg + 1):(j + 1) * (deg + 1)].tolist() for j in range(len(gens))])
+               for row in basis]
+        out["bases"][name] = dict(tokens=list(toks), deg_h=deg, gens=gens, A=A.tolist(), basis=basis.tolist(), equations=eqs)
+    cases = {
+        "main": dict(h1=("7", "5"), h2=("6", "5"), m=2, deg=5, N=200, p=0.1, gamma=0.6, seed=12345, ntr=40),
+        "short": dict(h1=("7", "5"), h2=("6", "5"), m=2, deg=5, N=31, p=0.3, gamma=0.55, seed=7, ntr=40),
+        "m3": dict(h1=("17", "13"), h2=("13", "17"), m=3, deg=6, N=130, p=0.05, gamma=0.7, seed=99, ntr=30),
+        "r13": dict(h1=("7", "5", "6"), h2=("7", "6", "5"), m=2, deg=4, N=97, p=0.2, gamma=0.5, seed=3, ntr=30),
+    }
+    for name, c in cases.items():
+        g1 = [[pec.parse_poly_token(t)] for t in c["h1"]]
+        g2 = [[pec.parse_poly_token(t)] for t in c["h2"]]
+        n, m, deg = len(g1), c["m"], c["deg"]
+        basis = pec.nullspace_mod2(pec.build_parity_system(g1, deg))
+        h_vec = [basis[0][j * (deg + 1):(j + 1) * (deg + 1)].tolist() for j in range(n)]       # comp_parity.py:148-150
+        template = [(j, s) for j, poly in enumerate(h_vec) for s, bit in enumerate(poly) if bit]   # :156-160
+        rec = dict(c, gens1=g1, gens2=g2, template=[list(t) for t in template], hyp=[])
+        for h, gens in enumerate((g1, g2)):
+            stream = ref_port.PARITY_STREAM_BASE + h
+            rows = []
+            for trial in range(c["ntr"]):
+                u, e = ref_port.philox_bits(c["seed"], stream, trial, c["N"] + m, n, ref_port.threshold_of(c["p"]))
+                v = cp.encode_convolutional(u[:c["N"]], gens, m)
+                y = [[v[j][t] ^ e[t][j] for t in range(c["N"] + m)] for j in range(n)]
+                decision, p_hat = cp.parity_detector(y, template, c["gamma"])
+                rows.append([bool(decision), p_hat])
+            rec["hyp"].append(dict(stream=stream, rows=rows))
+        out["trials"][name] = rec
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -298,9 +340,16 @@ def main():
     ap.add_argument("--skip-m3-symbolic", action="store_true")
     ap.add_argument("--m4-only", action="store_true", help="only (re)write m4_kats.json")
     ap.add_argument("--alpha-only", action="store_true", help="only (re)write alpha_kats.json")
+    ap.add_argument("--parity-only", action="store_true", help="only (re)write parity_kats.json")
     args = ap.parse_args()
     vm, pdp = load_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
+
+    with open(os.path.join(args.out, "parity_kats.json"), "w") as f:
+        json.dump(parity_golden(args.ref), f, separators=(",", ":"))
+    print("[parity] done", flush=True)
+    if args.parity_only:
+        return
 
     # alpha_exponent.py (Eq. 7): the reference's learn_transition_tensor / compute_error_exponent / fit_error_exponent
     if not args.m4_only:

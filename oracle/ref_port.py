@@ -331,6 +331,49 @@ def compute_error_exponent(P1_ijr, P2_ijr, u_grid=401):
     return float(-np.log(best)), float(best_u), rhos
 
 
+# ----------------------------------------------------------------------------- comp_parity.py (section IV baseline)
+PARITY_STREAM_BASE = 0x40000000
+
+
+def encode_convolutional(u_bits, generators, m):
+    """comp_parity.py:65-86 -- time-domain feed-forward encoder, n streams of len(u) + m bits."""
+    n, T = len(generators), len(u_bits) + m
+    out = [[0] * T for _ in range(n)]
+    for t in range(T):
+        for j in range(n):
+            acc = 0
+            for shift, bit in enumerate(generators[j][0]):          # :80-82
+                if bit and 0 <= t - shift < len(u_bits):
+                    acc ^= u_bits[t - shift]
+            out[j][t] = acc
+    return out
+
+
+def parity_satisfaction(y, template):
+    """comp_parity.py:93-116 -- (satisfied, total) over t in [max_delay, T)."""
+    T = len(y[0])
+    max_delay = max(s for _, s in template)                         # :101
+    satisfied = total = 0
+    for t in range(max_delay, T):                                   # :107-113
+        x = 0
+        for j, s in template:
+            x ^= y[j][t - s]
+        total += 1
+        satisfied += x == 0
+    return satisfied, total
+
+
+def parity_trial(generators, m, template, gamma, N, p, seed, stream, trial):
+    """One iteration of comp_parity.py:165-176 on MVD-PHILOX-2 bits: (decide_H1, satisfied, total)."""
+    n = len(generators)
+    u, e = philox_bits(seed, stream, trial, N + m, n, threshold_of(p))
+    v = encode_convolutional(u[:N], generators, m)                  # :167
+    y = [[v[j][t] ^ e[t][j] for t in range(N + m)] for j in range(n)]   # :171
+    sat, total = parity_satisfaction(y, template)
+    frac = sat / total if total > 0 else 0.0                        # :116
+    return frac >= gamma, sat, total                                # :131-132
+
+
 def timed_steps(gen1, gen2, m, k, n, N, p, num_iter, seed, trial_offset=0):
     """bench helper: run ``num_iter`` iterations of the trial loop (Pd_plotter.py:210-223) of one
     point with a fixed small learned P1; returns (steps done, tallies)."""

@@ -34,7 +34,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     out = {}
-    for name in ("code_kats", "sim_kats", "experiments", "m4_kats", "alpha_kats"):
+    for name in ("code_kats", "sim_kats", "experiments", "m4_kats", "alpha_kats", "parity_kats"):
         with open(os.path.join(GOLDEN, name + ".json")) as f:
             out[name] = json.load(f)
     return out

@@ -66,12 +66,20 @@ def test_struct_layouts_match_header():
     fields_seg = ["N", "threshold", "stream", "table", "enc_taps", "decide", "random_input", "trial_begin", "trial_end",
                   "bits_offset"]
     fields_src = ["mode", "bits_on_device", "seed", "bits", "bits_words"]
+    fields_par = ["N", "m", "n", "threshold", "stream", "decide", "enc_taps", "tmpl", "gamma", "trial_begin", "trial_end",
+                  "bits_offset"]
+    fields_bfs = ["S", "frontier", "iterations", "launches", "candidates", "closed", "max_metric", "ms", "reserved"]
     prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "mvd.h"', "int main(void){",
             'printf("%zu %zu\\n", sizeof(mvd_segment), sizeof(mvd_src));']
     for f in fields_seg:
         prog.append(f'printf("%zu\\n", offsetof(mvd_segment, {f}));')
     for f in fields_src:
         prog.append(f'printf("%zu\\n", offsetof(mvd_src, {f}));')
+    prog.append('printf("%zu %zu\\n", sizeof(mvd_parity_segment), sizeof(mvd_bfs_stats));')
+    for f in fields_par:
+        prog.append(f'printf("%zu\\n", offsetof(mvd_parity_segment, {f}));')
+    for f in fields_bfs:
+        prog.append(f'printf("%zu\\n", offsetof(mvd_bfs_stats, {f}));')
     prog.append("return 0;}")
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "t.c")
@@ -84,7 +92,11 @@ def test_struct_layouts_match_header():
     got_seg = [getattr(_capi.Segment, f).offset for f in fields_seg]
     got_src = [getattr(_capi.Src, f).offset for f in fields_src]
     assert vals[2:2 + len(fields_seg)] == got_seg
-    assert vals[2 + len(fields_seg):] == got_src
+    base = 2 + len(fields_seg) + len(fields_src)
+    assert vals[2 + len(fields_seg):base] == got_src
+    assert vals[base] == C.sizeof(_capi.ParitySegment) and vals[base + 1] == C.sizeof(_capi.BfsStats)
+    assert vals[base + 2:base + 2 + len(fields_par)] == [getattr(_capi.ParitySegment, f).offset for f in fields_par]
+    assert vals[base + 2 + len(fields_par):] == [getattr(_capi.BfsStats, f).offset for f in fields_bfs]
 
 
 def test_create_fails_without_a_device():
