@@ -1165,6 +1165,12 @@ int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment
     return MVD_OK;
 }
 
+int mvd_host_log_table(const double* values, double* out, uint64_t count) {
+    if (!values || !out) return MVD_E_INVALID;
+    for (uint64_t i = 0; i < count; ++i) out[i] = std::log(values[i] > 1e-300 ? values[i] : 1e-300);
+    return MVD_OK;
+}
+
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms) {
     if (!ctx || !ms) return MVD_E_INVALID;
     *ms = ctx->last_ms;

@@ -29,7 +29,7 @@ EXPORTS = (
     "mvd_set_code", "mvd_set_states", "mvd_enumerate_states", "mvd_get_states", "mvd_set_loglik",
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
-    "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect",
+    "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table",
 )
 
 
@@ -95,6 +95,7 @@ def load():
     lib.mvd_enumerate_states.argtypes = [vp, u32, P(u32)]
     lib.mvd_enumerate_states_gpu.argtypes = [vp, u32, u32, u32, P(BfsStats)]
     lib.mvd_bfs_levels.argtypes = [vp, vp, u32, P(u32)]
+    lib.mvd_host_log_table.argtypes = [vp, vp, u64]
     lib.mvd_parity_detect.argtypes = [vp, P(Src), P(ParitySegment), u32, vp, vp]
     lib.mvd_chernoff_rho_dense.argtypes = [vp, u32, u32, vp, vp, vp, u32, C.c_double, u32, vp, vp]
     lib.mvd_chernoff_rho.argtypes = [vp, u32, u32, vp, vp, vp, vp, vp, vp, u32, C.c_double, u32, vp, vp]

@@ -159,6 +159,9 @@ def _detector(gen_frozen, k, n, m, device=0):
     key = (gen_frozen, k, n, m, device)
     det = _DETECTORS.get(key)
     if det is None:
-        det = Detector(gen_frozen, k, n, m, device=device, table=state_table(gen_frozen, m, k, n))
+        if m >= 4:          # S = 2.5e4 .. 2.3e5: enumerate on the GPU (reference index order, mvd_enumerate_states_gpu)
+            det = Detector(gen_frozen, k, n, m, device=device, enumerate_with="gpu", max_states=1 << 20)
+        else:
+            det = Detector(gen_frozen, k, n, m, device=device, table=state_table(gen_frozen, m, k, n))
         _DETECTORS[key] = det
     return det

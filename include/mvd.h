@@ -131,6 +131,11 @@ int mvd_bfs_levels(mvd_ctx* ctx, uint32_t* sizes, uint32_t cap, uint32_t* nlevel
  * T(p = 1/2) (Pd_plotter.py:193-194).  Host float64, computed by the caller with libm log. */
 int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const double* logTref);
 
+/* Host helper: out[i] = log(max(values[i], 1e-300)) with the C library's log -- the function
+ * math.log calls per step at Pd_plotter.py:114-115, so tables built with it carry the reference's own
+ * terms.  Runs on the calling thread (no device work); for S 2^n of 10^5..10^6 entries per table. */
+int mvd_host_log_table(const double* values, double* out, uint64_t count);
+
 /* Transition counting: the loop Pd_plotter.py:158-163 for every segment (segment = one or more
  * chains of N steps; only steps t >= burn are counted).  Single-chain segments on the on-device
  * bit source with engine AUTO/FSM are walked chunk-parallel (exact; see csrc/mvd_learn2.cuh).  edge_counts: host, nsegs x S x R,

@@ -74,6 +74,25 @@ if "m56" in which:
         print(json.dumps(dict(case=name, m=m, N=N, trials=trials, kernel_ms=round(ms, 3), steps_per_s=N * trials / (ms * 1e-3),
                               int_ops_per_s=(5 * 2 ** m + 11) * N * trials / (ms * 1e-3))), flush=True)
         det.close()
+if "m4full" in which:
+    # BASELINE config 4 at the reference's own defaults (N_SPECTRUM_BY_M[4], learn_len = 200 S, 7 p's) through the public
+    # API; the reference cannot run this (dense S x S counts: 182 GB at S = 150 743)
+    for name, g1, g2, it in (("m4 (31,33) S=25751", [[[1,1,0,0,1]],[[1,1,0,1,1]]], [[[1,1,0,1,1]],[[1,1,0,0,1]]], 100000),
+                             ("m4 (23,35) S=150743", [[[1,0,0,1,1]],[[1,1,1,0,1]]], [[[1,1,1,0,1]],[[1,0,0,1,1]]], 100000)):
+        t0 = time.perf_counter()
+        d = {}
+        df = pdp.run_experiment(1, 2, 4, g1, g2, it, P7, None, 200, 1.0, 12345, details=d)
+        cold = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        d = {}
+        df = pdp.run_experiment(1, 2, 4, g1, g2, it, P7, None, 200, 1.0, 12345, details=d)
+        wall = time.perf_counter() - t0
+        det = vm._detector(codes.freeze_generator(g1), 1, 2, 4)
+        print(json.dumps(dict(case=f"run_experiment defaults {name} num_iter={it}", S=d["S"], learn_len=d["learn_len"],
+                              bfs=getattr(det, "bfs_stats", None) and {k: det.bfs_stats[k] for k in ("S", "ms", "iterations")},
+                              cold_wall_s=round(cold, 3), wall_s=round(wall, 3), detect_kernel_ms=round(d["detect_kernel_ms"], 3),
+                              steps=d["steps"], learn_steps=7 * d["learn_len"], steps_per_s=(d["steps"] + 7 * d["learn_len"]) / wall,
+                              Pd=df["Pd"].tolist(), Pc=df["Pc"].tolist())), flush=True)
 if "paper" in which:
     # python Pd_plotter.py as shipped: num_iter = 10^4 (reference default), wall time through the public API
     for it in (10000, 1000000):

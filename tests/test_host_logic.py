@@ -143,6 +143,19 @@ def test_numeric_T_edges_match_reference_symbolic(golden, name, pv):
         np.testing.assert_allclose(dense[np.arange(g["S"])[:, None], tab.nxt], got, rtol=0, atol=0)
 
 
+def test_host_log_table_is_math_log():
+    """The C helper behind large log-likelihood tables returns math.log(max(v, 1e-300)) bit for bit
+    (Pd_plotter.py:114-115) -- and _log_table switches to it without changing a single value."""
+    import math
+    from mvd import engine
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.random(20000), rng.random(2000) * 1e-6, [0.0, 1e-300, 1e-310, 1.0, 0.25, 0.5]])
+    got = engine._log_table(v)
+    want = np.array([math.log(max(x, 1e-300)) for x in v.tolist()])
+    assert np.array_equal(got, want)
+    assert np.array_equal(engine._log_table(v[:100]), want[:100])
+
+
 def test_log_prob_sequence_host(golden):
     """Host log_prob_sequence (Pd_plotter.py:106-116) reproduces the reference's per-trial sums."""
     import Pd_plotter as pdp
