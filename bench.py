@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default="acs", choices=["acs", "fsm"])
     ap.add_argument("--trials", type=int, default=1_000_000, help="Monte-Carlo trials per (N,p) point per GPU")
-    ap.add_argument("--ref-iters", type=int, default=300, help="reference arm: iterations per core per step")
+    ap.add_argument("--ref-iters", type=int, default=1000, help="reference arm: iterations per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the alternate-engine / bitstream legs")
     args = ap.parse_args()

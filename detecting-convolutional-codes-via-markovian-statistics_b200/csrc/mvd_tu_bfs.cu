@@ -19,7 +19,10 @@ struct Buf {
 
 template <int M>
 cudaError_t expand(const BfsParams& P, uint32_t nc, cudaStream_t st) {
-    bfs_expand_kernel<M><<<(nc + BFS_BLOCK - 1) / BFS_BLOCK, BFS_BLOCK, 0, st>>>(P);
+    constexpr int KW = BfsShape<M>::KW;
+    bfs_child_kernel<M><<<(P.nparents + BFS_BLOCK - 1) / BFS_BLOCK, BFS_BLOCK, 0, st>>>(P);
+    const uint32_t per_block = BFS_BLOCK * BFS_CPL;
+    bfs_probe_kernel<KW><<<(nc + per_block - 1) / per_block, BFS_BLOCK, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -63,13 +66,14 @@ int mvd_bfs_run(const MvdBfsConfig& cfg, cudaStream_t st, MvdBfsResult& res) {
                  cfg.max_states, need / 1e9, free_b / 1e9);
         return MVD_E_NOMEM;
     }
-    Buf keys, nxt, slots, ckeys, cslot, bsum, misc;
+    Buf keys, nxt, slots, ckeys, cslot, bsum, misc, wbits;
     BCK(keys.alloc((size_t)cfg.max_states * KW * 4));
     if (cfg.keep_next) BCK(nxt.alloc((size_t)cfg.max_states * R * 4));
     BCK(slots.alloc(cap * 4));
     BCK(ckeys.alloc(maxc * KW * 4));
     BCK(cslot.alloc(maxc * 4));
     BCK(bsum.alloc((nb_max + 1) * 4));
+    BCK(wbits.alloc(nb_max * (BFS_SCAN_BLOCK / 32) * 4));
     BCK(misc.alloc(16));
     cudaEvent_t e0, e1;
     BCK(cudaEventCreate(&e0));
@@ -88,6 +92,7 @@ int mvd_bfs_run(const MvdBfsConfig& cfg, cudaStream_t st, MvdBfsResult& res) {
     P.ckeys = ckeys.as<uint32_t>();
     P.cslot = cslot.as<uint32_t>();
     P.blocksum = bsum.as<uint32_t>();
+    P.winbits = wbits.as<uint32_t>();
     P.total = misc.as<uint32_t>();
     P.err = reinterpret_cast<int*>(misc.as<uint32_t>() + 2);
     P.n = n;
@@ -113,8 +118,8 @@ int mvd_bfs_run(const MvdBfsConfig& cfg, cudaStream_t st, MvdBfsResult& res) {
             h ^= h >> 29;
         }
         h *= 0xBF58476D1CE4E5B9ull;
-        const uint32_t slot = (uint32_t)(h >> 32) & P.mask, zero = 0;
-        BCK(cudaMemcpyAsync(P.slots + slot, &zero, 4, cudaMemcpyHostToDevice, st));
+        const uint32_t slot = (uint32_t)(h >> 32) & P.mask;
+        BCK(cudaMemsetAsync(P.slots + slot, 0, 4, st));                        // state 0 is final from the start
     }
 
     uint32_t S = 1, lo = 0, level_end = 1;
@@ -147,7 +152,7 @@ int mvd_bfs_run(const MvdBfsConfig& cfg, cudaStream_t st, MvdBfsResult& res) {
         BCK(cudaGetLastError());
         BCK(cudaMemcpyAsync(host_misc, misc.p, 12, cudaMemcpyDeviceToHost, st));
         BCK(cudaStreamSynchronize(st));
-        res.launches += 3;
+        res.launches += 4;
         res.iterations += 1;
         res.candidates += nc;
         if (host_misc[2]) {
