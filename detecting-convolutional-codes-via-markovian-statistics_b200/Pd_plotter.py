@@ -117,8 +117,11 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     the sequences are scored against (the reference hard-codes 1/2, :193-194; other values use the
     sympy-free numeric T(p) of :func:`mvd.codes.t_edge_table`); ``details`` a dict that receives tallies, tables and timings.
     """
+    import time
+
     import pandas as pd
 
+    t_start = time.perf_counter()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", 0))
     det = vm._detector(codes.freeze_generator(gen1), k, n, m, device)
@@ -127,10 +130,14 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
 
     # P1 for every distinct p (the reference's lru_cache, :123, learns once per p)
     distinct = list(dict.fromkeys(float(p) for p in p_vec))
+    t_learn0 = time.perf_counter()
     counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=learn_engine)
+    learn_kernel_ms = det.last_kernel_ms()
+    t_tables0 = time.perf_counter()
     # T_ref = T(1/2) = mult / 2^n (reference :193-194)
     det.set_models(tables, None if float(ref_p) == 0.5 else codes.t_edge_table(det.table, float(ref_p)))
     tindex = {p: i for i, p in enumerate(distinct)}
+    t_detect0 = time.perf_counter()
 
     rank, ws = dist.world()
     begin, end = dist.shard_range(int(num_iter), rank, ws, offset=int(trial_offset))
@@ -154,7 +161,9 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
         rows.append({"N": N, "p": p, "Pd": s1 / num_iter, "Pc": (s1 + s2) / (2 * num_iter)})   # reference :225-226
     if details is not None:
         details.update(tallies=tallies, edge_counts=counts, p1_tables=tables, distinct_p=distinct,
-                       detect_kernel_ms=kernel_ms, steps=2 * sum(N for N, _ in points) * int(num_iter),
+                       detect_kernel_ms=kernel_ms, learn_kernel_ms=learn_kernel_ms,
+                       wall_s=dict(setup=t_learn0 - t_start, learn=t_tables0 - t_learn0, tables=t_detect0 - t_tables0,
+                                   detect=time.perf_counter() - t_detect0), steps=2 * sum(N for N, _ in points) * int(num_iter),
                        learn_len=_learn_len(det.S, learn_len), S=det.S)
     return pd.DataFrame(rows, columns=["N", "p", "Pd", "Pc"])
 

@@ -52,6 +52,7 @@ struct mvd_ctx {
     float last_ms = 0.f;
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
     bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false;
+    int split_mode = 0;             // 0 = automatic, 1 = always split long trials along the time axis, 2 = never
     bool have_gfsm1 = false;
     bool tref_packed = false;       // log Tref = c * unit with c in {0, 2^j}: one-load NEXT walk possible
     double tref_unit = 0.0;
@@ -76,7 +77,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges;
 };
 
 namespace {
@@ -503,6 +504,22 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         if (out.counts) memset(out.counts, 0, 8 * (size_t)nsegs * SR);
         return MVD_OK;
     }
+    // few long trials (Pd-vs-N sweeps): split them along the time axis when that fills the GPU better
+    bool split = mode == MODE_DETECT && engine == MVD_ENGINE_FSM && !ctx->force_generic && ctx->split_mode != 2 &&
+                 src->mode == MVD_SRC_PHILOX && ctx->closed && trials > 0 && trials <= 0x7FFFFFFFull;
+    if (split) {
+        unsigned long long steps = 0, ew = 0, work = 0;
+        for (uint32_t i = 0; i < nsegs; ++i) {
+            const unsigned long long ntr = ds[i].trial_end - ds[i].trial_begin;
+            if (ds[i].N == 0) split = false;
+            steps += ntr * ds[i].N;
+            ew += ntr * (((unsigned long long)ds[i].N + 3ull) & ~3ull);
+            work += ntr * ((ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
+        }
+        split = split && ew * 4ull <= (6ull << 30) && work <= 0x7FFFFFFFull * (unsigned long long)SPLIT_BLOCK;
+        if (ctx->split_mode == 0)                              // automatic: under 1/4 of the threads the GPU holds, trials >= 4 chunks
+            split = split && trials * 4ull < 2048ull * sms && steps >= trials * 4ull * SPLIT_CH;
+    }
     const dim3 grid((unsigned)blocks);
     const bool n2 = (n == 2);
     cudaError_t le = cudaErrorInvalidValue;
@@ -532,6 +549,51 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         le = mvd_launch_learn(lin, lsmem, nsegs, ctx->stream, P, LP);
         ctx->launches += 2;
         ctx->last_fast = 1024;
+    } else if (split) {
+        // few long trials: one thread per (trial, chunk) walks the states, one per trial adds the log-likelihoods
+        // in step order (mvd_split.cuh)
+        std::vector<unsigned long long> meta(2 * (size_t)nsegs + 1);
+        unsigned long long w = 0, ew = 0;
+        const int eb = SR <= 256u ? 1 : (SR <= 65536u ? 2 : 4);
+        const unsigned long long spg = 16 / eb;
+        for (uint32_t i = 0; i < nsegs; ++i) {
+            const unsigned long long ntr = ds[i].trial_end - ds[i].trial_begin;
+            meta[i] = w;
+            meta[nsegs + 1 + i] = ew;
+            w += ntr * ((ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
+            ew += ntr * (((unsigned long long)ds[i].N + spg - 1) / spg) * 4ull;      // 16-byte groups, in 32-bit words
+        }
+        meta[nsegs] = w;
+        SplitParams SP{};
+        SP.edge_bytes = eb;
+        for (uint32_t i = 0; i < nsegs; ++i) SP.max_trials = std::max<unsigned long long>(SP.max_trials, ds[i].trial_end - ds[i].trial_begin);
+        if (nsegs > 65535) return fail(ctx, MVD_E_INVALID, "too many segments for one call");
+        SP.warm = ctx->learn_warm;
+        SP.nchains = (uint32_t)trials;
+        SP.nwork = w;
+        CK(ctx->d_smeta.reserve(meta.size() * 8 + 16));
+        CK(cudaMemcpyAsync(ctx->d_smeta.p, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SP.work_begin = ctx->d_smeta.as<unsigned long long>();
+        SP.edge_begin = SP.work_begin + nsegs + 1;
+        CK(ctx->d_lspec.reserve((size_t)w * 4));
+        CK(ctx->d_lend.reserve((size_t)w * 4));
+        CK(ctx->d_ldirty.reserve(4));
+        CK(cudaMemsetAsync(ctx->d_ldirty.p, 0, 4, ctx->stream));
+        CK(ctx->d_sedges.reserve((size_t)ew * 4));
+        SP.spec_start = ctx->d_lspec.as<uint32_t>();
+        SP.end = ctx->d_lend.as<uint32_t>();
+        SP.ndirty = ctx->d_ldirty.as<uint32_t>();
+        SP.edges = ctx->d_sedges.as<uint32_t>();
+        SP.ll_rep_shift = (size_t)SR * 128 <= 64 * 1024 ? 3 : 0;
+        const size_t nb = (size_t)SR * 4, lb = ((size_t)SR * 16) << SP.ll_rep_shift;
+        SP.nxt_in_smem = nb <= 64 * 1024;
+        SP.ll_in_smem = lb <= 64 * 1024;
+        SP.chain_block = SPLIT_BLOCK;                            // per-chain kernels: spread few chains over all SMs
+        while (SP.chain_block > 32 && (trials + SP.chain_block - 1) / SP.chain_block < 2 * sms) SP.chain_block >>= 1;
+        CK(cudaStreamSynchronize(ctx->stream));                 // meta is a stack-lifetime vector
+        le = mvd_launch_split(SP.nxt_in_smem, nb, SP.ll_in_smem, lb, ctx->stream, P, SP);
+        ctx->launches += 2;
+        ctx->last_fast = 16384;
     } else if (fast) {
         // segments travel as kernel parameters, DET2_MAXSEG per launch; grid.y = segment
         le = cudaSuccess;
@@ -555,7 +617,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     } else {
         le = mvd_launch_generic(engine, mode, n2, m, in_smem, grid, smem, ctx->stream, P);
     }
-    if (!fast && !(plearn && maxL > 0)) ctx->last_fast = 0;
+    if (!fast && !split && !(plearn && maxL > 0)) ctx->last_fast = 0;
     if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -565,6 +627,10 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     std::vector<uint32_t> hdirty;
     CK(cudaMemcpyAsync(&herr, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (mode == MODE_DETECT) {
+        if (split) {
+            hdirty.assign(1, 0u);
+            CK(cudaMemcpyAsync(hdirty.data(), ctx->d_ldirty.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         if (out.tallies) CK(cudaMemcpyAsync(out.tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
         if (out.logp) CK(cudaMemcpyAsync(out.logp, ctx->d_logp.p, 16 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
     } else if (mode == MODE_LEARN) {
@@ -637,7 +703,8 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1};
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
+                      &ctx->d_smeta, &ctx->d_sedges};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1196,6 +1263,11 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
     }
     if (option == MVD_OPT_NO_FSM1) {
         ctx->no_fsm1 = value != 0;
+        return MVD_OK;
+    }
+    if (option == MVD_OPT_SPLIT) {
+        if (value < 0 || value > 2) return fail(ctx, MVD_E_INVALID, "MVD_OPT_SPLIT takes 0, 1 or 2");
+        ctx->split_mode = (int)value;
         return MVD_OK;
     }
     if (option == MVD_OPT_LEARN_WARM) {

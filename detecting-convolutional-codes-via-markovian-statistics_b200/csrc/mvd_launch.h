@@ -69,3 +69,7 @@ cudaError_t mvd_launch_chernoff_dense(const ChernoffParams& P, cudaStream_t st);
 
 // parity-template baseline (mvd_tu_parity.cu, mvd_parity.cuh)
 cudaError_t mvd_launch_parity(dim3 grid, cudaStream_t st, const Params& P, const ParityBatch& B, uint32_t* satisfied);
+
+// detection trials split along the time axis (mvd_split.cuh, in mvd_tu_learn.cu)
+cudaError_t mvd_launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
+                             const SplitParams& SP);

@@ -51,10 +51,10 @@ __device__ __forceinline__ uint32_t lazy_bernoulli_t(uint32_t c0base, uint32_t c
 
 
 // received words of the 32-step block b of the chain of segment sg -> Rw[j] (bit t = received bit of output j)
-__device__ __forceinline__ void learn_block_words(const Params& P, const DevSeg& sg, uint32_t b, uint32_t valid,
-                                                  uint32_t* Rw) {
+__device__ __forceinline__ void chain_block_words(const Params& P, const DevSeg& sg, unsigned long long trial, uint32_t b,
+                                                  uint32_t valid, uint32_t* Rw) {
     const int n = P.n, m = P.m;
-    const uint32_t c1 = (uint32_t)sg.trial_begin, c2 = (uint32_t)(sg.trial_begin >> 32), c3 = sg.stream;
+    const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
     const uint32_t vmask = valid >= 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
     uint32_t U = 0, prevU = 0;
     if (sg.random_input) {
@@ -78,6 +78,11 @@ __device__ __forceinline__ void learn_block_words(const Params& P, const DevSeg&
             Rw[j] = o ^ E;
         }
     }
+}
+
+__device__ __forceinline__ void learn_block_words(const Params& P, const DevSeg& sg, uint32_t b, uint32_t valid,
+                                                  uint32_t* Rw) {
+    chain_block_words(P, sg, sg.trial_begin, b, valid, Rw);
 }
 
 __device__ __forceinline__ uint32_t word_of_step(const uint32_t* Rw, int n, uint32_t t) {

@@ -1,0 +1,254 @@
+// mvd_split.cuh -- detection trials split along the time axis: few, long trials (the Pd-vs-N sweep of
+// BASELINE config 3: N up to 10^5 at the reference's 10^4 iterations per point, divided over 8 GPUs).
+//
+// One thread per trial leaves the GPU empty when there are only a few thousand trials, and the chain of one
+// trial is sequential.  But only two things in Pd_plotter.py:210-223 are order-dependent: the Markov-state
+// trajectory (integers) and the two float64 sums of log_prob_sequence (:106-116).  So:
+//   1. split_walk_kernel  -- one thread per (trial, chunk of SPLIT_CH steps): the position-addressed bit
+//      source lets any chunk be generated on its own; the thread starts `warm` steps early from state 0 (the
+//      relative-metric recursion forgets its start), records the state it has at the chunk start and
+//      writes the edge index e_t = state * R + r_t of every step of its chunk;
+//   2. split_fix_kernel   -- one thread per trial: a chunk whose speculated start differs from the previous
+//      chunk's end is re-walked from the true state until both trajectories meet (exactly the
+//      speculate / check / fix scheme of the learning chains, mvd_learn2.cuh); after it the edge list is the
+//      sequential trajectory, bit for bit;
+//   3. split_score_kernel -- one thread per trial adds log P1[e_t] and log Tref[e_t] in step order, so both
+//      sums -- and the decision -- are the ones of the one-thread-per-trial kernels.
+#pragma once
+#include "mvd_learn2.cuh"
+
+__device__ __forceinline__ uint32_t split_find(const unsigned long long* begin, uint32_t n, unsigned long long x) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (begin[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// EB = bytes per stored edge index (1: S R <= 256, 2: <= 65 536, 4 otherwise); a 16-byte group holds 16 / EB steps
+template <int EB>
+__device__ __forceinline__ void split_put(uint4& grp, uint32_t pos, uint32_t e) {
+    const uint32_t sh = (pos * (uint32_t)EB * 8u) & 31u, w = (pos * (uint32_t)EB) >> 2;
+    const uint32_t v = e << sh;
+    if (w == 0) grp.x |= v; else if (w == 1) grp.y |= v; else if (w == 2) grp.z |= v; else grp.w |= v;
+}
+
+template <int EB>
+__device__ __forceinline__ uint32_t split_get(const uint4& grp, uint32_t pos) {
+    const uint32_t sh = (pos * (uint32_t)EB * 8u) & 31u, w = (pos * (uint32_t)EB) >> 2;
+    const uint32_t word = w == 0 ? grp.x : (w == 1 ? grp.y : (w == 2 ? grp.z : grp.w));
+    return EB == 4 ? word : ((word >> sh) & ((1u << (EB * 8)) - 1u));
+}
+
+template <bool SMEM, int EB>
+__global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t* nxt = P.nxt;
+    if (SMEM) {
+        uint32_t* s_nx = reinterpret_cast<uint32_t*>(smem_raw);
+        for (uint32_t i = threadIdx.x; i < P.SR; i += SPLIT_BLOCK) s_nx[i] = P.nxt[i];
+        __syncthreads();
+        nxt = s_nx;
+    }
+    const unsigned long long g = (unsigned long long)blockIdx.x * SPLIT_BLOCK + threadIdx.x;
+    if (g >= SP.nwork) return;
+    const uint32_t seg = split_find(SP.work_begin, P.nsegs, g);
+    const DevSeg sg = P.segs[seg];
+    const uint32_t N = sg.N;
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    const unsigned long long local = g - SP.work_begin[seg];
+    const uint32_t c = (uint32_t)(local / ntr);                   // a warp = one chunk of 32 consecutive trials
+    const unsigned long long tl = local % ntr;
+    const unsigned long long trial = sg.trial_begin + tl;
+    // edge of (trial tl, step t): 16-byte group (t / SPG) * ntr + tl, position t % SPG -- groups are trial-minor,
+    // so that the stores here and the loads of the scoring pass are coalesced across trials
+    constexpr uint32_t SPG = 16 / EB;
+    uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+    const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
+    uint32_t sx = 0;                                              // state 0 (exact when w_begin == 0)
+    uint32_t Rw[MVD_MAX_N];
+    for (uint32_t b = w_begin >> 5; b * 32u < t_end; ++b) {
+        const uint32_t t0 = b * 32u;
+        const uint32_t valid = min(32u, N - t0);
+        chain_block_words(P, sg, trial, b, valid, Rw);
+        if (t0 == t_begin) SP.spec_start[g] = sx;
+        const uint32_t nst = min(valid, t_end - t0);
+        if (t0 >= t_begin) {
+            // whole groups of the block are stored as one 16-byte word; a ragged tail group is stored as far as it goes
+            for (uint32_t q = 0; q * SPG < nst; ++q) {
+                uint4 grp = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t cnt = min(SPG, nst - q * SPG);
+#pragma unroll
+                for (uint32_t u = 0; u < SPG; ++u) {
+                    if (u < cnt) {
+                        const uint32_t e = sx + word_of_step(Rw, P.n, q * SPG + u);
+                        split_put<EB>(grp, u, e);
+                        sx = SMEM ? nxt[e] : __ldg(nxt + e);
+                    }
+                }
+                E4[(unsigned long long)(t0 / SPG + q) * ntr] = grp;
+            }
+        } else {
+            for (uint32_t t = 0; t < nst; ++t) {
+                const uint32_t e = sx + word_of_step(Rw, P.n, t);
+                sx = SMEM ? nxt[e] : __ldg(nxt + e);
+            }
+        }
+    }
+    SP.end[g] = sx;
+}
+
+// one thread per chain: repair the chunks whose speculated start state was wrong, in order
+template <int EB>
+__global__ void __launch_bounds__(SPLIT_BLOCK) split_fix_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
+    constexpr uint32_t SPG = 16 / EB;
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= SP.nchains) return;
+    // chain -> segment: out_offset = chains before the segment
+    uint32_t lo = 0, hi = P.nsegs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (P.segs[mid].out_offset <= q) lo = mid; else hi = mid;
+    }
+    const uint32_t seg = lo;
+    const DevSeg sg = P.segs[seg];
+    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    const unsigned long long tl = q - sg.out_offset;
+    const unsigned long long trial = sg.trial_begin + tl;
+    const unsigned long long w0 = SP.work_begin[seg] + tl;        // work item of chunk c: w0 + c * ntr
+    uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    uint32_t fixed = 0;
+    for (uint32_t c = 1; c < nch; ++c) {
+        uint32_t st = SP.end[w0 + (unsigned long long)(c - 1u) * ntr], ss = SP.spec_start[w0 + (unsigned long long)c * ntr];
+        if (st == ss) continue;
+        ++fixed;
+        const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+        uint32_t Rw[MVD_MAX_N];
+        bool merged = false;
+        for (uint32_t b = t_begin >> 5; b * 32u < t_end && !merged; ++b) {
+            const uint32_t t0 = b * 32u;
+            const uint32_t valid = min(32u, N - t0);
+            chain_block_words(P, sg, trial, b, valid, Rw);
+            const uint32_t nst = min(valid, t_end - t0);
+            for (uint32_t t = 0; t < nst; ++t) {
+                if (st == ss) {
+                    merged = true;
+                    break;
+                }
+                const uint32_t r = word_of_step(Rw, P.n, t);
+                {
+                    unsigned char* gb = reinterpret_cast<unsigned char*>(E4 + (unsigned long long)((t0 + t) / SPG) * ntr) + ((t0 + t) % SPG) * EB;
+                    const uint32_t e = st + r;
+                    if (EB == 1) *gb = (unsigned char)e;
+                    else if (EB == 2) *reinterpret_cast<unsigned short*>(gb) = (unsigned short)e;
+                    else *reinterpret_cast<uint32_t*>(gb) = e;
+                }
+                ss = __ldg(P.nxt + ss + r);
+                st = __ldg(P.nxt + st + r);
+            }
+        }
+        if (!merged && st != ss) SP.end[w0 + (unsigned long long)c * ntr] = st;   // the next chunk started from the wrong state too
+    }
+    if (fixed) atomicAdd(SP.ndirty, fixed);
+}
+
+// one thread per chain: the two sums of log_prob_sequence in step order, decision, tallies
+// grid (chunks of blockDim.x chains, segments); blockDim.x <= SPLIT_BLOCK is chosen by the host so that a few
+// thousand chains still spread over all SMs.
+// SMEM: the {log P1, log Tref} rows of the segment's table are staged in shared memory, replicated
+// 2^SP.ll_rep_shift times at 16-byte pitch (one copy per lane of a quarter warp, as in mvd_detect2.cuh) so that
+// the random row reads of a warp are bank-conflict free; read with ld.shared (a generic pointer that may be
+// shared or global costs a slower LD per step).
+template <bool SMEM>
+__device__ __forceinline__ double2 split_ll(const double2* g, uint32_t sbase, uint32_t sh, uint32_t e) {
+    if (SMEM) {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sbase + (e << sh)));
+        return v;
+    }
+    return __ldg(g + e);
+}
+
+template <bool SMEM, int EB>
+__global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t SPG = 16 / EB;
+    const uint32_t seg = blockIdx.y;
+    const DevSeg sg = P.segs[seg];
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    if ((unsigned long long)blockIdx.x * blockDim.x >= ntr) return;               // uniform: shorter segment
+    const double2* ll = P.ll + (size_t)sg.table * P.SR;
+    const uint32_t rs = (uint32_t)SP.ll_rep_shift, sh = rs + 4u;
+    uint32_t sbase = 0;
+    if (SMEM) {
+        double2* s_ll = reinterpret_cast<double2*>(smem_raw);
+        for (uint32_t i = threadIdx.x; i < (P.SR << rs); i += blockDim.x) s_ll[i] = ll[i >> rs];
+        __syncthreads();
+        sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + ((threadIdx.x & ((1u << rs) - 1u)) << 4);
+    }
+    const unsigned long long tl = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tl >= ntr) return;
+    const uint32_t q = (uint32_t)(sg.out_offset + tl);
+    const uint32_t N = sg.N;
+    const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    double a1 = 0.0, a0 = 0.0;
+    // The adds are one dependent chain per sum (Pd_plotter.py:114-115 in step order): all that can overlap are
+    // the loads.  With a few thousand chains on the whole GPU the edge stream needs many requests in flight per
+    // thread: a ring of K 16-byte groups, each slot refilled as soon as it is consumed.
+    constexpr uint32_t K = 12;
+    const uint32_t ngroups = N / SPG;
+    uint4 ring[K];
+#pragma unroll
+    for (uint32_t i = 0; i < K; ++i)
+        if (i < ngroups) ring[i] = __ldcs(E4 + (unsigned long long)i * ntr);
+    uint32_t g0 = 0;
+    for (; g0 + K <= ngroups; g0 += K) {
+#pragma unroll
+        for (uint32_t i = 0; i < K; ++i) {
+            const uint4 grp = ring[i];
+            if (g0 + K + i < ngroups) ring[i] = __ldcs(E4 + (unsigned long long)(g0 + K + i) * ntr);
+            double2 v[SPG];
+#pragma unroll
+            for (uint32_t u = 0; u < SPG; ++u) v[u] = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(grp, u));
+#pragma unroll
+            for (uint32_t u = 0; u < SPG; ++u) {
+                a1 += v[u].x;
+                a0 += v[u].y;
+            }
+        }
+    }
+    // the last < K whole groups are already in the ring; then the ragged tail group
+#pragma unroll
+    for (uint32_t i = 0; i < K; ++i) {
+        if (g0 + i < ngroups) {
+            const uint4 grp = ring[i];
+#pragma unroll
+            for (uint32_t u = 0; u < SPG; ++u) {
+                const double2 v = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(grp, u));
+                a1 += v.x;
+                a0 += v.y;
+            }
+        }
+    }
+    if (ngroups * SPG < N) {
+        const uint4 grp = __ldcs(E4 + (unsigned long long)ngroups * ntr);
+        for (uint32_t u = 0; u < N - ngroups * SPG; ++u) {
+            uint32_t e = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < SPG; ++w)
+                if (w == u) e = split_get<EB>(grp, w);
+            const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
+            a1 += v.x;
+            a0 += v.y;
+        }
+    }
+    const bool win = sg.decide == 0 ? (a1 > a0) : (a1 <= a0);                    // Pd_plotter.py:215 / :222
+    if (win) {
+        atomicAdd(P.tallies + seg, 1ull);
+        if (P.tallies2) atomicAdd(P.tallies2 + seg, 1ull);
+    }
+    if (P.logp) reinterpret_cast<double2*>(P.logp)[q] = make_double2(a1, a0);
+}

@@ -19,3 +19,45 @@ cudaError_t mvd_launch_learn(bool smem_tables, size_t lsmem, uint32_t nsegs, cud
     learn_fix_kernel<<<nsegs, 1024, 0, st>>>(P, LP);
     return cudaGetLastError();
 }
+
+// ---- detection trials split along the time axis (mvd_split.cuh)
+#include "mvd_split.cuh"
+
+namespace {
+template <int EB>
+cudaError_t launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
+                         const SplitParams& SP) {
+    const unsigned wblocks = (unsigned)((SP.nwork + SPLIT_BLOCK - 1) / SPLIT_BLOCK);
+    const unsigned cb = SP.chain_block;
+    const unsigned cblocks = (SP.nchains + cb - 1) / cb;
+    cudaError_t e;
+    if (nxt_smem) {
+        auto kern = split_walk_kernel<true, EB>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nxt_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<wblocks, SPLIT_BLOCK, nxt_bytes, st>>>(P, SP);
+    } else {
+        split_walk_kernel<false, EB><<<wblocks, SPLIT_BLOCK, 0, st>>>(P, SP);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    split_fix_kernel<EB><<<cblocks, cb, 0, st>>>(P, SP);
+    const dim3 sgrid((unsigned)((SP.max_trials + cb - 1) / cb), P.nsegs);
+    if (ll_smem) {
+        auto kern = split_score_kernel<true, EB>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<sgrid, cb, ll_bytes, st>>>(P, SP);
+    } else {
+        split_score_kernel<false, EB><<<sgrid, cb, 0, st>>>(P, SP);
+    }
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t mvd_launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
+                             const SplitParams& SP) {
+    if (SP.edge_bytes == 1) return launch_split<1>(nxt_smem, nxt_bytes, ll_smem, ll_bytes, st, P, SP);
+    if (SP.edge_bytes == 2) return launch_split<2>(nxt_smem, nxt_bytes, ll_smem, ll_bytes, st, P, SP);
+    return launch_split<4>(nxt_smem, nxt_bytes, ll_smem, ll_bytes, st, P, SP);
+}

@@ -84,6 +84,27 @@ struct LearnParams {
     int nxt_in_smem;
 };
 
+// ---- detection trials split along the time axis (mvd_split.cuh)
+#define SPLIT_CH 512u
+#define SPLIT_BLOCK 128
+
+struct SplitParams {
+    uint32_t warm;                          // warm-up steps (multiple of 32)
+    uint32_t nchains;
+    unsigned long long nwork;               // (chain, chunk) pairs
+    const unsigned long long* work_begin;   // [nsegs + 1] first work item of a segment (items: chunk-major, trial-minor)
+    const unsigned long long* edge_begin;   // [nsegs] first 32-bit word of a segment's 16-byte edge groups
+    uint32_t* spec_start;                   // [nwork] state * R at the chunk start (speculated)
+    uint32_t* end;                          // [nwork] state * R at the chunk end
+    uint32_t* edges;
+    uint32_t* ndirty;                       // [1] chunks repaired (performance counter)
+    int nxt_in_smem, ll_in_smem;
+    int ll_rep_shift;                       // log2 copies of a log-likelihood row in shared memory (0 or 3)
+    uint32_t chain_block;                   // threads per block of the per-chain kernels (fix, score)
+    unsigned long long max_trials;          // most trials of any segment (x extent of the scoring grid)
+    int edge_bytes;                         // bytes per stored edge index: 1 (S R <= 256), 2 (<= 65 536) or 4
+};
+
 // ---- parity-template baseline trials (mvd_parity.cuh)
 #define PARITY_BLOCK 256
 #define PARITY_MAXSEG 64

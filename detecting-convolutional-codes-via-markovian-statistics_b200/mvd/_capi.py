@@ -21,6 +21,7 @@ OPT_FORCE_GENERIC = 1
 OPT_NO_PAIR = 2
 OPT_LEARN_WARM = 3
 OPT_NO_FSM1 = 4
+OPT_SPLIT = 5
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 

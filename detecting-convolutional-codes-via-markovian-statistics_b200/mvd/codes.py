@@ -356,10 +356,20 @@ def p1_from_edge_counts(tab: StateTable, edge_counts: np.ndarray, laplace: float
     if S <= DENSE_LIMIT:
         P = p1_dense(tab, ec, laplace)
         return np.ascontiguousarray(P[np.arange(S)[:, None], tab.nxt])
-    same = tab.nxt[:, :, None] == tab.nxt[:, None, :]
-    cij = (same * ec[:, None, :]).sum(axis=2)
+    cij = np.zeros((S, R))
+    for r2, mask in enumerate(_same_successor_masks(tab)):       # c_ij = sum of the counts of every r' that reaches j
+        cij += mask * ec[:, r2:r2 + 1]
     denom = ec.sum(axis=1) + laplace * S
     return (cij + laplace) / denom[:, None]
+
+
+def _same_successor_masks(tab: StateTable):
+    """``masks[r2][i, r] = 1.0`` iff ``nxt[i, r2] == nxt[i, r]`` -- cached on the table (built once per code)."""
+    masks = getattr(tab, "_same_masks", None)
+    if masks is None:
+        masks = [(tab.nxt[:, r2:r2 + 1] == tab.nxt).astype(np.float64) for r2 in range(tab.R)]
+        tab._same_masks = masks
+    return masks
 
 
 def dense_from_edges(tab: StateTable, edge_values: np.ndarray, fill: float = 0.0) -> np.ndarray:

@@ -284,6 +284,10 @@ class Detector:
         """NEXT-table walk with separate log-likelihood and NEXT tables instead of the one-load entry."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_FSM1, 1 if on else 0))
 
+    def split_trials(self, mode: int = 0):
+        """Long trials split along the time axis (NEXT-table engine): 0 = automatic, 1 = whenever possible, 2 = never."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT, int(mode)))
+
     def learn_warm(self, steps: int = 128):
         """Warm-up steps of the chunk-parallel learning chains (0 = speculate cold: every chunk is
         repaired by the fix-up pass; results are identical)."""

@@ -214,13 +214,17 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * mvd_last_kernel_kind: 0 = the last launch was a generic kernel, otherwise
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
  * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
- * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius, 8192 = parity-template trials.
+ * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius, 8192 = parity-template trials,
+ * 16384 = detection trials split along the time axis (mvd_learn_stats then gives the chunks repaired).
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread
                                                                even for few trials, 0 = automatic              */
        MVD_OPT_LEARN_WARM = 3,     /* warm-up steps of the chunk-parallel learning chains (default 128) */
-       MVD_OPT_NO_FSM1 = 4 };      /* 1 = NEXT-table walk with separate log / NEXT tables (two loads per step) */
+       MVD_OPT_NO_FSM1 = 4,        /* 1 = NEXT-table walk with separate log / NEXT tables (two loads per step) */
+       MVD_OPT_SPLIT = 5 };        /* few long trials (NEXT-table engine, on-device bits) are split along the time axis
+                                      (csrc/mvd_split.cuh; identical results): 0 = when it fills the GPU better,
+                                      1 = whenever possible, 2 = never.  The warm-up is MVD_OPT_LEARN_WARM's. */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);

@@ -91,6 +91,7 @@ if "m4full" in which:
         print(json.dumps(dict(case=f"run_experiment defaults {name} num_iter={it}", S=d["S"], learn_len=d["learn_len"],
                               bfs=getattr(det, "bfs_stats", None) and {k: det.bfs_stats[k] for k in ("S", "ms", "iterations")},
                               cold_wall_s=round(cold, 3), wall_s=round(wall, 3), detect_kernel_ms=round(d["detect_kernel_ms"], 3),
+                              learn_kernel_ms=round(d["learn_kernel_ms"], 3), wall_breakdown_s={k: round(v, 4) for k, v in d["wall_s"].items()},
                               steps=d["steps"], learn_steps=7 * d["learn_len"], steps_per_s=(d["steps"] + 7 * d["learn_len"]) / wall,
                               Pd=df["Pd"].tolist(), Pc=df["Pc"].tolist())), flush=True)
 if "paper" in which:

@@ -320,6 +320,80 @@ def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
         assert co.log_prob(idx, rseq, N, 2, Tref) == lp_fast[t, 1]
 
 
+@pytest.mark.parametrize("warm", [128, 0])
+@pytest.mark.parametrize("dec,enc,Ns,p", [("c75", "c65", (1500, 3001), 0.1), ("c75", "c75", (513, 512), 0.3),
+                                          ("m3a", "m3b", (2050, 700), 0.05), ("m1", "m1", (4096, 33), 0.2)])
+def test_split_long_trials_vs_oracle(codes_spec, dets, dec, enc, Ns, p, warm):
+    """Few long trials split along the time axis (mvd_split.cuh: chunk walk / fix / in-order scoring): tallies
+    and per-trial float64 sums bit-identical to the oracle and to the one-thread-per-trial kernels, ragged
+    lengths, two segments of different N, with the default warm-up and with none (every chunk repaired)."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec[dec]
+    det = dets(dec)
+    tab, P1, Tref = _oracle_models(det, spec, p, 8000, 5)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(p)
+    ntr = 37
+    segs = [Seg(N=Ns[d], threshold=T, stream=30 + d, enc_taps=_taps(codes_spec[enc]), decide=d, trial_begin=5,
+                trial_end=5 + ntr) for d in (0, 1)]
+    det.split_trials(2)
+    plain_t, plain_lp = det.detect(segs, seed=77, engine="fsm", want_logp=True)
+    assert det.last_kernel_kind() != 16384
+    det.split_trials(1)
+    det.learn_warm(warm)
+    try:
+        tallies, lp = det.detect(segs, seed=77, engine="fsm", want_logp=True)
+        assert det.last_kernel_kind() == 16384
+        dirty = det.learn_dirty_chunks()
+    finally:
+        det.split_trials(0)
+        det.learn_warm(128)
+    assert np.array_equal(tallies, plain_t) and np.array_equal(lp, plain_lp)
+    for d in (0, 1):
+        want, wlp = co.run_trials(_taps(spec), _taps(codes_spec[enc]), spec["n"], spec["m"], Ns[d], T, 77, 30 + d, 5,
+                                  5 + ntr, tab, P1, Tref, d, want_logp=True)
+        assert int(tallies[d]) == want
+        assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
+    if warm == 0 and max(Ns) > 1024:
+        assert dirty > 0
+
+
+def test_split_is_automatic_for_few_long_trials(codes_spec, dets):
+    """Automatic choice: 64 trials of N = 20 000 take the split path, 50 000 trials of N = 500 do not; m = 4
+    (NEXT table in global memory) splits too and agrees with the unsplit run."""
+    from mvd import bitsource
+    from mvd.engine import Detector, Seg
+    det = dets("c75")
+    tab, P1, Tref = _oracle_models(det, codes_spec["c75"], 0.1, 8000, 5)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(0.1)
+    long_seg = [Seg(N=20000, threshold=T, stream=d, enc_taps=_taps(codes_spec["c65"]), decide=d, trial_begin=0, trial_end=64) for d in (0, 1)]
+    t1, lp1 = det.detect(long_seg, seed=3, engine="auto", want_logp=True)
+    assert det.last_kernel_kind() == 16384
+    det.split_trials(2)
+    try:
+        t2, lp2 = det.detect(long_seg, seed=3, engine="auto", want_logp=True)
+        assert det.last_kernel_kind() != 16384
+    finally:
+        det.split_trials(0)
+    assert np.array_equal(t1, t2) and np.array_equal(lp1, lp2)
+    det.detect([Seg(N=500, threshold=T, stream=0, decide=0, trial_begin=0, trial_end=50000)], seed=3, engine="auto")
+    assert det.last_kernel_kind() != 16384
+    spec = codes_spec["m4a"]
+    with Detector(spec["gen"], 1, 2, 4, enumerate_with="gpu", max_states=1 << 16) as d4:
+        _, P1, _ = _oracle_models(d4, spec, 0.05, 60000, 3)
+        d4.set_models([P1])
+        seg = [Seg(N=6000, threshold=bitsource.bsc_threshold(0.05), stream=1, enc_taps=_taps(codes_spec["m4b"]), decide=1,
+                   trial_begin=0, trial_end=40)]
+        a, la = d4.detect(seg, seed=8, engine="fsm", want_logp=True)
+        assert d4.last_kernel_kind() == 16384
+        d4.split_trials(2)
+        b, lb = d4.detect(seg, seed=8, engine="fsm", want_logp=True)
+        assert np.array_equal(a, b) and np.array_equal(la, lb)
+
+
 def test_detect_rules_are_complementary(codes_spec, dets):
     """On the *same* stream the H1 rule (>) and the H2 rule (<=) partition the trials."""
     from mvd import bitsource
