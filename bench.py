@@ -165,7 +165,7 @@ def run_reference_arm(args):
                              "sample": vals[-1]["sample"]},
             "e2e": {"value": value, "unit": "trellis-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, per_gpu_trials):
@@ -179,7 +179,27 @@ def workload_config(args, per_gpu_trials):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything libraries print (NCCL's version banner, warnings) goes to stderr; the one JSON line is written to
+    the process's original stdout by :func:`_emit`."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -381,7 +401,7 @@ def main():
                 line["cpu_baseline_c_oracle"] = c_oracle_throughput()
             except Exception as exc:     # the C oracle is optional for the bench
                 line["cpu_baseline_c_oracle"] = {"error": str(exc)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -589,24 +589,36 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             }
             UA = make_uint4(UA.y, UA.z, UA.w, 0u);
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
+            auto oct = [&](uint32_t wa, uint32_t wb) {                        // 8 steps = bits 0..15 of wa / wb
+                const uint32_t wa2 = wa >> 8, wb2 = wb >> 8;
+                eng.step(wa << 7, wb << 9, wb << 7);
+                eng.step(wa << 5, wb << 7, wb << 5);
+                eng.step(wa << 3, wb << 5, wb << 3);
+                eng.step(wa << 1, wb << 3, wb << 1);
+                eng.step(wa2 << 7, wb2 << 9, wb2 << 7);
+                eng.step(wa2 << 5, wb2 << 7, wb2 << 5);
+                eng.step(wa2 << 3, wb2 << 5, wb2 << 3);
+                eng.step(wa2 << 1, wb2 << 3, wb2 << 1);
+            };
+            if (valid == 32u) {
 #pragma unroll 1
-            for (uint32_t c = 0; c < valid; c += 8u) {
-                const uint32_t sh = (c & 8u) << 1;
-                const uint32_t wa = ((c & 16u) ? whi[0] : wlo[0]) >> sh;      // 8 steps = bits 0..15
-                const uint32_t wb = ((c & 16u) ? whi[1] : wlo[1]) >> sh;
-                if (c + 8u <= valid) {
-                    const uint32_t wa2 = wa >> 8, wb2 = wb >> 8;
-                    eng.step(wa << 7, wb << 9, wb << 7);
-                    eng.step(wa << 5, wb << 7, wb << 5);
-                    eng.step(wa << 3, wb << 5, wb << 3);
-                    eng.step(wa << 1, wb << 3, wb << 1);
-                    eng.step(wa2 << 7, wb2 << 9, wb2 << 7);
-                    eng.step(wa2 << 5, wb2 << 7, wb2 << 5);
-                    eng.step(wa2 << 3, wb2 << 5, wb2 << 3);
-                    eng.step(wa2 << 1, wb2 << 3, wb2 << 1);
-                } else {
-                    for (uint32_t j = 0; j < valid - c; ++j)
-                        eng.step((wa >> (2u * j)) << 7, (wb >> (2u * j)) << 9, (wb >> (2u * j)) << 7);
+                for (int h = 0; h < 2; ++h) {                                  // 16 steps per iteration (measured: 8 -> 6.98e11, 16 -> 7.07e11, 32 -> 6.92e11 steps/s)
+                    const uint32_t xa = h ? whi[0] : wlo[0], xb = h ? whi[1] : wlo[1];
+                    oct(xa, xb);
+                    oct(xa >> 16, xb >> 16);
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t c = 0; c < valid; c += 8u) {
+                    const uint32_t sh = (c & 8u) << 1;
+                    const uint32_t wa = ((c & 16u) ? whi[0] : wlo[0]) >> sh;
+                    const uint32_t wb = ((c & 16u) ? whi[1] : wlo[1]) >> sh;
+                    if (c + 8u <= valid) {
+                        oct(wa, wb);
+                    } else {
+                        for (uint32_t j = 0; j < valid - c; ++j)
+                            eng.step((wa >> (2u * j)) << 7, (wb >> (2u * j)) << 9, (wb >> (2u * j)) << 7);
+                    }
                 }
             }
         }
