@@ -125,22 +125,34 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
             // received word of step t = bits (2t+1, 2t) of (whi:wlo); first output is the MSB
             const uint32_t wlo = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
             const uint32_t whi = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+            auto oct = [&](uint32_t wv) {                                  // 8 steps = bits 0..15 of wv
+                const uint32_t wu = wv >> 8;                                 // steps 4..7: left shifts only (FMA pipe)
+                eng.step(roff<LLS, 0>(wv));
+                eng.step(roff<LLS, 1>(wv));
+                eng.step(roff<LLS, 2>(wv));
+                eng.step(roff<LLS, 3>(wv));
+                eng.step(roff<LLS, 0>(wu));
+                eng.step(roff<LLS, 1>(wu));
+                eng.step(roff<LLS, 2>(wu));
+                eng.step(roff<LLS, 3>(wu));
+            };
+            if (valid == 32u) {
 #pragma unroll 1
-            for (uint32_t c = 0; c < valid; c += 8u) {
-                const uint32_t wsel = (c & 16u) ? whi : wlo;
-                const uint32_t wv = wsel >> ((c & 8u) << 1);
-                if (c + 8u <= valid) {
-                    const uint32_t wu = wv >> 8;                     // steps 4..7: left shifts only (FMA pipe)
-                    eng.step(roff<LLS, 0>(wv));
-                    eng.step(roff<LLS, 1>(wv));
-                    eng.step(roff<LLS, 2>(wv));
-                    eng.step(roff<LLS, 3>(wv));
-                    eng.step(roff<LLS, 0>(wu));
-                    eng.step(roff<LLS, 1>(wu));
-                    eng.step(roff<LLS, 2>(wu));
-                    eng.step(roff<LLS, 3>(wu));
-                } else {
-                    for (uint32_t j = 0; j < valid - c; ++j) eng.step(((wv >> (2u * j)) & 3u) << LLS);
+                for (int h = 0; h < 2; ++h) {                                // 16 steps per iteration
+                    const uint32_t x = h ? whi : wlo;
+                    oct(x);
+                    oct(x >> 16);
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t c = 0; c < valid; c += 8u) {
+                    const uint32_t wsel = (c & 16u) ? whi : wlo;
+                    const uint32_t wv = wsel >> ((c & 8u) << 1);
+                    if (c + 8u <= valid) {
+                        oct(wv);
+                    } else {
+                        for (uint32_t j = 0; j < valid - c; ++j) eng.step(((wv >> (2u * j)) & 3u) << LLS);
+                    }
                 }
             }
         }

@@ -322,7 +322,8 @@ def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
 
 @pytest.mark.parametrize("warm", [128, 0])
 @pytest.mark.parametrize("dec,enc,Ns,p", [("c75", "c65", (1500, 3001), 0.1), ("c75", "c75", (513, 512), 0.3),
-                                          ("m3a", "m3b", (2050, 700), 0.05), ("m1", "m1", (4096, 33), 0.2)])
+                                          ("m3a", "m3b", (2050, 700), 0.05), ("m1", "m1", (4096, 33), 0.2),
+                                          ("r13", "r13", (1100, 600), 0.15)])
 def test_split_long_trials_vs_oracle(codes_spec, dets, dec, enc, Ns, p, warm):
     """Few long trials split along the time axis (mvd_split.cuh: chunk walk / fix / in-order scoring): tallies
     and per-trial float64 sums bit-identical to the oracle and to the one-thread-per-trial kernels, ragged
