@@ -59,6 +59,7 @@ struct mvd_ctx {
     std::vector<uint32_t> bfs_levels;   // level sizes of the last GPU enumeration
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
     uint32_t learn_warm = LEARN_WARM;
+    bool learn_warm_set = false;    // MVD_OPT_LEARN_WARM given: mvd_set_code keeps it
 
     // code
     bool have_code = false;
@@ -759,6 +760,10 @@ int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps) {
     ctx->have_code = true;
     ctx->have_states = false;
     ctx->ntables = 0;
+    // warm-up of the chunk-parallel chains: survivor paths of longer memories merge later.  Measured at m = 4
+    // (S = 150 743, p = 1/2): 2 841 of 235 536 chunks mis-speculated with 128 steps (40 ms in the serial fix pass),
+    // 21 with 256, none with 384 (0.7 ms).
+    if (!ctx->learn_warm_set) ctx->learn_warm = m <= 3 ? LEARN_WARM : LEARN_WARM * (uint32_t)(m - 1);
     return MVD_OK;
 }
 
@@ -1273,6 +1278,7 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
     if (option == MVD_OPT_LEARN_WARM) {
         if (value < 0 || value > (1 << 20) || (value & 31)) return fail(ctx, MVD_E_INVALID, "warm-up must be a multiple of 32 in [0, 2^20]");
         ctx->learn_warm = (uint32_t)value;
+        ctx->learn_warm_set = true;
         return MVD_OK;
     }
     return fail(ctx, MVD_E_INVALID, "unknown option %d", option);

@@ -131,9 +131,18 @@ __global__ void __launch_bounds__(LEARN_BLOCK) learn_spec_kernel(const __grid_co
             const uint32_t nst = min(valid, t_end - t0);
             for (uint32_t t = 0; t < nst; ++t) {
                 const uint32_t e = sx + word_of_step(Rw, P.n, t);
-                if (count && t0 + t >= P.burn) {
-                    if (SMEM) atomicAdd(hist + e, 1u);
-                    else atomicAdd(counts + e, 1ull);
+                const bool tally = count && t0 + t >= P.burn;
+                if (SMEM) {
+                    if (tally) atomicAdd(hist + e, 1u);
+                } else {
+                    // the chunks of a warp belong to one chain, and at low p a chain sits on a handful of edges:
+                    // lanes that count the same edge elect one of them to add the group's size (one global atomic
+                    // per distinct edge and step instead of up to 32 serialised ones on the same address)
+                    const unsigned here = __ballot_sync(__activemask(), tally);
+                    if (tally) {
+                        const unsigned peers = __match_any_sync(here, e);
+                        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + e, (unsigned long long)__popc(peers));
+                    }
                 }
                 sx = SMEM ? nxt[e] : __ldg(nxt + e);
             }

@@ -220,7 +220,7 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread
                                                                even for few trials, 0 = automatic              */
-       MVD_OPT_LEARN_WARM = 3,     /* warm-up steps of the chunk-parallel learning chains (default 128) */
+       MVD_OPT_LEARN_WARM = 3,     /* warm-up steps of the chunk-parallel chains (default 128 for m <= 3, 128 (m - 1) above) */
        MVD_OPT_NO_FSM1 = 4,        /* 1 = NEXT-table walk with separate log / NEXT tables (two loads per step) */
        MVD_OPT_SPLIT = 5 };        /* few long trials (NEXT-table engine, on-device bits) are split along the time axis
                                       (csrc/mvd_split.cuh; identical results): 0 = when it fills the GPU better,
