@@ -155,17 +155,20 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     kernel_ms = det.last_kernel_ms()
     tallies = dist.allreduce_sum(tallies.astype(np.int64))
 
-    rows = []
+    cols = {"N": [], "p": [], "Pd": [], "Pc": []}
     for q, (N, p) in enumerate(points):
         s1, s2 = int(tallies[2 * q]), int(tallies[2 * q + 1])
-        rows.append({"N": N, "p": p, "Pd": s1 / num_iter, "Pc": (s1 + s2) / (2 * num_iter)})   # reference :225-226
+        cols["N"].append(N)
+        cols["p"].append(p)
+        cols["Pd"].append(s1 / num_iter)                        # reference :225-226
+        cols["Pc"].append((s1 + s2) / (2 * num_iter))
     if details is not None:
         details.update(tallies=tallies, edge_counts=counts, p1_tables=tables, distinct_p=distinct,
                        detect_kernel_ms=kernel_ms, learn_kernel_ms=learn_kernel_ms,
                        wall_s=dict(setup=t_learn0 - t_start, learn=t_tables0 - t_learn0, tables=t_detect0 - t_tables0,
                                    detect=time.perf_counter() - t_detect0), steps=2 * sum(N for N, _ in points) * int(num_iter),
                        learn_len=_learn_len(det.S, learn_len), S=det.S)
-    return pd.DataFrame(rows, columns=["N", "p", "Pd", "Pc"])
+    return pd.DataFrame(cols, columns=["N", "p", "Pd", "Pc"])
 
 
 if __name__ == "__main__":

@@ -327,10 +327,8 @@ def dense_counts_from_edges(tab: StateTable, edge_counts: np.ndarray) -> np.ndar
     """The reference's ``counts`` matrix (Pd_plotter.py:158-163) from edge counts (small S)."""
     S = tab.S
     ec = np.asarray(edge_counts, dtype=np.float64).reshape(S, tab.R)
-    dense = np.zeros((S, S))
-    rows = np.repeat(np.arange(S), tab.R)
-    np.add.at(dense, (rows, tab.nxt.reshape(-1)), ec.reshape(-1))
-    return dense
+    flat = (np.arange(S, dtype=np.int64)[:, None] * S + tab.nxt).reshape(-1)     # (i, j) -> i * S + j; duplicates add up
+    return np.bincount(flat, weights=ec.reshape(-1), minlength=S * S).reshape(S, S)
 
 
 def p1_dense(tab: StateTable, edge_counts: np.ndarray, laplace: float) -> np.ndarray:

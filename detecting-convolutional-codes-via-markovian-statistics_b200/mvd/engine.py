@@ -41,11 +41,8 @@ def _log_table(values: np.ndarray) -> np.ndarray:
     """Elementwise ``math.log(max(v, 1e-300))`` (Pd_plotter.py:114-115) with libm's log -- the
     same function the reference calls per step, so device sums add bit-identical terms."""
     flat = np.ascontiguousarray(values, dtype=np.float64).ravel()
-    if flat.size <= 4096:
-        out = np.fromiter((math.log(v if v > 1e-300 else 1e-300) for v in flat.tolist()), dtype=np.float64, count=flat.size)
-    else:                                   # same libm call, in C (mvd_host_log_table): m = 4 tables have 10^6 entries
-        out = np.empty_like(flat)
-        _capi.check(_capi.load(), None, _capi.load().mvd_host_log_table(flat.ctypes.data, out.ctypes.data, flat.size))
+    out = np.empty_like(flat)               # the same libm call, made from C (mvd_host_log_table; bit-equal, tests)
+    _capi.check(_capi.load(), None, _capi.load().mvd_host_log_table(flat.ctypes.data, out.ctypes.data, flat.size))
     return out.reshape(np.shape(values))
 
 
