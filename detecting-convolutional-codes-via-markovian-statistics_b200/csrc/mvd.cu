@@ -74,11 +74,12 @@ struct mvd_ctx {
     std::vector<uint8_t> h_metrics;
     std::vector<uint32_t> h_next;
     uint32_t hcap = 0;
+    uint32_t ph_slots = 0;          // m = 3 perfect hash (mvd_detect3p.cuh), 0 = none
     // loglik
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht;
 };
 
 namespace {
@@ -219,6 +220,55 @@ int install_states(mvd_ctx* ctx) {
         CK(cudaMemcpyAsync(ctx->d_dstate.p, dst.data(), nkeys * 2, cudaMemcpyHostToDevice, ctx->stream));
         ctx->nkeys = S <= 0xFFFE ? nkeys : 0;
     }
+    // ---- perfect hash for m = 3, n = 2 (two-trials-per-thread ACS kernel, mvd_detect3p.cuh): hash, displace.
+    // key = klo | khi << 16 with klo = D0 + 8 D1 + 64 D2 + 512 D3 and khi likewise from D4..D7 (metrics <= 7);
+    // bucket = key * C1 >> 24, slot = ((key * C2 >> 21) + disp[bucket]) & (slots - 1).  Buckets are placed largest
+    // first, each with the smallest displacement that lands all its keys on free slots.
+    ctx->ph_slots = 0;
+    if (ctx->closed && ctx->m == 3 && ctx->n == 2 && ctx->max_metric <= 7 && S <= 1024) {
+        uint32_t slots = 256;
+        while (slots < 2 * S) slots <<= 1;
+        std::vector<uint32_t> key(S);
+        std::vector<std::vector<uint32_t>> bucket(256);
+        for (uint32_t i = 0; i < S; ++i) {
+            const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
+            const uint32_t klo = v[0] + 8u * v[1] + 64u * v[2] + 512u * v[3], khi = v[4] + 8u * v[5] + 64u * v[6] + 512u * v[7];
+            key[i] = klo | (khi << 16);
+            bucket[(key[i] * 0x9E3779B1u) >> 24].push_back(i);
+        }
+        std::vector<uint32_t> order(256);
+        for (uint32_t b = 0; b < 256; ++b) order[b] = b;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return bucket[a].size() > bucket[b].size(); });
+        std::vector<uint32_t> disp(256, 0u), table(slots, MVD_EMPTY);
+        bool built = true;
+        for (uint32_t oi = 0; oi < 256 && built; ++oi) {
+            const std::vector<uint32_t>& bk = bucket[order[oi]];
+            if (bk.empty()) break;
+            bool placed = false;
+            for (uint32_t d = 0; d < slots && !placed; ++d) {
+                bool ok2 = true;
+                for (size_t a = 0; a < bk.size() && ok2; ++a) {
+                    const uint32_t sa = (((key[bk[a]] * 0x85EBCA6Bu) >> 21) + d) & (slots - 1);
+                    ok2 = table[sa] == MVD_EMPTY;
+                    for (size_t c = 0; c < a && ok2; ++c)
+                        ok2 = sa != ((((key[bk[c]] * 0x85EBCA6Bu) >> 21) + d) & (slots - 1));
+                }
+                if (ok2) {
+                    for (uint32_t i : bk) table[(((key[i] * 0x85EBCA6Bu) >> 21) + d) & (slots - 1)] = i * (uint32_t)R;
+                    disp[order[oi]] = d;
+                    placed = true;
+                }
+            }
+            built = placed;
+        }
+        if (built) {
+            CK(ctx->d_phd.reserve(256 * 4));
+            CK(ctx->d_pht.reserve((size_t)slots * 4));
+            CK(cudaMemcpyAsync(ctx->d_phd.p, disp.data(), 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_pht.p, table.data(), (size_t)slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->ph_slots = slots;
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_states = true;
     ctx->ntables = 0;
@@ -351,13 +401,18 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     // pairing halves the thread count: only when the GPU stays full (3 blocks of 256 pair-threads per SM)
     const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && pair_smem <= 72 * 1024 &&
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
+    // m = 3: two trials per thread with the perfect-hash lookup (2 blocks of 256 pair-threads per SM)
+    const size_t pair3_smem = 2 * (size_t)ctx->ph_slots * 8 + 1024 + 128 + 128 + ((size_t)ctx->S * 4 << 5) + 64;
+    const bool pair3 = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && !det2_gt && ctx->m == 3 &&
+                       ctx->ph_slots && pair3_smem <= 113 * 1024 &&
+                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
     // few trials: smaller blocks so that every SM gets work (the kernels read blockDim.x)
-    uint32_t threads = pair ? DET2P_BLOCK : DET2_BLOCK;
+    uint32_t threads = (pair || pair3) ? DET2P_BLOCK : DET2_BLOCK;
     if (fast) {
-        const uint64_t per_thread = pair ? 2 : 1;
+        const uint64_t per_thread = (pair || pair3) ? 2 : 1;
         while (threads > 64 && (all_trials + threads * per_thread - 1) / (threads * per_thread) < 4 * sms) threads >>= 1;
     }
-    const uint32_t block = fast ? threads * (pair ? 2u : 1u) : MVD_BLOCK;
+    const uint32_t block = fast ? threads * ((pair || pair3) ? 2u : 1u) : MVD_BLOCK;
 
     // ---- segments
     std::vector<DevSeg> ds(nsegs);
@@ -440,6 +495,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
     P.error_flag = ctx->d_err.as<int>();
     P.fp = fplan;
+    P.fp.ph_d = ctx->d_phd.as<uint32_t>();
+    P.fp.ph_t = ctx->d_pht.as<uint32_t>();
+    P.fp.ph_slots = ctx->ph_slots;
 
     // ---- outputs
     if (mode == MODE_DETECT) {
@@ -610,10 +668,11 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             }
             if (maxblocks == 0) continue;
             const dim3 g2((unsigned)maxblocks, cnt);
-            le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
+            if (pair3) le = mvd_launch_det3_pair(g2, threads, pair3_smem, ctx->stream, P, B);
+            else le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }
-        ctx->last_fast = 1 + det2_lk + 16 * det2_lls + (pair ? 256 : 0) + (det2_gt ? 512 : 0);
+        ctx->last_fast = 1 + det2_lk + 16 * (pair3 ? 5 : det2_lls) + ((pair || pair3) ? 256 : 0) + (det2_gt ? 512 : 0);
         if (extra_launches > 1) ctx->launches += extra_launches - 1;  // the common increment below counts one
     } else {
         le = mvd_launch_generic(engine, mode, n2, m, in_smem, grid, smem, ctx->stream, P);
@@ -705,7 +764,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
                       &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
-                      &ctx->d_smeta, &ctx->d_sedges};
+                      &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

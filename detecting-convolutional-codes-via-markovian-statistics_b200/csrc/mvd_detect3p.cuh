@@ -1,0 +1,233 @@
+// mvd_detect3p.cuh -- ACS engine for memory m = 3 rate-1/2 codes (8 trellis states; the demo's second
+// predefined pair, S = 435 ... 987 Markov states): TWO trials per thread, the 16x2 SIMD lanes run across the two
+// trials as in detect2p_kernel (mvd_detect2.cuh), and the metric-vector -> Markov-state lookup (the state_index
+// dict of Pd_plotter.py:139) is a *perfect hash* built on the host for the closed state set:
+//
+//     key  = klo | khi << 16,  klo = D0 + 8 D1 + 64 D2 + 512 D3,  khi likewise from D4..D7   (metrics <= 7)
+//     slot = ((key * C2 >> 21) + disp[key * C1 >> 24]) & (slots - 1)                          (hash, displace)
+//
+// two dependent shared-memory reads and no probe loop, against ~1.3 probes of an open-addressing table with
+// key compares and a divergent loop in detect2_kernel<LK_HASH, 3> (54 warp-instructions per trellis step with a
+// branch-metric table, instead of 107).  Results are the same bit for bit (same Eq. 4-5 arithmetic, same sums in step order).
+//
+// Shared memory (absolute addresses; alignment lets one LOP3 form an address):
+//   [hash slots: slots x 2 copies x 4 B, aligned to its size][displacements 256 x 4 B, 1 KB aligned]
+//   [threshold masks 128 B][V(r) 16 B (+ pad)][log rows S x 4 x 2 copies x 16 B, 128 B aligned]
+#pragma once
+#include "mvd_detect2.cuh"
+
+#define PH3_C1 0x9E3779B1u
+#define PH3_C2 0x85EBCA6Bu
+
+// Branch metrics without a table read per branch: for a rate-1/2 code the metric of a branch with label L
+// against received word r is popc(L ^ r), so the 16 branch words of a step are 16 picks from the four
+// bytes V(r) = (d(0,r), d(1,r), d(2,r), d(3,r)).  One 4-byte read per trial gives V(r_A), V(r_B); branch
+// (ns, b) is PRMT(V_A, V_B, sel[ns][b]) = V_A[L] | V_B[L] << 16 with a kernel-constant selector (selector
+// nibbles with bit 3 set yield the replicated sign bit = 0).  16 PRMTs replace four LDS.128 (16 shared-memory
+// wavefronts per step pair): this kernel is shared-memory bound, the ALU pipe has room.
+struct PairEngine3 {
+    uint32_t Q[8];                    // (trial A, trial B) metrics of trellis states 0..7
+    uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
+    uint32_t kV, kD, kT, tmask;       // V(r) table (16 B) ; displacement table ; slot table | copy * 4 ; (slots - 1) << 3
+    uint32_t sel[16];                 // PRMT selector of branch (ns, b) at [2 ns + b]
+    double a1A, a0A, a1B, a0B;
+
+    __device__ __forceinline__ uint32_t lookup(uint32_t key) const {
+        const uint32_t d8 = lds_u32(kD | (((key * PH3_C1) >> 22) & 0x3FCu));          // displacement * 8
+        return lds_u32(kT | ((((key * PH3_C2) >> 18) + d8) & tmask));
+    }
+
+    // sA5 / sB5: r_A / r_B at bits 5..6 (log rows, 32-byte entries); sA2 / sB2: r_A / r_B at bits 2..3 (V table)
+    __device__ __forceinline__ void step(uint32_t sA5, uint32_t sB5, uint32_t sA2, uint32_t sB2) {
+        const double2 vA = lds_d2(sxA | (sA5 & 0x60u));
+        const double2 vB = lds_d2(sxB | (sB5 & 0x60u));
+        a1A += vA.x;
+        a0A += vA.y;
+        a1B += vB.x;
+        a0B += vB.y;
+        const uint32_t VA = lds_u32(kV | (sA2 & 0xCu)), VB = lds_u32(kV | (sB2 & 0xCu));
+        uint32_t n[8];
+#pragma unroll
+        for (int ns = 0; ns < 8; ++ns)                  // new state ns from predecessors ns >> 1 and (ns >> 1) + 4: Eq. 4, both trials
+            n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + 4] + __byte_perm(VA, VB, sel[2 * ns + 1]));
+        const uint32_t mn = __vimin3_u16x2(__vimin3_u16x2(n[0], n[1], n[2]), __vimin3_u16x2(n[3], n[4], n[5]), __vminu2(n[6], n[7]));
+#pragma unroll
+        for (int s = 0; s < 8; ++s) Q[s] = n[s] - mn;                           // Eq. 5
+        const uint32_t klo = ((Q[3] * 8u + Q[2]) * 8u + Q[1]) * 8u + Q[0];
+        const uint32_t khi = ((Q[7] * 8u + Q[6]) * 8u + Q[5]) * 8u + Q[4];
+        sxA = lookup(__byte_perm(klo, khi, 0x5410));     // klo.lo16 | khi.lo16 << 16
+        sxB = lookup(__byte_perm(klo, khi, 0x7632));     // klo.hi16 | khi.hi16 << 16
+    }
+};
+
+template <int DUMMY>
+__global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_constant__ Params P,
+                                                                  const __grid_constant__ SegBatch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevSeg& sg = B.s[blockIdx.y];
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    const uint32_t BS = blockDim.x;
+    const unsigned long long blk0 = (unsigned long long)blockIdx.x * (2u * BS);
+    if (blk0 >= ntr) return;
+    const uint32_t seg = sg.block_begin;
+    const unsigned long long tlA = blk0 + threadIdx.x, tlB = tlA + BS;
+    const bool actA = tlA < ntr, actB = tlB < ntr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t SR = P.SR;
+    const uint32_t slots = P.fp.ph_slots, tbytes = slots * 8u;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t a_T = (sbase + tbytes - 1u) & ~(tbytes - 1u);
+    const uint32_t a_D = a_T + tbytes;                       // tbytes >= 2 KB keeps the 1 KB alignment
+    const uint32_t a_tb = a_D + 1024u;
+    const uint32_t a_V = a_tb + 128u;                        // 16-byte table V(r), 16 B aligned
+    const uint32_t a_ll = a_V + 128u;
+    unsigned char* g = smem_raw - sbase;                     // generic pointer of shared address 0
+
+    if (threadIdx.x < 32u)
+        *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
+    {
+        const double2* llg = P.ll + (size_t)sg.table * SR;
+        for (uint32_t i = threadIdx.x; i < SR * 2u; i += BS)
+            *reinterpret_cast<double2*>(g + a_ll + ((i >> 1) << 5) + ((i & 1u) << 4)) = __ldg(llg + (i >> 1));
+    }
+    if (threadIdx.x < 4u) {                                  // V(r) = bytes popc(L ^ r), L = 0..3
+        const uint32_t r = threadIdx.x;
+        uint32_t v = 0;
+        for (uint32_t L = 0; L < 4u; ++L) v |= (uint32_t)__popc(L ^ r) << (8u * L);
+        *reinterpret_cast<uint32_t*>(g + a_V + 4u * r) = v;
+    }
+    for (uint32_t i = threadIdx.x; i < 256u; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i] << 3;
+    for (uint32_t i = threadIdx.x; i < slots * 2u; i += BS) {
+        const uint32_t row = P.fp.ph_t[i >> 1];              // state * 4, or MVD_EMPTY (never looked up)
+        *reinterpret_cast<uint32_t*>(g + a_T + 4u * i) = a_ll + ((row == MVD_EMPTY ? 0u : row) << 5) + ((i & 1u) << 4);
+    }
+    __syncthreads();
+
+    const uint4* tbm = reinterpret_cast<const uint4*>(g + a_tb);
+    PairEngine3 eng;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) eng.Q[s] = 0u;
+    eng.sxA = eng.sxB = a_ll + ((lane & 1u) << 4);           // state 0 = the all-zero vector
+    eng.kV = a_V;
+    eng.kD = a_D;
+    // label of branch (ns, b) from the branch-metric table of the decoder (P.bm[r][2 g + b] = distances to ns = 2g and
+    // 2g + 1 from predecessor g + 4 b): (d(L,0), d(L,1)) = (0,1), (1,0), (1,2), (2,1) for L = 0, 1, 2, 3
+#pragma unroll
+    for (int ns = 0; ns < 8; ++ns)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const uint32_t w0 = P.bm[0 * 8 + 2 * (ns >> 1) + b], w1 = P.bm[1 * 8 + 2 * (ns >> 1) + b];
+            const uint32_t d0 = (ns & 1) ? (w0 >> 16) : (w0 & 0xFFFFu), d1 = (ns & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
+            const uint32_t L = d0 == 0u ? 0u : (d0 == 2u ? 3u : (d1 == 0u ? 1u : 2u));
+            eng.sel[2 * ns + b] = L | 0x80u | ((4u + L) << 8) | 0x8000u;
+        }
+    eng.kT = a_T + ((lane & 1u) << 2);
+    eng.tmask = (slots - 1u) << 3;
+    eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
+
+    const uint32_t N = sg.N;
+    const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
+    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
+    const uint32_t c3 = sg.stream;
+    const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
+    uint32_t tm0[4], tm1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        tm0[i] = 0u - ((taps0 >> i) & 1u);
+        tm1[i] = 0u - ((taps1 >> i) & 1u);
+    }
+    uint32_t prevUA = 0, prevUB = 0;
+    const uint32_t nsb = (N + 127u) >> 7;
+    for (uint32_t sb = 0; sb < nsb; ++sb) {
+        uint4 UA = make_uint4(0, 0, 0, 0), UB = UA, EA0 = UA, EA1 = UA, EB0 = UA, EB1 = UA;
+        if (philox) {
+            UA = philox10(((4u * sb) << 6) | 32u, (uint32_t)trA, (uint32_t)(trA >> 32), c3, P);
+            UB = philox10(((4u * sb) << 6) | 32u, (uint32_t)trB, (uint32_t)(trB >> 32), c3, P);
+        } else {
+            const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 3ull * ntr;
+            if (actA) {
+                UA = __ldg(base + tlA);
+                EA0 = __ldg(base + ntr + tlA);
+                EA1 = __ldg(base + 2ull * ntr + tlA);
+            }
+            if (actB) {
+                UB = __ldg(base + tlB);
+                EB0 = __ldg(base + ntr + tlB);
+                EB1 = __ldg(base + 2ull * ntr + tlB);
+            }
+        }
+        if (!sg.random_input) UA = UB = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t0 = sb * 128u + (uint32_t)w * 32u;
+            if (t0 >= N) break;
+            const uint32_t valid = min(32u, N - t0);
+            const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+            uint32_t wlo[2], whi[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const uint32_t U = x ? UB.x : UA.x;                      // word w: the vectors rotate below
+                const bool act = x ? actB : actA;
+                const unsigned long long tr = x ? trB : trA;
+                uint32_t e0, e1;
+                if (philox) {
+                    const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
+                    e0 = lazy_bernoulli_s(cb, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
+                    e1 = lazy_bernoulli_s(cb | 8u, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
+                } else {
+                    e0 = pick(x ? EB0 : EA0, w);
+                    e1 = pick(x ? EB1 : EA1, w);
+                }
+                const uint32_t pu = x ? prevUB : prevUA;
+                uint32_t o0 = U & tm0[0], o1 = U & tm1[0];              // m = 3: four tap masks per output
+#pragma unroll
+                for (int i = 1; i <= 3; ++i) {
+                    const uint32_t sh = __funnelshift_l(pu, U, i);
+                    o0 ^= sh & tm0[i];
+                    o1 ^= sh & tm1[i];
+                }
+                if (x) prevUB = U; else prevUA = U;
+                const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
+                wlo[x] = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
+                whi[x] = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+            }
+            UA = make_uint4(UA.y, UA.z, UA.w, 0u);
+            UB = make_uint4(UB.y, UB.z, UB.w, 0u);
+            auto quad = [&](uint32_t wa, uint32_t wb) {                        // 4 steps = bits 0..7 of wa / wb
+                eng.step(wa << 5, wb << 5, wa << 2, wb << 2);
+                eng.step(wa << 3, wb << 3, wa, wb);
+                eng.step(wa << 1, wb << 1, wa >> 2, wb >> 2);
+                eng.step(wa >> 1, wb >> 1, wa >> 4, wb >> 4);
+            };
+#pragma unroll 1
+            for (uint32_t c = 0; c < valid; c += 8u) {
+                const uint32_t sh = (c & 8u) << 1;
+                const uint32_t wa = ((c & 16u) ? whi[0] : wlo[0]) >> sh;      // 8 steps = bits 0..15
+                const uint32_t wb = ((c & 16u) ? whi[1] : wlo[1]) >> sh;
+                if (c + 8u <= valid) {
+                    quad(wa, wb);
+                    quad(wa >> 8, wb >> 8);
+                } else {
+                    for (uint32_t j = 0; j < valid - c; ++j) {
+                        const uint32_t ra = (wa >> (2u * j)) & 3u, rb = (wb >> (2u * j)) & 3u;
+                        eng.step(ra << 5, rb << 5, ra << 2, rb << 2);
+                    }
+                }
+            }
+        }
+    }
+
+    const bool winA = actA && (sg.decide == 0 ? (eng.a1A > eng.a0A) : (eng.a1A <= eng.a0A));
+    const bool winB = actB && (sg.decide == 0 ? (eng.a1B > eng.a0B) : (eng.a1B <= eng.a0B));
+    const int cnt = __syncthreads_count(winA ? 1 : 0) + __syncthreads_count(winB ? 1 : 0);
+    if (threadIdx.x == 0 && cnt) {
+        atomicAdd(P.tallies + seg, (unsigned long long)cnt);
+        if (P.tallies2) atomicAdd(P.tallies2 + seg, (unsigned long long)cnt);
+    }
+    if (P.logp) {
+        double2* o = reinterpret_cast<double2*>(P.logp) + sg.out_offset;
+        if (actA) o[tlA] = make_double2(eng.a1A, eng.a0A);
+        if (actB) o[tlB] = make_double2(eng.a1B, eng.a0B);
+    }
+}

@@ -25,6 +25,9 @@ struct FastPlan {
     const uint32_t* tcode;             // packed NEXT walk: high word of the double c with log Tref[e] = c * tref_unit
     double tref_unit;
     const uint4* gfsm1;                // [ntables][S*R] packed NEXT-walk entries in global memory (large S)
+    const uint32_t* ph_d;              // m = 3 perfect hash (mvd_detect3p.cuh): displacement per bucket [256]
+    const uint32_t* ph_t;              //   slot -> state * R, or MVD_EMPTY [ph_slots]
+    uint32_t ph_slots;                 //   power of two, 0 = no perfect hash
 };
 
 struct Params {

@@ -251,7 +251,7 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
     else:
         want_lookup = (2 if path == "fast1" else 3) if engine == "fsm" else (0 if spec["m"] <= 2 else 1)
         assert kind != 0 and (kind - 1) % 16 == want_lookup
-        assert (kind >= 256) == (path == "fast" and engine == "acs" and spec["m"] == 2)
+        assert (kind >= 256) == (path == "fast" and engine == "acs" and spec["m"] in (2, 3))
     for d in (0, 1):
         want, wlp = co.run_trials(_taps(spec), _taps(codes_spec[enc]), spec["n"], spec["m"], N, T, 2024, 10 + d, 17,
                                   17 + ntr, tab, P1, Tref, d, want_logp=True)
