@@ -74,7 +74,7 @@ struct mvd_ctx {
     std::vector<uint8_t> h_metrics;
     std::vector<uint32_t> h_next;
     uint32_t hcap = 0;
-    uint32_t ph_slots = 0;          // m = 3 perfect hash (mvd_detect3p.cuh), 0 = none
+    uint32_t ph_slots = 0, ph_bshift = 24, ph_c2 = 0, ph_c4 = 0;   // m = 3 / 4 perfect hash (mvd_detect3p.cuh), 0 = none
     // loglik
     uint32_t ntables = 0;
 
@@ -220,53 +220,91 @@ int install_states(mvd_ctx* ctx) {
         CK(cudaMemcpyAsync(ctx->d_dstate.p, dst.data(), nkeys * 2, cudaMemcpyHostToDevice, ctx->stream));
         ctx->nkeys = S <= 0xFFFE ? nkeys : 0;
     }
-    // ---- perfect hash for m = 3, n = 2 (two-trials-per-thread ACS kernel, mvd_detect3p.cuh): hash, displace.
-    // key = klo | khi << 16 with klo = D0 + 8 D1 + 64 D2 + 512 D3 and khi likewise from D4..D7 (metrics <= 7);
-    // bucket = key * C1 >> 24, slot = ((key * C2 >> 21) + disp[bucket]) & (slots - 1).  Buckets are placed largest
-    // first, each with the smallest displacement that lands all its keys on free slots.
+    // ---- perfect hash for m = 3 / 4, n = 2 (two-trials-per-thread ACS kernels, mvd_detect3p.cuh): hash, displace.
+    // w0 = k0 | k1 << 16 (and w1 = k2 | k3 << 16 for m = 4) with k_i = D[4i] + 8 D[4i+1] + 64 D[4i+2] + 512 D[4i+3]
+    // (metrics <= 7); bucket = (w0 C1 + w1 C3) >> bshift, slot = (((w0 C2 + w1 C4) >> h2shift) + disp[bucket]) &
+    // (slots - 1).  Buckets are placed largest first, each with the smallest displacement that lands all its keys
+    // on free slots (single keys take the next free slot).
     ctx->ph_slots = 0;
-    if (ctx->closed && ctx->m == 3 && ctx->n == 2 && ctx->max_metric <= 7 && S <= 1024) {
-        uint32_t slots = 256;
+    if (ctx->closed && (ctx->m == 3 || ctx->m == 4) && ctx->n == 2 && ctx->max_metric <= 7 && (ctx->m == 4 || S <= 1024) && S <= (1u << 20)) {
+        uint32_t slots = 256, nb = 256;
         while (slots < 2 * S) slots <<= 1;
-        std::vector<uint32_t> key(S);
-        std::vector<std::vector<uint32_t>> bucket(256);
+        if (ctx->m == 4) while (nb < S / 4) nb <<= 1;
+        uint32_t lb = 0;
+        while ((1u << lb) < nb) ++lb;
+        const uint32_t bshift = 32 - lb, h2shift = ctx->m == 3 ? 21 : 11;
+        std::vector<uint32_t> h1(S), h2(S), w0(S), w1(S, 0u);
+        std::vector<uint32_t> bcount(nb + 1, 0u);
         for (uint32_t i = 0; i < S; ++i) {
             const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
-            const uint32_t klo = v[0] + 8u * v[1] + 64u * v[2] + 512u * v[3], khi = v[4] + 8u * v[5] + 64u * v[6] + 512u * v[7];
-            key[i] = klo | (khi << 16);
-            bucket[(key[i] * 0x9E3779B1u) >> 24].push_back(i);
-        }
-        std::vector<uint32_t> order(256);
-        for (uint32_t b = 0; b < 256; ++b) order[b] = b;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return bucket[a].size() > bucket[b].size(); });
-        std::vector<uint32_t> disp(256, 0u), table(slots, MVD_EMPTY);
-        bool built = true;
-        for (uint32_t oi = 0; oi < 256 && built; ++oi) {
-            const std::vector<uint32_t>& bk = bucket[order[oi]];
-            if (bk.empty()) break;
-            bool placed = false;
-            for (uint32_t d = 0; d < slots && !placed; ++d) {
-                bool ok2 = true;
-                for (size_t a = 0; a < bk.size() && ok2; ++a) {
-                    const uint32_t sa = (((key[bk[a]] * 0x85EBCA6Bu) >> 21) + d) & (slots - 1);
-                    ok2 = table[sa] == MVD_EMPTY;
-                    for (size_t c = 0; c < a && ok2; ++c)
-                        ok2 = sa != ((((key[bk[c]] * 0x85EBCA6Bu) >> 21) + d) & (slots - 1));
-                }
-                if (ok2) {
-                    for (uint32_t i : bk) table[(((key[i] * 0x85EBCA6Bu) >> 21) + d) & (slots - 1)] = i * (uint32_t)R;
-                    disp[order[oi]] = d;
-                    placed = true;
-                }
+            uint32_t w[2] = {0u, 0u};
+            for (int q = 0; q < nstate / 4; ++q) {
+                const uint32_t kq = v[4 * q] + 8u * v[4 * q + 1] + 64u * v[4 * q + 2] + 512u * v[4 * q + 3];
+                w[q >> 1] |= kq << (16 * (q & 1));
             }
-            built = placed;
+            w0[i] = w[0];
+            w1[i] = w[1];
+            h1[i] = (w[0] * 0x9E3779B1u + w[1] * 0xC2B2AE35u) >> bshift;
+            ++bcount[h1[i] + 1];
+        }
+        for (uint32_t b = 0; b < nb; ++b) bcount[b + 1] += bcount[b];          // bucket b = members[bcount[b] .. bcount[b+1])
+        std::vector<uint32_t> members(S), fill(bcount.begin(), bcount.end() - 1);
+        for (uint32_t i = 0; i < S; ++i) members[fill[h1[i]]++] = i;
+        std::vector<uint32_t> order(nb);
+        for (uint32_t b = 0; b < nb; ++b) order[b] = b;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return bcount[a + 1] - bcount[a] > bcount[b + 1] - bcount[b];
+        });
+        std::vector<uint32_t> disp(nb, 0u), table(slots, MVD_EMPTY);
+        bool built = false;
+        uint32_t c2 = 0x85EBCA6Bu, c4 = 0x27D4EB2Fu;
+        // two keys of one bucket with the same second hash cannot be separated by a displacement: try the next
+        // pair of (odd) multipliers -- about every second attempt succeeds at these sizes
+        for (uint32_t attempt = 0; attempt < 64 && !built; ++attempt, c2 += 0xC6574B56u, c4 += 0x3C6EF372u) {
+            for (uint32_t i = 0; i < S; ++i) h2[i] = (w0[i] * c2 + w1[i] * c4) >> h2shift;
+            std::fill(disp.begin(), disp.end(), 0u);
+            std::fill(table.begin(), table.end(), MVD_EMPTY);
+            built = true;
+            uint32_t next_free = 0;
+            for (uint32_t oi = 0; oi < nb && built; ++oi) {
+                const uint32_t b = order[oi], lo = bcount[b], hi = bcount[b + 1];
+                if (lo == hi) break;
+                if (hi - lo == 1) {                                            // any free slot will do
+                    while (next_free < slots && table[next_free] != MVD_EMPTY) ++next_free;
+                    if (next_free == slots) { built = false; break; }
+                    disp[b] = (next_free - h2[members[lo]]) & (slots - 1);
+                    table[next_free] = members[lo] * (uint32_t)R;
+                    continue;
+                }
+                bool placed = false;
+                for (uint32_t d = 0; d < slots && !placed; ++d) {
+                    bool ok2 = true;
+                    for (uint32_t a = lo; a < hi && ok2; ++a) {
+                        const uint32_t sa = (h2[members[a]] + d) & (slots - 1);
+                        ok2 = table[sa] == MVD_EMPTY;
+                        for (uint32_t c = lo; c < a && ok2; ++c) ok2 = sa != ((h2[members[c]] + d) & (slots - 1));
+                    }
+                    if (ok2) {
+                        for (uint32_t a = lo; a < hi; ++a) table[(h2[members[a]] + d) & (slots - 1)] = members[a] * (uint32_t)R;
+                        disp[b] = d;
+                        placed = true;
+                    }
+                }
+                built = placed;
+            }
+            if (built) {
+                ctx->ph_c2 = c2;
+                ctx->ph_c4 = c4;
+            }
         }
         if (built) {
-            CK(ctx->d_phd.reserve(256 * 4));
+            CK(ctx->d_phd.reserve((size_t)nb * 4));
             CK(ctx->d_pht.reserve((size_t)slots * 4));
-            CK(cudaMemcpyAsync(ctx->d_phd.p, disp.data(), 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_phd.p, disp.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->d_pht.p, table.data(), (size_t)slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
             ctx->ph_slots = slots;
+            ctx->ph_bshift = bshift;
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -403,9 +441,13 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
     // m = 3: two trials per thread with the perfect-hash lookup (2 blocks of 256 pair-threads per SM)
     const size_t pair3_smem = 2 * (size_t)ctx->ph_slots * 8 + 1024 + 128 + 128 + ((size_t)ctx->S * 4 << 5) + 64;
-    const bool pair3 = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && !det2_gt && ctx->m == 3 &&
-                       ctx->ph_slots && pair3_smem <= 113 * 1024 &&
-                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
+    const bool pair3s = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && !det2_gt && ctx->m == 3 &&
+                        ctx->ph_slots && pair3_smem <= 75 * 1024 &&
+                        (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
+    // m = 4: the same kernel with displacements, slots and log rows in global memory
+    const bool pair4 = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && det2_gt && ctx->m == 4 &&
+                       ctx->ph_slots && (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
+    const bool pair3 = pair3s || pair4;
     // few trials: smaller blocks so that every SM gets work (the kernels read blockDim.x)
     uint32_t threads = (pair || pair3) ? DET2P_BLOCK : DET2_BLOCK;
     if (fast) {
@@ -498,6 +540,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     P.fp.ph_d = ctx->d_phd.as<uint32_t>();
     P.fp.ph_t = ctx->d_pht.as<uint32_t>();
     P.fp.ph_slots = ctx->ph_slots;
+    P.fp.ph_bshift = ctx->ph_bshift;
+    P.fp.ph_c2 = ctx->ph_c2;
+    P.fp.ph_c4 = ctx->ph_c4;
 
     // ---- outputs
     if (mode == MODE_DETECT) {
@@ -668,11 +713,11 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             }
             if (maxblocks == 0) continue;
             const dim3 g2((unsigned)maxblocks, cnt);
-            if (pair3) le = mvd_launch_det3_pair(g2, threads, pair3_smem, ctx->stream, P, B);
+            if (pair3) le = mvd_launch_det3_pair(m, g2, threads, pair4 ? 4096 : pair3_smem, ctx->stream, P, B);
             else le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }
-        ctx->last_fast = 1 + det2_lk + 16 * (pair3 ? 5 : det2_lls) + ((pair || pair3) ? 256 : 0) + (det2_gt ? 512 : 0);
+        ctx->last_fast = 1 + det2_lk + 16 * (pair3s ? 5 : det2_lls) + ((pair || pair3) ? 256 : 0) + (det2_gt ? 512 : 0);
         if (extra_launches > 1) ctx->launches += extra_launches - 1;  // the common increment below counts one
     } else {
         le = mvd_launch_generic(engine, mode, n2, m, in_smem, grid, smem, ctx->stream, P);

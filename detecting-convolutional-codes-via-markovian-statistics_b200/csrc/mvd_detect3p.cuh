@@ -1,10 +1,14 @@
-// mvd_detect3p.cuh -- ACS engine for memory m = 3 rate-1/2 codes (8 trellis states; the demo's second
-// predefined pair, S = 435 ... 987 Markov states): TWO trials per thread, the 16x2 SIMD lanes run across the two
-// trials as in detect2p_kernel (mvd_detect2.cuh), and the metric-vector -> Markov-state lookup (the state_index
-// dict of Pd_plotter.py:139) is a *perfect hash* built on the host for the closed state set:
+// mvd_detect3p.cuh -- ACS engine for memory m = 3 and m = 4 rate-1/2 codes (8 / 16 trellis states; the demo's
+// second predefined pair, S = 435; m = 4: S = 25 751 ... 232 567): TWO trials per thread, the 16x2 SIMD lanes
+// run across the two trials as in detect2p_kernel (mvd_detect2.cuh), and the metric-vector -> Markov-state
+// lookup (the state_index dict of Pd_plotter.py:139) is a *perfect hash* built on the host for the closed set:
 //
-//     key  = klo | khi << 16,  klo = D0 + 8 D1 + 64 D2 + 512 D3,  khi likewise from D4..D7   (metrics <= 7)
-//     slot = ((key * C2 >> 21) + disp[key * C1 >> 24]) & (slots - 1)                          (hash, displace)
+//     w0   = k0 | k1 << 16,  k_i = D[4i] + 8 D[4i+1] + 64 D[4i+2] + 512 D[4i+3]   (metrics <= 7; m = 4: w1 from k2, k3)
+//     slot = (((w0 c2 + w1 c4) >> 11) + disp[(w0 C1 + w1 C3) >> bshift]) & (slots - 1)        (hash, displace;
+//                                                     c2, c4: odd multipliers the host build settles on)
+//
+// m = 3 keeps every table in shared memory; m = 4 (template GT) reads displacements, slots and log rows from
+// global memory (L2-resident), three dependent loads per trial-step instead of ~5.6 with open addressing.
 //
 // two dependent shared-memory reads and no probe loop, against ~1.3 probes of an open-addressing table with
 // key compares and a divergent loop in detect2_kernel<LK_HASH, 3> (54 warp-instructions per trellis step with a
@@ -17,7 +21,7 @@
 #include "mvd_detect2.cuh"
 
 #define PH3_C1 0x9E3779B1u
-#define PH3_C2 0x85EBCA6Bu
+#define PH3_C3 0xC2B2AE35u
 
 // Branch metrics without a table read per branch: for a rate-1/2 code the metric of a branch with label L
 // against received word r is popc(L ^ r), so the 16 branch words of a step are 16 picks from the four
@@ -25,44 +29,58 @@
 // (ns, b) is PRMT(V_A, V_B, sel[ns][b]) = V_A[L] | V_B[L] << 16 with a kernel-constant selector (selector
 // nibbles with bit 3 set yield the replicated sign bit = 0).  16 PRMTs replace four LDS.128 (16 shared-memory
 // wavefronts per step pair): this kernel is shared-memory bound, the ALU pipe has room.
-struct PairEngine3 {
-    uint32_t Q[8];                    // (trial A, trial B) metrics of trellis states 0..7
-    uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
-    uint32_t kV, kD, kT, tmask;       // V(r) table (16 B) ; displacement table ; slot table | copy * 4 ; (slots - 1) << 3
-    uint32_t sel[16];                 // PRMT selector of branch (ns, b) at [2 ns + b]
+template <int M, bool GT>
+struct PairEngineN {
+    static constexpr int NS = 1 << M, HALF = NS / 2;
+    uint32_t Q[NS];                   // (trial A, trial B) metrics of the trellis states
+    uint32_t sxA, sxB;                // smem: absolute address of this lane's copy of the current log row; GT: state * R
+    uint32_t kV, kD, kT, tmask;       // V(r) table (16 B) ; smem: displacement table ; slot table | copy * 4 ; (slots - 1) << 3
+    uint32_t sel[2 * NS];             // PRMT selector of branch (ns, b) at [2 ns + b]
+    const uint32_t* gD;               // GT: displacements, slots and log rows in global memory
+    const uint32_t* gT;
+    const double2* gll;
+    uint32_t bshift, gmask, c2, c4;   // c2, c4: multipliers of the second hash, chosen by the host build
     double a1A, a0A, a1B, a0B;
 
-    __device__ __forceinline__ uint32_t lookup(uint32_t key) const {
-        const uint32_t d8 = lds_u32(kD | (((key * PH3_C1) >> 22) & 0x3FCu));          // displacement * 8
-        return lds_u32(kT | ((((key * PH3_C2) >> 18) + d8) & tmask));
+    __device__ __forceinline__ uint32_t lookup(uint32_t w0, uint32_t w1) const {
+        if (GT) {
+            const uint32_t d = __ldg(gD + ((w0 * PH3_C1 + w1 * PH3_C3) >> bshift));
+            return __ldg(gT + ((((w0 * c2 + w1 * c4) >> 11) + d) & gmask));
+        }
+        const uint32_t d8 = lds_u32(kD | (((w0 * PH3_C1) >> 22) & 0x3FCu));           // displacement * 8
+        return lds_u32(kT | ((((w0 * c2) >> 18) + d8) & tmask));
     }
 
     // sA5 / sB5: r_A / r_B at bits 5..6 (log rows, 32-byte entries); sA2 / sB2: r_A / r_B at bits 2..3 (V table)
     __device__ __forceinline__ void step(uint32_t sA5, uint32_t sB5, uint32_t sA2, uint32_t sB2) {
-        const double2 vA = lds_d2(sxA | (sA5 & 0x60u));
-        const double2 vB = lds_d2(sxB | (sB5 & 0x60u));
+        const double2 vA = GT ? __ldg(gll + sxA + ((sA5 >> 5) & 3u)) : lds_d2(sxA | (sA5 & 0x60u));
+        const double2 vB = GT ? __ldg(gll + sxB + ((sB5 >> 5) & 3u)) : lds_d2(sxB | (sB5 & 0x60u));
         a1A += vA.x;
         a0A += vA.y;
         a1B += vB.x;
         a0B += vB.y;
         const uint32_t VA = lds_u32(kV | (sA2 & 0xCu)), VB = lds_u32(kV | (sB2 & 0xCu));
-        uint32_t n[8];
+        uint32_t n[NS];
 #pragma unroll
-        for (int ns = 0; ns < 8; ++ns)                  // new state ns from predecessors ns >> 1 and (ns >> 1) + 4: Eq. 4, both trials
-            n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + 4] + __byte_perm(VA, VB, sel[2 * ns + 1]));
-        const uint32_t mn = __vimin3_u16x2(__vimin3_u16x2(n[0], n[1], n[2]), __vimin3_u16x2(n[3], n[4], n[5]), __vminu2(n[6], n[7]));
+        for (int ns = 0; ns < NS; ++ns)                 // new state ns from predecessors ns >> 1 and (ns >> 1) + HALF: Eq. 4, both trials
+            n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, sel[2 * ns + 1]));
+        uint32_t mn = __vimin3_u16x2(__vimin3_u16x2(n[0], n[1], n[2]), __vimin3_u16x2(n[3], n[4], n[5]), __vminu2(n[6], n[7]));
+        if (NS == 16) mn = __vimin3_u16x2(mn, __vimin3_u16x2(n[8], n[9], n[10]), __vimin3_u16x2(__vimin3_u16x2(n[11], n[12], n[13]), n[14], n[15]));
 #pragma unroll
-        for (int s = 0; s < 8; ++s) Q[s] = n[s] - mn;                           // Eq. 5
-        const uint32_t klo = ((Q[3] * 8u + Q[2]) * 8u + Q[1]) * 8u + Q[0];
-        const uint32_t khi = ((Q[7] * 8u + Q[6]) * 8u + Q[5]) * 8u + Q[4];
-        sxA = lookup(__byte_perm(klo, khi, 0x5410));     // klo.lo16 | khi.lo16 << 16
-        sxB = lookup(__byte_perm(klo, khi, 0x7632));     // klo.hi16 | khi.hi16 << 16
+        for (int s = 0; s < NS; ++s) Q[s] = n[s] - mn;                          // Eq. 5
+        uint32_t k[NS / 4];
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) k[i] = ((Q[4 * i + 3] * 8u + Q[4 * i + 2]) * 8u + Q[4 * i + 1]) * 8u + Q[4 * i];
+        // low halves = trial A, high halves = trial B
+        sxA = lookup(__byte_perm(k[0], k[1], 0x5410), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x5410) : 0u);
+        sxB = lookup(__byte_perm(k[0], k[1], 0x7632), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x7632) : 0u);
     }
 };
 
-template <int DUMMY>
-__global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_constant__ Params P,
-                                                                  const __grid_constant__ SegBatch B) {
+template <int M, bool GT>
+__global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(const __grid_constant__ Params P,
+                                                                               const __grid_constant__ SegBatch B) {
+    constexpr int NS = 1 << M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevSeg& sg = B.s[blockIdx.y];
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
@@ -74,9 +92,9 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_c
     const bool actA = tlA < ntr, actB = tlB < ntr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t SR = P.SR;
-    const uint32_t slots = P.fp.ph_slots, tbytes = slots * 8u;
+    const uint32_t slots = P.fp.ph_slots, tbytes = GT ? 0u : slots * 8u;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t a_T = (sbase + tbytes - 1u) & ~(tbytes - 1u);
+    const uint32_t a_T = GT ? ((sbase + 1023u) & ~1023u) : ((sbase + tbytes - 1u) & ~(tbytes - 1u));
     const uint32_t a_D = a_T + tbytes;                       // tbytes >= 2 KB keeps the 1 KB alignment
     const uint32_t a_tb = a_D + 1024u;
     const uint32_t a_V = a_tb + 128u;                        // 16-byte table V(r), 16 B aligned
@@ -85,7 +103,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_c
 
     if (threadIdx.x < 32u)
         *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
-    {
+    if (!GT) {
         const double2* llg = P.ll + (size_t)sg.table * SR;
         for (uint32_t i = threadIdx.x; i < SR * 2u; i += BS)
             *reinterpret_cast<double2*>(g + a_ll + ((i >> 1) << 5) + ((i & 1u) << 4)) = __ldg(llg + (i >> 1));
@@ -96,27 +114,36 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_c
         for (uint32_t L = 0; L < 4u; ++L) v |= (uint32_t)__popc(L ^ r) << (8u * L);
         *reinterpret_cast<uint32_t*>(g + a_V + 4u * r) = v;
     }
-    for (uint32_t i = threadIdx.x; i < 256u; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i] << 3;
-    for (uint32_t i = threadIdx.x; i < slots * 2u; i += BS) {
-        const uint32_t row = P.fp.ph_t[i >> 1];              // state * 4, or MVD_EMPTY (never looked up)
-        *reinterpret_cast<uint32_t*>(g + a_T + 4u * i) = a_ll + ((row == MVD_EMPTY ? 0u : row) << 5) + ((i & 1u) << 4);
+    if (!GT) {
+        for (uint32_t i = threadIdx.x; i < 256u; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i] << 3;
+        for (uint32_t i = threadIdx.x; i < slots * 2u; i += BS) {
+            const uint32_t row = P.fp.ph_t[i >> 1];          // state * 4, or MVD_EMPTY (never looked up)
+            *reinterpret_cast<uint32_t*>(g + a_T + 4u * i) = a_ll + ((row == MVD_EMPTY ? 0u : row) << 5) + ((i & 1u) << 4);
+        }
     }
     __syncthreads();
 
     const uint4* tbm = reinterpret_cast<const uint4*>(g + a_tb);
-    PairEngine3 eng;
+    PairEngineN<M, GT> eng;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) eng.Q[s] = 0u;
-    eng.sxA = eng.sxB = a_ll + ((lane & 1u) << 4);           // state 0 = the all-zero vector
+    for (int s = 0; s < NS; ++s) eng.Q[s] = 0u;
+    eng.sxA = eng.sxB = GT ? 0u : a_ll + ((lane & 1u) << 4); // state 0 = the all-zero vector
+    eng.gD = P.fp.ph_d;
+    eng.gT = P.fp.ph_t;
+    eng.gll = P.ll + (size_t)sg.table * SR;
+    eng.bshift = P.fp.ph_bshift;
+    eng.gmask = slots - 1u;
+    eng.c2 = P.fp.ph_c2;
+    eng.c4 = P.fp.ph_c4;
     eng.kV = a_V;
     eng.kD = a_D;
     // label of branch (ns, b) from the branch-metric table of the decoder (P.bm[r][2 g + b] = distances to ns = 2g and
     // 2g + 1 from predecessor g + 4 b): (d(L,0), d(L,1)) = (0,1), (1,0), (1,2), (2,1) for L = 0, 1, 2, 3
 #pragma unroll
-    for (int ns = 0; ns < 8; ++ns)
+    for (int ns = 0; ns < NS; ++ns)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            const uint32_t w0 = P.bm[0 * 8 + 2 * (ns >> 1) + b], w1 = P.bm[1 * 8 + 2 * (ns >> 1) + b];
+            const uint32_t w0 = P.bm[0 * NS + 2 * (ns >> 1) + b], w1 = P.bm[1 * NS + 2 * (ns >> 1) + b];
             const uint32_t d0 = (ns & 1) ? (w0 >> 16) : (w0 & 0xFFFFu), d1 = (ns & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
             const uint32_t L = d0 == 0u ? 0u : (d0 == 2u ? 3u : (d1 == 0u ? 1u : 2u));
             eng.sel[2 * ns + b] = L | 0x80u | ((4u + L) << 8) | 0x8000u;
@@ -131,9 +158,9 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_c
     const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
     const uint32_t c3 = sg.stream;
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
-    uint32_t tm0[4], tm1[4];
+    uint32_t tm0[M + 1], tm1[M + 1];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i <= M; ++i) {
         tm0[i] = 0u - ((taps0 >> i) & 1u);
         tm1[i] = 0u - ((taps1 >> i) & 1u);
     }
@@ -180,9 +207,9 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect3p_kernel(const __grid_c
                     e1 = pick(x ? EB1 : EA1, w);
                 }
                 const uint32_t pu = x ? prevUB : prevUA;
-                uint32_t o0 = U & tm0[0], o1 = U & tm1[0];              // m = 3: four tap masks per output
+                uint32_t o0 = U & tm0[0], o1 = U & tm1[0];              // m + 1 tap masks per output
 #pragma unroll
-                for (int i = 1; i <= 3; ++i) {
+                for (int i = 1; i <= M; ++i) {
                     const uint32_t sh = __funnelshift_l(pu, U, i);
                     o0 ^= sh & tm0[i];
                     o1 ^= sh & tm1[i];

@@ -16,7 +16,7 @@ cudaError_t mvd_launch_det2_acs(int lk, int m, int lls, bool gt, dim3 grid, unsi
 cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned threads, size_t smem, cudaStream_t st,
                                 const Params& P, const SegBatch& B);
 cudaError_t mvd_launch_det2_pair(dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B);
-cudaError_t mvd_launch_det3_pair(dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B);
+cudaError_t mvd_launch_det3_pair(int m, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B);
 cudaError_t mvd_launch_learn(bool smem_tables, size_t lsmem, uint32_t nsegs, cudaStream_t st, const Params& P,
                              const LearnParams& LP);
 cudaError_t mvd_launch_int_peak(int blocks, cudaStream_t st, uint32_t* out, int iters, int mode);

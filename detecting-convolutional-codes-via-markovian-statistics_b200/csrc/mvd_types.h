@@ -28,6 +28,8 @@ struct FastPlan {
     const uint32_t* ph_d;              // m = 3 perfect hash (mvd_detect3p.cuh): displacement per bucket [256]
     const uint32_t* ph_t;              //   slot -> state * R, or MVD_EMPTY [ph_slots]
     uint32_t ph_slots;                 //   power of two, 0 = no perfect hash
+    uint32_t ph_bshift;                //   bucket = hash >> ph_bshift
+    uint32_t ph_c2, ph_c4;             //   multipliers of the second hash (chosen by the host build)
 };
 
 struct Params {

@@ -436,6 +436,15 @@ def test_m4_global_tables_vs_oracle(codes_spec):
                 assert (kind == 0) == generic and (generic or kind & 512)      # fast path with tables in global memory
                 assert int(t[0]) == want
                 assert np.array_equal(lp, wlp)
+        # ACS engine, two trials per thread with the perfect-hash lookup (mvd_detect3p.cuh, m = 4 variant)
+        det.no_pair(2)
+        try:
+            t, lp = det.detect([seg], seed=8, engine="acs", want_logp=True)
+            kind = det.last_kernel_kind()
+        finally:
+            det.no_pair(False)
+        assert kind & 256 and kind & 512
+        assert int(t[0]) == want and np.array_equal(lp, wlp)
         # learning chain through the global-memory histogram
         got = det.learn_counts([Seg(N=60000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=_taps(spec))],
                                burn=200, seed=3)[0]
@@ -485,6 +494,31 @@ def test_gpu_bfs_m4_vs_host_bfs(golden, codes_spec, name, S):
                 det.table = det._fetch_states(st["S"])
             assert det.S == S
             assert np.array_equal(det.table.metrics, om) and np.array_equal(det.table.nxt, on)
+
+
+def test_m4_large_table_acs_pair_matches_next_walk(codes_spec):
+    """m = 4 with S = 150 743 (the reference cannot run it: 182 GB of dense counts): the two-trials-per-thread ACS
+    kernel (perfect hash over 2^19 slots in global memory) and the NEXT-table walk give identical tallies and sums."""
+    from mvd import bitsource, codes
+    from mvd.engine import Detector, Seg
+    spec = codes_spec["m4c"]
+    with Detector(spec["gen"], 1, 2, 4, enumerate_with="gpu", max_states=1 << 18) as det:
+        assert det.S == 150743
+        T = bitsource.bsc_threshold(0.05)
+        counts = det.learn_counts([Seg(N=400000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=det.dec_taps)], burn=200, seed=3)[0]
+        det.set_models([codes.p1_from_edge_counts(det.table, counts, 1.0)])
+        taps2 = [det.dec_taps[1], det.dec_taps[0]]
+        segs = [Seg(N=300, threshold=T, stream=d, enc_taps=(det.dec_taps if d == 0 else taps2), decide=d, trial_begin=0, trial_end=3000)
+                for d in (0, 1)]
+        a, la = det.detect(segs, seed=5, engine="fsm", want_logp=True)
+        det.no_pair(2)
+        try:
+            b, lb = det.detect(segs, seed=5, engine="acs", want_logp=True)
+            kind = det.last_kernel_kind()
+        finally:
+            det.no_pair(False)
+        assert kind & 256 and kind & 512
+        assert np.array_equal(a, b) and np.array_equal(la, lb)
 
 
 def test_gpu_bfs_limits_and_count_only(codes_spec):
