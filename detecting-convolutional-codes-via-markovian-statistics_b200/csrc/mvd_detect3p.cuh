@@ -11,8 +11,8 @@
 // global memory (L2-resident), three dependent loads per trial-step instead of ~5.6 with open addressing.
 //
 // two dependent shared-memory reads and no probe loop, against ~1.3 probes of an open-addressing table with
-// key compares and a divergent loop in detect2_kernel<LK_HASH, 3> (54 warp-instructions per trellis step with a
-// branch-metric table, instead of 107).  Results are the same bit for bit (same Eq. 4-5 arithmetic, same sums in step order).
+// key compares and a divergent loop in detect2_kernel<LK_HASH, 3> (66 warp-instructions per trellis step instead of
+// 107 at m = 3).  Results are the same bit for bit (same Eq. 4-5 arithmetic, same sums in step order).
 //
 // Shared memory (absolute addresses; alignment lets one LOP3 form an address):
 //   [hash slots: slots x 2 copies x 4 B, aligned to its size][displacements 256 x 4 B, 1 KB aligned]
