@@ -373,3 +373,16 @@ def test_hot_path_fails_loudly_without_gpu():
     assert "no CPU fallback" in str(ei.value)
     with pytest.raises(_capi.MvdError):
         vm.simulate_markov_sequence(gen1, 2, 1, 2, 10, 0.1, True, 1)
+    # the other entry points of the reference (alpha_exponent.py, comp_parity.py) and the GPU enumeration
+    import alpha_exponent as ae
+    import comp_parity as cp
+    from mvd.engine import Detector
+    taps = [[1, 1, 1], [1, 0, 1]]
+    with pytest.raises(_capi.MvdError):
+        ae.learn_transition_tensor(taps, taps, 2, 0.1, length=100, burn_in=10, seed=1)
+    with pytest.raises(_capi.MvdError):
+        ae.compute_error_exponent(np.full((3, 3, 4), 1 / 12), np.full((3, 3, 4), 1 / 12), 5)
+    with pytest.raises(_capi.MvdError):
+        cp.run_parity_experiment(gen1, gen2, 2, [50], [0.1], 0.6, 10, 1)
+    with pytest.raises(_capi.MvdError):
+        Detector(gen1, 1, 2, 2, enumerate_with="gpu")
