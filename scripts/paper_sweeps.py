@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""The north-star target as one command: full Pd-vs-p and Pd-vs-N sweeps of the hybrid detector for the paper's
+code pairs at 10^6 trials per point, plus the parity-template baseline over the same grid, through the public
+entry points (Pd_plotter.run_experiment / comp_parity.run_parity_experiment).  Writes the CSVs the reference's
+plots_compare.py reads and one JSON line of wall times per sweep.
+usage: scripts/paper_sweeps.py [outdir] [trials]"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "detecting-convolutional-codes-via-markovian-statistics_b200"))
+import Pd_plotter as pdp
+import comp_parity as cp
+import parity_eqn_check as pec
+
+out = sys.argv[1] if len(sys.argv) > 1 else "results_experiments"
+trials = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+os.makedirs(out, exist_ok=True)
+P7 = [0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5]
+PAIRS = {
+    "m2_7_5_vs_6_5": (2, [[[1, 1, 1]], [[1, 0, 1]]], [[[1, 1, 0]], [[1, 0, 1]]]),              # Pd_plotter.py:247-248
+    "m3_demo": (3, [[[1, 1, 1, 1]], [[1, 0, 1, 1]]], [[[1, 0, 1, 1]], [[1, 1, 1, 1]]]),       # demo_script.py:49-50
+}
+
+
+def timed(fn):
+    fn()                                    # warm-up: module load, enumeration, allocation
+    t0 = time.perf_counter()
+    r = fn()
+    return r, time.perf_counter() - t0
+
+
+for name, (m, g1, g2) in PAIRS.items():
+    # Pd vs p at the reference's blocklengths and a few more
+    Ns = [50, 100, 200, 500, 1000]
+    d = {}
+    df, wall = timed(lambda: pdp.run_experiment(1, 2, m, g1, g2, trials, P7, None, 200, 1.0, 12345, N_spectrum=Ns, details=d))
+    df.to_csv(os.path.join(out, f"Pd_hybrid_{name}_vs_p.csv"), index=False)
+    print(json.dumps(dict(sweep=f"{name} Pd vs p", points=len(df), trials_per_point=trials, steps=d["steps"], wall_s=round(wall, 4),
+                          detect_kernel_ms=round(d["detect_kernel_ms"], 3), steps_per_s=d["steps"] / wall)), flush=True)
+    # Pd vs N at fixed p (BASELINE config 3: 10^2 .. 10^5)
+    Nv = [100, 200, 500, 1000, 2000, 5000, 10000, 100000]
+    d = {}
+    df, wall = timed(lambda: pdp.run_experiment(1, 2, m, g1, g2, trials, [0.05, 0.1], None, 200, 1.0, 12345, N_spectrum=Nv, details=d))
+    df.to_csv(os.path.join(out, f"Pd_hybrid_{name}_vs_N.csv"), index=False)
+    print(json.dumps(dict(sweep=f"{name} Pd vs N", points=len(df), trials_per_point=trials, steps=d["steps"], wall_s=round(wall, 4),
+                          detect_kernel_ms=round(d["detect_kernel_ms"], 3), steps_per_s=d["steps"] / wall)), flush=True)
+
+# parity-template baseline over the m = 2 grid (comp_parity.py; the CSV plots_compare.py --baseline expects)
+g1 = [[pec.parse_poly_token("7")], [pec.parse_poly_token("5")]]
+g2 = [[pec.parse_poly_token("6")], [pec.parse_poly_token("5")]]
+d = {}
+df, wall = timed(lambda: cp.run_parity_experiment(g1, g2, 2, [50, 100, 200, 500, 1000], P7, 0.6, trials, 12345, details=d))
+os.makedirs(os.path.join(out, "results_parity"), exist_ok=True)
+df.to_csv(os.path.join(out, "results_parity", "Pd_parity_results.csv"), index=False)
+print(json.dumps(dict(sweep="parity baseline (7,5) vs (6,5)", points=len(df), trials_per_point=trials, steps=d["steps"],
+                      wall_s=round(wall, 4), kernel_ms=round(d["kernel_ms"], 3), steps_per_s=d["steps"] / wall)), flush=True)
