@@ -12,13 +12,17 @@
 // the hybrid detector's (MVD-PHILOX-2 on the device, or host-supplied 128-bit words).
 // The decision compares the same float64 quotient the reference forms (satisfied / total >= gamma).
 #pragma once
-#include "mvd_kernels.cuh"
+#include "mvd_detect2.cuh"
 
 __global__ void __launch_bounds__(PARITY_BLOCK) parity_kernel(const __grid_constant__ Params P, const __grid_constant__ ParityBatch B,
                                                               uint32_t* __restrict__ satisfied_out) {
+    __shared__ uint4 tbm[8];                      // threshold-bit masks of this segment's p (lazy_bernoulli_s)
     const ParitySeg& sg = B.s[blockIdx.y];
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
     if ((unsigned long long)blockIdx.x * PARITY_BLOCK >= ntr) return;
+    if (threadIdx.x < 32u) reinterpret_cast<uint32_t*>(tbm)[threadIdx.x] = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
+    __syncthreads();
+    const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
     const unsigned long long tl = (unsigned long long)blockIdx.x * PARITY_BLOCK + threadIdx.x;
     const bool active = tl < ntr;
     const unsigned long long trial = sg.trial_begin + tl;
@@ -56,8 +60,8 @@ __global__ void __launch_bounds__(PARITY_BLOCK) parity_kernel(const __grid_const
             for (int j = 0; j < MVD_MAX_N; ++j) {
                 if (j < (int)n) {
                     uint32_t E;
-                    if (philox) E = lazy_bernoulli(((4u * sb + (uint32_t)w) << 6) | (8u * (uint32_t)j), c1, c2, c3, sg.threshold,
-                                                   (int)sg.dmin, active ? vmask : 0u, P);
+                    if (philox) E = lazy_bernoulli_s(((4u * sb + (uint32_t)w) << 6) | (8u * (uint32_t)j), c1, c2, c3, tbm, ncalls,
+                                                     active ? vmask : 0u, P);
                     else E = pick(Ew[j], w) & vmask;
                     const uint32_t taps = sg.enc_taps[j];
                     uint32_t o = (taps & 1u) ? U : 0u;
