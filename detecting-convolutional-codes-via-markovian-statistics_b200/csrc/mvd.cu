@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -332,8 +333,15 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
     const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 4;
     const size_t SR = (size_t)ctx->S * R;
     int lk;
-    if (engine == MVD_ENGINE_FSM && ctx->tref_packed && !ctx->no_fsm1 && 128 + (SR << 7) + 64 <= ctx->prop.sharedMemPerBlockOptin) {
-        // one-load NEXT walk: [masks][S*R entries x 8 copies x 16 B]
+    if (engine == MVD_ENGINE_FSM && ctx->tref_packed && !ctx->no_fsm1 && 128 + (SR << 4) + 64 <= ctx->prop.sharedMemPerBlockOptin) {
+        // one-load NEXT walk: [masks][S*R entries x 2^(LLS-4) copies x 16 B].  Eight copies make every row read
+        // conflict-free; when that leaves one block per SM (S = 435: 222 KB) fewer copies and more resident blocks win
+        // (measured at S = 435: 8 / 4 / 2 / 1 copies = 7.06e11 / 8.46e11 / 8.44e11 / 8.17e11 steps/s)
+        int lls = 7;
+        const char* force = getenv("MVD_FSM1_LLS");                 // experiments only
+        if (force && *force >= '4' && *force <= '7') lls = *force - '0';
+        else while (lls > 4 && 128 + (SR << lls) + 64 > 75 * 1024) --lls;
+        while (lls > 4 && 128 + (SR << lls) + 64 > ctx->prop.sharedMemPerBlockOptin) --lls;
         fp->off_tb = 0;
         fp->off_bm = fp->off_st = 128;
         fp->off_ll = 128;
@@ -343,8 +351,8 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
         fp->tcode = ctx->d_tcode.as<uint32_t>();
         fp->tref_unit = ctx->tref_unit;
         *lk_out = LK_FSM1;
-        *lls_out = 7;
-        *smem_out = 128 + (SR << 7);
+        *lls_out = lls;
+        *smem_out = 128 + (SR << lls);
         return true;
     }
     if (engine == MVD_ENGINE_FSM) lk = LK_FSM;

@@ -17,7 +17,12 @@ cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned th
                                 const Params& P, const SegBatch& B) {
     if (lk == LK_FSM1) {
         if (gt) return launch_one<LK_FSM1, 1, 4, true>(grid, threads, smem, st, P, B);
-        return launch_one<LK_FSM1, 1, 7, false>(grid, threads, smem, st, P, B);
+        switch (lls) {
+            case 4: return launch_one<LK_FSM1, 1, 4, false>(grid, threads, smem, st, P, B);
+            case 5: return launch_one<LK_FSM1, 1, 5, false>(grid, threads, smem, st, P, B);
+            case 6: return launch_one<LK_FSM1, 1, 6, false>(grid, threads, smem, st, P, B);
+            default: return launch_one<LK_FSM1, 1, 7, false>(grid, threads, smem, st, P, B);
+        }
     }
     if (lk != LK_FSM || gt) return cudaErrorInvalidValue;
     switch (lls) {
