@@ -678,6 +678,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         meta[nsegs] = w;
         SplitParams SP{};
         SP.edge_bytes = eb;
+        SP.fast_walk = (n == 2 && ctx->learn_warm % 128u == 0u) ? 1 : 0;
+        for (uint32_t i = 0; i < nsegs; ++i) SP.max_chunks = std::max<unsigned long long>(SP.max_chunks, (ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
         for (uint32_t i = 0; i < nsegs; ++i) SP.max_trials = std::max<unsigned long long>(SP.max_trials, ds[i].trial_end - ds[i].trial_begin);
         if (nsegs > 65535) return fail(ctx, MVD_E_INVALID, "too many segments for one call");
         SP.warm = ctx->learn_warm;

@@ -15,6 +15,7 @@
 //   3. split_score_kernel -- one thread per trial adds log P1[e_t] and log Tref[e_t] in step order, so both
 //      sums -- and the decision -- are the ones of the one-thread-per-trial kernels.
 #pragma once
+#include "mvd_detect2.cuh"
 #include "mvd_learn2.cuh"
 
 __device__ __forceinline__ uint32_t split_find(const unsigned long long* begin, uint32_t n, unsigned long long x) {
@@ -98,6 +99,116 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
         }
     }
     SP.end[g] = sx;
+}
+
+// The same walk for rate-1/2 codes, laid out like the one-trial-per-thread fast kernels (mvd_detect2.cuh): one info
+// call per 128-step superblock, warp-voted mask-based flips (a warp = 32 trials of ONE chunk, so its control flow is
+// uniform), bit-parallel encoder, received words interleaved once per 32 steps, 16 steps per straight-line stretch.
+// grid (ceil(nch * ntr32 / SPLIT_BLOCK), segments), ntr32 = trials rounded up to a multiple of 32.
+// Needs n = 2 and a warm-up that is a multiple of 128 steps; anything else takes split_walk_kernel.
+template <bool SMEM, int EB>
+__global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint4 tbm[8];
+    constexpr uint32_t SPG = 16 / EB;
+    const uint32_t seg = blockIdx.y;
+    const DevSeg sg = P.segs[seg];
+    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin, ntr32 = (ntr + 31ull) & ~31ull;
+    if ((unsigned long long)blockIdx.x * SPLIT_BLOCK >= nch * ntr32) return;      // uniform: shorter segment
+    const uint32_t* nxt = P.nxt;
+    if (SMEM) {
+        uint32_t* s_nx = reinterpret_cast<uint32_t*>(smem_raw);
+        for (uint32_t i = threadIdx.x; i < P.SR; i += SPLIT_BLOCK) s_nx[i] = P.nxt[i];
+        nxt = s_nx;
+    }
+    if (threadIdx.x < 32u) reinterpret_cast<uint32_t*>(tbm)[threadIdx.x] = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
+    __syncthreads();
+    const unsigned long long local = (unsigned long long)blockIdx.x * SPLIT_BLOCK + threadIdx.x;
+    const uint32_t c = (uint32_t)(local / ntr32);
+    if (c >= nch) return;                                          // whole warps (ntr32 is a multiple of 32)
+    const unsigned long long tl = local % ntr32;
+    const bool active = tl < ntr;
+    const unsigned long long trial = sg.trial_begin + tl;
+    const unsigned long long wid = SP.work_begin[seg] + (unsigned long long)c * ntr + tl;
+    uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+    const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
+    const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
+    const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
+    const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
+    const int m = P.m;
+    uint32_t sx = 0;                                               // state 0 (exact when w_begin == 0)
+    const uint32_t sb0 = w_begin >> 7;
+    uint32_t prevU = 0;
+    if (sb0 > 0u && sg.random_input) prevU = philox10(((4u * (sb0 - 1u)) << 6) | 32u, c1, c2, c3, P).w;
+    for (uint32_t sb = sb0; sb * 128u < t_end; ++sb) {
+        uint4 Uw = philox10(((4u * sb) << 6) | 32u, c1, c2, c3, P);
+        if (!sg.random_input) Uw = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t0 = sb * 128u + (uint32_t)w * 32u;
+            if (t0 >= t_end) break;
+            const uint32_t valid = min(32u, N - t0);
+            const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+            const uint32_t U = pick(Uw, w);
+            const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
+            const uint32_t e0 = lazy_bernoulli_s(cb, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
+            const uint32_t e1 = lazy_bernoulli_s(cb | 8u, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
+            uint32_t o0 = U & (0u - (taps0 & 1u)), o1 = U & (0u - (taps1 & 1u));
+#pragma unroll 1
+            for (int i = 1; i <= m; ++i) {
+                const uint32_t sh = __funnelshift_l(prevU, U, i);
+                o0 ^= sh & (0u - ((taps0 >> i) & 1u));
+                o1 ^= sh & (0u - ((taps1 >> i) & 1u));
+            }
+            prevU = U;
+            const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
+            // received word of step t = bits (2t+1, 2t) of (whi:wlo); first output is the MSB
+            const uint32_t wlo = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
+            const uint32_t whi = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+            if (t0 == t_begin && active) SP.spec_start[wid] = sx;
+            const bool emit = t0 >= t_begin && active;
+            if (valid == 32u) {
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t x = h ? whi : wlo;
+                    uint32_t e[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        e[j] = sx + ((x >> (2 * j)) & 3u);
+                        sx = SMEM ? nxt[e[j]] : __ldg(nxt + e[j]);
+                    }
+                    if (emit) {
+#pragma unroll
+                        for (int q = 0; q < 16 / (int)SPG; ++q) {
+                            uint4 grp = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                            for (int u = 0; u < (int)SPG; ++u) split_put<EB>(grp, (uint32_t)u, e[q * (int)SPG + u]);
+                            E4[(unsigned long long)((t0 + 16u * (uint32_t)h) / SPG + (uint32_t)q) * ntr] = grp;
+                        }
+                    }
+                }
+            } else {
+                const uint32_t nst = min(valid, t_end - t0);
+                for (uint32_t q = 0; q * SPG < nst; ++q) {
+                    uint4 grp = make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t cnt = min(SPG, nst - q * SPG);
+                    for (uint32_t u = 0; u < cnt; ++u) {
+                        const uint32_t t = q * SPG + u;
+                        const uint32_t r = ((t < 16u ? wlo : whi) >> (2u * (t & 15u))) & 3u;
+                        const uint32_t e = sx + r;
+#pragma unroll
+                        for (uint32_t z = 0; z < SPG; ++z)
+                            if (z == u) split_put<EB>(grp, z, e);
+                        sx = SMEM ? nxt[e] : __ldg(nxt + e);
+                    }
+                    if (emit) E4[(unsigned long long)(t0 / SPG + q) * ntr] = grp;
+                }
+            }
+        }
+    }
+    if (active) SP.end[wid] = sx;
 }
 
 // one thread per chain: repair the chunks whose speculated start state was wrong, in order

@@ -31,7 +31,19 @@ cudaError_t launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t l
     const unsigned cb = SP.chain_block;
     const unsigned cblocks = (SP.nchains + cb - 1) / cb;
     cudaError_t e;
-    if (nxt_smem) {
+    if (SP.fast_walk) {                                  // n = 2, warm-up a multiple of 128: the fast walk
+        unsigned long long mx = 0;
+        mx = ((SP.max_chunks * ((SP.max_trials + 31ull) & ~31ull)) + SPLIT_BLOCK - 1) / SPLIT_BLOCK;
+        const dim3 wgrid((unsigned)mx, P.nsegs);
+        if (nxt_smem) {
+            auto kern = split_walk2_kernel<true, EB>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nxt_bytes);
+            if (e != cudaSuccess) return e;
+            kern<<<wgrid, SPLIT_BLOCK, nxt_bytes, st>>>(P, SP);
+        } else {
+            split_walk2_kernel<false, EB><<<wgrid, SPLIT_BLOCK, 0, st>>>(P, SP);
+        }
+    } else if (nxt_smem) {
         auto kern = split_walk_kernel<true, EB>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nxt_bytes);
         if (e != cudaSuccess) return e;

@@ -108,6 +108,8 @@ struct SplitParams {
     uint32_t chain_block;                   // threads per block of the per-chain kernels (fix, score)
     unsigned long long max_trials;          // most trials of any segment (x extent of the scoring grid)
     int edge_bytes;                         // bytes per stored edge index: 1 (S R <= 256), 2 (<= 65 536) or 4
+    int fast_walk;                          // 1: split_walk2_kernel (n = 2, warm-up a multiple of 128)
+    unsigned long long max_chunks;          // most chunks of any segment
 };
 
 // ---- parity-template baseline trials (mvd_parity.cuh)
