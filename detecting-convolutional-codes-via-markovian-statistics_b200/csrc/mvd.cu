@@ -629,8 +629,16 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             work += ntr * ((ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
         }
         split = split && ew * 4ull <= (6ull << 30) && work <= 0x7FFFFFFFull * (unsigned long long)SPLIT_BLOCK;
-        if (ctx->split_mode == 0)                              // automatic: under 1/4 of the threads the GPU holds, trials >= 4 chunks
-            split = split && trials * 4ull < 2048ull * sms && steps >= trials * 4ull * SPLIT_CH;
+        if (ctx->split_mode == 0) {
+            // automatic: compare the two paths with measured rates (B200, m = 2).  One thread per trial: the chain of a
+            // trial costs ~63 ns per step until the GPU is full (~1e12 steps/s); split: the walk is work-bound at
+            // ~7.5e11 steps/s (warm-up included) and the in-order scoring costs ~12.5 ns per step of the longest trial.
+            uint32_t maxN = 0;
+            for (uint32_t i = 0; i < nsegs; ++i) maxN = std::max(maxN, ds[i].N);
+            const double t_plain = std::max((double)maxN * 63e-9, (double)steps / 1.0e12);
+            const double t_split = (double)steps / 7.5e11 + (double)maxN * 12.5e-9 + 15e-6;
+            split = split && maxN >= 4u * SPLIT_CH && t_split < 0.8 * t_plain;
+        }
     }
     const dim3 grid((unsigned)blocks);
     const bool n2 = (n == 2);
