@@ -386,3 +386,28 @@ def test_hot_path_fails_loudly_without_gpu():
         cp.run_parity_experiment(gen1, gen2, 2, [50], [0.1], 0.6, 10, 1)
     with pytest.raises(_capi.MvdError):
         Detector(gen1, 1, 2, 2, enumerate_with="gpu")
+
+
+def test_plots_compare_helpers_and_csv_chain(tmp_path, capsys):
+    """plots_compare drop-in (reference plots_compare.py:35-148): helper semantics, and the CSVs committed under
+    profiles/paper_sweeps (written by Pd_plotter.run_experiment / comp_parity.run_parity_experiment on the GPU) load."""
+    import os
+    import pandas as pd
+    import plots_compare as pc
+    assert pc.p_error([1.2, 0.75, -0.5]).tolist() == [0.0, 0.25, 1.0]
+    df = pd.DataFrame({"N": [500, 100, 100, 500], "p": [0.3, 0.2, 0.1, 0.1], "Pd": [0.1, 0.5, 0.9, 1.0], "Pc": [0.5, 0.7, 0.95, 1.0]})
+    x, y = pc.extract_by_N(df, 100)
+    assert x.tolist() == [0.1, 0.2] and y.tolist() == [0.95, 0.7]
+    x, y = pc.extract_by_p(df, 0.1 + 1e-12)
+    assert x.tolist() == [100, 500] and y.tolist() == [0.95, 1.0]
+    assert pc.extract_by_N(df, 7)[0].size == 0
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "paper_sweeps")
+    hybrid = os.path.join(root, "Pd_hybrid_m2_7_5_vs_6_5_vs_p.csv")
+    base = os.path.join(root, "results_parity", "Pd_parity_results.csv")
+    only_pd = tmp_path / "only_pd.csv"
+    pd.read_csv(base)[["N", "p", "Pd"]].to_csv(only_pd, index=False)          # a CSV without Pc: Pd stands in
+    h, b = pc.load_results(hybrid, str(only_pd))
+    assert list(h.columns) == ["N", "p", "Pd", "Pc"] and (b["Pc"] == b["Pd"]).all() and len(h) == 35 and len(b) == 35
+    pc.main(hybrid, base, str(tmp_path / "plots"))                              # plots, or tables without matplotlib
+    out = capsys.readouterr().out
+    assert os.listdir(tmp_path / "plots") or "P_err hybrid" in out
