@@ -11,6 +11,14 @@ import Pd_plotter as pdp
 import comp_parity as cp
 import parity_eqn_check as pec
 
+# under torchrun the trials of every point shard across the ranks (one allreduce of the tallies per sweep); rank 0 writes
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+
 out = sys.argv[1] if len(sys.argv) > 1 else "results_experiments"
 trials = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 os.makedirs(out, exist_ok=True)
@@ -23,9 +31,17 @@ PAIRS = {
 
 def timed(fn):
     fn()                                    # warm-up: module load, enumeration, allocation
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     r = fn()
     return r, time.perf_counter() - t0
+
+
+def emit(df, path, **info):
+    if rank == 0:
+        df.to_csv(path, index=False)
+        print(json.dumps(dict(n_gpus=world, **info)), flush=True)
 
 
 for name, (m, g1, g2) in PAIRS.items():
@@ -33,16 +49,14 @@ for name, (m, g1, g2) in PAIRS.items():
     Ns = [50, 100, 200, 500, 1000]
     d = {}
     df, wall = timed(lambda: pdp.run_experiment(1, 2, m, g1, g2, trials, P7, None, 200, 1.0, 12345, N_spectrum=Ns, details=d))
-    df.to_csv(os.path.join(out, f"Pd_hybrid_{name}_vs_p.csv"), index=False)
-    print(json.dumps(dict(sweep=f"{name} Pd vs p", points=len(df), trials_per_point=trials, steps=d["steps"], wall_s=round(wall, 4),
-                          detect_kernel_ms=round(d["detect_kernel_ms"], 3), steps_per_s=d["steps"] / wall)), flush=True)
+    emit(df, os.path.join(out, f"Pd_hybrid_{name}_vs_p.csv"), sweep=f"{name} Pd vs p", points=len(df), trials_per_point=trials,
+         steps=d["steps"], wall_s=round(wall, 4), detect_kernel_ms=round(d["detect_kernel_ms"], 3), steps_per_s=d["steps"] / wall)
     # Pd vs N at fixed p (BASELINE config 3: 10^2 .. 10^5)
     Nv = [100, 200, 500, 1000, 2000, 5000, 10000, 100000]
     d = {}
     df, wall = timed(lambda: pdp.run_experiment(1, 2, m, g1, g2, trials, [0.05, 0.1], None, 200, 1.0, 12345, N_spectrum=Nv, details=d))
-    df.to_csv(os.path.join(out, f"Pd_hybrid_{name}_vs_N.csv"), index=False)
-    print(json.dumps(dict(sweep=f"{name} Pd vs N", points=len(df), trials_per_point=trials, steps=d["steps"], wall_s=round(wall, 4),
-                          detect_kernel_ms=round(d["detect_kernel_ms"], 3), steps_per_s=d["steps"] / wall)), flush=True)
+    emit(df, os.path.join(out, f"Pd_hybrid_{name}_vs_N.csv"), sweep=f"{name} Pd vs N", points=len(df), trials_per_point=trials,
+         steps=d["steps"], wall_s=round(wall, 4), detect_kernel_ms=round(d["detect_kernel_ms"], 3), steps_per_s=d["steps"] / wall)
 
 # parity-template baseline over the m = 2 grid (comp_parity.py; the CSV plots_compare.py --baseline expects)
 g1 = [[pec.parse_poly_token("7")], [pec.parse_poly_token("5")]]
@@ -50,6 +64,7 @@ g2 = [[pec.parse_poly_token("6")], [pec.parse_poly_token("5")]]
 d = {}
 df, wall = timed(lambda: cp.run_parity_experiment(g1, g2, 2, [50, 100, 200, 500, 1000], P7, 0.6, trials, 12345, details=d))
 os.makedirs(os.path.join(out, "results_parity"), exist_ok=True)
-df.to_csv(os.path.join(out, "results_parity", "Pd_parity_results.csv"), index=False)
-print(json.dumps(dict(sweep="parity baseline (7,5) vs (6,5)", points=len(df), trials_per_point=trials, steps=d["steps"],
-                      wall_s=round(wall, 4), kernel_ms=round(d["kernel_ms"], 3), steps_per_s=d["steps"] / wall)), flush=True)
+emit(df, os.path.join(out, "results_parity", "Pd_parity_results.csv"), sweep="parity baseline (7,5) vs (6,5)", points=len(df),
+     trials_per_point=trials, steps=d["steps"], wall_s=round(wall, 4), kernel_ms=round(d["kernel_ms"], 3), steps_per_s=d["steps"] / wall)
+if world > 1:
+    dist.destroy_process_group()
