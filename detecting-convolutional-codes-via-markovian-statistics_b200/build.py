@@ -13,8 +13,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 UNITS = ["mvd.cu", "mvd_tu_generic_acs.cu", "mvd_tu_generic_fsm.cu", "mvd_tu_det2_acs.cu", "mvd_tu_det2_fsm.cu",
-         "mvd_tu_learn.cu", "mvd_tu_bfs.cu", "mvd_tu_chernoff.cu", "mvd_tu_parity.cu", "mvd_tu_det3_pair.cu"]
-HEADERS = ["mvd_types.h", "mvd_launch.h", "mvd_kernels.cuh", "mvd_detect2.cuh", "mvd_learn2.cuh", "mvd_bfs.cuh", "mvd_chernoff.cuh", "mvd_parity.cuh", "mvd_detect3p.cuh", "mvd_split.cuh"]
+         "mvd_tu_learn.cu", "mvd_tu_bfs.cu", "mvd_tu_chernoff.cu", "mvd_tu_parity.cu", "mvd_tu_det3_pair.cu", "mvd_tu_acsp.cu"]
+HEADERS = ["mvd_types.h", "mvd_launch.h", "mvd_kernels.cuh", "mvd_detect2.cuh", "mvd_learn2.cuh", "mvd_bfs.cuh", "mvd_chernoff.cuh", "mvd_parity.cuh", "mvd_detect3p.cuh", "mvd_split.cuh", "mvd_acsp.cuh"]
 DEPS = [os.path.join(CSRC, f) for f in UNITS + HEADERS] + [os.path.join(ROOT, "include", "mvd.h")]
 OBJ = os.path.join(PKG, "build")
 OUT = os.path.join(PKG, "libmvd.so")

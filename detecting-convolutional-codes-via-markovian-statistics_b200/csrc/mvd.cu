@@ -1133,6 +1133,62 @@ int mvd_acs_hash(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint6
     return run(ctx, MODE_HASH, MVD_ENGINE_ACS, src, seg, 1, o);
 }
 
+int mvd_acs_final(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint8_t* final_metrics) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!src || !seg || !final_metrics) return fail(ctx, MVD_E_INVALID, "null argument");
+    if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code has not been called");
+    if (ctx->n != 2 || ctx->m < 2) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final supports n = 2, m = 2..6 (use mvd_acs_hash)");
+    if (src->mode != MVD_SRC_PHILOX) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final takes the on-device bit source (use mvd_acs_hash)");
+    if (seg->trial_end < seg->trial_begin) return fail(ctx, MVD_E_INVALID, "trial_end < trial_begin");
+    CK(cudaSetDevice(ctx->device));
+    const int m = ctx->m, nstate = 1 << m, HALF = nstate / 2;
+    const uint64_t ntr = seg->trial_end - seg->trial_begin;
+    if (ntr == 0) return MVD_OK;
+    uint32_t sel[128] = {0};
+    for (int ns = 0; ns < nstate; ++ns)
+        for (int b = 0; b < 2; ++b) {
+            const uint32_t L = (uint32_t)label_of_branch((uint32_t)((ns >> 1) + b * HALF), (uint32_t)(ns & 1), ctx->dec_taps, 2);
+            sel[2 * ns + b] = L | 0x80u | ((4u + L) << 8) | 0x8000u;
+        }
+    DevSeg d{};
+    d.N = seg->N;
+    d.threshold = seg->threshold;
+    d.stream = seg->stream;
+    for (int j = 0; j < 2; ++j) {
+        if (seg->enc_taps[j] >> (m + 1)) return fail(ctx, MVD_E_INVALID, "encoder tap beyond memory m=%d", m);
+        d.enc_taps[j] = seg->enc_taps[j];
+    }
+    d.random_input = seg->random_input ? 1u : 0u;
+    d.dmin = seg->threshold ? (uint32_t)__builtin_ctz(seg->threshold) : 32u;
+    d.trial_begin = seg->trial_begin;
+    d.trial_end = seg->trial_end;
+    Params P{};
+    P.n = 2;
+    P.m = m;
+    P.src_mode = MVD_SRC_PHILOX;
+    {
+        uint32_t k0 = (uint32_t)src->seed, k1 = (uint32_t)(src->seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            P.rk0[r] = k0;
+            P.rk1[r] = k1;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+    }
+    CK(ctx->d_final.reserve((size_t)ntr * nstate));
+    const uint64_t blocks = (ntr + 2 * DET2P_BLOCK - 1) / (2 * DET2P_BLOCK);
+    if (blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one call");
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(mvd_launch_acsp(m, dim3((unsigned)blocks), DET2P_BLOCK, ctx->stream, P, d, sel, ctx->d_final.as<uint8_t>()));
+    ctx->launches += 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(final_metrics, ctx->d_final.p, (size_t)ntr * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->last_fast = 32768;
+    return MVD_OK;
+}
+
 int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next, const double* lp1, const double* lp2,
                      const double* lb1, const double* lb2, const double* u_vals, uint32_t nu, double tol, uint32_t max_iter,
                      double* rho, uint32_t* iters) {

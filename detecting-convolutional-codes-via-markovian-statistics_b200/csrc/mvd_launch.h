@@ -74,3 +74,7 @@ cudaError_t mvd_launch_parity(dim3 grid, cudaStream_t st, const Params& P, const
 // detection trials split along the time axis (mvd_split.cuh, in mvd_tu_learn.cu)
 cudaError_t mvd_launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
                              const SplitParams& SP);
+
+// Eq. 4-5 at m = 2..6, two trials per thread, final metric vectors only (mvd_tu_acsp.cu)
+cudaError_t mvd_launch_acsp(int m, dim3 grid, unsigned threads, cudaStream_t st, const Params& P, const DevSeg& sg,
+                            const uint32_t* sel, uint8_t* final_met);

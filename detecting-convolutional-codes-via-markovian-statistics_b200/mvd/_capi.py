@@ -30,7 +30,7 @@ EXPORTS = (
     "mvd_set_code", "mvd_set_states", "mvd_enumerate_states", "mvd_get_states", "mvd_set_loglik",
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
-    "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table",
+    "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table", "mvd_acs_final",
 )
 
 
@@ -106,6 +106,7 @@ def load():
     lib.mvd_detect.argtypes = [vp, P(Src), P(Segment), u32, i32, vp, vp, vp]
     lib.mvd_trace.argtypes = [vp, P(Src), P(Segment), i32, vp, vp]
     lib.mvd_acs_hash.argtypes = [vp, P(Src), P(Segment), vp, vp]
+    lib.mvd_acs_final.argtypes = [vp, P(Src), P(Segment), vp]
     lib.mvd_last_kernel_ms.argtypes = [vp, P(C.c_float)]
     lib.mvd_launch_count.argtypes = [vp, P(u64)]
     lib.mvd_int_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]

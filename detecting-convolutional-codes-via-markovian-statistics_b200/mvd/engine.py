@@ -230,6 +230,13 @@ class Detector:
         del keep
         return h, fin
 
+    def acs_final(self, seg: Seg, seed: Optional[int] = None) -> np.ndarray:
+        """Final metric vectors uint8 [ntrials, 2^m] of the Eq. 4-5 recursion, throughput form (``mvd_acs_final``)."""
+        src, _ = self._src(seed, None)
+        fin = np.zeros((seg.ntrials, 1 << self.m), dtype=np.uint8)
+        self._ck(self.lib.mvd_acs_final(self.ctx, C.byref(src), self._segments([seg]), fin.ctypes.data))
+        return fin
+
     # ------------------------------------------------------------------ error exponent (alpha_exponent.py)
     def chernoff_rho_edges(self, nxt, lp1, lp2, lb1, lb2, u_vals, tol: float = 1e-14, max_iter: int = 100000):
         """rho(M(u)) for every u (Eq. 7) from edge-form log tensors; see ``mvd_chernoff_rho``."""

@@ -204,6 +204,11 @@ typedef struct mvd_parity_segment {
 int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment* segs, uint32_t nsegs,
                       uint64_t* tallies, uint32_t* satisfied);
 
+/* Throughput form of the same recursion (n = 2, on-device bits): two trials per thread, all 2^m metric pairs
+ * in registers (csrc/mvd_acsp.cuh); only the final vectors D_N come back (ntrials x 2^m bytes), the same bytes
+ * mvd_acs_hash returns in final_metrics.  BASELINE config 4: m = 4..6, up to 64 trellis states. */
+int mvd_acs_final(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint8_t* final_metrics);
+
 /* Timing of the last learn/detect/trace launch on the context's stream (CUDA events), and the
  * number of kernels this library has launched since creation. */
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms);
@@ -215,6 +220,7 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * 1 + lookup (0 direct table, 1 hash table, 2 NEXT-table walk, 3 one-load NEXT-table walk) + 16 * log2(bytes per log-likelihood row entry)
  * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
  * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius, 8192 = parity-template trials,
+ * 32768 = mvd_acs_final,
  * 16384 = detection trials split along the time axis (mvd_learn_stats then gives the chunks repaired).
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */

@@ -559,6 +559,12 @@ def test_acs_hash_large_memory(codes_spec, name):
             wh, wf = co.acs_hash(taps, taps, spec["n"], spec["m"], 257, U, E)
             assert int(h[t]) == wh
             assert np.array_equal(fin[t], wf)
+        # throughput form (two trials per thread, every metric pair in registers): the same final vectors
+        fin2 = det.acs_final(seg, seed=31)
+        assert det.last_kernel_kind() == 32768
+        assert np.array_equal(fin2, fin)
+        odd = Seg(N=33, threshold=T, stream=5, enc_taps=taps, trial_begin=7, trial_end=7 + 513)     # ragged block, odd trial count
+        assert np.array_equal(det.acs_final(odd, seed=9), det.acs_hash(odd, seed=9)[1])
 
 
 def test_engines_and_sources_agree_at_scale(codes_spec, dets):
