@@ -710,6 +710,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         const size_t nb = (size_t)SR * 4, lb = ((size_t)SR * 16) << SP.ll_rep_shift;
         SP.nxt_in_smem = nb <= 64 * 1024;
         SP.ll_in_smem = lb <= 64 * 1024;
+        SP.ring_offset = SP.ll_in_smem ? (uint32_t)((lb + 127) & ~(size_t)127) : 0u;   // the scoring kernel's cp.async ring follows its table
         SP.chain_block = SPLIT_BLOCK;                            // per-chain kernels: spread few chains over all SMs
         while (SP.chain_block > 32 && (trials + SP.chain_block - 1) / SP.chain_block < 2 * sms) SP.chain_block >>= 1;
         CK(cudaStreamSynchronize(ctx->stream));                 // meta is a stack-lifetime vector

@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_fix_kernel(const __grid_con
 // 2^SP.ll_rep_shift times at 16-byte pitch (one copy per lane of a quarter warp, as in mvd_detect2.cuh) so that
 // the random row reads of a warp are bank-conflict free; read with ld.shared (a generic pointer that may be
 // shared or global costs a slower LD per step).
+#define SPLIT_RING 32u                 // 16-byte groups of the edge stream in flight per scoring thread
+
 template <bool SMEM>
 __device__ __forceinline__ double2 split_ll(const double2* g, uint32_t sbase, uint32_t sh, uint32_t e) {
     if (SMEM) {
@@ -306,42 +308,36 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
     const uint32_t N = sg.N;
     const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
     double a1 = 0.0, a0 = 0.0;
-    // The adds are one dependent chain per sum (Pd_plotter.py:114-115 in step order): all that can overlap are
-    // the loads.  With a few thousand chains on the whole GPU the edge stream needs many requests in flight per
-    // thread: a ring of K 16-byte groups, each slot refilled as soon as it is consumed.
-    constexpr uint32_t K = 12;
+    // The adds are one dependent chain per sum (Pd_plotter.py:114-115 in step order): all that can overlap are the
+    // loads.  With one warp per SM a load sees the whole DRAM latency (~2 000 cycles = 13 groups at 9.5 cycles per
+    // step; measured: every group cost ~200 cycles of stall with a 12-deep register ring), so the edge stream goes
+    // through an asynchronous shared-memory ring of SPLIT_RING groups per thread (cp.async), refilled as it is consumed.
     const uint32_t ngroups = N / SPG;
-    uint4 ring[K];
-#pragma unroll
-    for (uint32_t i = 0; i < K; ++i)
-        if (i < ngroups) ring[i] = __ldcs(E4 + (unsigned long long)i * ntr);
-    uint32_t g0 = 0;
-    for (; g0 + K <= ngroups; g0 += K) {
-#pragma unroll
-        for (uint32_t i = 0; i < K; ++i) {
-            const uint4 grp = ring[i];
-            if (g0 + K + i < ngroups) ring[i] = __ldcs(E4 + (unsigned long long)(g0 + K + i) * ntr);
-            double2 v[SPG];
-#pragma unroll
-            for (uint32_t u = 0; u < SPG; ++u) v[u] = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(grp, u));
-#pragma unroll
-            for (uint32_t u = 0; u < SPG; ++u) {
-                a1 += v[u].x;
-                a0 += v[u].y;
-            }
-        }
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(smem_raw) + SP.ring_offset + threadIdx.x * 16u;
+    const uint32_t rstride = blockDim.x * 16u;                    // slot s of this thread: ring0 + s * rstride
+#pragma unroll 1
+    for (uint32_t i = 0; i < SPLIT_RING; ++i) {
+        if (i < ngroups)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + i * rstride), "l"(E4 + (unsigned long long)i * ntr));
+        asm volatile("cp.async.commit_group;");
     }
-    // the last < K whole groups are already in the ring; then the ragged tail group
+    uint32_t slot = 0;
+#pragma unroll 1
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(SPLIT_RING - 1));
+        uint4 grp;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(grp.x), "=r"(grp.y), "=r"(grp.z), "=r"(grp.w) : "r"(ring0 + slot * rstride));
+        double2 v[SPG];
 #pragma unroll
-    for (uint32_t i = 0; i < K; ++i) {
-        if (g0 + i < ngroups) {
-            const uint4 grp = ring[i];
+        for (uint32_t u = 0; u < SPG; ++u) v[u] = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(grp, u));
+        if (g + SPLIT_RING < ngroups)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + slot * rstride), "l"(E4 + (unsigned long long)(g + SPLIT_RING) * ntr));
+        asm volatile("cp.async.commit_group;");
+        slot = slot + 1u == SPLIT_RING ? 0u : slot + 1u;
 #pragma unroll
-            for (uint32_t u = 0; u < SPG; ++u) {
-                const double2 v = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(grp, u));
-                a1 += v.x;
-                a0 += v.y;
-            }
+        for (uint32_t u = 0; u < SPG; ++u) {
+            a1 += v[u].x;
+            a0 += v[u].y;
         }
     }
     if (ngroups * SPG < N) {

@@ -55,13 +55,18 @@ cudaError_t launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t l
     if (e != cudaSuccess) return e;
     split_fix_kernel<EB><<<cblocks, cb, 0, st>>>(P, SP);
     const dim3 sgrid((unsigned)((SP.max_trials + cb - 1) / cb), P.nsegs);
+    const size_t ring_bytes = (size_t)cb * 16 * 32;      // SPLIT_RING groups of 16 bytes per thread
+    const size_t sbytes = (size_t)SP.ring_offset + ring_bytes;
     if (ll_smem) {
         auto kern = split_score_kernel<true, EB>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_bytes);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
         if (e != cudaSuccess) return e;
-        kern<<<sgrid, cb, ll_bytes, st>>>(P, SP);
+        kern<<<sgrid, cb, sbytes, st>>>(P, SP);
     } else {
-        split_score_kernel<false, EB><<<sgrid, cb, 0, st>>>(P, SP);
+        auto kern = split_score_kernel<false, EB>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
+        if (e != cudaSuccess) return e;
+        kern<<<sgrid, cb, sbytes, st>>>(P, SP);
     }
     return cudaGetLastError();
 }

@@ -109,6 +109,7 @@ struct SplitParams {
     unsigned long long max_trials;          // most trials of any segment (x extent of the scoring grid)
     int edge_bytes;                         // bytes per stored edge index: 1 (S R <= 256), 2 (<= 65 536) or 4
     int fast_walk;                          // 1: split_walk2_kernel (n = 2, warm-up a multiple of 128)
+    uint32_t ring_offset;                   // scoring kernel: byte offset of the cp.async ring in dynamic shared memory
     unsigned long long max_chunks;          // most chunks of any segment
 };
 
