@@ -9,7 +9,6 @@ Call order mirrors the reference's experiment (Pd_plotter.py:176-235):
 from __future__ import annotations
 
 import ctypes as C
-import math
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence
 

@@ -14,7 +14,6 @@ which the reference calls (Pd_plotter.py:149,212,219) but never defines -- runs 
 """
 from __future__ import annotations
 
-import itertools
 from functools import lru_cache
 
 import numpy as np
