@@ -1200,7 +1200,9 @@ int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next,
     for (size_t e = 0; e < KR; ++e)
         if (next[e] >= K) return fail(ctx, MVD_E_INVALID, "next[%zu]=%u out of range (K=%u)", e, next[e], K);
     CK(cudaSetDevice(ctx->device));
-    const size_t per_u = (KR + 3 * (size_t)K) * 8;
+    // weights in scratch while it fits L2-ish sizes; beyond that they are recomputed in every product (mvd_chernoff.cuh)
+    const bool recompute = (KR + (size_t)K) * 8 * nu > ((size_t)96 << 20);
+    const size_t per_u = recompute ? 2 * (size_t)K * 8 : (KR + 3 * (size_t)K) * 8;
     uint32_t ub = (uint32_t)std::max<size_t>(1, std::min<size_t>(nu, ((size_t)8 << 30) / per_u));
     DevBuf d_in, d_scr, d_out;
     const size_t in_bytes = KR * 4 + 2 * KR * 8 + 2 * (size_t)K * 8 + (size_t)nu * 8;
@@ -1230,9 +1232,15 @@ int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next,
     P.lb1 = g_lb1;
     P.lb2 = g_lb2;
     P.tol = tol;
-    P.wd = d_scr.as<double>();
-    P.bgR = P.wd + (size_t)ub * KR;
-    P.xa = P.bgR + (size_t)ub * K;
+    if (recompute) {
+        P.wd = nullptr;
+        P.bgR = nullptr;
+        P.xa = d_scr.as<double>();
+    } else {
+        P.wd = d_scr.as<double>();
+        P.bgR = P.wd + (size_t)ub * KR;
+        P.xa = P.bgR + (size_t)ub * K;
+    }
     P.xb = P.xa + (size_t)ub * K;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (uint32_t u0 = 0; u0 < nu; u0 += ub) {

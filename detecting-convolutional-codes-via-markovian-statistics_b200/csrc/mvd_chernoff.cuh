@@ -40,22 +40,29 @@ __device__ __forceinline__ double chernoff_block_sum(double v, double* red) {
     return red[32];
 }
 
+// RECOMPUTE = false: w(u) - bg(u) and R bg(u) are built once per u into global scratch and re-read by every product
+// (small K: the scratch stays in L2).  RECOMPUTE = true: they are recomputed from the log tables in every product --
+// at K > ~10^5 the 401 x K x R x 8-byte scratch (3 GB at K = 232 567) is streamed from DRAM once per product while the
+// log tables (64 B per row, shared by all u) stay in L2, and a handful of products suffice there.
+template <bool RECOMPUTE>
 __global__ void __launch_bounds__(CHERNOFF_BLOCK) chernoff_rho_kernel(const __grid_constant__ ChernoffParams P) {
     __shared__ double red[33];
     const uint32_t ui = blockIdx.x;
     if (ui >= P.nu) return;
     const uint32_t K = P.K, R = P.R;
     const double u = P.u_vals[ui], v = 1.0 - u;
-    double* wd = P.wd + (size_t)ui * K * R;
-    double* bgR = P.bgR + (size_t)ui * K;
+    double* wd = RECOMPUTE ? nullptr : P.wd + (size_t)ui * K * R;
+    double* bgR = RECOMPUTE ? nullptr : P.bgR + (size_t)ui * K;
     double* x = P.xa + (size_t)ui * K;
     double* y = P.xb + (size_t)ui * K;
     for (uint32_t i = threadIdx.x; i < K; i += CHERNOFF_BLOCK) {
-        const double bg = exp(u * P.lb1[i] + v * P.lb2[i]);
-        bgR[i] = bg * (double)R;
-        for (uint32_t r = 0; r < R; ++r) {
-            const size_t e = (size_t)i * R + r;
-            wd[e] = exp(u * P.lp1[e] + v * P.lp2[e]) - bg;
+        if (!RECOMPUTE) {
+            const double bg = exp(u * P.lb1[i] + v * P.lb2[i]);
+            bgR[i] = bg * (double)R;
+            for (uint32_t r = 0; r < R; ++r) {
+                const size_t e = (size_t)i * R + r;
+                wd[e] = exp(u * P.lp1[e] + v * P.lp2[e]) - bg;
+            }
         }
         x[i] = 1.0 / (double)K;
     }
@@ -66,10 +73,17 @@ __global__ void __launch_bounds__(CHERNOFF_BLOCK) chernoff_rho_kernel(const __gr
         // sum(x) = 1 by construction
         double part = 0.0;
         for (uint32_t i = threadIdx.x; i < K; i += CHERNOFF_BLOCK) {
-            double acc = bgR[i];
+            double acc, bg = 0.0;
+            if (RECOMPUTE) {
+                bg = exp(u * __ldg(P.lb1 + i) + v * __ldg(P.lb2 + i));
+                acc = bg * (double)R;
+            } else {
+                acc = bgR[i];
+            }
             for (uint32_t r = 0; r < R; ++r) {
                 const size_t e = (size_t)i * R + r;
-                acc = fma(wd[e], x[P.nxt[e]], acc);
+                const double w = RECOMPUTE ? exp(u * __ldg(P.lp1 + e) + v * __ldg(P.lp2 + e)) - bg : wd[e];
+                acc = fma(w, x[P.nxt[e]], acc);
             }
             y[i] = acc;
             part += acc;
