@@ -155,20 +155,17 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     kernel_ms = det.last_kernel_ms()
     tallies = dist.allreduce_sum(tallies.astype(np.int64))
 
-    cols = {"N": [], "p": [], "Pd": [], "Pc": []}
-    for q, (N, p) in enumerate(points):
-        s1, s2 = int(tallies[2 * q]), int(tallies[2 * q + 1])
-        cols["N"].append(N)
-        cols["p"].append(p)
-        cols["Pd"].append(s1 / num_iter)                        # reference :225-226
-        cols["Pc"].append((s1 + s2) / (2 * num_iter))
+    t64 = np.asarray(tallies, dtype=np.int64)
+    s1, s2 = t64[0::2], t64[1::2]
+    cols = {"N": np.array([N for N, _ in points]), "p": np.array([p for _, p in points], dtype=np.float64),
+            "Pd": s1 / num_iter, "Pc": (s1 + s2) / (2 * num_iter)}                        # reference :225-226
     if details is not None:
         details.update(tallies=tallies, edge_counts=counts, p1_tables=tables, distinct_p=distinct,
                        detect_kernel_ms=kernel_ms, learn_kernel_ms=learn_kernel_ms,
                        wall_s=dict(setup=t_learn0 - t_start, learn=t_tables0 - t_learn0, tables=t_detect0 - t_tables0,
                                    detect=time.perf_counter() - t_detect0), steps=2 * sum(N for N, _ in points) * int(num_iter),
                        learn_len=_learn_len(det.S, learn_len), S=det.S)
-    return pd.DataFrame(cols, columns=["N", "p", "Pd", "Pc"])
+    return pd.DataFrame(cols, index=pd.RangeIndex(len(points)), copy=False)      # columns N, p, Pd, Pc (reference :228-235)
 
 
 if __name__ == "__main__":
