@@ -740,3 +740,29 @@ def test_learn_P1_empirical_contract(golden):
     tab = __import__("viterbi_markov").state_table(g["gen1"], 2, 1, 2)
     assert np.array_equal(P[np.arange(31)[:, None], tab.nxt], want)
     assert pdp.learn_P1_empirical(gens, 1, 2, 2, 0.1, None, 200, 1.0, 123)[2] is P      # lru_cache, Pd_plotter.py:123
+
+
+def test_integration_md_stub_runs_as_written():
+    """The ctypes stub INTEGRATION.md shows a maintainer of the reference (section B) is executed verbatim against
+    libmvd.so, with the reference-side objects it expects in scope, and must reproduce run_experiment's tallies."""
+    import os
+    import re
+    import Pd_plotter as pdp
+    import viterbi_markov as vm
+    from mvd import _capi, codes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"## B\..*?```python\n(.*?)```", text, flags=re.S).group(1)
+    block = block.replace('C.CDLL("libmvd.so")', f'C.CDLL("{_capi.LIB_PATH}")')
+    k, n, m = 1, 2, 2
+    gen1, gen2 = [[[1, 1, 1]], [[1, 0, 1]]], [[[1, 1, 0]], [[1, 0, 1]]]
+    states, transitions, all_r = vm.enumerate_markov_states_allzero(gen1, m, k, n)
+    env = dict(vm=vm, k=k, n=n, m=m, gen1=gen1, gen2=gen2, states=states, all_r=all_r, index={s: i for i, s in enumerate(states)},
+               trellis=vm.build_trellis(gen1, m, k), S=len(states), seed=12345, p=0.1, N=300, num_iter=4000,
+               learn_len_eff=max(5000, 200 * len(states)), learn_burn=200, laplace=1.0,
+               T_ref=vm.numeric_T(states, transitions, all_r, 0.5))
+    exec(compile(block, "INTEGRATION.md", "exec"), env)
+    d = {}
+    df = pdp.run_experiment(k, n, m, gen1, gen2, 4000, [0.1], None, 200, 1.0, 12345, N_spectrum=[300], details=d)
+    assert env["tallies"].tolist() == [int(v) for v in d["tallies"]]
+    assert env["Pd"] == df["Pd"][0] and env["Pc"] == df["Pc"][0]
