@@ -766,3 +766,21 @@ def test_integration_md_stub_runs_as_written():
     df = pdp.run_experiment(k, n, m, gen1, gen2, 4000, [0.1], None, 200, 1.0, 12345, N_spectrum=[300], details=d)
     assert env["tallies"].tolist() == [int(v) for v in d["tallies"]]
     assert env["Pd"] == df["Pd"][0] and env["Pc"] == df["Pc"][0]
+    # the second snippet: comp_parity.py's Monte-Carlo loop through mvd_parity_detect
+    import ctypes as C
+    import comp_parity as cp
+    import parity_eqn_check as pec
+    snippet = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "mvd_parity_detect" in b][0]
+    generators = [[pec.parse_poly_token("7")], [pec.parse_poly_token("5")]]
+    other = [[pec.parse_poly_token("6")], [pec.parse_poly_token("5")]]
+    template, _ = cp.template_from_generators(generators, 2)
+    ctx = C.c_void_p()
+    assert env["lib"].mvd_create(C.byref(ctx), 0) == 0
+    env.update(generators=generators, other=other, template=template, gamma=0.6, trials=5000, N=200, ctx=ctx,
+               tallies=np.zeros(2, dtype=np.uint64))
+    exec(compile(snippet, "INTEGRATION.md#parity", "exec"), env)
+    env["lib"].mvd_destroy(ctx)
+    tm = cp._template_masks(template, 2)
+    want = cp.ParityContext().run([dict(N=200, m=2, taps=cp._tap_masks(g), tmpl=tm, gamma=0.6, decide=h, threshold=env["T"], stream=h,
+                                        trial_begin=0, trial_end=5000) for h, g in enumerate((generators, other))], seed=12345)
+    assert env["tallies"].tolist() == want.tolist() and env["accuracy"] == want[0] / 5000
