@@ -478,8 +478,8 @@ struct PairEngine {
         Q1 = n1 - mn;
         Q2 = n2 - mn;
         Q3 = n3 - mn;
-        // key = s1 | s0 << 2 | s3 << 4 | s2 << 6 per trial (the direct table's index), times 128
-        const uint32_t t7 = Q1 * 128u + Q0 * 512u + Q3 * 2048u + Q2 * 8192u;
+        // key = s1 | s0 << 2 | s3 << 4 | s2 << 6 per trial (the direct table's index), times 128: three IMADs
+        const uint32_t t7 = ((Q2 * 4u + Q3) * 4u + Q0) * 4u + Q1;           // metrics are kept times 128 (branch metrics too)
         sxA = lds_u32((t7 & 0xFFFFu) + kst);
         sxB = lds_u32((t7 >> 16) + kst);
     }
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
         const uint32_t wa = P.bm[rA * 4u + 2u * gg + b], wb = P.bm[rB * 4u + 2u * gg + b];
         const uint32_t da = h ? (wa >> 16) : (wa & 0xFFFFu), db = h ? (wb >> 16) : (wb & 0xFFFFu);
         *reinterpret_cast<uint32_t*>(g + a_bm + (wd >> 2) * 2048u + (rA << 7) + (rB << 9) + (c << 4) + 4u * (wd & 3u)) =
-            da | (db << 16);
+            (da << 7) | (db << 23);                              // times 128: the metric pairs then form the table offset by Horner
     }
     for (uint32_t i = threadIdx.x; i < 256u * 32u; i += BS) {
         const uint32_t st = P.fp.dstate[i >> 5];
