@@ -451,13 +451,46 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     return v;
 }
 
+// lazy_bernoulli_s with the threshold masks addressed in the shared window (ld.shared, no generic pointer)
+__device__ __forceinline__ uint32_t lazy_bernoulli_a(uint32_t c0base, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t a_tbm, int ncalls, uint32_t vmask, const Params& P) {
+    uint32_t und = vmask, e = 0;
+    for (int k = 0; k < ncalls; ++k) {
+        if (!__any_sync(0xFFFFFFFFu, und != 0u)) break;
+        const uint4 w = philox10(c0base + (uint32_t)k, c1, c2, c3, P);
+        const uint4 tb = lds_v4(a_tbm + 16u * (uint32_t)k);
+        e |= und & ~w.x & tb.x;
+        und &= ~(w.x ^ tb.x);
+        e |= und & ~w.y & tb.y;
+        und &= ~(w.y ^ tb.y);
+        e |= und & ~w.z & tb.z;
+        und &= ~(w.z ^ tb.z);
+        e |= und & ~w.w & tb.w;
+        und &= ~(w.w ^ tb.w);
+    }
+    return e;
+}
+
+// (a & m) | (b & ~m) as one LOP3
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
 struct PairEngine {
     uint32_t Q0, Q1, Q2, Q3;          // (trial A, trial B) metrics of trellis states 0..3
     uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
     uint32_t kbm, kst;                // branch-metric plane 0 | copy * 16 ; state table + lane * 4
     double a1A, a0A, a1B, a0B;
 
-    // sA, sB7: r_A, r_B at bits 7..8; sB: r_B at bits 9..10 (other bits arbitrary)
+    // sA, sB7: r_A, r_B at bits 7..8; sB: r_B at bits 9..10 (other bits arbitrary).
+    // NORM = false leaves the metrics un-normalised (Eq. 5 deferred): the minimum is still taken, but only
+    // to correct the table key, key(D' - min) = key(D') - 85 min (85 = 1 + 4 + 16 + 64, one IMAD on the packed
+    // pair, exact modulo 2^32 whatever the low lane carries into the high one), which replaces the four
+    // subtractions.  A stretch of 8 steps adds at most 8 n = 16 to a lane (times 128: 2 432 < 2^16), and its
+    // last step runs with NORM = true, so every loop boundary sees D = D' - min(D') as the reference does.
+    template <bool NORM>
     __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7) {
         const uint32_t rA = sA & 0x180u;
         const double2 vA = lds_d2(sxA | rA);
@@ -474,18 +507,27 @@ struct PairEngine {
         const uint32_t n2 = __viaddmin_u16x2(Q1, b1.x, Q3 + b1.y);
         const uint32_t n3 = __viaddmin_u16x2(Q1, b1.z, Q3 + b1.w);
         const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);       // per-trial minimum
-        Q0 = n0 - mn;                                                       // Eq. 5 (no borrow: every lane >= its minimum)
-        Q1 = n1 - mn;
-        Q2 = n2 - mn;
-        Q3 = n3 - mn;
-        // key = s1 | s0 << 2 | s3 << 4 | s2 << 6 per trial (the direct table's index), times 128: three IMADs
-        const uint32_t t7 = ((Q2 * 4u + Q3) * 4u + Q0) * 4u + Q1;           // metrics are kept times 128 (branch metrics too)
+        uint32_t t7;
+        if (NORM) {
+            Q0 = n0 - mn;                                                   // Eq. 5 (no borrow: every lane >= its minimum)
+            Q1 = n1 - mn;
+            Q2 = n2 - mn;
+            Q3 = n3 - mn;
+            // key = s1 | s0 << 2 | s3 << 4 | s2 << 6 per trial (the direct table's index), times 128: three IMADs
+            t7 = ((Q2 * 4u + Q3) * 4u + Q0) * 4u + Q1;                      // metrics are kept times 128 (branch metrics too)
+        } else {
+            Q0 = n0;
+            Q1 = n1;
+            Q2 = n2;
+            Q3 = n3;
+            t7 = ((n2 * 4u + n3) * 4u + n0) * 4u + n1 - 85u * mn;
+        }
         sxA = lds_u32((t7 & 0xFFFFu) + kst);
         sxB = lds_u32((t7 >> 16) + kst);
     }
 };
 
-template <int DUMMY>
+template <int PHILOX>
 __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_constant__ Params P,
                                                                   const __grid_constant__ SegBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -531,7 +573,6 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     }
     __syncthreads();
 
-    const uint4* tbm = reinterpret_cast<const uint4*>(g + a_tb);
     PairEngine eng;
     eng.Q0 = eng.Q1 = eng.Q2 = eng.Q3 = 0u;
     eng.sxA = eng.sxB = a_ll + ((lane & 7u) << 4);            // state 0 = the all-zero vector
@@ -541,19 +582,26 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
 
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
-    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    constexpr bool philox = PHILOX != 0;               // the bit source is a template parameter: the bit-stream words are not live in the Philox instance
     const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
     const uint32_t c3 = sg.stream;
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
     const uint32_t tm00 = 0u - (taps0 & 1u), tm01 = 0u - ((taps0 >> 1) & 1u), tm02 = 0u - ((taps0 >> 2) & 1u);
     const uint32_t tm10 = 0u - (taps1 & 1u), tm11 = 0u - ((taps1 >> 1) & 1u), tm12 = 0u - ((taps1 >> 2) & 1u);
     uint32_t prevUA = 0, prevUB = 0;
+    // Philox counter words and activity masks of the two trials, pinned in registers: left to itself the
+    // compiler re-derives them from blockIdx / threadIdx / the segment record before every lazy loop
+    // (~50 instructions per flip word)
+    uint32_t c1A = (uint32_t)trA, c2A = (uint32_t)(trA >> 32), c1B = (uint32_t)trB, c2B = (uint32_t)(trB >> 32);
+    uint32_t mA = actA ? 0xFFFFFFFFu : 0u, mB = actB ? 0xFFFFFFFFu : 0u;
+    uint32_t c3p = c3, a_tbp = a_tb;
+    asm volatile("" : "+r"(c1A), "+r"(c2A), "+r"(c1B), "+r"(c2B), "+r"(mA), "+r"(mB), "+r"(c3p), "+r"(a_tbp));
     const uint32_t nsb = (N + 127u) >> 7;
     for (uint32_t sb = 0; sb < nsb; ++sb) {
         uint4 UA = make_uint4(0, 0, 0, 0), UB = UA, EA0 = UA, EA1 = UA, EB0 = UA, EB1 = UA;
         if (philox) {
-            UA = philox10(((4u * sb) << 6) | 32u, (uint32_t)trA, (uint32_t)(trA >> 32), c3, P);
-            UB = philox10(((4u * sb) << 6) | 32u, (uint32_t)trB, (uint32_t)(trB >> 32), c3, P);
+            UA = philox10(((4u * sb) << 6) | 32u, c1A, c2A, c3p, P);
+            UB = philox10(((4u * sb) << 6) | 32u, c1B, c2B, c3p, P);
         } else {
             const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 3ull * ntr;
             if (actA) {
@@ -574,21 +622,34 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             if (t0 >= N) break;
             const uint32_t valid = min(32u, N - t0);
             const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
-            uint32_t wlo[2], whi[2];
+            uint32_t wev[2], wod[2];                    // received pairs of the even / odd steps (see below)
+            uint32_t eA0, eA1, eB0, eB1;
+            if (philox) {
+                // the four flip words of this 32-step block (2 trials x 2 outputs) through ONE copy of the lazy
+                // loop; the results rotate through four registers (no dispatch on the word index)
+                uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask;
+                asm volatile("" : "+r"(cb), "+r"(vm));
+                eA0 = eA1 = eB0 = eB1 = 0u;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const bool second = j >= 2;
+                    const uint32_t e = lazy_bernoulli_a(cb | (((uint32_t)j & 1u) << 3), second ? c1B : c1A, second ? c2B : c2A, c3p, a_tbp,
+                                                        ncalls, (second ? mB : mA) & vm, P);
+                    eA0 = eA1;
+                    eA1 = eB0;
+                    eB0 = eB1;
+                    eB1 = e;
+                }
+            } else {
+                eA0 = pick(EA0, w);
+                eA1 = pick(EA1, w);
+                eB0 = pick(EB0, w);
+                eB1 = pick(EB1, w);
+            }
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
                 const uint32_t U = x ? UB.x : UA.x;                      // word w: the vectors rotate below
-                const bool act = x ? actB : actA;
-                const unsigned long long tr = x ? trB : trA;
-                uint32_t e0, e1;
-                if (philox) {
-                    const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
-                    e0 = lazy_bernoulli_s(cb, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
-                    e1 = lazy_bernoulli_s(cb | 8u, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
-                } else {
-                    e0 = pick(x ? EB0 : EA0, w);
-                    e1 = pick(x ? EB1 : EA1, w);
-                }
+                const uint32_t e0 = x ? eB0 : eA0, e1 = x ? eB1 : eA1;
                 const uint32_t pu = x ? prevUB : prevUA;
                 uint32_t o0 = U & tm00, o1 = U & tm10;                  // m = 2: three tap masks per output
                 const uint32_t sh1 = __funnelshift_l(pu, U, 1), sh2 = __funnelshift_l(pu, U, 2);
@@ -596,40 +657,44 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
                 o1 ^= (sh1 & tm11) ^ (sh2 & tm12);
                 if (x) prevUB = U; else prevUA = U;
                 const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
-                wlo[x] = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
-                whi[x] = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+                // r_t = (R0 bit t, R1 bit t) without a Morton interleave: two bit-selects put the pairs of the
+                // even steps into one word and those of the odd steps into another, both at bits (t | 1, t & ~1)
+                wev[x] = bitsel(R1, R0 << 1, 0x55555555u);
+                wod[x] = bitsel(R1 >> 1, R0, 0x55555555u);
             }
             UA = make_uint4(UA.y, UA.z, UA.w, 0u);
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
-            auto oct = [&](uint32_t wa, uint32_t wb) {                        // 8 steps = bits 0..15 of wa / wb
-                const uint32_t wa2 = wa >> 8, wb2 = wb >> 8;
-                eng.step(wa << 7, wb << 9, wb << 7);
-                eng.step(wa << 5, wb << 7, wb << 5);
-                eng.step(wa << 3, wb << 5, wb << 3);
-                eng.step(wa << 1, wb << 3, wb << 1);
-                eng.step(wa2 << 7, wb2 << 9, wb2 << 7);
-                eng.step(wa2 << 5, wb2 << 7, wb2 << 5);
-                eng.step(wa2 << 3, wb2 << 5, wb2 << 3);
-                eng.step(wa2 << 1, wb2 << 3, wb2 << 1);
+            // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
+            auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
+                eng.step<false>(ea << 7, eb << 9, eb << 7);
+                eng.step<false>(oa << 7, ob << 9, ob << 7);
+                eng.step<false>(ea << 5, eb << 7, eb << 5);
+                eng.step<false>(oa << 5, ob << 7, ob << 5);
+                eng.step<false>(ea << 3, eb << 5, eb << 3);
+                eng.step<false>(oa << 3, ob << 5, ob << 3);
+                eng.step<false>(ea << 1, eb << 3, eb << 1);
+                eng.step<true>(oa << 1, ob << 3, ob << 1);
             };
             if (valid == 32u) {
+                uint32_t ea = wev[0], oa = wod[0], eb = wev[1], ob = wod[1];
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {                                  // 16 steps per iteration (measured: 8 -> 6.98e11, 16 -> 7.07e11, 32 -> 6.92e11 steps/s)
-                    const uint32_t xa = h ? whi[0] : wlo[0], xb = h ? whi[1] : wlo[1];
-                    oct(xa, xb);
-                    oct(xa >> 16, xb >> 16);
+                    oct(ea, oa, eb, ob);
+                    oct(ea >> 8, oa >> 8, eb >> 8, ob >> 8);
+                    ea >>= 16; oa >>= 16; eb >>= 16; ob >>= 16;
                 }
             } else {
 #pragma unroll 1
                 for (uint32_t c = 0; c < valid; c += 8u) {
-                    const uint32_t sh = (c & 8u) << 1;
-                    const uint32_t wa = ((c & 16u) ? whi[0] : wlo[0]) >> sh;
-                    const uint32_t wb = ((c & 16u) ? whi[1] : wlo[1]) >> sh;
+                    const uint32_t ea = wev[0] >> c, oa = wod[0] >> c, eb = wev[1] >> c, ob = wod[1] >> c;
                     if (c + 8u <= valid) {
-                        oct(wa, wb);
+                        oct(ea, oa, eb, ob);
                     } else {
-                        for (uint32_t j = 0; j < valid - c; ++j)
-                            eng.step((wa >> (2u * j)) << 7, (wb >> (2u * j)) << 9, (wb >> (2u * j)) << 7);
+                        for (uint32_t j = 0; j < valid - c; ++j) {
+                            const uint32_t sh = j & ~1u;
+                            const uint32_t wa = ((j & 1u) ? oa : ea) >> sh, wb = ((j & 1u) ? ob : eb) >> sh;
+                            eng.step<true>(wa << 7, wb << 9, wb << 7);
+                        }
                     }
                 }
             }
