@@ -52,7 +52,7 @@ struct mvd_ctx {
     uint64_t launches = 0;
     float last_ms = 0.f;
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
-    bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false;
+    bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false, no_antipodal = false;
     int split_mode = 0;             // 0 = automatic, 1 = always split long trials along the time axis, 2 = never
     bool have_gfsm1 = false;
     bool tref_packed = false;       // log Tref = c * unit with c in {0, 2^j}: one-load NEXT walk possible
@@ -537,6 +537,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     P.nxt = ctx->d_nxt.as<uint32_t>();
     P.ll = ctx->d_ll.as<double2>();
     P.bm = ctx->d_bm.as<uint32_t>();
+    P.bm_antipodal = !ctx->no_antipodal;
+    for (int j = 0; j < ctx->n; ++j)
+        if (!(ctx->dec_taps[j] & 1u) || !((ctx->dec_taps[j] >> ctx->m) & 1u)) P.bm_antipodal = 0;
     P.hkeys = ctx->d_hkeys.as<uint32_t>();
     P.hvals = ctx->d_hvals.as<uint32_t>();
     P.hcap = ctx->hcap;
@@ -1455,6 +1458,10 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
     }
     if (option == MVD_OPT_NO_FSM1) {
         ctx->no_fsm1 = value != 0;
+        return MVD_OK;
+    }
+    if (option == MVD_OPT_NO_ANTIPODAL) {
+        ctx->no_antipodal = value != 0;
         return MVD_OK;
     }
     if (option == MVD_OPT_SPLIT) {

@@ -445,6 +445,11 @@ __device__ __forceinline__ double2 lds_d2(uint32_t a) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -490,7 +495,11 @@ struct PairEngine {
     // pair, exact modulo 2^32 whatever the low lane carries into the high one), which replaces the four
     // subtractions.  A stretch of 8 steps adds at most 8 n = 16 to a lane (times 128: 2 432 < 2^16), and its
     // last step runs with NORM = true, so every loop boundary sees D = D' - min(D') as the reference does.
-    template <bool NORM>
+    // ANTI: every generator has its first and its last tap set (e.g. (7,5)), so the four branches of a
+    // butterfly carry the labels X, ~X, ~X, X and d(~X, r) = n - d(X, r): one 8-byte read (X of the two
+    // butterflies, 2 wavefronts) and two subtractions replace the two 16-byte reads (8 wavefronts) of the
+    // general table.
+    template <bool NORM, bool ANTI>
     __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7) {
         const uint32_t rA = sA & 0x180u;
         const double2 vA = lds_d2(sxA | rA);
@@ -500,12 +509,22 @@ struct PairEngine {
         a1B += vB.x;
         a0B += vB.y;
         const uint32_t boff = kbm | rA | (sB & 0x600u);
-        const uint4 b0 = lds_v4(boff);                 // ns 0: (pred 0, pred 2), ns 1: (pred 0, pred 2)
-        const uint4 b1 = lds_v4(boff + 2048u);         // ns 2: (pred 1, pred 3), ns 3: (pred 1, pred 3)
-        const uint32_t n0 = __viaddmin_u16x2(Q0, b0.x, Q2 + b0.y);          // Eq. 4, both trials
-        const uint32_t n1 = __viaddmin_u16x2(Q0, b0.z, Q2 + b0.w);
-        const uint32_t n2 = __viaddmin_u16x2(Q1, b1.x, Q3 + b1.y);
-        const uint32_t n3 = __viaddmin_u16x2(Q1, b1.z, Q3 + b1.w);
+        uint32_t n0, n1, n2, n3;
+        if (ANTI) {
+            const uint2 px = lds_v2(boff);                 // d(0 -> 0), d(1 -> 2) for (r_A, r_B)
+            const uint32_t c0 = 0x01000100u - px.x, c1 = 0x01000100u - px.y;    // n = 2, times 128, both lanes
+            n0 = __viaddmin_u16x2(Q0, px.x, Q2 + c0);                           // Eq. 4, both trials
+            n1 = __viaddmin_u16x2(Q0, c0, Q2 + px.x);
+            n2 = __viaddmin_u16x2(Q1, px.y, Q3 + c1);
+            n3 = __viaddmin_u16x2(Q1, c1, Q3 + px.y);
+        } else {
+            const uint4 b0 = lds_v4(boff);                 // ns 0: (pred 0, pred 2), ns 1: (pred 0, pred 2)
+            const uint4 b1 = lds_v4(boff + 2048u);         // ns 2: (pred 1, pred 3), ns 3: (pred 1, pred 3)
+            n0 = __viaddmin_u16x2(Q0, b0.x, Q2 + b0.y);    // Eq. 4, both trials
+            n1 = __viaddmin_u16x2(Q0, b0.z, Q2 + b0.w);
+            n2 = __viaddmin_u16x2(Q1, b1.x, Q3 + b1.y);
+            n3 = __viaddmin_u16x2(Q1, b1.z, Q3 + b1.w);
+        }
         const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);       // per-trial minimum
         uint32_t t7;
         if (NORM) {
@@ -527,7 +546,7 @@ struct PairEngine {
     }
 };
 
-template <int PHILOX>
+template <int PHILOX, int ANTI>
 __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_constant__ Params P,
                                                                   const __grid_constant__ SegBatch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -558,7 +577,16 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     }
     // pair branch metrics: row (rA | rB << 2), word (ns, b): lo = d(pred_b -> ns | rA), hi = ... | rB
     // P.bm[r][2 g + b] = (d(pred -> 2g), d(pred -> 2g+1)) for pred = g + 2 b
-    for (uint32_t i = threadIdx.x; i < 16u * 8u * 8u; i += BS) {
+    if (ANTI) {
+        // row (rA | rB << 2), 16 copies of 8 bytes (LDS.64 is served per half warp): {d(0 -> 0), d(1 -> 2)} pairs
+        for (uint32_t i = threadIdx.x; i < 16u * 16u; i += BS) {
+            const uint32_t c = i & 15u, row = i >> 4, rA = row & 3u, rB = row >> 2;
+            const uint32_t x0 = (P.bm[rA * 4u] & 0xFFFFu) << 7 | (P.bm[rB * 4u] & 0xFFFFu) << 23;
+            const uint32_t x1 = (P.bm[rA * 4u + 2u] & 0xFFFFu) << 7 | (P.bm[rB * 4u + 2u] & 0xFFFFu) << 23;
+            *reinterpret_cast<uint2*>(g + a_bm + (rA << 7) + (rB << 9) + (c << 3)) = make_uint2(x0, x1);
+        }
+    }
+    for (uint32_t i = ANTI ? 16u * 8u * 8u : threadIdx.x; i < 16u * 8u * 8u; i += BS) {
         const uint32_t c = i & 7u, wd = (i >> 3) & 7u, row = i >> 6;
         const uint32_t rA = row & 3u, rB = row >> 2, ns = wd >> 1, b = wd & 1u, gg = ns >> 1, h = ns & 1u;
         const uint32_t wa = P.bm[rA * 4u + 2u * gg + b], wb = P.bm[rB * 4u + 2u * gg + b];
@@ -576,7 +604,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     PairEngine eng;
     eng.Q0 = eng.Q1 = eng.Q2 = eng.Q3 = 0u;
     eng.sxA = eng.sxB = a_ll + ((lane & 7u) << 4);            // state 0 = the all-zero vector
-    eng.kbm = a_bm + ((lane & 7u) << 4);
+    eng.kbm = ANTI ? a_bm + ((lane & 15u) << 3) : a_bm + ((lane & 7u) << 4);
     eng.kst = a_st + lane * 4u;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
 
@@ -666,14 +694,14 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
             // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
             auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
-                eng.step<false>(ea << 7, eb << 9, eb << 7);
-                eng.step<false>(oa << 7, ob << 9, ob << 7);
-                eng.step<false>(ea << 5, eb << 7, eb << 5);
-                eng.step<false>(oa << 5, ob << 7, ob << 5);
-                eng.step<false>(ea << 3, eb << 5, eb << 3);
-                eng.step<false>(oa << 3, ob << 5, ob << 3);
-                eng.step<false>(ea << 1, eb << 3, eb << 1);
-                eng.step<true>(oa << 1, ob << 3, ob << 1);
+                eng.step<false, ANTI != 0>(ea << 7, eb << 9, eb << 7);
+                eng.step<false, ANTI != 0>(oa << 7, ob << 9, ob << 7);
+                eng.step<false, ANTI != 0>(ea << 5, eb << 7, eb << 5);
+                eng.step<false, ANTI != 0>(oa << 5, ob << 7, ob << 5);
+                eng.step<false, ANTI != 0>(ea << 3, eb << 5, eb << 3);
+                eng.step<false, ANTI != 0>(oa << 3, ob << 5, ob << 3);
+                eng.step<false, ANTI != 0>(ea << 1, eb << 3, eb << 1);
+                eng.step<true, ANTI != 0>(oa << 1, ob << 3, ob << 1);
             };
             if (valid == 32u) {
                 uint32_t ea = wev[0], oa = wod[0], eb = wev[1], ob = wod[1];
@@ -693,7 +721,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
                         for (uint32_t j = 0; j < valid - c; ++j) {
                             const uint32_t sh = j & ~1u;
                             const uint32_t wa = ((j & 1u) ? oa : ea) >> sh, wb = ((j & 1u) ? ob : eb) >> sh;
-                            eng.step<true>(wa << 7, wb << 9, wb << 7);
+                            eng.step<true, ANTI != 0>(wa << 7, wb << 9, wb << 7);
                         }
                     }
                 }

@@ -35,7 +35,8 @@ cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned th
 }
 
 cudaError_t mvd_launch_det2_pair(dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
-    auto kern = P.src_mode == MVD_SRC_PHILOX ? detect2p_kernel<1> : detect2p_kernel<0>;
+    const bool ph = P.src_mode == MVD_SRC_PHILOX;
+    auto kern = P.bm_antipodal ? (ph ? detect2p_kernel<1, 1> : detect2p_kernel<0, 1>) : (ph ? detect2p_kernel<1, 0> : detect2p_kernel<0, 0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, threads, smem, st>>>(P, B);

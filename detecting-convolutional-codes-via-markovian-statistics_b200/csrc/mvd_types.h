@@ -45,6 +45,7 @@ struct Params {
     const double2* ll;              // [ntables][SR]  {log P1, log Tref}
     // ACS constants
     const uint32_t* bm;             // [R][2 * NP] branch metrics, 16x2 packed
+    int bm_antipodal;               // every decoder tap mask has bit 0 and bit m set: the labels of a butterfly are X, ~X, ~X, X
     const uint32_t* hkeys;          // [KW][hcap] nibble-packed metric keys
     const uint32_t* hvals;          // [hcap] state * R, or MVD_EMPTY
     uint32_t hcap;                  // power of two

@@ -22,6 +22,7 @@ OPT_NO_PAIR = 2
 OPT_LEARN_WARM = 3
 OPT_NO_FSM1 = 4
 OPT_SPLIT = 5
+OPT_NO_ANTIPODAL = 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 

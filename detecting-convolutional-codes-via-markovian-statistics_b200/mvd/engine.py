@@ -287,6 +287,11 @@ class Detector:
         """NEXT-table walk with separate log-likelihood and NEXT tables instead of the one-load entry."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_FSM1, 1 if on else 0))
 
+    def no_antipodal(self, on: bool = True):
+        """Two-trials-per-thread m = 2 kernel with the general branch-metric table even for codes whose
+        generators all have their first and last tap set (the complement-label short cut is the default there)."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_NO_ANTIPODAL, 1 if on else 0))
+
     def split_trials(self, mode: int = 0):
         """Long trials split along the time axis (NEXT-table engine): 0 = automatic, 1 = whenever possible, 2 = never."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT, int(mode)))

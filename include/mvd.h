@@ -228,9 +228,12 @@ enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one t
                                                                even for few trials, 0 = automatic              */
        MVD_OPT_LEARN_WARM = 3,     /* warm-up steps of the chunk-parallel chains (default 128 for m <= 3, 128 (m - 1) above) */
        MVD_OPT_NO_FSM1 = 4,        /* 1 = NEXT-table walk with separate log / NEXT tables (two loads per step) */
-       MVD_OPT_SPLIT = 5 };        /* few long trials (NEXT-table engine, on-device bits) are split along the time axis
+       MVD_OPT_SPLIT = 5,          /* few long trials (NEXT-table engine, on-device bits) are split along the time axis
                                       (csrc/mvd_split.cuh; identical results): 0 = when it fills the GPU better,
                                       1 = whenever possible, 2 = never.  The warm-up is MVD_OPT_LEARN_WARM's. */
+       MVD_OPT_NO_ANTIPODAL = 6 }; /* 1 = the two-trials-per-thread m = 2 kernel reads the general branch-metric table even
+                                      when every decoder generator has its first and last tap set (the complement-label
+                                      short cut; identical results) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);

@@ -217,14 +217,16 @@ def _oracle_models(det, spec, p, learn_len, seed):
     return tab, P1, codes.tref_half_table(det.table)
 
 
-@pytest.mark.parametrize("path", ["fast", "fast1", "generic"])
+@pytest.mark.parametrize("path", ["fast", "fastg", "fast1", "generic"])
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("dec,enc,N,p", [("c75", "c65", 500, 0.1), ("c75", "c75", 200, 0.3), ("m3a", "m3b", 333, 0.05),
                                          ("r13", "r13", 97, 0.15), ("m1", "m1", 64, 0.2), ("c75", "c65", 7, 0.4),
-                                         ("c75", "c65", 129, 0.001), ("m3a", "m3a", 40, 0.5)])
+                                         ("c75", "c65", 129, 0.001), ("m3a", "m3a", 40, 0.5), ("c65", "c75", 300, 0.1)])
 def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
     """Tallies and per-trial float64 sums vs the oracle, 3000 trials, both decision rules; through
-    the fast kernels (mvd_detect2.cuh: n = 2 codes with shared-memory tables) and the generic ones."""
+    the fast kernels (mvd_detect2.cuh: n = 2 codes with shared-memory tables) and the generic ones.
+    "fastg" = the pair kernel with the general branch-metric table where the complement-label short cut
+    would apply ((7,5) has both end taps set in both generators, (6,5) has not and always takes it)."""
     import c_oracle as co
     from mvd import bitsource
     from mvd.engine import Seg
@@ -239,6 +241,7 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
     det.force_generic(path == "generic")
     det.no_pair(1 if path == "fast1" else 2)
     det.no_fsm1(path == "fast1")
+    det.no_antipodal(path == "fastg")
     try:
         tallies, lp = det.detect(segs, seed=2024, engine=engine, want_logp=True)
         kind = det.last_kernel_kind()
@@ -246,6 +249,9 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
         det.force_generic(False)
         det.no_pair(False)
         det.no_fsm1(False)
+        det.no_antipodal(False)
+    if path == "fastg":
+        path = "fast"
     if path == "generic" or spec["n"] != 2:
         assert kind == 0
     else:
