@@ -483,10 +483,19 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
     return d;
 }
 
+__device__ __forceinline__ uint32_t madlo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 struct PairEngine {
     uint32_t Q0, Q1, Q2, Q3;          // (trial A, trial B) metrics of trellis states 0..3
     uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
     uint32_t kbm, kst;                // branch-metric plane 0 | copy * 16 ; state table + lane * 4
+    uint32_t km1;                     // -1 from the kernel parameters: n - d as an IMAD on the FMA pipe (a visible constant
+                                      // would make it an IADD3 on the ALU pipe, the busiest one).  Measured and rejected: the
+                                      // state-table addresses and the >> 8 / >> 16 as IMAD.HI (7.68e11 -> 7.24e11 steps/s)
     double a1A, a0A, a1B, a0B;
 
     // sA, sB7: r_A, r_B at bits 7..8; sB: r_B at bits 9..10 (other bits arbitrary).
@@ -501,18 +510,18 @@ struct PairEngine {
     // general table.
     template <bool NORM, bool ANTI>
     __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7) {
-        const uint32_t rA = sA & 0x180u;
-        const double2 vA = lds_d2(sxA | rA);
+        const uint32_t rAB = bitsel(sA, sB, 0x180u);                        // r_A at bits 7..8, r_B at bits 9..10
+        const double2 vA = lds_d2(sxA | (rAB & 0x180u));
         const double2 vB = lds_d2(sxB | (sB7 & 0x180u));
         a1A += vA.x;
         a0A += vA.y;
         a1B += vB.x;
         a0B += vB.y;
-        const uint32_t boff = kbm | rA | (sB & 0x600u);
+        const uint32_t boff = kbm | (rAB & 0x780u);
         uint32_t n0, n1, n2, n3;
         if (ANTI) {
             const uint2 px = lds_v2(boff);                 // d(0 -> 0), d(1 -> 2) for (r_A, r_B)
-            const uint32_t c0 = 0x01000100u - px.x, c1 = 0x01000100u - px.y;    // n = 2, times 128, both lanes
+            const uint32_t c0 = madlo(px.x, km1, 0x01000100u), c1 = madlo(px.y, km1, 0x01000100u);    // n - d: n = 2, times 128, both lanes
             n0 = __viaddmin_u16x2(Q0, px.x, Q2 + c0);                           // Eq. 4, both trials
             n1 = __viaddmin_u16x2(Q0, c0, Q2 + px.x);
             n2 = __viaddmin_u16x2(Q1, px.y, Q3 + c1);
@@ -607,6 +616,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     eng.kbm = ANTI ? a_bm + ((lane & 15u) << 3) : a_bm + ((lane & 7u) << 4);
     eng.kst = a_st + lane * 4u;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
+    eng.km1 = P.fma_km1;
 
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);

@@ -45,6 +45,8 @@ struct Params {
     const double2* ll;              // [ntables][SR]  {log P1, log Tref}
     // ACS constants
     const uint32_t* bm;             // [R][2 * NP] branch metrics, 16x2 packed
+    // -1 as a launch-time constant: a multiplier the compiler cannot turn back into an ALU-pipe subtraction
+    uint32_t fma_km1 = 0xFFFFFFFFu;
     int bm_antipodal;               // every decoder tap mask has bit 0 and bit m set: the labels of a butterfly are X, ~X, ~X, X
     const uint32_t* hkeys;          // [KW][hcap] nibble-packed metric keys
     const uint32_t* hvals;          // [hcap] state * R, or MVD_EMPTY
