@@ -77,7 +77,7 @@ struct PairEngineN {
     }
 };
 
-template <int M, bool GT>
+template <int M, bool GT, int PHILOX>
 __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(const __grid_constant__ Params P,
                                                                                const __grid_constant__ SegBatch B) {
     constexpr int NS = 1 << M;
@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     }
     __syncthreads();
 
-    const uint4* tbm = reinterpret_cast<const uint4*>(g + a_tb);
     PairEngineN<M, GT> eng;
 #pragma unroll
     for (int s = 0; s < NS; ++s) eng.Q[s] = 0u;
@@ -154,9 +153,12 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
 
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
-    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    constexpr bool philox = PHILOX != 0;              // bit source as a template parameter (see detect2p_kernel)
     const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
-    const uint32_t c3 = sg.stream;
+    // Philox counter words, activity masks, stream id and mask-table address pinned in registers (see detect2p_kernel)
+    uint32_t c1A = (uint32_t)trA, c2A = (uint32_t)(trA >> 32), c1B = (uint32_t)trB, c2B = (uint32_t)(trB >> 32);
+    uint32_t mA = actA ? 0xFFFFFFFFu : 0u, mB = actB ? 0xFFFFFFFFu : 0u, c3 = sg.stream, a_tbp = a_tb;
+    asm volatile("" : "+r"(c1A), "+r"(c2A), "+r"(c1B), "+r"(c2B), "+r"(mA), "+r"(mB), "+r"(c3), "+r"(a_tbp));
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
     uint32_t tm0[M + 1], tm1[M + 1];
 #pragma unroll
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     for (uint32_t sb = 0; sb < nsb; ++sb) {
         uint4 UA = make_uint4(0, 0, 0, 0), UB = UA, EA0 = UA, EA1 = UA, EB0 = UA, EB1 = UA;
         if (philox) {
-            UA = philox10(((4u * sb) << 6) | 32u, (uint32_t)trA, (uint32_t)(trA >> 32), c3, P);
-            UB = philox10(((4u * sb) << 6) | 32u, (uint32_t)trB, (uint32_t)(trB >> 32), c3, P);
+            UA = philox10(((4u * sb) << 6) | 32u, c1A, c2A, c3, P);
+            UB = philox10(((4u * sb) << 6) | 32u, c1B, c2B, c3, P);
         } else {
             const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 3ull * ntr;
             if (actA) {
@@ -191,21 +193,33 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
             if (t0 >= N) break;
             const uint32_t valid = min(32u, N - t0);
             const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
-            uint32_t wlo[2], whi[2];
+            uint32_t wev[2], wod[2];                    // received pairs of the even / odd steps
+            uint32_t eA0, eA1, eB0, eB1;
+            if (philox) {
+                // four flip words (2 trials x 2 outputs) through one copy of the lazy loop, results rotate
+                uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask;
+                asm volatile("" : "+r"(cb), "+r"(vm));
+                eA0 = eA1 = eB0 = eB1 = 0u;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const bool second = j >= 2;
+                    const uint32_t e = lazy_bernoulli_a(cb | (((uint32_t)j & 1u) << 3), second ? c1B : c1A, second ? c2B : c2A, c3, a_tbp,
+                                                        ncalls, (second ? mB : mA) & vm, P);
+                    eA0 = eA1;
+                    eA1 = eB0;
+                    eB0 = eB1;
+                    eB1 = e;
+                }
+            } else {
+                eA0 = pick(EA0, w);
+                eA1 = pick(EA1, w);
+                eB0 = pick(EB0, w);
+                eB1 = pick(EB1, w);
+            }
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
                 const uint32_t U = x ? UB.x : UA.x;                      // word w: the vectors rotate below
-                const bool act = x ? actB : actA;
-                const unsigned long long tr = x ? trB : trA;
-                uint32_t e0, e1;
-                if (philox) {
-                    const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
-                    e0 = lazy_bernoulli_s(cb, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
-                    e1 = lazy_bernoulli_s(cb | 8u, (uint32_t)tr, (uint32_t)(tr >> 32), c3, tbm, ncalls, act ? vmask : 0u, P);
-                } else {
-                    e0 = pick(x ? EB0 : EA0, w);
-                    e1 = pick(x ? EB1 : EA1, w);
-                }
+                const uint32_t e0 = x ? eB0 : eA0, e1 = x ? eB1 : eA1;
                 const uint32_t pu = x ? prevUB : prevUA;
                 uint32_t o0 = U & tm0[0], o1 = U & tm1[0];              // m + 1 tap masks per output
 #pragma unroll
@@ -216,28 +230,32 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
                 }
                 if (x) prevUB = U; else prevUA = U;
                 const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
-                wlo[x] = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
-                whi[x] = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+                // r_t = (R0 bit t, R1 bit t): two bit-selects instead of a Morton interleave (see detect2p_kernel)
+                wev[x] = bitsel(R1, R0 << 1, 0x55555555u);
+                wod[x] = bitsel(R1 >> 1, R0, 0x55555555u);
             }
             UA = make_uint4(UA.y, UA.z, UA.w, 0u);
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
-            auto quad = [&](uint32_t wa, uint32_t wb) {                        // 4 steps = bits 0..7 of wa / wb
-                eng.step(wa << 5, wb << 5, wa << 2, wb << 2);
-                eng.step(wa << 3, wb << 3, wa, wb);
-                eng.step(wa << 1, wb << 1, wa >> 2, wb >> 2);
-                eng.step(wa >> 1, wb >> 1, wa >> 4, wb >> 4);
+            // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
+            auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
+                eng.step(ea << 5, eb << 5, ea << 2, eb << 2);
+                eng.step(oa << 5, ob << 5, oa << 2, ob << 2);
+                eng.step(ea << 3, eb << 3, ea, eb);
+                eng.step(oa << 3, ob << 3, oa, ob);
+                eng.step(ea << 1, eb << 1, ea >> 2, eb >> 2);
+                eng.step(oa << 1, ob << 1, oa >> 2, ob >> 2);
+                eng.step(ea >> 1, eb >> 1, ea >> 4, eb >> 4);
+                eng.step(oa >> 1, ob >> 1, oa >> 4, ob >> 4);
             };
 #pragma unroll 1
             for (uint32_t c = 0; c < valid; c += 8u) {
-                const uint32_t sh = (c & 8u) << 1;
-                const uint32_t wa = ((c & 16u) ? whi[0] : wlo[0]) >> sh;      // 8 steps = bits 0..15
-                const uint32_t wb = ((c & 16u) ? whi[1] : wlo[1]) >> sh;
+                const uint32_t ea = wev[0] >> c, oa = wod[0] >> c, eb = wev[1] >> c, ob = wod[1] >> c;
                 if (c + 8u <= valid) {
-                    quad(wa, wb);
-                    quad(wa >> 8, wb >> 8);
+                    oct(ea, oa, eb, ob);
                 } else {
                     for (uint32_t j = 0; j < valid - c; ++j) {
-                        const uint32_t ra = (wa >> (2u * j)) & 3u, rb = (wb >> (2u * j)) & 3u;
+                        const uint32_t sh = j & ~1u;
+                        const uint32_t ra = (((j & 1u) ? oa : ea) >> sh) & 3u, rb = (((j & 1u) ? ob : eb) >> sh) & 3u;
                         eng.step(ra << 5, rb << 5, ra << 2, rb << 2);
                     }
                 }
