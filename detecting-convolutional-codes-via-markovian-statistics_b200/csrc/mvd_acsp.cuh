@@ -41,19 +41,25 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M <= 4 ? 3 : (M == 5 ? 2 : 1)) ac
     uint32_t Q[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) Q[s] = 0u;
-    auto step = [&](uint32_t sA2, uint32_t sB2) {              // r_A / r_B at bits 2..3
+    // norm (warp-uniform) = false defers Eq. 5: nothing reads the metrics between steps here, so the minimum is
+    // only removed every 8th step and at the end of a 32-step word (a lane grows by at most 2 per step; D_N is
+    // the same vector either way)
+    auto step = [&](uint32_t sA2, uint32_t sB2, bool norm) {   // r_A / r_B at bits 2..3
         const uint32_t VA = lds_u32(kV | (sA2 & 0xCu)), VB = lds_u32(kV | (sB2 & 0xCu));
         uint32_t n[NS];
 #pragma unroll
         for (int ns = 0; ns < NS; ++ns)                        // Eq. 4, both trials
             n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, S.sel[2 * ns]),
                                      Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, S.sel[2 * ns + 1]));
-        uint32_t mn = n[0];
+        uint32_t mn = 0u;
+        if (norm) {
+            mn = n[0];
 #pragma unroll
-        for (int s = 1; s + 1 < NS; s += 2) mn = __vimin3_u16x2(mn, n[s], n[s + 1]);
-        mn = __vminu2(mn, n[NS - 1]);
+            for (int s = 1; s + 1 < NS; s += 2) mn = __vimin3_u16x2(mn, n[s], n[s + 1]);
+            mn = __vminu2(mn, n[NS - 1]);
+        }
 #pragma unroll
-        for (int s = 0; s < NS; ++s) Q[s] = n[s] - mn;         // Eq. 5
+        for (int s = 0; s < NS; ++s) Q[s] = n[s] - mn;         // Eq. 5 (mn = 0: deferred)
     };
 
     const uint32_t N = sg.N;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M <= 4 ? 3 : (M == 5 ? 2 : 1)) ac
             for (uint32_t t = 0; t < valid; ++t) {
                 const uint32_t wa = (t & 16u) ? whi[0] : wlo[0], wb = (t & 16u) ? whi[1] : wlo[1];
                 const uint32_t sh = 2u * (t & 15u);
-                step((wa >> sh) << 2, (wb >> sh) << 2);
+                step((wa >> sh) << 2, (wb >> sh) << 2, M >= 6 || (t & 7u) == 7u || t + 1u == valid);   // m = 6 (one block per SM): deferring measured slower (9.75e10 -> 9.43e10)
             }
         }
     }

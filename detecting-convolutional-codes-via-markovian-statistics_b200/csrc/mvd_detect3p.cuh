@@ -51,7 +51,11 @@ struct PairEngineN {
         return lds_u32(kT | ((((w0 * c2) >> 18) + d8) & tmask));
     }
 
-    // sA5 / sB5: r_A / r_B at bits 5..6 (log rows, 32-byte entries); sA2 / sB2: r_A / r_B at bits 2..3 (V table)
+    // sA5 / sB5: r_A / r_B at bits 5..6 (log rows, 32-byte entries); sA2 / sB2: r_A / r_B at bits 2..3 (V table).
+    // NORM = false defers Eq. 5 (as PairEngine::step of the m = 2 kernel): the key words are corrected by
+    // 585 min (585 = 1 + 8 + 64 + 512) instead of subtracting the minimum from all 2^m metrics; the last step
+    // of every 8-step stretch normalises, so a lane grows by at most 16 in between.
+    template <bool NORM>
     __device__ __forceinline__ void step(uint32_t sA5, uint32_t sB5, uint32_t sA2, uint32_t sB2) {
         const double2 vA = GT ? __ldg(gll + sxA + ((sA5 >> 5) & 3u)) : lds_d2(sxA | (sA5 & 0x60u));
         const double2 vB = GT ? __ldg(gll + sxB + ((sB5 >> 5) & 3u)) : lds_d2(sxB | (sB5 & 0x60u));
@@ -67,10 +71,13 @@ struct PairEngineN {
         uint32_t mn = __vimin3_u16x2(__vimin3_u16x2(n[0], n[1], n[2]), __vimin3_u16x2(n[3], n[4], n[5]), __vminu2(n[6], n[7]));
         if (NS == 16) mn = __vimin3_u16x2(mn, __vimin3_u16x2(n[8], n[9], n[10]), __vimin3_u16x2(__vimin3_u16x2(n[11], n[12], n[13]), n[14], n[15]));
 #pragma unroll
-        for (int s = 0; s < NS; ++s) Q[s] = n[s] - mn;                          // Eq. 5
+        for (int s = 0; s < NS; ++s) Q[s] = NORM ? n[s] - mn : n[s];            // Eq. 5 (or deferred)
         uint32_t k[NS / 4];
 #pragma unroll
-        for (int i = 0; i < NS / 4; ++i) k[i] = ((Q[4 * i + 3] * 8u + Q[4 * i + 2]) * 8u + Q[4 * i + 1]) * 8u + Q[4 * i];
+        for (int i = 0; i < NS / 4; ++i) {
+            k[i] = ((Q[4 * i + 3] * 8u + Q[4 * i + 2]) * 8u + Q[4 * i + 1]) * 8u + Q[4 * i];
+            if (!NORM) k[i] -= 585u * mn;
+        }
         // low halves = trial A, high halves = trial B
         sxA = lookup(__byte_perm(k[0], k[1], 0x5410), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x5410) : 0u);
         sxB = lookup(__byte_perm(k[0], k[1], 0x7632), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x7632) : 0u);
@@ -238,14 +245,14 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
             // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
             auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
-                eng.step(ea << 5, eb << 5, ea << 2, eb << 2);
-                eng.step(oa << 5, ob << 5, oa << 2, ob << 2);
-                eng.step(ea << 3, eb << 3, ea, eb);
-                eng.step(oa << 3, ob << 3, oa, ob);
-                eng.step(ea << 1, eb << 1, ea >> 2, eb >> 2);
-                eng.step(oa << 1, ob << 1, oa >> 2, ob >> 2);
-                eng.step(ea >> 1, eb >> 1, ea >> 4, eb >> 4);
-                eng.step(oa >> 1, ob >> 1, oa >> 4, ob >> 4);
+                eng.step<false>(ea << 5, eb << 5, ea << 2, eb << 2);
+                eng.step<false>(oa << 5, ob << 5, oa << 2, ob << 2);
+                eng.step<false>(ea << 3, eb << 3, ea, eb);
+                eng.step<false>(oa << 3, ob << 3, oa, ob);
+                eng.step<false>(ea << 1, eb << 1, ea >> 2, eb >> 2);
+                eng.step<false>(oa << 1, ob << 1, oa >> 2, ob >> 2);
+                eng.step<false>(ea >> 1, eb >> 1, ea >> 4, eb >> 4);
+                eng.step<true>(oa >> 1, ob >> 1, oa >> 4, ob >> 4);
             };
 #pragma unroll 1
             for (uint32_t c = 0; c < valid; c += 8u) {
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
                     for (uint32_t j = 0; j < valid - c; ++j) {
                         const uint32_t sh = j & ~1u;
                         const uint32_t ra = (((j & 1u) ? oa : ea) >> sh) & 3u, rb = (((j & 1u) ? ob : eb) >> sh) & 3u;
-                        eng.step(ra << 5, rb << 5, ra << 2, rb << 2);
+                        eng.step<true>(ra << 5, rb << 5, ra << 2, rb << 2);
                     }
                 }
             }
