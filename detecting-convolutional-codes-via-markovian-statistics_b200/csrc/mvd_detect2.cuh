@@ -63,6 +63,55 @@ __device__ __forceinline__ uint32_t lazy_bernoulli_s(uint32_t c0base, uint32_t c
     return e;
 }
 
+// absolute shared-window loads (ld.shared: no generic-address conversion)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// lazy_bernoulli_s with the threshold masks addressed in the shared window (ld.shared, no generic pointer)
+__device__ __forceinline__ uint32_t lazy_bernoulli_a(uint32_t c0base, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t a_tbm, int ncalls, uint32_t vmask, const Params& P) {
+    uint32_t und = vmask, e = 0;
+    for (int k = 0; k < ncalls; ++k) {
+        if (!__any_sync(0xFFFFFFFFu, und != 0u)) break;
+        const uint4 w = philox10(c0base + (uint32_t)k, c1, c2, c3, P);
+        const uint4 tb = lds_v4(a_tbm + 16u * (uint32_t)k);
+        e |= und & ~w.x & tb.x;
+        und &= ~(w.x ^ tb.x);
+        e |= und & ~w.y & tb.y;
+        und &= ~(w.y ^ tb.y);
+        e |= und & ~w.z & tb.z;
+        und &= ~(w.z ^ tb.z);
+        e |= und & ~w.w & tb.w;
+        und &= ~(w.w ^ tb.w);
+    }
+    return e;
+}
+
+// (a & m) | (b & ~m) as one LOP3
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
 // ------------------------------------------------------------------------------------------ driver (n = 2)
 // MM = encoder memory when known at compile time (ACS kernels), 0 = read it from the parameters
 template <int LLS, int MM, class Eng>
@@ -72,7 +121,11 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);      // Philox calls per flip word, at most
     const bool philox = P.src_mode == MVD_SRC_PHILOX;
-    const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
+    // Philox counter words, activity mask and mask-table address pinned in registers: otherwise they are
+    // re-derived from blockIdx / threadIdx / the segment record before every lazy loop (see detect2p_kernel)
+    uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream, am = active ? 0xFFFFFFFFu : 0u;
+    uint32_t a_tbp = (uint32_t)__cvta_generic_to_shared(tbm);
+    asm volatile("" : "+r"(c1), "+r"(c2), "+r"(am));
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
     uint32_t prevU = 0;
     const uint32_t nsb = (N + 127u) >> 7;
@@ -96,9 +149,14 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
             const uint32_t U = pick(Uw, w);
             uint32_t e0, e1;
             if (philox) {
-                const uint32_t cb = (4u * sb + (uint32_t)w) << 6;
-                e0 = lazy_bernoulli_s(cb, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
-                e1 = lazy_bernoulli_s(cb | 8u, c1, c2, c3, tbm, ncalls, active ? vmask : 0u, P);
+                uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask & am;
+                asm volatile("" : "+r"(vm));
+                e0 = e1 = 0u;
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {                               // one copy of the lazy loop for both outputs
+                    e0 = e1;
+                    e1 = lazy_bernoulli_a(cb | ((uint32_t)j << 3), c1, c2, c3, a_tbp, ncalls, vm, P);
+                }
             } else {
                 e0 = pick(E0, w);
                 e1 = pick(E1, w);
@@ -122,36 +180,36 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
             }
             prevU = U;
             const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;            // BSC
-            // received word of step t = bits (2t+1, 2t) of (whi:wlo); first output is the MSB
-            const uint32_t wlo = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
-            const uint32_t whi = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
-            auto oct = [&](uint32_t wv) {                                  // 8 steps = bits 0..15 of wv
-                const uint32_t wu = wv >> 8;                                 // steps 4..7: left shifts only (FMA pipe)
-                eng.step(roff<LLS, 0>(wv));
-                eng.step(roff<LLS, 1>(wv));
-                eng.step(roff<LLS, 2>(wv));
-                eng.step(roff<LLS, 3>(wv));
-                eng.step(roff<LLS, 0>(wu));
-                eng.step(roff<LLS, 1>(wu));
-                eng.step(roff<LLS, 2>(wu));
-                eng.step(roff<LLS, 3>(wu));
+            // received word of step t = (R0 bit t, R1 bit t), first output is the MSB: two bit-selects put the pairs
+            // of the even steps into one word and those of the odd steps into another, at bits (t | 1, t & ~1)
+            const uint32_t wev = bitsel(R1, R0 << 1, 0x55555555u), wod = bitsel(R1 >> 1, R0, 0x55555555u);
+            auto oct = [&](uint32_t ev, uint32_t od) {                     // 8 steps = bits 0..7 of ev and od
+                eng.step(roff<LLS, 0>(ev));
+                eng.step(roff<LLS, 0>(od));
+                eng.step(roff<LLS, 1>(ev));
+                eng.step(roff<LLS, 1>(od));
+                eng.step(roff<LLS, 2>(ev));
+                eng.step(roff<LLS, 2>(od));
+                eng.step(roff<LLS, 3>(ev));
+                eng.step(roff<LLS, 3>(od));
             };
             if (valid == 32u) {
+                uint32_t ev = wev, od = wod;
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {                                // 16 steps per iteration
-                    const uint32_t x = h ? whi : wlo;
-                    oct(x);
-                    oct(x >> 16);
+                    oct(ev, od);
+                    oct(ev >> 8, od >> 8);
+                    ev >>= 16;
+                    od >>= 16;
                 }
             } else {
 #pragma unroll 1
                 for (uint32_t c = 0; c < valid; c += 8u) {
-                    const uint32_t wsel = (c & 16u) ? whi : wlo;
-                    const uint32_t wv = wsel >> ((c & 8u) << 1);
+                    const uint32_t ev = wev >> c, od = wod >> c;
                     if (c + 8u <= valid) {
-                        oct(wv);
+                        oct(ev, od);
                     } else {
-                        for (uint32_t j = 0; j < valid - c; ++j) eng.step(((wv >> (2u * j)) & 3u) << LLS);
+                        for (uint32_t j = 0; j < valid - c; ++j) eng.step(((((j & 1u) ? od : ev) >> (j & ~1u)) & 3u) << LLS);
                     }
                 }
             }
@@ -434,54 +492,6 @@ __global__ void __launch_bounds__(DET2_BLOCK, (LK == LK_FSM1 || LK == LK_FSM) ? 
 // All table reads use absolute shared-memory addresses (ld.shared) whose alignment lets a single
 // LOP3 build them: log rows are 512-byte aligned (address = row | r * 128), the branch-metric planes
 // 2048-byte aligned (address = plane | r_A * 128 | r_B * 512 | copy * 16).
-
-__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ double2 lds_d2(uint32_t a) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-
-// lazy_bernoulli_s with the threshold masks addressed in the shared window (ld.shared, no generic pointer)
-__device__ __forceinline__ uint32_t lazy_bernoulli_a(uint32_t c0base, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                     uint32_t a_tbm, int ncalls, uint32_t vmask, const Params& P) {
-    uint32_t und = vmask, e = 0;
-    for (int k = 0; k < ncalls; ++k) {
-        if (!__any_sync(0xFFFFFFFFu, und != 0u)) break;
-        const uint4 w = philox10(c0base + (uint32_t)k, c1, c2, c3, P);
-        const uint4 tb = lds_v4(a_tbm + 16u * (uint32_t)k);
-        e |= und & ~w.x & tb.x;
-        und &= ~(w.x ^ tb.x);
-        e |= und & ~w.y & tb.y;
-        und &= ~(w.y ^ tb.y);
-        e |= und & ~w.z & tb.z;
-        und &= ~(w.z ^ tb.z);
-        e |= und & ~w.w & tb.w;
-        und &= ~(w.w ^ tb.w);
-    }
-    return e;
-}
-
-// (a & m) | (b & ~m) as one LOP3
-__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
-    return d;
-}
 
 __device__ __forceinline__ uint32_t madlo(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
