@@ -349,8 +349,8 @@ def main():
             "peak_alu_pipe_only": alu_gops, "frac_alu_pipe_only": ach / alu_gops,
             "ops_per_step": {"core": OPS_CORE, "f64_adds": 2,
                              "note": "SURVEY 8(d): 2^(m+k+1) + 2^m + 3n + 5 at m=2, k=1, n=2; bit generation is not "
-                                     "counted (ncu: 38.6 warp-instructions issued per trellis step, ~20 of them Philox + "
-                                     "lazy Bernoulli + interleave, profiles/r01d_*)"},
+                                     "counted (ncu: 33.0 warp-instructions issued per trellis step, ~15 of them Philox + "
+                                     "lazy Bernoulli + encode, profiles/r01n_*)"},
             "peak_source": "libmvd mvd_int_peak(), measured in this run on this GPU: `peak` = alternating LOP3/IMAD chains "
                            "(ALU + FMA pipes = warp-instruction issue rate, the most any integer code can retire); "
                            "`peak_alu_pipe_only` = LOP3-only chains (min/shift/logic/permute can only issue there). "
