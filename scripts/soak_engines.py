@@ -32,12 +32,14 @@ for name, m, g1, g2, ntr, how in CODES:
         det.no_pair(opt.get("pair", 0))
         det.no_fsm1(opt.get("no_fsm1", False))
         det.split_trials(opt.get("split", 2))
+        det.no_antipodal(opt.get("no_antipodal", False))
         t0 = time.perf_counter()
         t = det.detect(segs, seed=2026, engine=engine)
         results[tag] = (t.copy(), det.last_kernel_kind(), round(det.last_kernel_ms(), 3))
-        det.force_generic(False); det.no_pair(0); det.no_fsm1(False); det.split_trials(0)
+        det.force_generic(False); det.no_pair(0); det.no_fsm1(False); det.split_trials(0); det.no_antipodal(False)
 
     run("acs pair", "acs", pair=2)
+    run("acs pair general table", "acs", pair=2, no_antipodal=True)
     run("acs one trial", "acs", pair=1)
     run("next walk one load", "fsm")
     run("next walk two loads", "fsm", no_fsm1=True)
