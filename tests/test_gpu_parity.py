@@ -291,14 +291,17 @@ def test_detect_against_numeric_T_of_any_p(codes_spec, dets, engine, dec, enc):
         assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
 
 
+@pytest.mark.parametrize("pair", [0, 2])
+@pytest.mark.parametrize("dec,enc", [("c75", "c65"), ("c65", "c75"), ("m3a", "m3b")])
 @pytest.mark.parametrize("engine", ENGINES)
-def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
-    """Host-supplied bit streams through the fast kernels == generic kernels == oracle sums."""
+def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine, dec, enc, pair):
+    """Host-supplied bit streams through the fast kernels == generic kernels == oracle sums; pair = 2 forces the
+    two-trials-per-thread kernels (their bit-stream instances: complement-label and general table at m = 2, m = 3)."""
     import c_oracle as co
     from mvd import bitsource
     from mvd.engine import Seg
-    det = dets("c75")
-    spec = codes_spec["c75"]
+    det = dets(dec)
+    spec = codes_spec[dec]
     tab, P1, Tref = _oracle_models(det, spec, 0.1, 6200, 123)
     det.set_models([P1])
     rng = np.random.default_rng(11)
@@ -306,10 +309,16 @@ def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
     u = rng.integers(0, 2, (ntr, N), dtype=np.uint8)
     e = (rng.random((ntr, 2, N)) < 0.12).astype(np.uint8)
     bits = bitsource.pack_bitstreams(u, e)
-    taps2 = _taps(codes_spec["c65"])
+    taps2 = _taps(codes_spec[enc])
     seg = Seg(N=N, enc_taps=taps2, decide=1, trial_begin=0, trial_end=ntr)
-    t_fast, lp_fast = det.detect([seg], bits=bits, engine=engine, want_logp=True)
-    assert det.last_kernel_kind() != 0
+    det.no_pair(pair)
+    try:
+        t_fast, lp_fast = det.detect([seg], bits=bits, engine=engine, want_logp=True)
+        kind = det.last_kernel_kind()
+    finally:
+        det.no_pair(0)
+    assert kind != 0
+    assert (kind >= 256) == (pair == 2 and engine == "acs")
     det.force_generic(True)
     try:
         t_gen, lp_gen = det.detect([seg], bits=bits, engine=engine, want_logp=True)
@@ -321,7 +330,7 @@ def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine):
     for t in range(40):
         U = bitsource.bits_to_words(u[t])[:(N + 31) // 32]
         E = bitsource.bits_to_words(e[t])[:, :(N + 31) // 32]
-        idx, rseq, _ = co.simulate(_taps(spec), taps2, 2, 2, N, U, E, tab)
+        idx, rseq, _ = co.simulate(_taps(spec), taps2, 2, spec["m"], N, U, E, tab)
         assert co.log_prob(idx, rseq, N, 2, P1) == lp_fast[t, 0]
         assert co.log_prob(idx, rseq, N, 2, Tref) == lp_fast[t, 1]
 
