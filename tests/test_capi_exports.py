@@ -43,6 +43,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.mvd_abi_version() == 1
 
 
+def test_option_constants_match_header():
+    """The ctypes mirror's MVD_OPT_* values are the header's (mvd_set_option)."""
+    from mvd import _capi
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    opts = dict(re.findall(r"\bMVD_(OPT_[A-Z0-9_]+)\s*=\s*(\d+)", text))
+    assert set(opts) == {"OPT_FORCE_GENERIC", "OPT_NO_PAIR", "OPT_LEARN_WARM", "OPT_NO_FSM1", "OPT_SPLIT", "OPT_NO_ANTIPODAL"}
+    for name, value in opts.items():
+        assert getattr(_capi, name) == int(value), name
+
+
 def test_library_is_built_for_sm_100a():
     from mvd import _capi
     out = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True)
