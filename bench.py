@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--engine acs|fsm] [--trials T]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference ...      # the reference's own run_experiment on host cores
 
 One "step" = one pass of the paper sweep of Pd_plotter.py (BASELINE configs[1]): codes (7,5) vs
 (6,5), N = 500, p in {0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5}, both hypotheses, ``--trials`` Monte-Carlo
@@ -11,18 +11,24 @@ trials per point *per GPU* (default 10^6, the north-star target; the reference s
 That is 2 * 500 * 7 * trials trellis steps per GPU per step.
 
 value : device-resident throughput -- tables already on the GPU, on-device Philox bit source, one
-        kernel launch per step; wall time between synchronised brackets, max over ranks.
-e2e   : the same sweep through the public API ``Pd_plotter.run_experiment`` from host data: learning
-        chains (GPU), Laplace/normalise (host), table upload H2D, detection launch, tallies D2H,
-        allreduce, DataFrame.
+        kernel launch per step; wall time between synchronised brackets, max over ranks (weak scaling).
+e2e   : the same sweep through the public API ``Pd_plotter.run_experiment`` from host data, nothing cached:
+        learning chains (GPU), Laplace/normalise (host), table upload H2D, detection launch, allreduce,
+        tallies D2H, DataFrame.  Bytes are counted at libmvd's copy call sites (mvd_copy_stats).
 roofline : the binding unit is the SM integer pipe, peak measured on this GPU in this run
-        with libmvd's IADD/LOP3 micro-kernel; the HBM view of the bit-stream kernel is reported too.
-cpu_baseline : the reference's Python path (oracle/ref_port.py, reference data structures and
-        math.log per step) on this box's host cores, bounded sample.
+        with libmvd's LOP3/IMAD micro-kernel; the HBM view of the bit-stream kernel is reported too.
+strong : a fixed total of --strong-trials per point sharded over the N ranks through run_experiment (models
+        cached, tallies reduced on the device); on N > 1 rank 0 also runs the whole range alone: the tallies
+        must be identical (tallies_equal_1gpu) and efficiency_vs_n1 = t_1 / (N t_N).
+paper_sweep : wall time of the north-star sweeps (35-point Pd-vs-p, 16-point Pd-vs-N) through run_experiment.
+sustained : the resident loop repeated for >= --sustain-s seconds with clocks and power sampled.
+cpu_baseline : the reference's own ``run_experiment`` (oracle/_ref, injected simulator) on this box's host
+        cores, bounded sample; falls back to the Python port (oracle/ref_port.py) when oracle/_ref is absent.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -43,17 +49,21 @@ SEED = 12345                                # Pd_plotter.py:70
 K, NOUT, M = 1, 2, 2
 OPS_CORE = 5 * (1 << M) + 11                # 31 int-ops / step at m = 2
 METRIC = "trellis-steps/sec (whole box) for Pd-vs-p Monte-Carlo sweep"
+SWEEP_P_NS = [50, 100, 200, 500, 1000]      # scripts/paper_sweeps.py: Pd vs p (x 7 p = 35 points)
+SWEEP_N_NS = [100, 200, 500, 1000, 2000, 5000, 10000, 100000]   # Pd vs N (x 2 p = 16 points), BASELINE config 3
+SWEEP_N_PS = [0.05, 0.1]
 
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+    """Samples SM clock, power and throttle reasons with NVML while the timed region runs."""
 
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
     NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80, "sync_boost": 0x10}
 
-    def __init__(self, index: int):
-        self.samples, self.reasons, self.max_mhz, self.ok = [], 0, None, False
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.samples, self.power, self.reasons, self.max_mhz, self.ok = [], [], 0, None, False
+        self.period = period_s
         self._stop = threading.Event()
         try:
             import pynvml
@@ -71,12 +81,16 @@ class ClockSampler:
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
                     self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         if self.ok:
@@ -93,35 +107,81 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         s = sorted(self.samples)
         names = [n for n, bit in {**self.BAD, **self.NOTE}.items() if self.reasons & bit]
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": names, "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": names, "samples": len(s)}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
 def _port_worker(args):
     import ref_port
-    gen1, gen2, N, p, iters, seed, offset = args
+    gen1, gen2, N, p_vec, iters, seed, offset = args
     t0 = time.perf_counter()
-    steps, tallies = ref_port.timed_steps(gen1, gen2, M, K, NOUT, N, p, iters, seed, trial_offset=offset)
-    return steps, time.perf_counter() - t0, tallies
+    rows = ref_port.run_experiment(K, NOUT, M, gen1, gen2, iters, p_vec, None, 200, 1.0, seed, N_spectrum=[N], trial_offset=offset)
+    return 2 * N * iters * len(p_vec), time.perf_counter() - t0, len(rows)
 
 
-def cpu_port_throughput(iters_per_core: int, cores: int) -> dict:
-    """Reference trial loop (Pd_plotter.py:210-223) via the Python port on ``cores`` processes."""
-    import multiprocessing as mp
-    jobs = [(GEN1, GEN2, N_BLOCK, 0.1, iters_per_core, SEED, i * iters_per_core) for i in range(cores)]
-    t0 = time.perf_counter()
-    if cores == 1:
-        res = [_port_worker(jobs[0])]
-    else:
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_port_worker, jobs)
-    wall = time.perf_counter() - t0
-    steps = sum(r[0] for r in res)
-    return {"value": steps / wall, "unit": "trellis-steps/s", "cores": cores, "kind": "port",
-            "sample": f"(7,5)/(6,5) N={N_BLOCK} p=0.1, {iters_per_core} iterations x 2 hypotheses per core "
-                      f"(+ one 6200-step learning chain per core), oracle/ref_port.py (pure Python, reference data "
-                      f"structures), {wall:.1f} s wall",
-            "steps": steps, "wall_s": wall}
+class PortPool:
+    """Fallback when oracle/_ref is absent: the pure-Python port of the reference (oracle/ref_port.py).  Every step
+    re-learns the 7 chains of 6 200 steps inside the timed sample; those steps are counted."""
+    kind = "port"
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores)
+        self.next_offset = 0
+        self.symbolic_s = 0.0
+        self.warm_wall_s = 0.0
+
+    def step(self, iters):
+        jobs = [(GEN1, GEN2, N_BLOCK, P_VEC, iters, SEED, self.next_offset + i * iters) for i in range(self.cores)]
+        self.next_offset += self.cores * iters
+        t0 = time.perf_counter()
+        res = self.pool.map(_port_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        learn = len(P_VEC) * 6200 * self.cores
+        return dict(steps=sum(r[0] for r in res) + learn, wall_s=wall)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def make_cpu_pool(cores):
+    """The reference's own run_experiment when its files are available (oracle/_ref, else /root/reference)."""
+    import ref_harness
+    if ref_harness.ref_dir() is not None:
+        cfg = (K, NOUT, M, GEN1, GEN2, P_VEC, None, 200, 1.0, SEED, [N_BLOCK])
+        pool = ref_harness.Pool(cfg, cores)
+        pool.kind = "reference"
+        return pool
+    return PortPool(cores)
+
+
+def cpu_sample_text(pool, iters, steps, wall):
+    what = ("the reference's unmodified Pd_plotter.run_experiment from oracle/_ref (simulate_markov_sequence injected on its "
+            "own branch/step/trellis functions, matplotlib stubbed, sympy T(p) memoised: %.1f s, and P1 learning, lru_cached by "
+            "the reference itself, both outside the timed sample)" % pool.symbolic_s) if pool.kind == "reference" else \
+           "oracle/ref_port.py (pure-Python port; learning chains inside the sample and counted)"
+    return (f"(7,5)/(6,5) N={N_BLOCK} p_vec={P_VEC}, {iters} Monte-Carlo iterations x 2 hypotheses x 7 p per core on {pool.cores} "
+            f"cores = {steps} trellis steps in {wall:.1f} s; {what}")
+
+
+def cpu_throughput(cores, iters, reps=1):
+    pool = make_cpu_pool(cores)
+    try:
+        pool.step(max(1, iters // 8))                            # untimed warm-up pass
+        steps = wall = 0
+        for _ in range(reps):
+            r = pool.step(iters)
+            steps += r["steps"]
+            wall += r["wall_s"]
+    finally:
+        pool.close()
+    return {"value": steps / wall, "unit": "trellis-steps/s", "cores": cores, "kind": pool.kind,
+            "sample": cpu_sample_text(pool, iters, steps, wall), "sympy_T_build_s": pool.symbolic_s}
 
 
 def c_oracle_throughput(ntrials: int = 2000) -> dict:
@@ -142,36 +202,43 @@ def c_oracle_throughput(ntrials: int = 2000) -> dict:
 
 
 def run_reference_arm(args):
+    """``--impl reference``: the reference's CPU implementation of the path on all host cores, same config / metric /
+    unit as the GPU arm; every step is a bounded sample (``--ref-iters`` iterations of the whole sweep per core)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # bounded sample: every step ~ 8 s of wall on all cores
-    per_core = max(4, min(args.ref_iters, (args.ref_iters * 10) // max(1, args.steps)))   # whole run stays ~ 2 min
-    vals = []
-    for _ in range(args.warmup and 1):
-        cpu_port_throughput(max(2, per_core // 8), cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        vals.append(cpu_port_throughput(per_core, cores))
-    wall = time.perf_counter() - t0
-    steps = sum(v["steps"] for v in vals)
-    value = steps / sum(v["wall_s"] for v in vals)
+    iters = max(1, args.ref_iters)
+    pool = make_cpu_pool(cores)
+    try:
+        for _ in range(args.warmup):
+            pool.step(max(1, iters // 8))
+        res = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res.append(pool.step(iters))
+        wall = time.perf_counter() - t0
+    finally:
+        pool.close()
+    steps = sum(r["steps"] for r in res)
+    value = steps / sum(r["wall_s"] for r in res)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "trellis-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": workload_config(args, per_gpu_trials=None),
-            "cpu_baseline": {"value": value, "unit": "trellis-steps/s", "cores": cores, "kind": "port",
-                             "sample": vals[-1]["sample"]},
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "trellis-steps/s", "cores": cores, "kind": pool.kind,
+                             "sample": cpu_sample_text(pool, iters, res[-1]["steps"], res[-1]["wall_s"]) + " per step",
+                             "sympy_T_build_s": pool.symbolic_s, "warm_wall_s": pool.warm_wall_s},
             "e2e": {"value": value, "unit": "trellis-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
 
 
-def workload_config(args, per_gpu_trials):
+def workload_config(args):
+    """Identical for both arms (the driver compares the dicts): the workload, not how an arm samples it."""
     return {"workload": "Pd_plotter.py paper sweep (BASELINE configs[1]): (7,5) vs (6,5), k=1 n=2 m=2, S=31 Markov states, "
                         f"N={N_BLOCK}, p_vec={P_VEC}, both hypotheses, learn_len=6200 burn=200 laplace=1",
-            "trials_per_point_per_gpu": per_gpu_trials, "engine": args.engine,
+            "trials_per_point_per_gpu": int(args.trials), "engine": args.engine,
             "bit_source": "on-device Philox4x32-10, position-addressed (MVD-PHILOX-2)",
             "l2_policy": "no input stream to cache: bits are generated in registers, tables (<4 KB) live in shared "
                          "memory; the bit-stream variant reads > 2 GB per step (>> 126 MB L2)",
@@ -198,6 +265,11 @@ def _emit(line: dict):
     out.flush()
 
 
+def _sha(t) -> str:
+    import numpy as np
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(t, dtype=np.int64)).tobytes()).hexdigest()[:16]
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -207,9 +279,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default="acs", choices=["acs", "fsm"])
     ap.add_argument("--trials", type=int, default=1_000_000, help="Monte-Carlo trials per (N,p) point per GPU")
-    ap.add_argument("--ref-iters", type=int, default=1000, help="reference arm: iterations per core per step")
+    ap.add_argument("--strong-trials", type=int, default=1_000_000, help="strong-scaling / paper-sweep legs: trials per point in total")
+    ap.add_argument("--sustain-s", type=float, default=10.0, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--ref-iters", type=int, default=30, help="CPU arm: iterations of the whole sweep per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the alternate-engine / bitstream legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the alternate-engine / bitstream / sweep / sustained legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -231,7 +305,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
-                                timeout=datetime.timedelta(seconds=120))
+                                timeout=datetime.timedelta(seconds=300))
 
     import Pd_plotter as pdp
     import viterbi_markov as vm
@@ -267,11 +341,12 @@ def main():
         segs.append(Seg(N=N_BLOCK, threshold=T, stream=2 * q, table=q, enc_taps=t1, decide=0, trial_begin=begin, trial_end=end))
         segs.append(Seg(N=N_BLOCK, threshold=T, stream=2 * q + 1, table=q, enc_taps=t2, decide=1, trial_begin=begin, trial_end=end))
     d_tallies = torch.zeros(len(segs), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
 
     def device_pass(engine):
-        d_tallies.zero_()
-        torch.cuda.synchronize()                 # d_tallies is zeroed on torch's stream, used on libmvd's
-        det.detect(segs, seed=SEED, engine=engine, d_tallies_ptr=d_tallies.data_ptr())
+        if world > 1:
+            torch.cuda.current_stream().synchronize()     # the previous pass's all_reduce still reads d_tallies
+        det.detect(segs, seed=SEED, engine=engine, d_tallies_ptr=d_tallies.data_ptr(), host_tallies=False)
         if world > 1:
             dist.all_reduce(d_tallies, op=dist.ReduceOp.SUM)     # the one data-path collective
         return det.last_kernel_ms()
@@ -296,19 +371,22 @@ def main():
     kernel_ms = float(np.mean(kms))
     final_tallies = d_tallies.cpu().numpy().copy()
 
-    # ---- e2e through the public API (host data in, DataFrame out), every step
+    # ---- e2e through the public API (host data in, DataFrame out), every step, nothing cached
     def api_pass():
         det_details = {}
         df = pdp.run_experiment(K, NOUT, M, GEN1, GEN2, trials * world, P_VEC, None, 200, 1.0, SEED,
-                                engine=args.engine, device=local_rank, details=det_details)
+                                engine=args.engine, device=local_rank, details=det_details, cache_models=False)
         api_pass.df, api_pass.details = df, det_details
         return det_details["detect_kernel_ms"]
 
-    dt_e2e, _, launches_e2e = timed(api_pass, args.steps, args.warmup)
+    for _ in range(args.warmup):
+        api_pass()
+    h2d0, d2h0 = det.copy_stats()
+    dt_e2e, _, launches_e2e = timed(api_pass, args.steps, 0)
+    h2d1, d2h1 = det.copy_stats()
     e2e_value = steps_per_pass * args.steps / dt_e2e
-    S, R = det.S, det.R
-    h2d = len(P_VEC) * S * R * 16 + 2 * len(segs) * 96 + len(P_VEC) * 96      # log tables + segment descriptors
-    d2h = len(segs) * 8 + len(P_VEC) * S * R * 8 + 8                          # tallies + edge counts + flags
+    h2d = (h2d1 - h2d0) / args.steps
+    d2h = (d2h1 - d2h0) / args.steps + (8 * len(segs) if world > 1 else 0)     # + the reduced tallies read by torch (N > 1)
     # the API path must give the same tallies as the resident path (same seeds, same trial ids)
     api_t = api_pass.details["tallies"]
     same = bool(np.array_equal(np.asarray(api_t, dtype=np.int64), final_tallies.astype(np.int64)))
@@ -316,44 +394,111 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "trellis-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16x2 metrics + f64 log-likelihood", "data": "synthetic",
-            "config": workload_config(args, trials),
+            "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "trellis-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * dt_e2e / args.steps, "api": "Pd_plotter.run_experiment",
+                    "bytes_counted": "libmvd cudaMemcpyAsync call sites (mvd_copy_stats), per rank",
+                    "ms_per_step": 1e3 * dt_e2e / args.steps, "api": "Pd_plotter.run_experiment(cache_models=False)",
                     "tallies_equal_resident_path": same},
             "gpu_launches": launches, "gpu_launches_e2e": launches_e2e, "clocks": clocks,
-            "kernel_ms_per_step": kernel_ms,
+            "kernel_ms_per_step": kernel_ms, "tallies_sha": _sha(final_tallies),
             "pd_pc": [{"p": p, "Pd": int(final_tallies[2 * q]) / (trials * world),
                        "Pc": (int(final_tallies[2 * q]) + int(final_tallies[2 * q + 1])) / (2 * trials * world)}
                       for q, p in enumerate(P_VEC)]}
+
+    # ---- strong scaling + the north-star sweeps: a FIXED total of trials per point, sharded over the ranks
+    def sweep(num_iter, p_vec, Ns, engine, shard=True, reps=3):
+        d = {}
+        run = lambda: pdp.run_experiment(K, NOUT, M, GEN1, GEN2, num_iter, p_vec, None, 200, 1.0, SEED, N_spectrum=Ns,
+                                         engine=engine, device=local_rank, details=d, shard=shard)
+        run()                                                    # learn / upload once: later calls hit the model cache
+        best = None
+        for _ in range(reps):
+            if shard:
+                sync_all()
+            else:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run()
+            w = time.perf_counter() - t0
+            w = max_over_ranks(w) if shard else w
+            best = w if best is None else min(best, w)
+        return best, d
+
+    if not args.no_extras:
+        T_total = int(args.strong_trials)
+        t_n, d_n = sweep(T_total, P_VEC, [N_BLOCK], args.engine)
+        strong = {"trials_total_per_point": T_total, "workload": "the bench sweep (7 p x N=500 x 2 hypotheses) through run_experiment, "
+                  "models cached, tallies all-reduced on the device", "ms_per_sweep": 1e3 * t_n,
+                  "detect_kernel_ms": d_n["detect_kernel_ms"], "tallies_sha": _sha(d_n["tallies"]),
+                  "steps_per_s": d_n["steps"] / t_n}
+        if world > 1:
+            t_1, d_1 = (None, None)
+            if rank == 0:                                        # the same range on ONE GPU (the others wait at the barrier)
+                t_1, d_1 = sweep(T_total, P_VEC, [N_BLOCK], args.engine, shard=False)
+            sync_all()
+            if rank == 0:
+                strong.update(ms_per_sweep_1gpu=1e3 * t_1, efficiency_vs_n1=t_1 / (world * t_n),
+                              tallies_equal_1gpu=bool(np.array_equal(np.asarray(d_1["tallies"], dtype=np.int64),
+                                                                     np.asarray(d_n["tallies"], dtype=np.int64))))
+        else:
+            strong.update(ms_per_sweep_1gpu=1e3 * t_n, efficiency_vs_n1=1.0, tallies_equal_1gpu=True)
+        line["strong"] = strong
+        ps = {"trials_per_point": T_total, "api": "Pd_plotter.run_experiment (models cached), best of 3",
+              "pd_vs_p_points": len(SWEEP_P_NS) * len(P_VEC), "pd_vs_n_points": len(SWEEP_N_NS) * len(SWEEP_N_PS)}
+        for eng in ("acs", "auto"):
+            tp, dp = sweep(T_total, P_VEC, SWEEP_P_NS, eng)
+            tn, dn = sweep(T_total, SWEEP_N_PS, SWEEP_N_NS, eng, reps=2)
+            ps[eng] = {"pd_vs_p_ms": 1e3 * tp, "pd_vs_p_kernel_ms": dp["detect_kernel_ms"], "pd_vs_p_steps": dp["steps"],
+                       "pd_vs_n_ms": 1e3 * tn, "pd_vs_n_kernel_ms": dn["detect_kernel_ms"], "pd_vs_n_steps": dn["steps"],
+                       "pd_vs_p_sha": _sha(dp["tallies"]), "pd_vs_n_sha": _sha(dn["tallies"])}
+        line["paper_sweep"] = ps
+
+        # ---- sustained: the resident loop for >= sustain_s seconds, clocks and power sampled throughout
+        if args.sustain_s > 0:
+            reps = max(args.steps, int(args.sustain_s / max(dt / args.steps, 1e-6)) + 1)
+            with ClockSampler(local_rank, period_s=0.1) as sclk:
+                dts, kms_s, _ = timed(lambda: device_pass(args.engine), reps, 1)
+            sc = sclk.summary()
+            line["sustained"] = {"seconds": dts, "passes": reps, "value": steps_per_pass * reps / dts,
+                                 "kernel_ms_per_step": float(np.mean(kms_s)), "sm_mhz_median": sc.get("sm_mhz"),
+                                 "power_w_max": sc.get("power_w_max"), "reasons": sc.get("reasons"), "samples": sc.get("samples")}
 
     if rank == 0:
         # ---- roofline: integer pipe (binding) measured on this device, this run
         alu_gops, mixed_gops = det.int_peak()
         rate_kernel = steps_per_pass_rank / (kernel_ms * 1e-3)             # this GPU's kernel-only rate
-        peaks = {}
+        peaks, traffic, mix = {}, None, {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 peaks = json.load(f)
         except Exception:
             pass
-        traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(f"{args.engine}_detect")
+                tj = json.load(f)
+            traffic = tj.get(f"{args.engine}_detect")
+            mix = tj.get(f"{args.engine}_detect_instr_mix", {})
         except Exception:
             pass
+        info = det.device_info()
+        nominal = info["sm_count"] * 4 * 32 * (clocks.get("sm_max_mhz") or 1965) * 1e6 * 1e-9      # one warp instruction / cycle / SMSP
         ach = OPS_CORE * rate_kernel * 1e-9
+        rng_ops = mix.get("bit_source_instr_per_step")
         line["roofline"] = {
             "bound": "int_alu", "unit": "Gop/s",
             "achieved": ach, "peak": mixed_gops, "frac": ach / mixed_gops,
             "peak_alu_pipe_only": alu_gops, "frac_alu_pipe_only": ach / alu_gops,
-            "ops_per_step": {"core": OPS_CORE, "f64_adds": 2,
-                             "note": "SURVEY 8(d): 2^(m+k+1) + 2^m + 3n + 5 at m=2, k=1, n=2; bit generation is not "
-                                     "counted (ncu: 33.0 warp-instructions issued per trellis step, ~15 of them Philox + "
-                                     "lazy Bernoulli + encode, profiles/r01n_*)"},
+            "peak_nominal": nominal, "frac_of_nominal": ach / nominal,
+            "frac_core_plus_rng": (OPS_CORE + rng_ops) * rate_kernel * 1e-9 / mixed_gops if rng_ops else None,
+            "ops_per_step": {"core": OPS_CORE, "f64_adds": 2, "rng_executed": rng_ops,
+                             "instr_issued_per_step": mix.get("instr_per_step"), "instr_mix_source": mix.get("source"),
+                             "note": "core = SURVEY 8(d): 2^(m+k+1) + 2^m + 3n + 5 at m=2, k=1, n=2; rng_executed = thread "
+                                     "instructions per trellis step the kernel spends on Philox + lazy Bernoulli + encode "
+                                     "(ncu source page, profiles/); frac counts core only, frac_core_plus_rng adds them"},
             "peak_source": "libmvd mvd_int_peak(), measured in this run on this GPU: `peak` = alternating LOP3/IMAD chains "
                            "(ALU + FMA pipes = warp-instruction issue rate, the most any integer code can retire); "
-                           "`peak_alu_pipe_only` = LOP3-only chains (min/shift/logic/permute can only issue there). "
+                           "`peak_alu_pipe_only` = LOP3-only chains (min/shift/logic/permute can only issue there); "
+                           "`peak_nominal` = SMs x 4 schedulers x 32 lanes x max SM clock. "
                            "MEASURED_PEAKS.json has no integer figure; the path moves ~0 HBM bytes (bits are generated in "
                            "registers), so the HBM roofline does not bind it -- see roofline_hbm_bitstream for the HBM view",
             "kernel": ("detect2p_kernel (two trials/thread ACS)" if args.engine == "acs" else "detect2_kernel<FSM1> (one-load NEXT walk)"),
@@ -393,10 +538,9 @@ def main():
             del bits
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            base = cpu_port_throughput(args.ref_iters, cores)
-            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            one = cpu_port_throughput(max(20, args.ref_iters // 3), 1)      # as shipped: the reference is single-process
-            line["cpu_baseline_1core"] = {k: one[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            base = cpu_throughput(cores, max(4, 2 * args.ref_iters))
+            line["cpu_baseline"] = base
+            line["cpu_baseline_1core"] = cpu_throughput(1, max(4, args.ref_iters // 2))       # as shipped: single-process
             try:
                 line["cpu_baseline_c_oracle"] = c_oracle_throughput()
             except Exception as exc:     # the C oracle is optional for the bench

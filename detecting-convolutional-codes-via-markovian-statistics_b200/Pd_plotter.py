@@ -9,7 +9,8 @@ What changed is where the work happens.  The reference's triple loop (Pd_plotter
 becomes: one GPU launch that walks the learning chains of all distinct p, a few hundred
 host float64 divisions (Laplace + row normalisation), and one GPU launch for every trial of every
 (N, p, hypothesis) of the sweep.  Trials shard across ranks under torchrun and the tallies are
-combined with a single allreduce (:mod:`mvd.dist`).
+combined with a single allreduce on the device (:mod:`mvd.dist`; the process group is joined lazily from the torchrun
+environment, rank 0 writes the CSV).
 
 Random bits: the reference never defines its simulator.  Here every chain is keyed --
 learning chain: (seed, LEARN_STREAM, trial 0); trial ``i`` of hypothesis ``h`` at sweep point
@@ -26,7 +27,7 @@ import numpy as np
 
 import viterbi_markov as vm
 from mvd import bitsource, codes, dist
-from mvd.engine import Seg
+from mvd.engine import Seg, fresh_seed
 
 # Reference Pd_plotter.py:67-75
 DEFAULTS = {
@@ -89,6 +90,27 @@ def _learn_edge_tables(det, p_list, learn_len, learn_burn, laplace, seed, engine
     return counts, tables
 
 
+def _models_for(det, distinct, learn_len, learn_burn, laplace, seed, learn_engine, ref_p, use_cache=True):
+    """Learned tables of one detector, cached per (p list, learn_len, burn, laplace, seed, ...) like the reference's
+    ``lru_cache`` on ``learn_P1_empirical`` (Pd_plotter.py:123): a repeated sweep neither relearns nor re-uploads.
+    Returns (counts, tables, learn_kernel_ms, cached)."""
+    key = (tuple(distinct), None if learn_len is None else int(learn_len), int(learn_burn), float(laplace), int(seed),
+           str(learn_engine), float(ref_p))
+    cache = det.__dict__.setdefault("_model_cache", {})
+    hit = cache.get(key) if use_cache else None
+    if hit is None:
+        counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=learn_engine)
+        if len(cache) >= 8:
+            cache.pop(next(iter(cache)))
+        hit = cache[key] = (counts, tables, det.last_kernel_ms())
+    cached = use_cache and getattr(det, "_models_key", None) == key
+    if not cached:
+        # T_ref = T(1/2) = mult / 2^n (reference :193-194)
+        det.set_models(hit[1], None if float(ref_p) == 0.5 else codes.t_edge_table(det.table, float(ref_p)))
+        det._models_key = key
+    return hit[0], hit[1], hit[2], cached
+
+
 @lru_cache(maxsize=128)
 def learn_P1_empirical(gens_tuple, k, n, m, p, learn_len, learn_burn, laplace, seed):
     """Empirical P1 for hypothesis H1 (reference Pd_plotter.py:123-169).
@@ -105,7 +127,7 @@ def learn_P1_empirical(gens_tuple, k, n, m, p, learn_len, learn_burn, laplace, s
 
 def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, laplace, seed, *,
                    N_spectrum=None, engine="auto", learn_engine="auto", device=None, trial_offset=0, details=None,
-                   ref_p=0.5):
+                   ref_p=0.5, cache_models=True, shard=True):
     """Hybrid detector over all (N, p) points -> DataFrame[N, p, Pd, Pc]
     (reference Pd_plotter.py:176-235; positional signature identical).
 
@@ -115,13 +137,20 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     NEXT table, identical counts); ``device`` the CUDA ordinal
     (default LOCAL_RANK or 0); ``ref_p`` the crossover of the theoretical reference chain T(ref_p)
     the sequences are scored against (the reference hard-codes 1/2, :193-194; other values use the
-    sympy-free numeric T(p) of :func:`mvd.codes.t_edge_table`); ``details`` a dict that receives tallies, tables and timings.
+    sympy-free numeric T(p) of :func:`mvd.codes.t_edge_table`); ``details`` a dict that receives tallies, tables and timings;
+    ``cache_models=False`` relearns P1 and re-uploads the tables even if this detector already holds them for the same
+    arguments (the default mirrors the reference's ``lru_cache`` on ``learn_P1_empirical``, :123); ``shard=False`` makes
+    this process run every trial itself even inside a torchrun job (no collective).
     """
     import time
 
     import pandas as pd
 
     t_start = time.perf_counter()
+    if seed is None:
+        seed = fresh_seed()
+        if shard and dist.world()[1] > 1:                         # every rank must use rank 0's key
+            seed = int(dist.allreduce_sum(np.array([seed if dist.world()[0] == 0 else 0], dtype=np.int64))[0])
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", 0))
     det = vm._detector(codes.freeze_generator(gen1), k, n, m, device)
@@ -131,41 +160,50 @@ def run_experiment(k, n, m, gen1, gen2, num_iter, p_vec, learn_len, learn_burn, 
     # P1 for every distinct p (the reference's lru_cache, :123, learns once per p)
     distinct = list(dict.fromkeys(float(p) for p in p_vec))
     t_learn0 = time.perf_counter()
-    counts, tables = _learn_edge_tables(det, distinct, learn_len, learn_burn, laplace, seed, engine=learn_engine)
-    learn_kernel_ms = det.last_kernel_ms()
-    t_tables0 = time.perf_counter()
-    # T_ref = T(1/2) = mult / 2^n (reference :193-194)
-    det.set_models(tables, None if float(ref_p) == 0.5 else codes.t_edge_table(det.table, float(ref_p)))
+    counts, tables, learn_kernel_ms, cached = _models_for(det, distinct, learn_len, learn_burn, laplace, seed, learn_engine, ref_p,
+                                                          use_cache=bool(cache_models))
     tindex = {p: i for i, p in enumerate(distinct)}
     t_detect0 = time.perf_counter()
 
-    rank, ws = dist.world()
+    rank, ws = dist.world() if shard else (0, 1)
     begin, end = dist.shard_range(int(num_iter), rank, ws, offset=int(trial_offset))
-    segs, points = [], []
-    for N in spectrum:
-        for p in p_vec:
-            q = len(points)
-            T = bitsource.bsc_threshold(float(p))
-            segs.append(Seg(N=int(N), threshold=T, stream=2 * q, table=tindex[float(p)], enc_taps=taps1,
-                            decide=0, trial_begin=begin, trial_end=end))
-            segs.append(Seg(N=int(N), threshold=T, stream=2 * q + 1, table=tindex[float(p)], enc_taps=taps2,
-                            decide=1, trial_begin=begin, trial_end=end))
-            points.append((N, p))
-    tallies = det.detect(segs, seed=int(seed), engine=engine)
-    kernel_ms = det.last_kernel_ms()
-    tallies = dist.allreduce_sum(tallies.astype(np.int64))
+    # one mvd_segment per (N, p, hypothesis), N-major / p-minor like the reference's loops (:198-199);
+    # stream 2q + h keys the bits of hypothesis h at point q
+    npts = len(spectrum) * len(p_vec)
+    Ncol = np.repeat(np.asarray(spectrum, dtype=np.int64), len(p_vec))
+    pcol = np.tile(np.asarray([float(p) for p in p_vec], dtype=np.float64), len(spectrum))
+    thr = np.tile(np.asarray([bitsource.bsc_threshold(float(p)) for p in p_vec], dtype=np.uint32), len(spectrum))
+    tcol = np.tile(np.asarray([tindex[float(p)] for p in p_vec], dtype=np.uint32), len(spectrum))
+    taps = np.tile(np.asarray([taps1, taps2], dtype=np.uint32), (npts, 1))
+    segs = det.segment_array(N=np.repeat(Ncol, 2), threshold=np.repeat(thr, 2), stream=np.arange(2 * npts), table=np.repeat(tcol, 2),
+                             enc_taps=taps, decide=np.tile(np.asarray([0, 1], dtype=np.uint32), npts),
+                             trial_begin=begin, trial_end=end)
+    if ws > 1 and dist.backend() == "nccl":
+        # tallies stay on the device: kernel -> one all_reduce over NVLink -> one D2H of the reduced vector
+        import torch
+        buf = det.__dict__.get("_d_tallies")
+        if buf is None or buf.numel() < len(segs) or buf.device.index != device:
+            buf = det._d_tallies = torch.zeros(max(64, len(segs)), dtype=torch.int64, device=f"cuda:{device}")
+        view = buf[:len(segs)]
+        det.detect(segs, seed=int(seed), engine=engine, d_tallies_ptr=view.data_ptr(), host_tallies=False)
+        kernel_ms = det.last_kernel_ms()
+        dist.allreduce_sum_device(view)
+        tallies = view.cpu().numpy()
+    else:
+        tallies = det.detect(segs, seed=int(seed), engine=engine)
+        kernel_ms = det.last_kernel_ms()
+        tallies = dist.allreduce_sum(tallies.astype(np.int64)) if ws > 1 else tallies.astype(np.int64)
 
     t64 = np.asarray(tallies, dtype=np.int64)
     s1, s2 = t64[0::2], t64[1::2]
-    cols = {"N": np.array([N for N, _ in points]), "p": np.array([p for _, p in points], dtype=np.float64),
-            "Pd": s1 / num_iter, "Pc": (s1 + s2) / (2 * num_iter)}                        # reference :225-226
+    cols = {"N": Ncol, "p": pcol, "Pd": s1 / num_iter, "Pc": (s1 + s2) / (2 * num_iter)}   # reference :225-226
     if details is not None:
         details.update(tallies=tallies, edge_counts=counts, p1_tables=tables, distinct_p=distinct,
-                       detect_kernel_ms=kernel_ms, learn_kernel_ms=learn_kernel_ms,
-                       wall_s=dict(setup=t_learn0 - t_start, learn=t_tables0 - t_learn0, tables=t_detect0 - t_tables0,
-                                   detect=time.perf_counter() - t_detect0), steps=2 * sum(N for N, _ in points) * int(num_iter),
-                       learn_len=_learn_len(det.S, learn_len), S=det.S)
-    return pd.DataFrame(cols, index=pd.RangeIndex(len(points)), copy=False)      # columns N, p, Pd, Pc (reference :228-235)
+                       detect_kernel_ms=kernel_ms, learn_kernel_ms=learn_kernel_ms, models_cached=cached,
+                       wall_s=dict(setup=t_learn0 - t_start, learn_and_tables=t_detect0 - t_learn0,
+                                   detect=time.perf_counter() - t_detect0), steps=2 * int(Ncol.sum()) * int(num_iter),
+                       learn_len=_learn_len(det.S, learn_len), S=det.S, kernel_kind=det.last_kernel_kind())
+    return pd.DataFrame(cols, index=pd.RangeIndex(npts), copy=False)      # columns N, p, Pd, Pc (reference :228-235)
 
 
 if __name__ == "__main__":
@@ -178,7 +216,8 @@ if __name__ == "__main__":
     df = run_experiment(k, n, m, gen1, gen2, DEFAULTS["num_iter"], DEFAULTS["p_vec"], DEFAULTS["learn_len"],
                         DEFAULTS["learn_burn"], DEFAULTS["laplace"], DEFAULTS["seed"])
 
-    os.makedirs(DEFAULTS["save_dir"], exist_ok=True)
-    out_csv = os.path.join(DEFAULTS["save_dir"], "Pd_hybrid_results.csv")
-    df.to_csv(out_csv, index=False)
-    print("Saved results to", out_csv)
+    if dist.is_rank0():                      # under torchrun every rank holds the same (all-reduced) table
+        os.makedirs(DEFAULTS["save_dir"], exist_ok=True)
+        out_csv = os.path.join(DEFAULTS["save_dir"], "Pd_hybrid_results.csv")
+        df.to_csv(out_csv, index=False)
+        print("Saved results to", out_csv)

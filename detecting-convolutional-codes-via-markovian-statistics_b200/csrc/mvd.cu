@@ -59,6 +59,7 @@ struct mvd_ctx {
     double tref_unit = 0.0;
     std::vector<uint32_t> bfs_levels;   // level sizes of the last GPU enumeration
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;   // counted at every host<->device copy this context issues (mvd_copy_stats)
     uint32_t learn_warm = LEARN_WARM;
     bool learn_warm_set = false;    // MVD_OPT_LEARN_WARM given: mvd_set_code keeps it
 
@@ -93,6 +94,16 @@ int fail(mvd_ctx* c, int code, const char* fmt, ...) {
     va_end(ap);
     if (c) c->err = buf; else g_create_error = buf;
     return code;
+}
+
+// every host<->device copy of the library goes through these two: the byte counters are what bench.py reports
+inline cudaError_t h2d(mvd_ctx* c, void* dst, const void* src, size_t bytes) {
+    c->h2d_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+}
+inline cudaError_t d2h(mvd_ctx* c, void* dst, const void* src, size_t bytes) {
+    c->d2h_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
 }
 
 #define CK(call)                                                                                      \
@@ -144,7 +155,7 @@ int install_states(mvd_ctx* ctx) {
     }
     CK(cudaSetDevice(ctx->device));
     CK(ctx->d_nxt.reserve(SR * 4));
-    CK(cudaMemcpyAsync(ctx->d_nxt.p, pre.data(), SR * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_nxt.p, pre.data(), SR * 4));
     // hash table: metric vector -> state * R
     const int nkw = (nstate + 7) / 8;
     uint32_t cap = 64;
@@ -169,8 +180,8 @@ int install_states(mvd_ctx* ctx) {
     ctx->hcap = cap;
     CK(ctx->d_hkeys.reserve(keys.size() * 4));
     CK(ctx->d_hvals.reserve(vals.size() * 4));
-    CK(cudaMemcpyAsync(ctx->d_hkeys.p, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_hvals.p, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_hkeys.p, keys.data(), keys.size() * 4));
+    CK(h2d(ctx, ctx->d_hvals.p, vals.data(), vals.size() * 4));
     // ---- closure: metrics[next[i][r]] == Eq.4-5(metrics[i], r) for every (i, r), state 0 = all-zero.
     // Only closed tables may take the fast kernels, which do not check for unknown vectors.
     {
@@ -218,7 +229,7 @@ int install_states(mvd_ctx* ctx) {
             dst[hi + (lo << b)] = (uint16_t)i;
         }
         CK(ctx->d_dstate.reserve(nkeys * 2));
-        CK(cudaMemcpyAsync(ctx->d_dstate.p, dst.data(), nkeys * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d(ctx, ctx->d_dstate.p, dst.data(), nkeys * 2));
         ctx->nkeys = S <= 0xFFFE ? nkeys : 0;
     }
     // ---- perfect hash for m = 3 / 4, n = 2 (two-trials-per-thread ACS kernels, mvd_detect3p.cuh): hash, displace.
@@ -301,8 +312,8 @@ int install_states(mvd_ctx* ctx) {
         if (built) {
             CK(ctx->d_phd.reserve((size_t)nb * 4));
             CK(ctx->d_pht.reserve((size_t)slots * 4));
-            CK(cudaMemcpyAsync(ctx->d_phd.p, disp.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->d_pht.p, table.data(), (size_t)slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(h2d(ctx, ctx->d_phd.p, disp.data(), (size_t)nb * 4));
+            CK(h2d(ctx, ctx->d_pht.p, table.data(), (size_t)slots * 4));
             CK(cudaStreamSynchronize(ctx->stream));
             ctx->ph_slots = slots;
             ctx->ph_bshift = bshift;
@@ -472,6 +483,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         if (s.trial_end < s.trial_begin) return fail(ctx, MVD_E_INVALID, "segment %u: trial_end < trial_begin", i);
         if (mode == MODE_DETECT && s.table >= ctx->ntables) return fail(ctx, MVD_E_INVALID, "segment %u: table %u >= %u", i, s.table, ctx->ntables);
         if (s.decide > 1) return fail(ctx, MVD_E_INVALID, "segment %u: decide must be 0 or 1", i);
+        // MVD-PHILOX-2 addresses a call as (32-step block << 6) | slot in one 32-bit counter word: block < 2^26
+        if (src->mode == MVD_SRC_PHILOX && s.N >= 0x80000000u)
+            return fail(ctx, MVD_E_INVALID, "segment %u: N = %u >= 2^31 overflows the position-addressed Philox counter", i, s.N);
         DevSeg& d = ds[i];
         d.N = s.N;
         d.threshold = s.threshold;
@@ -526,12 +540,12 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             P.bits = reinterpret_cast<const uint4*>(src->bits);
         } else {
             CK(ctx->d_bits.reserve((size_t)need_words * 16));
-            CK(cudaMemcpyAsync(ctx->d_bits.p, src->bits, (size_t)need_words * 16, cudaMemcpyHostToDevice, ctx->stream));
+            CK(h2d(ctx, ctx->d_bits.p, src->bits, (size_t)need_words * 16));
             P.bits = ctx->d_bits.as<uint4>();
         }
     }
     CK(ctx->d_segs.reserve(sizeof(DevSeg) * nsegs));
-    CK(cudaMemcpyAsync(ctx->d_segs.p, ds.data(), sizeof(DevSeg) * nsegs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_segs.p, ds.data(), sizeof(DevSeg) * nsegs));
     P.segs = ctx->d_segs.as<DevSeg>();
     P.nsegs = nsegs;
     P.nxt = ctx->d_nxt.as<uint32_t>();
@@ -560,7 +574,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         CK(ctx->d_tallies.reserve(8 * (size_t)nsegs));
         CK(cudaMemsetAsync(ctx->d_tallies.p, 0, 8 * (size_t)nsegs, ctx->stream));
         P.tallies = ctx->d_tallies.as<unsigned long long>();
-        P.tallies2 = reinterpret_cast<unsigned long long*>(out.d_tallies);
+        P.tallies2 = nullptr;               // d_tallies receives a device-to-device copy after the launch (below)
         if (out.logp) {
             CK(ctx->d_logp.reserve(16 * (size_t)trials));
             P.logp = ctx->d_logp.as<double>();
@@ -615,6 +629,10 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     P.tables_in_smem = in_smem ? 1 : 0;
 
     if (blocks == 0) {
+        if (mode == MODE_DETECT && out.d_tallies) {
+            CK(cudaMemsetAsync(out.d_tallies, 0, 8 * (size_t)nsegs, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         if (out.tallies) memset(out.tallies, 0, 8 * (size_t)nsegs);
         if (out.counts) memset(out.counts, 0, 8 * (size_t)nsegs * SR);
         return MVD_OK;
@@ -629,7 +647,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             if (ds[i].N == 0) split = false;
             steps += ntr * ds[i].N;
             ew += ntr * (((unsigned long long)ds[i].N + 3ull) & ~3ull);
-            work += ntr * ((ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
+            work += ntr * (((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
         }
         split = split && ew * 4ull <= (6ull << 30) && work <= 0x7FFFFFFFull * (unsigned long long)SPLIT_BLOCK;
         if (ctx->split_mode == 0) {
@@ -683,21 +701,21 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             const unsigned long long ntr = ds[i].trial_end - ds[i].trial_begin;
             meta[i] = w;
             meta[nsegs + 1 + i] = ew;
-            w += ntr * ((ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
+            w += ntr * (((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
             ew += ntr * (((unsigned long long)ds[i].N + spg - 1) / spg) * 4ull;      // 16-byte groups, in 32-bit words
         }
         meta[nsegs] = w;
         SplitParams SP{};
         SP.edge_bytes = eb;
         SP.fast_walk = (n == 2 && ctx->learn_warm % 128u == 0u) ? 1 : 0;
-        for (uint32_t i = 0; i < nsegs; ++i) SP.max_chunks = std::max<unsigned long long>(SP.max_chunks, (ds[i].N + SPLIT_CH - 1) / SPLIT_CH);
+        for (uint32_t i = 0; i < nsegs; ++i) SP.max_chunks = std::max<unsigned long long>(SP.max_chunks, ((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
         for (uint32_t i = 0; i < nsegs; ++i) SP.max_trials = std::max<unsigned long long>(SP.max_trials, ds[i].trial_end - ds[i].trial_begin);
         if (nsegs > 65535) return fail(ctx, MVD_E_INVALID, "too many segments for one call");
         SP.warm = ctx->learn_warm;
         SP.nchains = (uint32_t)trials;
         SP.nwork = w;
         CK(ctx->d_smeta.reserve(meta.size() * 8 + 16));
-        CK(cudaMemcpyAsync(ctx->d_smeta.p, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d(ctx, ctx->d_smeta.p, meta.data(), meta.size() * 8));
         SP.work_begin = ctx->d_smeta.as<unsigned long long>();
         SP.edge_begin = SP.work_begin + nsegs + 1;
         CK(ctx->d_lspec.reserve((size_t)w * 4));
@@ -748,32 +766,34 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (mode == MODE_DETECT && out.d_tallies)
+        CK(cudaMemcpyAsync(out.d_tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToDevice, ctx->stream));
 
     // ---- read back
     int herr = 0;
     std::vector<uint32_t> hdirty;
-    CK(cudaMemcpyAsync(&herr, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, &herr, ctx->d_err.p, sizeof(int)));
     if (mode == MODE_DETECT) {
         if (split) {
             hdirty.assign(1, 0u);
-            CK(cudaMemcpyAsync(hdirty.data(), ctx->d_ldirty.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(d2h(ctx, hdirty.data(), ctx->d_ldirty.p, 4));
         }
-        if (out.tallies) CK(cudaMemcpyAsync(out.tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out.logp) CK(cudaMemcpyAsync(out.logp, ctx->d_logp.p, 16 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out.tallies) CK(d2h(ctx, out.tallies, ctx->d_tallies.p, 8 * (size_t)nsegs));
+        if (out.logp) CK(d2h(ctx, out.logp, ctx->d_logp.p, 16 * (size_t)trials));
     } else if (mode == MODE_LEARN) {
-        if (out.counts) CK(cudaMemcpyAsync(out.counts, ctx->d_counts.p, 8 * (size_t)nsegs * SR, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out.counts) CK(d2h(ctx, out.counts, ctx->d_counts.p, 8 * (size_t)nsegs * SR));
         if (plearn && maxL > 0) {
             hdirty.assign(nsegs, 0u);
-            CK(cudaMemcpyAsync(hdirty.data(), ctx->d_ldirty.p, 4 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(d2h(ctx, hdirty.data(), ctx->d_ldirty.p, 4 * (size_t)nsegs));
         }
     } else if (mode == MODE_TRACE) {
         const size_t cells = (size_t)trials * ((size_t)segs[0].N + 1);
-        CK(cudaMemcpyAsync(out.trace_idx, ctx->d_trace_idx.p, 4 * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(d2h(ctx, out.trace_idx, ctx->d_trace_idx.p, 4 * cells));
         if (out.trace_met && engine == MVD_ENGINE_ACS)
-            CK(cudaMemcpyAsync(out.trace_met, ctx->d_trace_met.p, cells * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(d2h(ctx, out.trace_met, ctx->d_trace_met.p, cells * nstate));
     } else {
-        CK(cudaMemcpyAsync(out.hashes, ctx->d_hashes.p, 8 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out.final_met) CK(cudaMemcpyAsync(out.final_met, ctx->d_final.p, (size_t)trials * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(d2h(ctx, out.hashes, ctx->d_hashes.p, 8 * (size_t)trials));
+        if (out.final_met) CK(d2h(ctx, out.final_met, ctx->d_final.p, (size_t)trials * nstate));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
@@ -881,7 +901,7 @@ int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps) {
             bm[((size_t)r * NP + g) * 2 + 1] = d(g + HALF, 0) | (d(g + HALF, 1) << 16);
         }
     CK(ctx->d_bm.reserve(bm.size() * 4));
-    CK(cudaMemcpyAsync(ctx->d_bm.p, bm.data(), bm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_bm.p, bm.data(), bm.size() * 4));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_code = true;
     ctx->have_states = false;
@@ -1047,7 +1067,7 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
             inter[2 * (t * SR + e) + 1] = logTref[e];
         }
     CK(ctx->d_ll.reserve(inter.size() * 8));
-    CK(cudaMemcpyAsync(ctx->d_ll.p, inter.data(), inter.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_ll.p, inter.data(), inter.size() * 8));
     // log Tref[e] == c[e] * unit exactly, c = 0 or a power of two?  (unit = the non-zero value of least magnitude)
     {
         double unit = 0.0;
@@ -1072,7 +1092,7 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
         ctx->have_gfsm1 = false;
         if (ok) {
             CK(ctx->d_tcode.reserve(SR * 4));
-            CK(cudaMemcpyAsync(ctx->d_tcode.p, code.data(), SR * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(h2d(ctx, ctx->d_tcode.p, code.data(), SR * 4));
             if (128 + (SR << 7) + 64 > ctx->prop.sharedMemPerBlockOptin && SR < (1ull << 28)) {
                 // large S: packed NEXT-walk entries {log P1, next row byte offset, c} stay in global memory
                 std::vector<uint32_t> pk(4 * SR * ntables);
@@ -1087,7 +1107,7 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
                         o[3] = code[e];
                     }
                 CK(ctx->d_gfsm1.reserve(pk.size() * 4));
-                CK(cudaMemcpyAsync(ctx->d_gfsm1.p, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CK(h2d(ctx, ctx->d_gfsm1.p, pk.data(), pk.size() * 4));
                 CK(cudaStreamSynchronize(ctx->stream));
                 ctx->have_gfsm1 = true;
             }
@@ -1143,6 +1163,7 @@ int mvd_acs_final(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint
     if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code has not been called");
     if (ctx->n != 2 || ctx->m < 2) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final supports n = 2, m = 2..6 (use mvd_acs_hash)");
     if (src->mode != MVD_SRC_PHILOX) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final takes the on-device bit source (use mvd_acs_hash)");
+    if (seg->N >= 0x80000000u) return fail(ctx, MVD_E_INVALID, "N = %u >= 2^31 overflows the position-addressed Philox counter", seg->N);
     if (seg->trial_end < seg->trial_begin) return fail(ctx, MVD_E_INVALID, "trial_end < trial_begin");
     CK(cudaSetDevice(ctx->device));
     const int m = ctx->m, nstate = 1 << m, HALF = nstate / 2;
@@ -1186,7 +1207,7 @@ int mvd_acs_final(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint
     CK(mvd_launch_acsp(m, dim3((unsigned)blocks), DET2P_BLOCK, ctx->stream, P, d, sel, ctx->d_final.as<uint8_t>()));
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(final_metrics, ctx->d_final.p, (size_t)ntr * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, final_metrics, ctx->d_final.p, (size_t)ntr * nstate));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_fast = 32768;
@@ -1219,12 +1240,12 @@ int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next,
     double* g_lb2 = g_lb1 + K;
     double* g_u = g_lb2 + K;
     uint32_t* g_nxt = reinterpret_cast<uint32_t*>(g_u + nu);
-    CK(cudaMemcpyAsync(g_lp1, lp1, KR * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_lp2, lp2, KR * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_lb1, lb1, (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_lb2, lb2, (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_u, u_vals, (size_t)nu * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_nxt, next, KR * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, g_lp1, lp1, KR * 8));
+    CK(h2d(ctx, g_lp2, lp2, KR * 8));
+    CK(h2d(ctx, g_lb1, lb1, (size_t)K * 8));
+    CK(h2d(ctx, g_lb2, lb2, (size_t)K * 8));
+    CK(h2d(ctx, g_u, u_vals, (size_t)nu * 8));
+    CK(h2d(ctx, g_nxt, next, KR * 4));
     ChernoffParams P;
     P.K = K;
     P.R = R;
@@ -1255,9 +1276,9 @@ int mvd_chernoff_rho(mvd_ctx* ctx, uint32_t K, uint32_t R, const uint32_t* next,
         ctx->launches += 1;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(rho, d_out.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, rho, d_out.p, (size_t)nu * 8));
     std::vector<uint32_t> it(nu);
-    CK(cudaMemcpyAsync(it.data(), d_out.as<double>() + nu, (size_t)nu * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, it.data(), d_out.as<double>() + nu, (size_t)nu * 4));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_fast = 4096;
@@ -1288,9 +1309,9 @@ int mvd_chernoff_rho_dense(mvd_ctx* ctx, uint32_t K, uint32_t R, const double* l
     double* g_lp1 = d_in.as<double>();
     double* g_lp2 = g_lp1 + KKR;
     double* g_u = g_lp2 + KKR;
-    CK(cudaMemcpyAsync(g_lp1, logP1, KKR * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_lp2, logP2, KKR * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(g_u, u_vals, (size_t)nu * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, g_lp1, logP1, KKR * 8));
+    CK(h2d(ctx, g_lp2, logP2, KKR * 8));
+    CK(h2d(ctx, g_u, u_vals, (size_t)nu * 8));
     ChernoffParams P;
     memset(&P, 0, sizeof P);
     P.K = K;
@@ -1312,9 +1333,9 @@ int mvd_chernoff_rho_dense(mvd_ctx* ctx, uint32_t K, uint32_t R, const double* l
         ctx->launches += 1;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(rho, d_out.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, rho, d_out.p, (size_t)nu * 8));
     std::vector<uint32_t> it(nu);
-    CK(cudaMemcpyAsync(it.data(), d_out.as<double>() + nu, (size_t)nu * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, it.data(), d_out.as<double>() + nu, (size_t)nu * 4));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_fast = 4097;
@@ -1392,7 +1413,7 @@ int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment
             P.bits = reinterpret_cast<const uint4*>(src->bits);
         } else {
             CK(ctx->d_bits.reserve((size_t)need_words * 16));
-            CK(cudaMemcpyAsync(ctx->d_bits.p, src->bits, (size_t)need_words * 16, cudaMemcpyHostToDevice, ctx->stream));
+            CK(h2d(ctx, ctx->d_bits.p, src->bits, (size_t)need_words * 16));
             P.bits = ctx->d_bits.as<uint4>();
         }
     }
@@ -1419,8 +1440,8 @@ int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment
         ctx->launches += 1;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToHost, ctx->stream));
-    if (satisfied && trials) CK(cudaMemcpyAsync(satisfied, d_sat, 4 * (size_t)trials, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(d2h(ctx, tallies, ctx->d_tallies.p, 8 * (size_t)nsegs));
+    if (satisfied && trials) CK(d2h(ctx, satisfied, d_sat, 4 * (size_t)trials));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_fast = 8192;
@@ -1436,6 +1457,13 @@ int mvd_host_log_table(const double* values, double* out, uint64_t count) {
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms) {
     if (!ctx || !ms) return MVD_E_INVALID;
     *ms = ctx->last_ms;
+    return MVD_OK;
+}
+
+int mvd_copy_stats(mvd_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!ctx) return MVD_E_INVALID;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
     return MVD_OK;
 }
 

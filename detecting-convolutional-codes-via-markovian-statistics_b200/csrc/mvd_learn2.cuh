@@ -116,39 +116,52 @@ __global__ void __launch_bounds__(LEARN_BLOCK) learn_spec_kernel(const __grid_co
     }
     unsigned long long* counts = P.counts + (size_t)seg * SR;
     const uint32_t c = blockIdx.x * LEARN_BLOCK + threadIdx.x;
-    if (c < (L + LEARN_CH - 1u) / LEARN_CH) {
-        const uint32_t t_begin = c * LEARN_CH;
-        const uint32_t t_end = min(L, t_begin + LEARN_CH);
-        const uint32_t w_begin = t_begin >= LP.warm ? t_begin - LP.warm : 0u;
-        uint32_t sx = 0;                                          // state 0 (exact when w_begin == 0)
-        uint32_t Rw[MVD_MAX_N];
-        for (uint32_t b = w_begin >> 5; b * 32u < t_end; ++b) {
-            const uint32_t t0 = b * 32u;
+    // Every lane of a warp runs the same trip counts (warm / 32 + LEARN_CH / 32 blocks of 32 steps) with a per-lane
+    // `live` predicate: chunks whose warm-up reaches back past step 0, the ragged last chunk and lanes beyond the last
+    // chunk idle through the iterations they do not have, so the full-mask votes below are reached by all 32 lanes
+    // together (the programming model's requirement for __ballot_sync / __match_any_sync).
+    const bool have = c < (L + LEARN_CH - 1u) / LEARN_CH;
+    const uint32_t t_begin = have ? c * LEARN_CH : 0u;
+    const uint32_t t_end = have ? min(L, t_begin + LEARN_CH) : 0u;
+    const uint32_t nblk = (LP.warm + LEARN_CH) >> 5;              // warm is a multiple of 32 (mvd_set_option)
+    const int b_first = (int)(t_begin >> 5) - (int)(LP.warm >> 5);
+    uint32_t sx = 0;                                              // state 0 (exact when the walk starts at step 0)
+    uint32_t Rw[MVD_MAX_N];
+    for (uint32_t kb = 0; kb < nblk; ++kb) {
+        const int bi = b_first + (int)kb;
+        const uint32_t b = bi > 0 ? (uint32_t)bi : 0u;
+        const uint32_t t0 = b * 32u;
+        const bool live = have && bi >= 0 && t0 < t_end;
+        uint32_t nst = 0;
+        bool count = false;
+        if (live) {
             const uint32_t valid = min(32u, L - t0);
             learn_block_words(P, sg, b, valid, Rw);
             if (t0 == t_begin) LP.spec_start[(size_t)seg * LP.nchunks + c] = sx;
-            const bool count = t0 >= t_begin;
-            const uint32_t nst = min(valid, t_end - t0);
+            count = t0 >= t_begin;
+            nst = min(valid, t_end - t0);
+        }
+        if (SMEM) {
             for (uint32_t t = 0; t < nst; ++t) {
                 const uint32_t e = sx + word_of_step(Rw, P.n, t);
-                const bool tally = count && t0 + t >= P.burn;
-                if (SMEM) {
-                    if (tally) atomicAdd(hist + e, 1u);
-                } else {
-                    // the chunks of a warp belong to one chain, and at low p a chain sits on a handful of edges:
-                    // lanes that count the same edge elect one of them to add the group's size (one global atomic
-                    // per distinct edge and step instead of up to 32 serialised ones on the same address)
-                    const unsigned here = __ballot_sync(__activemask(), tally);
-                    if (tally) {
-                        const unsigned peers = __match_any_sync(here, e);
-                        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + e, (unsigned long long)__popc(peers));
-                    }
-                }
-                sx = SMEM ? nxt[e] : __ldg(nxt + e);
+                if (count && t0 + t >= P.burn) atomicAdd(hist + e, 1u);
+                sx = nxt[e];
+            }
+        } else {
+            for (uint32_t t = 0; t < 32u; ++t) {
+                const bool step = t < nst;
+                const uint32_t e = step ? sx + word_of_step(Rw, P.n, t) : 0u;
+                const bool tally = step && count && t0 + t >= P.burn;
+                // the chunks of a warp belong to one chain, and at low p a chain sits on a handful of edges:
+                // lanes that count the same edge elect one of them to add the group's size (one global atomic
+                // per distinct edge and step instead of up to 32 serialised ones on the same address)
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, tally ? e : 0xFFFFFFFFu);
+                if (tally && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + e, (unsigned long long)__popc(peers));
+                if (step) sx = __ldg(nxt + e);
             }
         }
-        LP.end[(size_t)seg * LP.nchunks + c] = sx;
     }
+    if (have) LP.end[(size_t)seg * LP.nchunks + c] = sx;
     if (SMEM) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < SR; i += LEARN_BLOCK) {

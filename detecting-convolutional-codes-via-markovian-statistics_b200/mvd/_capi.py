@@ -11,6 +11,7 @@ import os
 
 MAX_N = 4
 MAX_M = 6
+ABI_VERSION = 2          # must equal MVD_ABI_VERSION of include/mvd.h: the struct layouts below mirror that header
 
 SRC_PHILOX, SRC_BITSTREAM = 0, 1
 ENGINE_AUTO, ENGINE_ACS, ENGINE_FSM = 0, 1, 2
@@ -32,6 +33,7 @@ EXPORTS = (
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
     "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table", "mvd_acs_final",
+    "mvd_copy_stats",
 )
 
 
@@ -86,6 +88,9 @@ def load():
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     P = C.POINTER
     lib.mvd_abi_version.restype = i32
+    if lib.mvd_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {lib.mvd_abi_version()}, this binding expects {ABI_VERSION}: "
+                          f"rebuild it (python __graft_entry__.py)")
     lib.mvd_create.argtypes = [P(vp), i32]
     lib.mvd_destroy.argtypes = [vp]
     lib.mvd_last_error.argtypes = [vp]
@@ -110,6 +115,7 @@ def load():
     lib.mvd_acs_final.argtypes = [vp, P(Src), P(Segment), vp]
     lib.mvd_last_kernel_ms.argtypes = [vp, P(C.c_float)]
     lib.mvd_launch_count.argtypes = [vp, P(u64)]
+    lib.mvd_copy_stats.argtypes = [vp, P(u64), P(u64)]
     lib.mvd_int_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
     lib.mvd_set_option.argtypes = [vp, i32, C.c_int64]
     lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]

@@ -6,6 +6,10 @@ is keyed by its *global* trial id, so rank r of W simply takes the contiguous id
 any W.  The only data-path collective is a single ``all_reduce(SUM)`` of the int64 tally vector
 (NCCL over NVLink on GPUs; gloo in the CPU tests).  The reference has no equivalent: its trial
 loop is serial (Pd_plotter.py:198-223).
+
+Under ``torchrun ... Pd_plotter.py`` nobody has called ``init_process_group`` when
+``run_experiment`` starts: :func:`ensure_init` does it lazily from the torchrun environment
+(``WORLD_SIZE`` > 1), NCCL when a CUDA device is present, gloo otherwise.
 """
 from __future__ import annotations
 
@@ -15,15 +19,47 @@ from typing import Tuple
 import numpy as np
 
 
+def ensure_init() -> None:
+    """Join the torchrun job if there is one and no process group exists yet (idempotent)."""
+    ws = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    if ws <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or dist.is_initialized():
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    import datetime
+    timeout = datetime.timedelta(seconds=int(os.environ.get("MVD_DIST_TIMEOUT_S", "300")))
+    if torch.cuda.is_available():
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timeout)
+    else:
+        dist.init_process_group("gloo", timeout=timeout)
+
+
 def world() -> Tuple[int, int]:
-    """(rank, world_size) from torch.distributed if initialised, else from the torchrun env."""
+    """(rank, world_size): of the torch.distributed group, joining the torchrun job first if its
+    environment is present (``WORLD_SIZE`` > 1); (0, 1) for a plain single process."""
     try:
+        ensure_init()
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(), dist.get_world_size()
-    except Exception:
+    except ImportError:
         pass
     return 0, 1
+
+
+def is_rank0() -> bool:
+    return world()[0] == 0
+
+
+def backend() -> str:
+    import torch.distributed as dist
+    return dist.get_backend() if dist.is_available() and dist.is_initialized() else "none"
 
 
 def shard_range(total: int, rank: int, world_size: int, offset: int = 0) -> Tuple[int, int]:
@@ -38,7 +74,7 @@ def shard_range(total: int, rank: int, world_size: int, offset: int = 0) -> Tupl
 
 
 def allreduce_sum(values: np.ndarray, device: str | None = None) -> np.ndarray:
-    """Sum an integer vector over all ranks (no-op for a single process)."""
+    """Sum an integer vector that lives on the host over all ranks (no-op for a single process)."""
     rank, ws = world()
     arr = np.asarray(values)
     if ws == 1:
@@ -47,8 +83,7 @@ def allreduce_sum(values: np.ndarray, device: str | None = None) -> np.ndarray:
     import torch.distributed as dist
 
     t = torch.from_numpy(arr.astype(np.int64))
-    backend = dist.get_backend()
-    if backend == "nccl":
+    if dist.get_backend() == "nccl":
         dev = device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
         t = t.to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -56,7 +91,7 @@ def allreduce_sum(values: np.ndarray, device: str | None = None) -> np.ndarray:
 
 
 def allreduce_sum_device(tensor):
-    """In-place SUM allreduce of a device tensor (used when tallies are left on the GPU)."""
+    """In-place SUM allreduce of a device tensor (tallies left on the GPU by ``mvd_detect``)."""
     _, ws = world()
     if ws > 1:
         import torch.distributed as dist

@@ -36,6 +36,21 @@ class Seg:
         return self.trial_end - self.trial_begin
 
 
+# numpy view of ``mvd_segment`` (include/mvd.h; layout checked against the header in tests/test_capi_exports.py):
+# sweeps of hundreds of segments are filled column-wise instead of one ctypes attribute at a time
+SEG_DTYPE = np.dtype({"names": ["N", "threshold", "stream", "table", "enc_taps", "decide", "random_input", "trial_begin",
+                                "trial_end", "bits_offset"],
+                      "formats": ["<u4", "<u4", "<u4", "<u4", ("<u4", (_capi.MAX_N,)), "<u4", "<u4", "<u8", "<u8", "<u8"],
+                      "offsets": [0, 4, 8, 12, 16, 32, 36, 40, 48, 56], "itemsize": 64})
+assert SEG_DTYPE.itemsize == C.sizeof(_capi.Segment)
+
+
+def fresh_seed() -> int:
+    """seed=None: a fresh 64-bit Philox key from numpy's global generator (the reference idiom: no reseed,
+    alpha_exponent.py:105-106) -- never a silent fixed stream."""
+    return int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
+
+
 def _log_table(values: np.ndarray) -> np.ndarray:
     """Elementwise ``math.log(max(v, 1e-300))`` (Pd_plotter.py:114-115) with libm's log -- the
     same function the reference calls per step, so device sums add bit-identical terms."""
@@ -143,7 +158,24 @@ class Detector:
     def taps_of(self, gen) -> List[int]:
         return codes.tap_masks(codes.freeze_generator(gen), self.m, self.k)
 
-    def _segments(self, segs: Sequence[Seg]):
+    def segment_array(self, N, threshold, stream, table, enc_taps, decide, trial_begin, trial_end, random_input=1,
+                      bits_offset=0) -> np.ndarray:
+        """``mvd_segment`` records as one numpy structured array; every argument broadcasts over the segments
+        (``enc_taps``: [nsegs, n] or [n])."""
+        n = len(np.atleast_1d(np.asarray(N)))
+        a = np.zeros(n, dtype=SEG_DTYPE)
+        a["N"], a["threshold"], a["table"], a["decide"] = N, threshold, table, decide
+        a["stream"] = np.asarray(stream, dtype=np.uint64) & 0xFFFFFFFF
+        taps = np.atleast_2d(np.asarray(enc_taps, dtype=np.uint32))
+        a["enc_taps"][:, :taps.shape[1]] = taps
+        a["random_input"], a["trial_begin"], a["trial_end"], a["bits_offset"] = random_input, trial_begin, trial_end, bits_offset
+        return a
+
+    def _segments(self, segs):
+        if isinstance(segs, np.ndarray):                         # prebuilt records (segment_array)
+            if segs.dtype != SEG_DTYPE or not segs.flags.c_contiguous:
+                raise TypeError("segment arrays must be contiguous with dtype engine.SEG_DTYPE")
+            return C.cast(segs.ctypes.data, C.POINTER(_capi.Segment))
         arr = (_capi.Segment * len(segs))()
         for a, s in zip(arr, segs):
             a.N, a.threshold, a.stream, a.table = int(s.N), int(s.threshold), int(s.stream) & 0xFFFFFFFF, int(s.table)
@@ -160,7 +192,7 @@ class Detector:
         src = _capi.Src()
         if bits is None and bits_device_ptr is None:
             src.mode = _capi.SRC_PHILOX
-            src.seed = int(seed or 0) & 0xFFFFFFFFFFFFFFFF
+            src.seed = (fresh_seed() if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
             return src, None
         src.mode = _capi.SRC_BITSTREAM
         src.seed = 0
@@ -196,16 +228,23 @@ class Detector:
         self._ck(self.lib.mvd_set_loglik(self.ctx, len(tabs), self.logP1.ctypes.data, self.logTref.ctypes.data))
         self.ntables = len(tabs)
 
-    def detect(self, segs: Sequence[Seg], seed: Optional[int] = None, bits=None, engine: str = "auto",
-               want_logp: bool = False, d_tallies_ptr: Optional[int] = None, bits_device_ptr=None, bits_words=0):
-        """Successes per segment (uint64 [nsegs]) and optionally (logp1, logp_ref) per trial."""
+    def detect(self, segs, seed: Optional[int] = None, bits=None, engine: str = "auto",
+               want_logp: bool = False, d_tallies_ptr: Optional[int] = None, bits_device_ptr=None, bits_words=0,
+               host_tallies: bool = True):
+        """Successes per segment (uint64 [nsegs]) and optionally (logp1, logp_ref) per trial.  ``segs``: a list of
+        :class:`Seg` or a :meth:`segment_array`.  ``d_tallies_ptr``: device uint64[nsegs] that receives this call's
+        tallies (for a device-side allreduce); with ``host_tallies=False`` nothing but the error flag comes back to
+        the host and ``None`` is returned in place of the tallies."""
         src, keep = self._src(seed, bits, bits_device_ptr, bits_words)
-        tallies = np.zeros(len(segs), dtype=np.uint64)
+        if not host_tallies and not d_tallies_ptr:
+            raise ValueError("host_tallies=False needs d_tallies_ptr")
+        tallies = np.zeros(len(segs), dtype=np.uint64) if host_tallies else None
         logp = None
         if want_logp:
-            logp = np.zeros((sum(s.ntrials for s in segs), 2), dtype=np.float64)
+            ntr = int((segs["trial_end"] - segs["trial_begin"]).sum()) if isinstance(segs, np.ndarray) else sum(s.ntrials for s in segs)
+            logp = np.zeros((ntr, 2), dtype=np.float64)
         self._ck(self.lib.mvd_detect(self.ctx, C.byref(src), self._segments(segs), len(segs), _capi.ENGINES[engine],
-                                     tallies.ctypes.data, logp.ctypes.data if want_logp else None,
+                                     tallies.ctypes.data if host_tallies else None, logp.ctypes.data if want_logp else None,
                                      C.c_void_p(d_tallies_ptr) if d_tallies_ptr else None))
         del keep
         return (tallies, logp) if want_logp else tallies
@@ -268,6 +307,12 @@ class Detector:
         ms = C.c_float()
         self._ck(self.lib.mvd_last_kernel_ms(self.ctx, C.byref(ms)))
         return float(ms.value)
+
+    def copy_stats(self):
+        """(host -> device bytes, device -> host bytes) this context has copied so far, counted at the copy call sites."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.mvd_copy_stats(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def launch_count(self) -> int:
         v = C.c_uint64()

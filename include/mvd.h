@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MVD_ABI_VERSION 1
+#define MVD_ABI_VERSION 2
 #define MVD_MAX_N 4   /* outputs per step (R = 2^n <= 16)            */
 #define MVD_MAX_M 6   /* encoder memory  (2^m <= 64 trellis states)  */
 
@@ -145,8 +145,9 @@ int mvd_learn_counts(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, 
 
 /* Detection trials: Pd_plotter.py:210-223.  tallies: host, nsegs (successes per segment).
  * logp (optional, host): 2 doubles (logp1, logp_ref) per trial, segments concatenated.
- * d_tallies (optional, device uint64[nsegs]): also accumulate there, for a device-side
- * allreduce; pass NULL otherwise. */
+ * d_tallies (optional, device uint64[nsegs]): receives a copy of this call's tallies on the
+ * context's stream (complete when the call returns), for a device-side allreduce; then `tallies`
+ * may be NULL and nothing but the 4-byte error flag crosses PCIe.  Pass NULL otherwise. */
 int mvd_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
                int engine, uint64_t* tallies, double* logp, void* d_tallies);
 
@@ -213,6 +214,10 @@ int mvd_acs_final(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint
  * number of kernels this library has launched since creation. */
 int mvd_last_kernel_ms(mvd_ctx* ctx, float* ms);
 int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
+/* Bytes this context has copied host -> device and device -> host since creation, counted at the
+ * cudaMemcpyAsync call sites of the library (tables, segment descriptors, bit streams in; tallies, counts,
+ * log-likelihoods, error flags out).  bench.py reports the per-step difference as e2e.h2d/d2h_bytes_per_step. */
+int mvd_copy_stats(mvd_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 /* Options.  MVD_OPT_FORCE_GENERIC (value 0/1): 1 = never take the fast detection kernels
  * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.

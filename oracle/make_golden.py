@@ -333,6 +333,20 @@ def parity_golden(ref_path):
     return out
 
 
+# The reference's run_experiment, unmodified, on the injected simulator.  c75_c65_n1000 is BASELINE config 1
+# (demo_script.py predefined (2,1,2) pair at N = 1000, the demo's p grid, reduced Monte-Carlo trials).
+EXPERIMENTS = {
+    "c75_c65_small": lambda vm, pdp: experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=40,
+                                                       p_vec=[0.01, 0.05, 0.1, 0.2, 0.3], N_list=[100, 500], seed=123),
+    "c75_c65_lap": lambda vm, pdp: experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=30, p_vec=[0.1, 0.5],
+                                                     N_list=[64], seed=12345, laplace=0.1, learn_len=3000, learn_burn=10),
+    "m3_small": lambda vm, pdp: experiment_golden(vm, pdp, CODES["m3a"], CODES["m3b"], num_iter=12, p_vec=[0.05, 0.2],
+                                                  N_list=[200], seed=123),
+    "c75_c65_n1000": lambda vm, pdp: experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=24,
+                                                       p_vec=[0.01, 0.05, 0.1, 0.2, 0.3], N_list=[1000], seed=123),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -341,9 +355,23 @@ def main():
     ap.add_argument("--m4-only", action="store_true", help="only (re)write m4_kats.json")
     ap.add_argument("--alpha-only", action="store_true", help="only (re)write alpha_kats.json")
     ap.add_argument("--parity-only", action="store_true", help="only (re)write parity_kats.json")
+    ap.add_argument("--add-experiments", action="store_true",
+                    help="only add the experiments missing from experiments.json (existing entries are kept byte for byte)")
     args = ap.parse_args()
     vm, pdp = load_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
+
+    if args.add_experiments:
+        path = os.path.join(args.out, "experiments.json")
+        with open(path) as f:
+            exps = json.load(f)
+        for name, make in EXPERIMENTS.items():
+            if name not in exps:
+                exps[name] = make(vm, pdp)
+                print("[exp]", name, exps[name]["reference_seconds"], "s", flush=True)
+        with open(path, "w") as f:
+            json.dump(exps, f, separators=(",", ":"))
+        return
 
     with open(os.path.join(args.out, "parity_kats.json"), "w") as f:
         json.dump(parity_golden(args.ref), f, separators=(",", ":"))
@@ -419,16 +447,9 @@ def main():
     print("[sim] done", flush=True)
 
     exps = {}
-    exps["c75_c65_small"] = experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=40,
-                                              p_vec=[0.01, 0.05, 0.1, 0.2, 0.3], N_list=[100, 500], seed=123)
-    print("[exp] c75_c65_small", exps["c75_c65_small"]["reference_seconds"], "s", flush=True)
-    exps["c75_c65_lap"] = experiment_golden(vm, pdp, CODES["c75"], CODES["c65"], num_iter=30,
-                                            p_vec=[0.1, 0.5], N_list=[64], seed=12345, laplace=0.1,
-                                            learn_len=3000, learn_burn=10)
-    print("[exp] c75_c65_lap", flush=True)
-    exps["m3_small"] = experiment_golden(vm, pdp, CODES["m3a"], CODES["m3b"], num_iter=12,
-                                         p_vec=[0.05, 0.2], N_list=[200], seed=123)
-    print("[exp] m3_small", exps["m3_small"]["reference_seconds"], "s", flush=True)
+    for name, make in EXPERIMENTS.items():
+        exps[name] = make(vm, pdp)
+        print("[exp]", name, exps[name]["reference_seconds"], "s", flush=True)
     with open(os.path.join(args.out, "experiments.json"), "w") as f:
         json.dump(exps, f, separators=(",", ":"))
     print("golden vectors written to", os.path.abspath(args.out))

@@ -31,6 +31,39 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _gpu_unavailable_reason():
+    """None when libmvd.so loads and mvd_create succeeds on device 0, else why not."""
+    import ctypes as C
+    try:
+        from mvd import _capi
+        lib = _capi.load()
+    except Exception as exc:                       # missing / stale library
+        return f"libmvd.so unusable: {exc}"
+    ctx = C.c_void_p()
+    rc = lib.mvd_create(C.byref(ctx), 0)
+    if rc != 0:
+        return "no CUDA device: " + (lib.mvd_last_error(None) or b"").decode(errors="replace")
+    lib.mvd_destroy(ctx)
+    return None
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a CPU-only box: gpu-marked tests are skipped (with the reason), not failed, so host-logic
+    regressions are not buried.  When the marker expression asks for gpu tests explicitly (-m gpu) nothing is
+    skipped: on the GPU box a missing device or library must fail loudly."""
+    if "gpu" in (config.getoption("-m") or "") and "not gpu" not in (config.getoption("-m") or ""):
+        return
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items:
+        return
+    reason = _gpu_unavailable_reason()
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     out = {}

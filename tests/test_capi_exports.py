@@ -40,7 +40,18 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _capi.LIB_PATH], text=True)
     exported = set(re.findall(r"\bT (mvd_[a-z0-9_]+)", out))
     assert set(names) <= exported
-    assert lib.mvd_abi_version() == 1
+    header_abi = int(re.search(r"#define MVD_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+    assert lib.mvd_abi_version() == header_abi == _capi.ABI_VERSION
+
+
+def test_stale_library_is_rejected(monkeypatch):
+    """A libmvd.so whose ABI version differs from the ctypes mirror's must not load (struct layouts would be wrong)."""
+    from mvd import _capi
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "ABI_VERSION", _capi.ABI_VERSION + 1)
+    with pytest.raises(ImportError) as ei:
+        _capi.load()
+    assert "ABI version" in str(ei.value)
 
 
 def test_option_constants_match_header():
@@ -135,3 +146,23 @@ def test_missing_library_is_an_import_error(monkeypatch):
     with pytest.raises(ImportError) as ei:
         _capi.load()
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_numpy_segment_records_match_the_ctypes_struct():
+    """engine.SEG_DTYPE (column-wise filling of a sweep's segments) has mvd_segment's layout, and
+    Detector.segment_array fills the same bytes as the per-field ctypes path."""
+    import numpy as np
+    from mvd import _capi, engine
+    assert engine.SEG_DTYPE.itemsize == C.sizeof(_capi.Segment)
+    for name in engine.SEG_DTYPE.names:
+        assert engine.SEG_DTYPE.fields[name][1] == getattr(_capi.Segment, name).offset, name
+    fake = engine.Detector.__new__(engine.Detector)          # no device needed for the two packers
+    fake.dec_taps = [7, 5]
+    segs = [engine.Seg(N=500 + i, threshold=1000 * i + 7, stream=2 * i + 1, table=i % 3, enc_taps=[7 - i % 2, 5], decide=i % 2,
+                       random_input=True, trial_begin=10, trial_end=10 + 3 * i, bits_offset=0) for i in range(6)]
+    a = fake._segments(segs)
+    b = fake.segment_array(N=[s.N for s in segs], threshold=[s.threshold for s in segs], stream=[s.stream for s in segs],
+                           table=[s.table for s in segs], enc_taps=[list(s.enc_taps) for s in segs], decide=[s.decide for s in segs],
+                           trial_begin=10, trial_end=[s.trial_end for s in segs])
+    assert bytes(a) == b.tobytes()
+    fake.ctx = None                                          # __del__ must not touch a context that was never created

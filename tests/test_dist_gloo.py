@@ -100,3 +100,37 @@ def test_two_rank_tallies_equal_single_process():
     whole = [co.run_trials(t1, t1, 2, 2, 100, T, 123, 0, 0, 301, otab, P1, Tref, 0),
              co.run_trials(t1, t2, 2, 2, 100, T, 123, 1, 0, 301, otab, P1, Tref, 1)]
     assert whole == res[0][2]
+
+
+def _lazy_worker(rank, world, port, q):
+    """What `torchrun ... Pd_plotter.py` gives a process: the rendezvous environment, but nobody has called
+    init_process_group.  mvd.dist must join the job by itself (silent single-process fallback)."""
+    sys.path.insert(0, os.path.join(ROOT, "detecting-convolutional-codes-via-markovian-statistics_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), CUDA_VISIBLE_DEVICES="")
+    import torch.distributed as td
+    from mvd import dist
+    assert not td.is_initialized()
+    got = dist.world()                                      # joins lazily (gloo: no CUDA device here)
+    assert td.is_initialized() and dist.backend() == "gloo"
+    begin, end = dist.shard_range(1001, *got)
+    total = dist.allreduce_sum(np.array([end - begin, rank + 1], dtype=np.int64))
+    q.put((rank, got, total.tolist(), dist.is_rank0()))
+    td.destroy_process_group()
+
+
+def test_world_joins_the_torchrun_job_lazily():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lazy_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [(0, 2), (1, 2)]
+    assert res[0][2] == res[1][2] == [1001, 3]
+    assert [r[3] for r in res] == [True, False]

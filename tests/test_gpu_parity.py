@@ -167,7 +167,7 @@ def test_learn_counts_many_chains(codes_spec, dets):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small"])
+@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small", "c75_c65_n1000"])
 def test_run_experiment_matches_reference(golden, exp, engine):
     """Drop-in run_experiment == the reference's run_experiment (unmodified, injected simulator):
     identical Pd / Pc, P1 and per-trial log-likelihoods."""
@@ -511,20 +511,33 @@ def test_gpu_bfs_m4_vs_host_bfs(golden, codes_spec, name, S):
             assert np.array_equal(det.table.metrics, om) and np.array_equal(det.table.nxt, on)
 
 
-def test_m4_large_table_acs_pair_matches_next_walk(codes_spec):
-    """m = 4 with S = 150 743 (the reference cannot run it: 182 GB of dense counts): the two-trials-per-thread ACS
-    kernel (perfect hash over 2^19 slots in global memory) and the NEXT-table walk give identical tallies and sums."""
+def test_m4_large_table_vs_oracle(codes_spec):
+    """m = 4 with S = 150 743, the largest checkable configuration (the reference cannot run it: 182 GB of dense
+    counts): learning-chain edge counts (4 x 10^5 steps, Pd_plotter.py:158-163), detection tallies and per-trial
+    float64 sums (Pd_plotter.py:210-223) of the NEXT-table walk, of the two-trials-per-thread ACS kernel (perfect hash
+    over 2^19 slots in global memory) and of the generic checked kernel, all bit-identical to the C oracle."""
+    import c_oracle as co
     from mvd import bitsource, codes
     from mvd.engine import Detector, Seg
     spec = codes_spec["m4c"]
     with Detector(spec["gen"], 1, 2, 4, enumerate_with="gpu", max_states=1 << 18) as det:
         assert det.S == 150743
+        tab = co.Table(det.table.metrics, 4)
         T = bitsource.bsc_threshold(0.05)
-        counts = det.learn_counts([Seg(N=400000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=det.dec_taps)], burn=200, seed=3)[0]
-        det.set_models([codes.p1_from_edge_counts(det.table, counts, 1.0)])
+        L = 400000
+        counts = det.learn_counts([Seg(N=L, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=det.dec_taps)], burn=200, seed=3)[0]
+        assert det.last_kernel_kind() == 1024
+        want_counts, _ = co.learn_chain(det.dec_taps, det.dec_taps, 2, 4, L, 200, T, 3, bitsource.LEARN_STREAM, 0, tab)
+        assert np.array_equal(counts, want_counts) and int(counts.sum()) == L - 200
+        P1 = codes.p1_from_edge_counts(det.table, counts, 1.0)
+        Tref = codes.tref_half_table(det.table)
+        det.set_models([P1])
         taps2 = [det.dec_taps[1], det.dec_taps[0]]
-        segs = [Seg(N=300, threshold=T, stream=d, enc_taps=(det.dec_taps if d == 0 else taps2), decide=d, trial_begin=0, trial_end=3000)
+        ntr = 3000
+        segs = [Seg(N=300, threshold=T, stream=d, enc_taps=(det.dec_taps if d == 0 else taps2), decide=d, trial_begin=0, trial_end=ntr)
                 for d in (0, 1)]
+        want = [co.run_trials(det.dec_taps, det.dec_taps if d == 0 else taps2, 2, 4, 300, T, 5, d, 0, ntr, tab, P1, Tref, d,
+                              want_logp=True) for d in (0, 1)]
         a, la = det.detect(segs, seed=5, engine="fsm", want_logp=True)
         det.no_pair(2)
         try:
@@ -533,7 +546,95 @@ def test_m4_large_table_acs_pair_matches_next_walk(codes_spec):
         finally:
             det.no_pair(False)
         assert kind & 256 and kind & 512
-        assert np.array_equal(a, b) and np.array_equal(la, lb)
+        det.force_generic(True)
+        try:
+            c, lc = det.detect(segs, seed=5, engine="acs", want_logp=True)
+            assert det.last_kernel_kind() == 0
+        finally:
+            det.force_generic(False)
+        for t, lp in ((a, la), (b, lb), (c, lc)):
+            for d in (0, 1):
+                assert int(t[d]) == want[d][0]
+                assert np.array_equal(lp[d * ntr:(d + 1) * ntr], want[d][1])
+
+
+@pytest.mark.parametrize("dec,enc,p", [("c75", "c65", 0.1), ("m3a", "m3b", 0.05)])
+def test_config3_blocklengths_vs_oracle(codes_spec, dets, dec, enc, p):
+    """BASELINE config 3 (Pd vs blocklength, N = 10^2 .. 10^5): N = 10^4, 10^5 and the ragged 100 003 through the
+    time-split path, the one-thread-per-trial NEXT walk and the ACS kernels -- tallies and per-trial float64 sums
+    bit-identical to the C oracle over the whole length."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec[dec]
+    det = dets(dec)
+    tab, P1, Tref = _oracle_models(det, spec, p, 8000, 5)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(p)
+    ntr = 9
+    Ns = (10000, 100000, 100003)
+    segs = [Seg(N=N, threshold=T, stream=40 + 2 * i + d, enc_taps=_taps(codes_spec[enc if d else dec]), decide=d, trial_begin=3,
+                trial_end=3 + ntr) for i, N in enumerate(Ns) for d in (0, 1)]
+    want = [co.run_trials(_taps(spec), _taps(codes_spec[enc if d else dec]), spec["n"], spec["m"], N, T, 77, 40 + 2 * i + d, 3,
+                          3 + ntr, tab, P1, Tref, d, want_logp=True) for i, N in enumerate(Ns) for d in (0, 1)]
+    runs = []
+    det.split_trials(1)
+    try:
+        runs.append(det.detect(segs, seed=77, engine="fsm", want_logp=True))
+        assert det.last_kernel_kind() == 16384
+        det.split_trials(0)
+        runs.append(det.detect(segs, seed=77, engine="auto", want_logp=True))       # automatic choice: few long trials split
+        assert det.last_kernel_kind() == 16384
+        det.split_trials(2)
+        runs.append(det.detect(segs, seed=77, engine="fsm", want_logp=True))
+        assert det.last_kernel_kind() != 16384
+        runs.append(det.detect(segs, seed=77, engine="acs", want_logp=True))
+    finally:
+        det.split_trials(0)
+    for tallies, lp in runs:
+        for j, (wt, wlp) in enumerate(want):
+            assert int(tallies[j]) == wt
+            assert np.array_equal(lp[j * ntr:(j + 1) * ntr], wlp)
+
+
+_BENCH_GEOMETRY_WANT = {}
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_bench_geometry_one_segment_vs_oracle(codes_spec, dets, engine):
+    """The launch geometry bench.py times (BASELINE configs[1]: 7 p x 2 hypotheses = 14 segments in one launch,
+    grid.y = 14, N = 500, P1 learned per p as run_experiment does) at 2 x 10^5 trials per segment: the tallies of the
+    p = 0.1 point -- both hypotheses, every one of the 2 x 10^5 trials -- equal the C oracle's, and every other
+    segment equals its own single-segment launch."""
+    import c_oracle as co
+    import Pd_plotter as pdp
+    from mvd import bitsource
+    from mvd.engine import Seg
+    det = dets("c75")
+    p_vec = [0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5]
+    _, tables = pdp._learn_edge_tables(det, p_vec, None, 200, 1.0, 12345)
+    det.set_models(tables)
+    t1, t2 = _taps(codes_spec["c75"]), _taps(codes_spec["c65"])
+    ntr = 200_000
+    segs = []
+    for q, p in enumerate(p_vec):
+        T = bitsource.bsc_threshold(p)
+        segs.append(Seg(N=500, threshold=T, stream=2 * q, table=q, enc_taps=t1, decide=0, trial_begin=0, trial_end=ntr))
+        segs.append(Seg(N=500, threshold=T, stream=2 * q + 1, table=q, enc_taps=t2, decide=1, trial_begin=0, trial_end=ntr))
+    tallies = det.detect(segs, seed=12345, engine=engine)
+    kind = det.last_kernel_kind()
+    assert kind != 0 and ((kind & 256) != 0) == (engine == "acs")           # the headline kernels, not the generic ones
+    tab = co.Table(det.table.metrics, 2)
+    Tref = __import__("mvd.codes", fromlist=["codes"]).tref_half_table(det.table)
+    q = 2
+    for h, enc in enumerate((t1, t2)):
+        if h not in _BENCH_GEOMETRY_WANT:                                    # 10^8 oracle steps: once for both engines
+            _BENCH_GEOMETRY_WANT[h] = co.run_trials(t1, enc, 2, 2, 500, bitsource.bsc_threshold(0.1), 12345, 2 * q + h, 0, ntr,
+                                                    tab, tables[q], Tref, h)
+        assert int(tallies[2 * q + h]) == _BENCH_GEOMETRY_WANT[h]
+    assert 0 < int(tallies[2 * q]) < ntr                                     # p = 0.1 is the informative point (Pd ~ 0.26)
+    for j in (0, 7, 13):
+        assert int(det.detect([segs[j]], seed=12345, engine=engine)[0]) == int(tallies[j])
 
 
 def test_gpu_bfs_limits_and_count_only(codes_spec):

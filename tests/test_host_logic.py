@@ -173,7 +173,7 @@ def test_log_prob_sequence_host(golden):
         pdp.log_prob_sequence([(9, 9, 9, 9), (0, 0, 0, 0)], index, Tref)
 
 
-@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small"])
+@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small", "c75_c65_n1000"])
 def test_p1_from_edge_counts(golden, exp):
     """Host Laplace + row normalisation (Pd_plotter.py:166-167) from oracle edge counts == the
     reference's learned P1 on every edge; off-edge entries == the reference's minimum."""

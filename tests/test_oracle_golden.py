@@ -195,7 +195,7 @@ def test_philox_known_answers():
 
 
 # ------------------------------------------------------------------ experiments (Pd / Pc / P1 / logp)
-@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small"])
+@pytest.mark.parametrize("exp", ["c75_c65_small", "c75_c65_lap", "m3_small", "c75_c65_n1000"])
 def test_c_oracle_experiment_matches_reference(golden, exp):
     """The whole path on the CPU oracle == the reference's run_experiment (unmodified, with the
     injected simulator): P1 (edge form), every per-trial log-likelihood in call order, Pd, Pc."""
