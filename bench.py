@@ -334,7 +334,13 @@ def main():
 
     # ---- resident setup (outside the timed region of `value`): learn P1, upload tables
     counts, tables = pdp._learn_edge_tables(det, P_VEC, None, 200, 1.0, SEED)
-    det.set_models(tables)
+
+    def install_bench_models():
+        """The 7 log-likelihood tables of the bench sweep (run_experiment legs in between install their own)."""
+        det.set_models(tables)
+        det._models_key = None
+
+    install_bench_models()
     segs = []
     for q, p in enumerate(P_VEC):
         T = bitsource.bsc_threshold(p)
@@ -454,6 +460,7 @@ def main():
         line["paper_sweep"] = ps
 
         # ---- sustained: the resident loop for >= sustain_s seconds, clocks and power sampled throughout
+        install_bench_models()
         if args.sustain_s > 0:
             reps = max(args.steps, int(args.sustain_s / max(dt / args.steps, 1e-6)) + 1)
             with ClockSampler(local_rank, period_s=0.1) as sclk:
@@ -508,6 +515,7 @@ def main():
         }
         if not args.no_extras and world == 1:       # single-GPU legs only: nothing below may enter a collective
             other = "fsm" if args.engine == "acs" else "acs"
+            install_bench_models()
             dto, kmo, _ = timed(lambda: device_pass(other), max(3, args.steps // 2), 3)
             line["alt_engine"] = {"engine": other, "value": steps_per_pass * max(3, args.steps // 2) / dto,
                                   "kernel_ms_per_step": float(np.mean(kmo)),

@@ -77,11 +77,13 @@ struct mvd_ctx {
     std::vector<uint32_t> h_next;
     uint32_t hcap = 0;
     uint32_t ph_slots = 0, ph_bshift = 24, ph_c2 = 0, ph_c4 = 0;   // m = 3 / 4 perfect hash (mvd_detect3p.cuh), 0 = none
+    uint32_t ph_nb = 0, ph_slot0 = 0;
+    bool have_llslot = false;       // m = 4: log rows stored by hash slot (d_llslot) for the loaded tables
     // loglik
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot;
 };
 
 namespace {
@@ -317,11 +319,14 @@ int install_states(mvd_ctx* ctx) {
             CK(cudaStreamSynchronize(ctx->stream));
             ctx->ph_slots = slots;
             ctx->ph_bshift = bshift;
+            ctx->ph_nb = nb;
+            ctx->ph_slot0 = disp[0] & (slots - 1);          // the all-zero vector: w0 = w1 = 0, bucket 0, second hash 0
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_states = true;
     ctx->ntables = 0;
+    ctx->have_llslot = false;
     return MVD_OK;
 }
 
@@ -465,7 +470,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
                         (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
     // m = 4: the same kernel with displacements, slots and log rows in global memory
     const bool pair4 = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && det2_gt && ctx->m == 4 &&
-                       ctx->ph_slots && (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
+                       ctx->ph_slots && ctx->have_llslot && (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
     const bool pair3 = pair3s || pair4;
     // few trials: smaller blocks so that every SM gets work (the kernels read blockDim.x)
     uint32_t threads = (pair || pair3) ? DET2P_BLOCK : DET2_BLOCK;
@@ -568,6 +573,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     P.fp.ph_bshift = ctx->ph_bshift;
     P.fp.ph_c2 = ctx->ph_c2;
     P.fp.ph_c4 = ctx->ph_c4;
+    P.fp.ph_nb = ctx->ph_nb;
+    P.fp.ph_slot0 = ctx->ph_slot0;
+    P.fp.ll_slot = ctx->d_llslot.as<double2>();
 
     // ---- outputs
     if (mode == MODE_DETECT) {
@@ -753,7 +761,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             }
             if (maxblocks == 0) continue;
             const dim3 g2((unsigned)maxblocks, cnt);
-            if (pair3) le = mvd_launch_det3_pair(m, g2, threads, pair4 ? 4096 : pair3_smem, ctx->stream, P, B);
+            // m = 4: the bucket displacements ride in shared memory when they fit beside two resident blocks
+            const size_t pair4_smem = 4096 + ((size_t)ctx->ph_nb * 4 <= 64 * 1024 ? (size_t)ctx->ph_nb * 4 : 0);
+            if (pair3) le = mvd_launch_det3_pair(m, g2, threads, pair4 ? pair4_smem : pair3_smem, ctx->stream, P, B);
             else le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }
@@ -851,7 +861,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
                       &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
-                      &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht};
+                      &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1112,6 +1122,15 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
                 ctx->have_gfsm1 = true;
             }
         }
+    }
+    // m = 4 two-trials-per-thread ACS kernel: the same rows in hash-slot order (64 B per slot and table)
+    ctx->have_llslot = false;
+    if (ctx->ph_slots && ctx->m == 4 && (size_t)ctx->ph_slots * 64 * ntables <= ((size_t)24 << 30)) {
+        CK(ctx->d_llslot.reserve((size_t)ctx->ph_slots * 64 * ntables));
+        CK(mvd_launch_slot_rows(ctx->d_ll.as<double2>(), ctx->d_pht.as<uint32_t>(), ctx->ph_slots, (uint32_t)SR, ntables,
+                                ctx->d_llslot.as<double2>(), ctx->stream));
+        ctx->launches += 1;
+        ctx->have_llslot = true;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ntables = ntables;

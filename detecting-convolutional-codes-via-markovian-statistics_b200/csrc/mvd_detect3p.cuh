@@ -7,8 +7,12 @@
 //     slot = (((w0 c2 + w1 c4) >> 11) + disp[(w0 C1 + w1 C3) >> bshift]) & (slots - 1)        (hash, displace;
 //                                                     c2, c4: odd multipliers the host build settles on)
 //
-// m = 3 keeps every table in shared memory; m = 4 (template GT) reads displacements, slots and log rows from
-// global memory (L2-resident), three dependent loads per trial-step instead of ~5.6 with open addressing.
+// m = 3 keeps every table in shared memory.  m = 4 (template GT; S = 25 751 ... 232 567) cannot: there the log rows are
+// stored BY SLOT in global memory (FastPlan::ll_slot, built once per mvd_set_loglik by slot_rows_kernel), so the slot
+// itself is the row index and the slot -> state table is never read: one displacement read (shared memory when the
+// bucket table fits, template DS; else L2) and one 16-byte row read per trial-step.  The first version read
+// displacement, slot and row from L2 -- three dependent gathers per trial-step, L1 wavefront-bound at 74 % with
+// `long_scoreboard` the top stall (profiles/r02a_m4_pair_ncu_full.txt).
 //
 // two dependent shared-memory reads and no probe loop, against ~1.3 probes of an open-addressing table with
 // key compares and a divergent loop in detect2_kernel<LK_HASH, 3> (66 warp-instructions per trellis step instead of
@@ -29,7 +33,7 @@
 // (ns, b) is PRMT(V_A, V_B, sel[ns][b]) = V_A[L] | V_B[L] << 16 with a kernel-constant selector (selector
 // nibbles with bit 3 set yield the replicated sign bit = 0).  16 PRMTs replace four LDS.128 (16 shared-memory
 // wavefronts per step pair): this kernel is shared-memory bound, the ALU pipe has room.
-template <int M, bool GT>
+template <int M, bool GT, bool DS = false>
 struct PairEngineN {
     static constexpr int NS = 1 << M, HALF = NS / 2;
     uint32_t Q[NS];                   // (trial A, trial B) metrics of the trellis states
@@ -44,8 +48,9 @@ struct PairEngineN {
 
     __device__ __forceinline__ uint32_t lookup(uint32_t w0, uint32_t w1) const {
         if (GT) {
-            const uint32_t d = __ldg(gD + ((w0 * PH3_C1 + w1 * PH3_C3) >> bshift));
-            return __ldg(gT + ((((w0 * c2 + w1 * c4) >> 11) + d) & gmask));
+            const uint32_t b = (w0 * PH3_C1 + w1 * PH3_C3) >> bshift;
+            const uint32_t d = DS ? lds_u32(kD + (b << 2)) : __ldg(gD + b);
+            return ((((w0 * c2 + w1 * c4) >> 11) + d) & gmask) << 2;           // slot * R: the row index of ll_slot
         }
         const uint32_t d8 = lds_u32(kD | (((w0 * PH3_C1) >> 22) & 0x3FCu));           // displacement * 8
         return lds_u32(kT | ((((w0 * c2) >> 18) + d8) & tmask));
@@ -84,7 +89,17 @@ struct PairEngineN {
     }
 };
 
-template <int M, bool GT, int PHILOX>
+// ll_slot[t][slot * 4 + r] = ll[t][state(slot) * 4 + r]: the log rows of every table in hash-slot order
+__global__ void slot_rows_kernel(const double2* __restrict__ ll, const uint32_t* __restrict__ pht, uint32_t slots, uint32_t SR,
+                                 uint32_t ntables, double2* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)slots * 4u) return;
+    const uint32_t st = pht[idx >> 2];                       // state * R, or MVD_EMPTY (never looked up)
+    for (uint32_t t = 0; t < ntables; ++t)
+        out[(size_t)t * slots * 4u + idx] = st == MVD_EMPTY ? make_double2(0.0, 0.0) : ll[(size_t)t * SR + st + (idx & 3u)];
+}
+
+template <int M, bool GT, int PHILOX, bool DS = false>
 __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(const __grid_constant__ Params P,
                                                                                const __grid_constant__ SegBatch B) {
     constexpr int NS = 1 << M;
@@ -121,6 +136,8 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
         for (uint32_t L = 0; L < 4u; ++L) v |= (uint32_t)__popc(L ^ r) << (8u * L);
         *reinterpret_cast<uint32_t*>(g + a_V + 4u * r) = v;
     }
+    if (GT && DS)                                            // bucket displacements: ph_nb x 4 B after the V table
+        for (uint32_t i = threadIdx.x; i < P.fp.ph_nb; i += BS) *reinterpret_cast<uint32_t*>(g + a_ll + 4u * i) = P.fp.ph_d[i];
     if (!GT) {
         for (uint32_t i = threadIdx.x; i < 256u; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i] << 3;
         for (uint32_t i = threadIdx.x; i < slots * 2u; i += BS) {
@@ -130,19 +147,19 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     }
     __syncthreads();
 
-    PairEngineN<M, GT> eng;
+    PairEngineN<M, GT, DS> eng;
 #pragma unroll
     for (int s = 0; s < NS; ++s) eng.Q[s] = 0u;
-    eng.sxA = eng.sxB = GT ? 0u : a_ll + ((lane & 1u) << 4); // state 0 = the all-zero vector
+    eng.sxA = eng.sxB = GT ? P.fp.ph_slot0 << 2 : a_ll + ((lane & 1u) << 4); // state 0 = the all-zero vector
     eng.gD = P.fp.ph_d;
     eng.gT = P.fp.ph_t;
-    eng.gll = P.ll + (size_t)sg.table * SR;
+    eng.gll = GT ? P.fp.ll_slot + (size_t)sg.table * slots * 4u : P.ll + (size_t)sg.table * SR;
     eng.bshift = P.fp.ph_bshift;
     eng.gmask = slots - 1u;
     eng.c2 = P.fp.ph_c2;
     eng.c4 = P.fp.ph_c4;
     eng.kV = a_V;
-    eng.kD = a_D;
+    eng.kD = (GT && DS) ? a_ll : a_D;
     // label of branch (ns, b) from the branch-metric table of the decoder (P.bm[r][2 g + b] = distances to ns = 2g and
     // 2g + 1 from predecessor g + 4 b): (d(L,0), d(L,1)) = (0,1), (1,0), (1,2), (2,1) for L = 0, 1, 2, 3
 #pragma unroll

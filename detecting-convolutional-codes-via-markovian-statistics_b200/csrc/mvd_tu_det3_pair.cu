@@ -10,10 +10,24 @@ cudaError_t mvd_launch_det3_pair(int m, dim3 grid, unsigned threads, size_t smem
         if (e != cudaSuccess) return e;
         kern<<<grid, threads, smem, st>>>(P, B);
     } else if (m == 4) {
-        if (ph) detect3p_kernel<4, true, 1><<<grid, threads, smem, st>>>(P, B);      // tables stay in global memory (L2)
-        else detect3p_kernel<4, true, 0><<<grid, threads, smem, st>>>(P, B);
+        // log rows by slot in global memory (L2); bucket displacements in shared memory when smem says so (> 4 KB)
+        const bool ds = smem > 4096;
+        auto kern = ds ? (ph ? detect3p_kernel<4, true, 1, true> : detect3p_kernel<4, true, 0, true>)
+                       : (ph ? detect3p_kernel<4, true, 1, false> : detect3p_kernel<4, true, 0, false>);
+        if (ds) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, threads, smem, st>>>(P, B);
     } else {
         return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t mvd_launch_slot_rows(const double2* ll, const uint32_t* pht, uint32_t slots, uint32_t SR, uint32_t ntables, double2* out,
+                                 cudaStream_t st) {
+    const size_t n = (size_t)slots * 4u;
+    slot_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ll, pht, slots, SR, ntables, out);
     return cudaGetLastError();
 }

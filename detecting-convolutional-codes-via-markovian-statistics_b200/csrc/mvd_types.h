@@ -30,6 +30,9 @@ struct FastPlan {
     uint32_t ph_slots;                 //   power of two, 0 = no perfect hash
     uint32_t ph_bshift;                //   bucket = hash >> ph_bshift
     uint32_t ph_c2, ph_c4;             //   multipliers of the second hash (chosen by the host build)
+    uint32_t ph_nb;                    //   number of buckets (= entries of ph_d)
+    uint32_t ph_slot0;                 //   slot of Markov state 0 (the all-zero vector)
+    const double2* ll_slot;            // m = 4: log-likelihood rows indexed by hash SLOT, [ntables][ph_slots * R] (no slot -> state read)
 };
 
 struct Params {

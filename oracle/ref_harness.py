@@ -42,8 +42,9 @@ def _import_reference(path):
     """Import the reference's two modules under private names (the product ships drop-ins with the same names)."""
     import importlib.util
     import warnings
-    for name in ("matplotlib", "matplotlib.pyplot"):
-        sys.modules.setdefault(name, types.ModuleType(name))
+    stubbed = [name for name in ("matplotlib", "matplotlib.pyplot") if name not in sys.modules]
+    for name in stubbed:
+        sys.modules[name] = types.ModuleType(name)
     warnings.simplefilter("ignore")                       # invalid escape sequences in the reference's docstrings
     saved = {k: sys.modules.get(k) for k in ("viterbi_markov", "Pd_plotter")}
     try:
@@ -60,6 +61,8 @@ def _import_reference(path):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+        for name in stubbed:                             # the stubs must not outlive the import (other code probes matplotlib)
+            sys.modules.pop(name, None)
     return mods["viterbi_markov"], mods["Pd_plotter"]
 
 
