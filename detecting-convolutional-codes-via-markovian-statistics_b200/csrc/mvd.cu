@@ -503,6 +503,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         d.decide = s.decide;
         d.random_input = s.random_input ? 1u : 0u;
         d.dmin = s.threshold ? (uint32_t)__builtin_ctz(s.threshold) : 32u;
+        if (getenv("MVD_HACK_NCALLS2") && d.dmin < 24u) d.dmin = 24u;     // TIMING EXPERIMENT ONLY (wrong bits): at most 2 calls per flip word
         const uint64_t ntr = s.trial_end - s.trial_begin;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one call");
         d.block_begin = (uint32_t)blocks;

@@ -38,6 +38,17 @@ def ensure_init() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timeout)
     else:
         dist.init_process_group("gloo", timeout=timeout)
+    import atexit
+    atexit.register(_shutdown)                # the group this module created is torn down at interpreter exit
+
+
+def _shutdown() -> None:
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def world() -> Tuple[int, int]:
