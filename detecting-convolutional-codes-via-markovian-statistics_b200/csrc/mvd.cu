@@ -456,7 +456,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool fast = mode == MODE_DETECT && !ctx->force_generic &&
                       plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
-    const size_t pair_smem = 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 128 + 32768;
+    const size_t pair_smem = 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 128 + 32768 + (DET2P_BLOCK / 32) * 1536;   // + straggler queues
     uint64_t all_trials = 0;
     for (uint32_t i = 0; i < nsegs; ++i) all_trials += segs[i].trial_end >= segs[i].trial_begin ? segs[i].trial_end - segs[i].trial_begin : 0;
     const uint64_t sms = (uint64_t)ctx->prop.multiProcessorCount;

@@ -105,6 +105,95 @@ __device__ __forceinline__ uint32_t lazy_bernoulli_a(uint32_t c0base, uint32_t c
     return e;
 }
 
+// ------------------------------------------------------------------------------------------ flip words of a 32-step block
+// The four flip words of a 32-step block (2 trials x 2 outputs), MVD-PHILOX-2 bits.  With the warp-wide vote of
+// lazy_bernoulli_a a third call of a word is made by all 32 threads whenever ONE of the warp's 1 024 lanes is still
+// undecided after 8 levels (98 % of the time) although it serves ~4 of them, a fourth 22 % of the time: 3.2 calls
+// per word, 60 % more than any single word needs (measured: capping the calls at two runs the headline kernel
+// 18 % faster).  Here calls 0 and 1 of every word (levels 31..24) are made by everybody without a vote, and what is
+// still undecided afterwards -- 2^-8 of the lanes, ~15 of a warp's 128 words -- is queued in shared memory as
+// (owner lane, word, undecided mask) items.  The lanes of the warp then pick up ONE item each, make the owner's
+// later calls for it (the calls are addressed by position: any thread can make them) and hand the flips back
+// through shared memory: one Philox call per item instead of one per thread and word.  Same words as
+// lazy_bernoulli_a, bit for bit.
+//   a_q: this warp's 1 536 bytes of shared memory: [128 items x {owner | word << 5, undecided mask}][32 owners x 4 words]
+//   m0, m1: activity masks of the two trials (all-ones / zero), already restricted to the valid steps
+struct FlipWords {
+    uint32_t e0, e1, e2, e3;          // trial A output 0, 1; trial B output 0, 1
+};
+
+__device__ __forceinline__ void philox_levels(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t a_tbk, uint32_t& und,
+                                              uint32_t& e, const Params& P) {
+    const uint4 w = philox10(c0, c1, c2, c3, P);
+    const uint4 tb = lds_v4(a_tbk);
+    e |= und & ~w.x & tb.x;
+    und &= ~(w.x ^ tb.x);
+    e |= und & ~w.y & tb.y;
+    und &= ~(w.y ^ tb.y);
+    e |= und & ~w.z & tb.z;
+    und &= ~(w.z ^ tb.z);
+    e |= und & ~w.w & tb.w;
+    und &= ~(w.w ^ tb.w);
+}
+
+__device__ __forceinline__ FlipWords flip_words4(uint32_t cb, uint32_t c1A, uint32_t c2A, uint32_t c1B, uint32_t c2B, uint32_t c3,
+                                                 uint32_t m0, uint32_t m1, uint32_t a_tb, int ncalls, uint32_t a_q, uint32_t lane,
+                                                 uint32_t bs, const Params& P) {
+    uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+    const int nc2 = ncalls < 2 ? ncalls : 2;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {                       // one copy of the call code for the four words; results rotate
+        const bool second = j >= 2;
+        uint32_t und = second ? m1 : m0, e = 0;
+        const uint32_t c0 = cb | (((uint32_t)j & 1u) << 3), c1 = second ? c1B : c1A, c2 = second ? c2B : c2A;
+#pragma unroll 1
+        for (int k = 0; k < nc2; ++k) philox_levels(c0 + (uint32_t)k, c1, c2, c3, a_tb + 16u * (uint32_t)k, und, e, P);
+        e0 = e1; e1 = e2; e2 = e3; e3 = e;
+        u0 = u1; u1 = u2; u2 = u3; u3 = und;
+    }
+    if (ncalls > 2 && __any_sync(0xFFFFFFFFu, (u0 | u1 | u2 | u3) != 0u)) {
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, u0 != 0u), b1 = __ballot_sync(0xFFFFFFFFu, u1 != 0u);
+        const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, u2 != 0u), b3 = __ballot_sync(0xFFFFFFFFu, u3 != 0u);
+        const uint32_t n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), total = n2 + __popc(b3);
+        if (u0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * __popc(b0 & lt)), "r"(lane), "r"(u0) : "memory");
+        if (u1) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * (n0 + __popc(b1 & lt))), "r"(lane | 32u), "r"(u1) : "memory");
+        if (u2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * (n1 + __popc(b2 & lt))), "r"(lane | 64u), "r"(u2) : "memory");
+        if (u3) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * (n2 + __popc(b3 & lt))), "r"(lane | 96u), "r"(u3) : "memory");
+        __syncwarp();
+        const unsigned long long trA = ((unsigned long long)c2A << 32) | c1A;
+#pragma unroll 1
+        for (uint32_t base = 0; base < total; base += 32u) {
+            const uint32_t i = base + lane;
+            const bool mine = i < total;
+            uint2 it = make_uint2(lane, 0u);
+            if (mine) it = lds_v2(a_q + 8u * i);
+            unsigned long long tr = __shfl_sync(0xFFFFFFFFu, trA, (int)(it.x & 31u));     // the owner's trial id (trial A)
+            if (it.x & 64u) tr += bs;                                                       // words 2, 3: its trial B
+            if (mine) {
+                uint32_t und = it.y, e = 0;
+                uint32_t c0 = cb | ((it.x & 32u) >> 2) | 2u;
+                int k = 2;
+                do {
+                    philox_levels(c0, (uint32_t)tr, (uint32_t)(tr >> 32), c3, a_tb + 16u * (uint32_t)k, und, e, P);
+                    ++c0;
+                    ++k;
+                } while (und != 0u && k < ncalls);
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(a_q + 1024u + 4u * (it.x & 127u)), "r"(e) : "memory");
+            }
+        }
+        __syncwarp();
+        if (u0) e0 |= lds_u32(a_q + 1024u + 4u * lane);
+        if (u1) e1 |= lds_u32(a_q + 1024u + 4u * (lane | 32u));
+        if (u2) e2 |= lds_u32(a_q + 1024u + 4u * (lane | 64u));
+        if (u3) e3 |= lds_u32(a_q + 1024u + 4u * (lane | 96u));
+        __syncwarp();                                   // the queue is reused by the next block
+    }
+    FlipWords f;
+    f.e0 = e0; f.e1 = e1; f.e2 = e2; f.e3 = e3;
+    return f;
+}
+
 // (a & m) | (b & ~m) as one LOP3
 __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
     uint32_t d;
@@ -580,11 +669,13 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t SR = P.SR;
     // absolute shared addresses: [bm plane 0 (2 KB)][bm plane 1 (2 KB)][log rows SR x 128][masks 128][state 256 x 128]
+    //                            [straggler queues: 1 536 B per warp]
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_bm = (sbase + 2047u) & ~2047u;
     const uint32_t a_ll = a_bm + 4096u;
     const uint32_t a_tb = a_ll + (SR << 7);
     const uint32_t a_st = a_tb + 128u;
+    const uint32_t a_sq = a_st + 32768u + (threadIdx.x >> 5) * 1536u;   // this warp's straggler queue (flip_words4)
     unsigned char* g = smem_raw - sbase;                      // generic pointer of shared address 0
 
     if (threadIdx.x < 32u)
@@ -673,21 +764,14 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             uint32_t wev[2], wod[2];                    // received pairs of the even / odd steps (see below)
             uint32_t eA0, eA1, eB0, eB1;
             if (philox) {
-                // the four flip words of this 32-step block (2 trials x 2 outputs) through ONE copy of the lazy
-                // loop; the results rotate through four registers (no dispatch on the word index)
+                // the four flip words of this 32-step block (2 trials x 2 outputs): two calls each, stragglers by item
                 uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask;
                 asm volatile("" : "+r"(cb), "+r"(vm));
-                eA0 = eA1 = eB0 = eB1 = 0u;
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    const bool second = j >= 2;
-                    const uint32_t e = lazy_bernoulli_a(cb | (((uint32_t)j & 1u) << 3), second ? c1B : c1A, second ? c2B : c2A, c3p, a_tbp,
-                                                        ncalls, (second ? mB : mA) & vm, P);
-                    eA0 = eA1;
-                    eA1 = eB0;
-                    eB0 = eB1;
-                    eB1 = e;
-                }
+                const FlipWords f = flip_words4(cb, c1A, c2A, c1B, c2B, c3p, mA & vm, mB & vm, a_tbp, ncalls, a_sq, lane, BS, P);
+                eA0 = f.e0;
+                eA1 = f.e1;
+                eB0 = f.e2;
+                eB1 = f.e3;
             } else {
                 eA0 = pick(EA0, w);
                 eA1 = pick(EA1, w);
