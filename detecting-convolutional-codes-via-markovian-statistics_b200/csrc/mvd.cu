@@ -72,6 +72,9 @@ struct mvd_ctx {
     bool closed = false;            // every successor of every state is in the table (fast kernels)
     int max_metric = 0;
     uint32_t nkeys = 0;             // direct metric-vector -> state table (m <= 2), 0 = none
+    bool linkey_ok = false;         // m = 2: offset-invariant linear key of the pair kernel found (d_dstate2)
+    int32_t kc[4] = {0, 0, 0, 0};   //   key = sum kc[s] D[s] + kbias, sum kc = 0, injective on the states, in [0, 256)
+    int32_t kbias = 0;
     uint32_t S = 0;
     std::vector<uint8_t> h_metrics;
     std::vector<uint32_t> h_next;
@@ -83,7 +86,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot;
 };
 
 namespace {
@@ -233,6 +236,51 @@ int install_states(mvd_ctx* ctx) {
         CK(ctx->d_dstate.reserve(nkeys * 2));
         CK(h2d(ctx, ctx->d_dstate.p, dst.data(), nkeys * 2));
         ctx->nkeys = S <= 0xFFFE ? nkeys : 0;
+    }
+    // ---- m = 2 pair kernel: offset-invariant key.  key(D) = sum_s c_s D[s] + bias with sum_s c_s = 0 is the same for
+    // D' and D' - min(D'), so un-normalised steps need no minimum at all (mvd_detect2.cuh, PairEngine::step).  The
+    // coefficients are searched here: injective on this decoder's S metric vectors with all keys inside [0, 256).
+    ctx->linkey_ok = false;
+    if (ctx->nkeys && ctx->m == 2) {
+        const int spans[2] = {12, 48};
+        for (int pass = 0; pass < 2 && !ctx->linkey_ok; ++pass) {
+            const int Rg = spans[pass];
+            for (int c1 = -Rg; c1 <= Rg && !ctx->linkey_ok; ++c1)
+                for (int c2 = -Rg; c2 <= Rg && !ctx->linkey_ok; ++c2)
+                    for (int c3 = -Rg; c3 <= Rg; ++c3) {
+                        const int c0 = -(c1 + c2 + c3);
+                        int lo = 1 << 30, hi = -(1 << 30);
+                        for (uint32_t i = 0; i < S; ++i) {
+                            const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
+                            const int key = c0 * v[0] + c1 * v[1] + c2 * v[2] + c3 * v[3];
+                            lo = key < lo ? key : lo;
+                            hi = key > hi ? key : hi;
+                        }
+                        if (hi - lo > 255) continue;
+                        uint64_t seen[4] = {0, 0, 0, 0};
+                        bool inj = true;
+                        for (uint32_t i = 0; i < S && inj; ++i) {
+                            const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
+                            const int key = c0 * v[0] + c1 * v[1] + c2 * v[2] + c3 * v[3] - lo;
+                            inj = !((seen[key >> 6] >> (key & 63)) & 1ull);
+                            seen[key >> 6] |= 1ull << (key & 63);
+                        }
+                        if (!inj) continue;
+                        ctx->kc[0] = c0; ctx->kc[1] = c1; ctx->kc[2] = c2; ctx->kc[3] = c3;
+                        ctx->kbias = -lo;
+                        ctx->linkey_ok = true;
+                        break;
+                    }
+        }
+        if (ctx->linkey_ok) {
+            std::vector<uint16_t> dst(256, (uint16_t)0xFFFF);
+            for (uint32_t i = 0; i < S; ++i) {
+                const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
+                dst[ctx->kc[0] * v[0] + ctx->kc[1] * v[1] + ctx->kc[2] * v[2] + ctx->kc[3] * v[3] + ctx->kbias] = (uint16_t)i;
+            }
+            CK(ctx->d_dstate2.reserve(256 * 2));
+            CK(h2d(ctx, ctx->d_dstate2.p, dst.data(), 256 * 2));
+        }
     }
     // ---- perfect hash for m = 3 / 4, n = 2 (two-trials-per-thread ACS kernels, mvd_detect3p.cuh): hash, displace.
     // w0 = k0 | k1 << 16 (and w1 = k2 | k3 << 16 for m = 4) with k_i = D[4i] + 8 D[4i+1] + 64 D[4i+2] + 512 D[4i+3]
@@ -456,12 +504,16 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool fast = mode == MODE_DETECT && !ctx->force_generic &&
                       plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
-    const size_t pair_smem = 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 128 + 32768 + (DET2P_BLOCK / 32) * 1536;   // + straggler queues
+    // (layout of detect2p_kernel: straggler queues, masks, branch metrics, log rows, then the state table at a 32 KB-aligned
+    // absolute shared address; the dynamic window starts after the 1 KB the system reserves)
+    const size_t pair_sbase = 1024;
+    const size_t pair_st = (pair_sbase + DET2P_QUEUES + 128 + 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 32767) & ~(size_t)32767;
+    const size_t pair_smem = pair_st + 32768 - pair_sbase;
     uint64_t all_trials = 0;
     for (uint32_t i = 0; i < nsegs; ++i) all_trials += segs[i].trial_end >= segs[i].trial_begin ? segs[i].trial_end - segs[i].trial_begin : 0;
     const uint64_t sms = (uint64_t)ctx->prop.multiProcessorCount;
     // pairing halves the thread count: only when the GPU stays full (3 blocks of 256 pair-threads per SM)
-    const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && pair_smem <= 72 * 1024 &&
+    const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && ctx->linkey_ok && pair_smem <= 110 * 1024 &&
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
     // m = 3: two trials per thread with the perfect-hash lookup (2 blocks of 256 pair-threads per SM)
     const size_t pair3_smem = 2 * (size_t)ctx->ph_slots * 8 + 1024 + 128 + 128 + ((size_t)ctx->S * 4 << 5) + 64;
@@ -568,6 +620,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
     P.error_flag = ctx->d_err.as<int>();
     P.fp = fplan;
+    P.fp.dstate2 = ctx->d_dstate2.as<uint16_t>();
+    for (int i = 0; i < 4; ++i) P.fp.kc[i] = (uint32_t)ctx->kc[i];
+    P.fp.kcb = ((uint32_t)ctx->kbias << 7) * 0x00010001u;
     P.fp.ph_d = ctx->d_phd.as<uint32_t>();
     P.fp.ph_t = ctx->d_pht.as<uint32_t>();
     P.fp.ph_slots = ctx->ph_slots;
@@ -818,6 +873,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     }
     if (herr & 1) return fail(ctx, MVD_E_UNKNOWN_STATE, "a relative-metric vector was not in the state table (KeyError)");
     if (herr & 2) return fail(ctx, MVD_E_UNKNOWN_STATE, "relative metric exceeded 15 (hash key overflow)");
+    if (herr & 4) return fail(ctx, MVD_E_CUDA, "pair kernel: the dynamic shared window does not start where the host's layout assumed");
     return MVD_OK;
 }
 
@@ -861,7 +917,7 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
                       &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot};
     for (DevBuf* b : bufs) b->release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -23,6 +23,8 @@
 #pragma once
 #include "mvd_kernels.cuh"
 
+#include <type_traits>
+
 
 __device__ __forceinline__ uint32_t spread16(uint32_t x) {      // bit i -> bit 2i  (x < 2^16)
     x = (x | (x << 8)) & 0x00FF00FFu;
@@ -109,84 +111,110 @@ __device__ __forceinline__ uint32_t lazy_bernoulli_a(uint32_t c0base, uint32_t c
 // The four flip words of a 32-step block (2 trials x 2 outputs), MVD-PHILOX-2 bits.  With the warp-wide vote of
 // lazy_bernoulli_a a third call of a word is made by all 32 threads whenever ONE of the warp's 1 024 lanes is still
 // undecided after 8 levels (98 % of the time) although it serves ~4 of them, a fourth 22 % of the time: 3.2 calls
-// per word, 60 % more than any single word needs (measured: capping the calls at two runs the headline kernel
-// 18 % faster).  Here calls 0 and 1 of every word (levels 31..24) are made by everybody without a vote, and what is
-// still undecided afterwards -- 2^-8 of the lanes, ~15 of a warp's 128 words -- is queued in shared memory as
-// (owner lane, word, undecided mask) items.  The lanes of the warp then pick up ONE item each, make the owner's
-// later calls for it (the calls are addressed by position: any thread can make them) and hand the flips back
-// through shared memory: one Philox call per item instead of one per thread and word.  Same words as
-// lazy_bernoulli_a, bit for bit.
-//   a_q: this warp's 1 536 bytes of shared memory: [128 items x {owner | word << 5, undecided mask}][32 owners x 4 words]
-//   m0, m1: activity masks of the two trials (all-ones / zero), already restricted to the valid steps
+// per word, 60 % more than any single word needs.  Here calls 0 and 1 of every word (levels 31..24) are made by
+// everybody without a vote -- eight independent calls, two of them in flight at a time -- and what is still undecided
+// afterwards (2^-8 of the lanes, ~15 of a warp's 128 words) is queued in shared memory as (owner lane | word << 5,
+// undecided mask) items.  The lanes of the warp then pick up ONE item each, make the owner's later calls for it (the
+// calls are addressed by position: any thread can make them) and write the flips back into the item, where the
+// owner collects them: one Philox call per item instead of one per thread and word.  Same words as lazy_bernoulli_a,
+// bit for bit.
+//
+// Four levels of the comparison uniform < T from one call, least significant level first: lt = "these four bits of
+// the uniform are below T's" needs one LOP3 per level ((~w & t) | (~(w ^ t) & lt)), "all four equal" one per level,
+// and one more merges lt into the flips: 9 instead of the 12 of the level-by-level form of lazy_bernoulli_a.
+__device__ __forceinline__ uint32_t lt_step(uint32_t w, uint32_t t, uint32_t lt) {      // (~w & t) | (~(w ^ t) & lt)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x8E;" : "=r"(d) : "r"(w), "r"(t), "r"(lt));
+    return d;
+}
+__device__ __forceinline__ uint32_t eq_step(uint32_t w, uint32_t t, uint32_t u) {        // u & ~(w ^ t)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x82;" : "=r"(d) : "r"(w), "r"(t), "r"(u));
+    return d;
+}
+__device__ __forceinline__ void levels4(const uint4& w, const uint4& tb, uint32_t& und, uint32_t& e) {
+    uint32_t lt = ~w.w & tb.w;
+    lt = lt_step(w.z, tb.z, lt);
+    lt = lt_step(w.y, tb.y, lt);
+    lt = lt_step(w.x, tb.x, lt);
+    e |= und & lt;
+    und = eq_step(w.x, tb.x, und);
+    und = eq_step(w.y, tb.y, und);
+    und = eq_step(w.z, tb.z, und);
+    und = eq_step(w.w, tb.w, und);
+}
+
 struct FlipWords {
     uint32_t e0, e1, e2, e3;          // trial A output 0, 1; trial B output 0, 1
 };
 
-__device__ __forceinline__ void philox_levels(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t a_tbk, uint32_t& und,
-                                              uint32_t& e, const Params& P) {
-    const uint4 w = philox10(c0, c1, c2, c3, P);
-    const uint4 tb = lds_v4(a_tbk);
-    e |= und & ~w.x & tb.x;
-    und &= ~(w.x ^ tb.x);
-    e |= und & ~w.y & tb.y;
-    und &= ~(w.y ^ tb.y);
-    e |= und & ~w.z & tb.z;
-    und &= ~(w.z ^ tb.z);
-    e |= und & ~w.w & tb.w;
-    und &= ~(w.w ^ tb.w);
-}
-
+//   a_q: this warp's queue in shared memory, 128 items x {owner | word << 5, undecided mask -> flips}
+//   vm : the valid steps of the block (undecided lanes to start with)
 __device__ __forceinline__ FlipWords flip_words4(uint32_t cb, uint32_t c1A, uint32_t c2A, uint32_t c1B, uint32_t c2B, uint32_t c3,
-                                                 uint32_t m0, uint32_t m1, uint32_t a_tb, int ncalls, uint32_t a_q, uint32_t lane,
+                                                 uint32_t vm, uint32_t a_tb, int ncalls, uint32_t a_q, uint32_t lane,
                                                  uint32_t bs, const Params& P) {
-    uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-    const int nc2 = ncalls < 2 ? ncalls : 2;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {                       // one copy of the call code for the four words; results rotate
-        const bool second = j >= 2;
-        uint32_t und = second ? m1 : m0, e = 0;
-        const uint32_t c0 = cb | (((uint32_t)j & 1u) << 3), c1 = second ? c1B : c1A, c2 = second ? c2B : c2A;
-#pragma unroll 1
-        for (int k = 0; k < nc2; ++k) philox_levels(c0 + (uint32_t)k, c1, c2, c3, a_tb + 16u * (uint32_t)k, und, e, P);
-        e0 = e1; e1 = e2; e2 = e3; e3 = e;
-        u0 = u1; u1 = u2; u2 = u3; u3 = und;
+    uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, u0 = vm, u1 = vm, u2 = vm, u3 = vm;
+    if (ncalls > 0) {
+        const uint4 tb = lds_v4(a_tb);
+        const uint4 wa = philox10(cb, c1A, c2A, c3, P), wb = philox10(cb | 8u, c1A, c2A, c3, P);
+        levels4(wa, tb, u0, e0);
+        levels4(wb, tb, u1, e1);
+        const uint4 wc = philox10(cb, c1B, c2B, c3, P), wd = philox10(cb | 8u, c1B, c2B, c3, P);
+        levels4(wc, tb, u2, e2);
+        levels4(wd, tb, u3, e3);
+    }
+    if (ncalls > 1) {
+        const uint4 tb = lds_v4(a_tb + 16u);
+        const uint4 wa = philox10(cb | 1u, c1A, c2A, c3, P), wb = philox10(cb | 9u, c1A, c2A, c3, P);
+        levels4(wa, tb, u0, e0);
+        levels4(wb, tb, u1, e1);
+        const uint4 wc = philox10(cb | 1u, c1B, c2B, c3, P), wd = philox10(cb | 9u, c1B, c2B, c3, P);
+        levels4(wc, tb, u2, e2);
+        levels4(wd, tb, u3, e3);
     }
     if (ncalls > 2 && __any_sync(0xFFFFFFFFu, (u0 | u1 | u2 | u3) != 0u)) {
-        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t lt = ~(0xFFFFFFFFu << lane);
         const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, u0 != 0u), b1 = __ballot_sync(0xFFFFFFFFu, u1 != 0u);
         const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, u2 != 0u), b3 = __ballot_sync(0xFFFFFFFFu, u3 != 0u);
         const uint32_t n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), total = n2 + __popc(b3);
-        if (u0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * __popc(b0 & lt)), "r"(lane), "r"(u0) : "memory");
-        if (u1) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * (n0 + __popc(b1 & lt))), "r"(lane | 32u), "r"(u1) : "memory");
-        if (u2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * (n1 + __popc(b2 & lt))), "r"(lane | 64u), "r"(u2) : "memory");
-        if (u3) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a_q + 8u * (n2 + __popc(b3 & lt))), "r"(lane | 96u), "r"(u3) : "memory");
+        const uint32_t p0 = a_q + 8u * __popc(b0 & lt), p1 = a_q + 8u * (n0 + __popc(b1 & lt));
+        const uint32_t p2 = a_q + 8u * (n1 + __popc(b2 & lt)), p3 = a_q + 8u * (n2 + __popc(b3 & lt));
+        if (u0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(p0), "r"(lane), "r"(u0) : "memory");
+        if (u1) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(p1), "r"(lane | 32u), "r"(u1) : "memory");
+        if (u2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(p2), "r"(lane | 64u), "r"(u2) : "memory");
+        if (u3) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(p3), "r"(lane | 96u), "r"(u3) : "memory");
         __syncwarp();
-        const unsigned long long trA = ((unsigned long long)c2A << 32) | c1A;
 #pragma unroll 1
         for (uint32_t base = 0; base < total; base += 32u) {
             const uint32_t i = base + lane;
             const bool mine = i < total;
             uint2 it = make_uint2(lane, 0u);
             if (mine) it = lds_v2(a_q + 8u * i);
-            unsigned long long tr = __shfl_sync(0xFFFFFFFFu, trA, (int)(it.x & 31u));     // the owner's trial id (trial A)
-            if (it.x & 64u) tr += bs;                                                       // words 2, 3: its trial B
+            uint32_t t1 = __shfl_sync(0xFFFFFFFFu, c1A, (int)(it.x & 31u));             // the owner's trial id (trial A)
+            uint32_t t2 = __shfl_sync(0xFFFFFFFFu, c2A, (int)(it.x & 31u));
+            if (it.x & 64u) {                                                           // words 2, 3: its trial B
+                t1 += bs;
+                t2 += t1 < bs ? 1u : 0u;
+            }
             if (mine) {
                 uint32_t und = it.y, e = 0;
                 uint32_t c0 = cb | ((it.x & 32u) >> 2) | 2u;
                 int k = 2;
                 do {
-                    philox_levels(c0, (uint32_t)tr, (uint32_t)(tr >> 32), c3, a_tb + 16u * (uint32_t)k, und, e, P);
+                    const uint4 w = philox10(c0, t1, t2, c3, P);
+                    const uint4 tb = lds_v4(a_tb + 16u * (uint32_t)k);
+                    levels4(w, tb, und, e);
                     ++c0;
                     ++k;
                 } while (und != 0u && k < ncalls);
-                asm volatile("st.shared.u32 [%0], %1;" :: "r"(a_q + 1024u + 4u * (it.x & 127u)), "r"(e) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(a_q + 8u * i + 4u), "r"(e) : "memory");
             }
         }
         __syncwarp();
-        if (u0) e0 |= lds_u32(a_q + 1024u + 4u * lane);
-        if (u1) e1 |= lds_u32(a_q + 1024u + 4u * (lane | 32u));
-        if (u2) e2 |= lds_u32(a_q + 1024u + 4u * (lane | 64u));
-        if (u3) e3 |= lds_u32(a_q + 1024u + 4u * (lane | 96u));
+        if (u0) e0 |= lds_u32(p0 + 4u);
+        if (u1) e1 |= lds_u32(p1 + 4u);
+        if (u2) e2 |= lds_u32(p2 + 4u);
+        if (u3) e3 |= lds_u32(p3 + 4u);
         __syncwarp();                                   // the queue is reused by the next block
     }
     FlipWords f;
@@ -589,26 +617,29 @@ __device__ __forceinline__ uint32_t madlo(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 struct PairEngine {
-    uint32_t Q0, Q1, Q2, Q3;          // (trial A, trial B) metrics of trellis states 0..3
+    uint32_t Q0, Q1, Q2, Q3;          // (trial A, trial B) metrics of trellis states 0..3, times 128
     uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
-    uint32_t kbm, kst;                // branch-metric plane 0 | copy * 16 ; state table + lane * 4
+    uint32_t kbm, kst;                // branch-metric plane 0 | copy * 16 ; state table (32 KB-aligned) | lane * 4
     uint32_t km1;                     // -1 from the kernel parameters: n - d as an IMAD on the FMA pipe (a visible constant
                                       // would make it an IADD3 on the ALU pipe, the busiest one).  Measured and rejected: the
                                       // state-table addresses and the >> 8 / >> 16 as IMAD.HI (7.68e11 -> 7.24e11 steps/s)
     double a1A, a0A, a1B, a0B;
 
     // sA, sB7: r_A, r_B at bits 7..8; sB: r_B at bits 9..10 (other bits arbitrary).
-    // NORM = false leaves the metrics un-normalised (Eq. 5 deferred): the minimum is still taken, but only
-    // to correct the table key, key(D' - min) = key(D') - 85 min (85 = 1 + 4 + 16 + 64, one IMAD on the packed
-    // pair, exact modulo 2^32 whatever the low lane carries into the high one), which replaces the four
-    // subtractions.  A stretch of 8 steps adds at most 8 n = 16 to a lane (times 128: 2 432 < 2^16), and its
-    // last step runs with NORM = true, so every loop boundary sees D = D' - min(D') as the reference does.
+    // The state table is indexed by an OFFSET-INVARIANT key: key(D) = sum_s c_s D[s] + bias with sum_s c_s = 0
+    // (coefficients found by the host: injective on this decoder's metric vectors, keys in [0, 256)), so
+    // key(D') = key(D' - min D') and a step needs the minimum only when it normalises (Eq. 5): four IMADs on the
+    // FMA pipe on the packed pair -- exact modulo 2^32 whatever the low lane carries into the high one, because
+    // the true result of either lane is in [0, 2^15) -- and no VIMNMX3 / VIMNMX on the ALU pipe, the busiest one.
+    // NORM = false leaves the metrics un-normalised (Eq. 5 deferred): a stretch of 16 steps adds at most 16 n = 32
+    // to a lane (times 128: 4 480 < 2^16), and its last step runs with NORM = true, so every loop boundary sees
+    // D = D' - min(D') as the reference does.
     // ANTI: every generator has its first and its last tap set (e.g. (7,5)), so the four branches of a
     // butterfly carry the labels X, ~X, ~X, X and d(~X, r) = n - d(X, r): one 8-byte read (X of the two
     // butterflies, 2 wavefronts) and two subtractions replace the two 16-byte reads (8 wavefronts) of the
     // general table.
     template <bool NORM, bool ANTI>
-    __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7) {
+    __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7, const Params& P) {
         const uint32_t rAB = bitsel(sA, sB, 0x180u);                        // r_A at bits 7..8, r_B at bits 9..10
         const double2 vA = lds_d2(sxA | (rAB & 0x180u));
         const double2 vB = lds_d2(sxB | (sB7 & 0x180u));
@@ -633,23 +664,22 @@ struct PairEngine {
             n2 = __viaddmin_u16x2(Q1, b1.x, Q3 + b1.y);
             n3 = __viaddmin_u16x2(Q1, b1.z, Q3 + b1.w);
         }
-        const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);       // per-trial minimum
-        uint32_t t7;
+        const uint32_t t7 = madlo(n3, P.fp.kc[3], madlo(n2, P.fp.kc[2], madlo(n1, P.fp.kc[1], madlo(n0, P.fp.kc[0], P.fp.kcb))));
         if (NORM) {
+            const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);   // per-trial minimum
             Q0 = n0 - mn;                                                   // Eq. 5 (no borrow: every lane >= its minimum)
             Q1 = n1 - mn;
             Q2 = n2 - mn;
             Q3 = n3 - mn;
-            // key = s1 | s0 << 2 | s3 << 4 | s2 << 6 per trial (the direct table's index), times 128: three IMADs
-            t7 = ((Q2 * 4u + Q3) * 4u + Q0) * 4u + Q1;                      // metrics are kept times 128 (branch metrics too)
         } else {
             Q0 = n0;
             Q1 = n1;
             Q2 = n2;
             Q3 = n3;
-            t7 = ((n2 * 4u + n3) * 4u + n0) * 4u + n1 - 85u * mn;
         }
-        sxA = lds_u32((t7 & 0xFFFFu) + kst);
+        uint32_t aA;
+        asm("lop3.b32 %0, %1, 0xFFFF, %2, 0xEA;" : "=r"(aA) : "r"(t7), "r"(kst));       // (t7 & 0xFFFF) | kst
+        sxA = lds_u32(aA);
         sxB = lds_u32((t7 >> 16) + kst);
     }
 };
@@ -668,15 +698,24 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     const bool actA = tlA < ntr, actB = tlB < ntr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t SR = P.SR;
-    // absolute shared addresses: [bm plane 0 (2 KB)][bm plane 1 (2 KB)][log rows SR x 128][masks 128][state 256 x 128]
-    //                            [straggler queues: 1 536 B per warp]
+    // absolute shared addresses, laid out downwards from the state table, which sits at a 32 KB-aligned address so
+    // that `key * 128 | table | lane * 4` is ONE LOP3:
+    //   [straggler queues: 1 KB per warp][...][masks 128][bm plane 0 (2 KB)][bm plane 1 (2 KB)][log rows SR x 128][state 256 x 128]
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t a_bm = (sbase + 2047u) & ~2047u;
-    const uint32_t a_ll = a_bm + 4096u;
-    const uint32_t a_tb = a_ll + (SR << 7);
-    const uint32_t a_st = a_tb + 128u;
-    const uint32_t a_sq = a_st + 32768u + (threadIdx.x >> 5) * 1536u;   // this warp's straggler queue (flip_words4)
+    const uint32_t a_st = (sbase + (uint32_t)DET2P_QUEUES + 128u + 2048u + 4096u + (SR << 7) + 32767u) & ~32767u;
+    const uint32_t a_ll = a_st - (SR << 7);
+    const uint32_t a_bm = (a_ll - 4096u) & ~2047u;
+    const uint32_t a_tb = a_bm - 128u;
+    uint32_t a_sq = sbase + (threadIdx.x >> 5) * 1024u;      // this warp's straggler queue (flip_words4)
     unsigned char* g = smem_raw - sbase;                      // generic pointer of shared address 0
+    {
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (a_st + 32768u - sbase > dyn) {                    // the host sized the window for another base address
+            if (threadIdx.x == 0) atomicOr(P.error_flag, 4);
+            return;
+        }
+    }
 
     if (threadIdx.x < 32u)
         *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
@@ -705,7 +744,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             (da << 7) | (db << 23);                              // times 128: the metric pairs then form the table offset by Horner
     }
     for (uint32_t i = threadIdx.x; i < 256u * 32u; i += BS) {
-        const uint32_t st = P.fp.dstate[i >> 5];
+        const uint32_t st = P.fp.dstate2[i >> 5];                      // by the offset-invariant key (PairEngine::step)
         const uint32_t row = st == 0xFFFFu ? 0u : st * 4u;
         *reinterpret_cast<uint32_t*>(g + a_st + 4u * i) = a_ll + (row << 7) + (((i & 31u) & 7u) << 4);
     }
@@ -732,9 +771,9 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     // compiler re-derives them from blockIdx / threadIdx / the segment record before every lazy loop
     // (~50 instructions per flip word)
     uint32_t c1A = (uint32_t)trA, c2A = (uint32_t)(trA >> 32), c1B = (uint32_t)trB, c2B = (uint32_t)(trB >> 32);
-    uint32_t mA = actA ? 0xFFFFFFFFu : 0u, mB = actB ? 0xFFFFFFFFu : 0u;
+    // (an inactive trial of the last block draws bits like any other; nothing of it is counted or stored)
     uint32_t c3p = c3, a_tbp = a_tb;
-    asm volatile("" : "+r"(c1A), "+r"(c2A), "+r"(c1B), "+r"(c2B), "+r"(mA), "+r"(mB), "+r"(c3p), "+r"(a_tbp));
+    asm volatile("" : "+r"(c1A), "+r"(c2A), "+r"(c1B), "+r"(c2B), "+r"(c3p), "+r"(a_tbp), "+r"(a_sq));
     const uint32_t nsb = (N + 127u) >> 7;
     for (uint32_t sb = 0; sb < nsb; ++sb) {
         uint4 UA = make_uint4(0, 0, 0, 0), UB = UA, EA0 = UA, EA1 = UA, EB0 = UA, EB1 = UA;
@@ -767,7 +806,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
                 // the four flip words of this 32-step block (2 trials x 2 outputs): two calls each, stragglers by item
                 uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask;
                 asm volatile("" : "+r"(cb), "+r"(vm));
-                const FlipWords f = flip_words4(cb, c1A, c2A, c1B, c2B, c3p, mA & vm, mB & vm, a_tbp, ncalls, a_sq, lane, BS, P);
+                const FlipWords f = flip_words4(cb, c1A, c2A, c1B, c2B, c3p, vm, a_tbp, ncalls, a_sq, lane, BS, P);
                 eA0 = f.e0;
                 eA1 = f.e1;
                 eB0 = f.e2;
@@ -796,23 +835,25 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             }
             UA = make_uint4(UA.y, UA.z, UA.w, 0u);
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
-            // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
-            auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
-                eng.step<false, ANTI != 0>(ea << 7, eb << 9, eb << 7);
-                eng.step<false, ANTI != 0>(oa << 7, ob << 9, ob << 7);
-                eng.step<false, ANTI != 0>(ea << 5, eb << 7, eb << 5);
-                eng.step<false, ANTI != 0>(oa << 5, ob << 7, ob << 5);
-                eng.step<false, ANTI != 0>(ea << 3, eb << 5, eb << 3);
-                eng.step<false, ANTI != 0>(oa << 3, ob << 5, ob << 3);
-                eng.step<false, ANTI != 0>(ea << 1, eb << 3, eb << 1);
-                eng.step<true, ANTI != 0>(oa << 1, ob << 3, ob << 1);
+            // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob); the last one
+            // normalises (Eq. 5) if NORM8
+            auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob, auto norm8) {
+                constexpr bool NORM8 = decltype(norm8)::value;
+                eng.step<false, ANTI != 0>(ea << 7, eb << 9, eb << 7, P);
+                eng.step<false, ANTI != 0>(oa << 7, ob << 9, ob << 7, P);
+                eng.step<false, ANTI != 0>(ea << 5, eb << 7, eb << 5, P);
+                eng.step<false, ANTI != 0>(oa << 5, ob << 7, ob << 5, P);
+                eng.step<false, ANTI != 0>(ea << 3, eb << 5, eb << 3, P);
+                eng.step<false, ANTI != 0>(oa << 3, ob << 5, ob << 3, P);
+                eng.step<false, ANTI != 0>(ea << 1, eb << 3, eb << 1, P);
+                eng.step<NORM8, ANTI != 0>(oa << 1, ob << 3, ob << 1, P);
             };
             if (valid == 32u) {
                 uint32_t ea = wev[0], oa = wod[0], eb = wev[1], ob = wod[1];
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {                                  // 16 steps per iteration (measured: 8 -> 6.98e11, 16 -> 7.07e11, 32 -> 6.92e11 steps/s)
-                    oct(ea, oa, eb, ob);
-                    oct(ea >> 8, oa >> 8, eb >> 8, ob >> 8);
+                    oct(ea, oa, eb, ob, std::false_type{});
+                    oct(ea >> 8, oa >> 8, eb >> 8, ob >> 8, std::true_type{});
                     ea >>= 16; oa >>= 16; eb >>= 16; ob >>= 16;
                 }
             } else {
@@ -820,12 +861,12 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
                 for (uint32_t c = 0; c < valid; c += 8u) {
                     const uint32_t ea = wev[0] >> c, oa = wod[0] >> c, eb = wev[1] >> c, ob = wod[1] >> c;
                     if (c + 8u <= valid) {
-                        oct(ea, oa, eb, ob);
+                        oct(ea, oa, eb, ob, std::true_type{});
                     } else {
                         for (uint32_t j = 0; j < valid - c; ++j) {
                             const uint32_t sh = j & ~1u;
                             const uint32_t wa = ((j & 1u) ? oa : ea) >> sh, wb = ((j & 1u) ? ob : eb) >> sh;
-                            eng.step<true, ANTI != 0>(wa << 7, wb << 9, wb << 7);
+                            eng.step<true, ANTI != 0>(wa << 7, wb << 9, wb << 7, P);
                         }
                     }
                 }

@@ -22,6 +22,8 @@ struct FastPlan {
     uint32_t off_tb, off_bm, off_st, off_ll;   // byte offsets into dynamic shared memory
     uint32_t key_mul, nkeys;           // direct metric-vector -> state table (m <= 2)
     const uint16_t* dstate;            // [nkeys] state index or 0xFFFF
+    const uint16_t* dstate2;           // [256] the same through the pair kernel's offset-invariant key (m = 2)
+    uint32_t kc[4], kcb;               //   key * 128 = sum kc[s] (128 D[s]) + bias * 128, both 16-bit lanes (kcb carries the bias twice)
     const uint32_t* tcode;             // packed NEXT walk: high word of the double c with log Tref[e] = c * tref_unit
     double tref_unit;
     const uint4* gfsm1;                // [ntables][S*R] packed NEXT-walk entries in global memory (large S)
@@ -73,6 +75,7 @@ struct Params {
 // ---- fast detection kernels (mvd_detect2.cuh)
 #define DET2_BLOCK 512
 #define DET2P_BLOCK 256
+#define DET2P_QUEUES ((DET2P_BLOCK / 32) * 1024)   // straggler queues of the pair kernel: 128 items x 8 bytes per warp
 #define DET2_MAXSEG 96          // segments per launch: they travel in the kernel parameters (uniform registers)
 
 struct SegBatch {
