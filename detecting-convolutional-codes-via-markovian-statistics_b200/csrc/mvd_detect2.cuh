@@ -616,6 +616,10 @@ __device__ __forceinline__ uint32_t madlo(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
+// metrics are kept times 128 with this base in both lanes: an un-normalised ANTI step can lower a lane by n * 128 = 256,
+// 16 steps by 4 096
+#define PAIR_BASE2 0x20002000u
+
 struct PairEngine {
     uint32_t Q0, Q1, Q2, Q3;          // (trial A, trial B) metrics of trellis states 0..3, times 128
     uint32_t sxA, sxB;                // absolute address of this lane's copy of the current log row
@@ -625,37 +629,38 @@ struct PairEngine {
                                       // state-table addresses and the >> 8 / >> 16 as IMAD.HI (7.68e11 -> 7.24e11 steps/s)
     double a1A, a0A, a1B, a0B;
 
-    // sA, sB7: r_A, r_B at bits 7..8; sB: r_B at bits 9..10 (other bits arbitrary).
+    // sAB: r_A at bits 7..8 and r_B at bits 9..10; sB7: r_B at bits 7..8 (other bits arbitrary).
     // The state table is indexed by an OFFSET-INVARIANT key: key(D) = sum_s c_s D[s] + bias with sum_s c_s = 0
     // (coefficients found by the host: injective on this decoder's metric vectors, keys in [0, 256)), so
     // key(D') = key(D' - min D') and a step needs the minimum only when it normalises (Eq. 5): four IMADs on the
     // FMA pipe on the packed pair -- exact modulo 2^32 whatever the low lane carries into the high one, because
-    // the true result of either lane is in [0, 2^15) -- and no VIMNMX3 / VIMNMX on the ALU pipe, the busiest one.
-    // NORM = false leaves the metrics un-normalised (Eq. 5 deferred): a stretch of 16 steps adds at most 16 n = 32
-    // to a lane (times 128: 4 480 < 2^16), and its last step runs with NORM = true, so every loop boundary sees
-    // D = D' - min(D') as the reference does.
-    // ANTI: every generator has its first and its last tap set (e.g. (7,5)), so the four branches of a
-    // butterfly carry the labels X, ~X, ~X, X and d(~X, r) = n - d(X, r): one 8-byte read (X of the two
-    // butterflies, 2 wavefronts) and two subtractions replace the two 16-byte reads (8 wavefronts) of the
-    // general table.
+    // the true result of either lane is in [0, 2^15) -- and no VIMNMX3 / VIMNMX on the ALU pipe.
+    // NORM = false leaves the metrics un-normalised (Eq. 5 deferred); the last step of a 16-step stretch runs with
+    // NORM = true and re-bases every lane to PAIR_BASE + (D' - min D'), so every loop boundary sees the reference's
+    // normalised vector (plus a constant the key does not see).
+    // ANTI: every generator has its first and its last tap set (e.g. (7,5)), so the four branches of a butterfly
+    // carry the labels X, ~X, ~X, X and d(~X, r) = n - d(X, r).  With x = d(X, r) the butterfly is
+    //   D'[0] = x + min(D[0], D[2] + (n - 2x)),   D'[1] = x + min(D[0] + (n - 2x), D[2]),
+    // i.e. ONE VIADDMNMX per new state with no separate addition, both results carrying the same offset x; the
+    // second butterfly carries y, so only its two results need an addition (of y - x) and the common offset x is
+    // dropped (the key does not see it; a lane falls by at most n per step, hence PAIR_BASE).  One 16-byte read
+    // {n - 2x, n - 2y, y - x} per step; the general table takes two and four additions.
     template <bool NORM, bool ANTI>
-    __device__ __forceinline__ void step(uint32_t sA, uint32_t sB, uint32_t sB7, const Params& P) {
-        const uint32_t rAB = bitsel(sA, sB, 0x180u);                        // r_A at bits 7..8, r_B at bits 9..10
-        const double2 vA = lds_d2(sxA | (rAB & 0x180u));
+    __device__ __forceinline__ void step(uint32_t sAB, uint32_t sB7, const Params& P) {
+        const double2 vA = lds_d2(sxA | (sAB & 0x180u));
         const double2 vB = lds_d2(sxB | (sB7 & 0x180u));
         a1A += vA.x;
         a0A += vA.y;
         a1B += vB.x;
         a0B += vB.y;
-        const uint32_t boff = kbm | (rAB & 0x780u);
+        const uint32_t boff = kbm | (sAB & 0x780u);
         uint32_t n0, n1, n2, n3;
         if (ANTI) {
-            const uint2 px = lds_v2(boff);                 // d(0 -> 0), d(1 -> 2) for (r_A, r_B)
-            const uint32_t c0 = madlo(px.x, km1, 0x01000100u), c1 = madlo(px.y, km1, 0x01000100u);    // n - d: n = 2, times 128, both lanes
-            n0 = __viaddmin_u16x2(Q0, px.x, Q2 + c0);                           // Eq. 4, both trials
-            n1 = __viaddmin_u16x2(Q0, c0, Q2 + px.x);
-            n2 = __viaddmin_u16x2(Q1, px.y, Q3 + c1);
-            n3 = __viaddmin_u16x2(Q1, c1, Q3 + px.y);
+            const uint4 t = lds_v4(boff);                  // n - 2 d(0 -> 0), n - 2 d(1 -> 2), d(1 -> 2) - d(0 -> 0) for (r_A, r_B)
+            n0 = __viaddmin_u16x2(Q2, t.x, Q0);            // Eq. 4, both trials
+            n1 = __viaddmin_u16x2(Q0, t.x, Q2);
+            n2 = __viaddmin_u16x2(Q3, t.y, Q1) + t.z;
+            n3 = __viaddmin_u16x2(Q1, t.y, Q3) + t.z;
         } else {
             const uint4 b0 = lds_v4(boff);                 // ns 0: (pred 0, pred 2), ns 1: (pred 0, pred 2)
             const uint4 b1 = lds_v4(boff + 2048u);         // ns 2: (pred 1, pred 3), ns 3: (pred 1, pred 3)
@@ -666,7 +671,7 @@ struct PairEngine {
         }
         const uint32_t t7 = madlo(n3, P.fp.kc[3], madlo(n2, P.fp.kc[2], madlo(n1, P.fp.kc[1], madlo(n0, P.fp.kc[0], P.fp.kcb))));
         if (NORM) {
-            const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);   // per-trial minimum
+            const uint32_t mn = __vminu2(__vimin3_u16x2(n0, n1, n2), n3) - PAIR_BASE2;   // per-trial minimum, less the base
             Q0 = n0 - mn;                                                   // Eq. 5 (no borrow: every lane >= its minimum)
             Q1 = n1 - mn;
             Q2 = n2 - mn;
@@ -681,6 +686,15 @@ struct PairEngine {
         asm("lop3.b32 %0, %1, 0xFFFF, %2, 0xEA;" : "=r"(aA) : "r"(t7), "r"(kst));       // (t7 & 0xFFFF) | kst
         sxA = lds_u32(aA);
         sxB = lds_u32((t7 >> 16) + kst);
+    }
+
+    // Eq. 5 on its own (the ragged last block of a trial)
+    __device__ __forceinline__ void normalise() {
+        const uint32_t mn = __vminu2(__vimin3_u16x2(Q0, Q1, Q2), Q3) - PAIR_BASE2;
+        Q0 -= mn;
+        Q1 -= mn;
+        Q2 -= mn;
+        Q3 -= mn;
     }
 };
 
@@ -727,12 +741,16 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     // pair branch metrics: row (rA | rB << 2), word (ns, b): lo = d(pred_b -> ns | rA), hi = ... | rB
     // P.bm[r][2 g + b] = (d(pred -> 2g), d(pred -> 2g+1)) for pred = g + 2 b
     if (ANTI) {
-        // row (rA | rB << 2), 16 copies of 8 bytes (LDS.64 is served per half warp): {d(0 -> 0), d(1 -> 2)} pairs
-        for (uint32_t i = threadIdx.x; i < 16u * 16u; i += BS) {
-            const uint32_t c = i & 15u, row = i >> 4, rA = row & 3u, rB = row >> 2;
-            const uint32_t x0 = (P.bm[rA * 4u] & 0xFFFFu) << 7 | (P.bm[rB * 4u] & 0xFFFFu) << 23;
-            const uint32_t x1 = (P.bm[rA * 4u + 2u] & 0xFFFFu) << 7 | (P.bm[rB * 4u + 2u] & 0xFFFFu) << 23;
-            *reinterpret_cast<uint2*>(g + a_bm + (rA << 7) + (rB << 9) + (c << 3)) = make_uint2(x0, x1);
+        // row (rA | rB << 2), 8 copies of 16 bytes: {n - 2x, n - 2y, y - x, 0} with x = d(0 -> 0), y = d(1 -> 2), times 128;
+        // the first two are added lane by lane (VIADDMNMX), the third as one 32-bit word
+        for (uint32_t i = threadIdx.x; i < 16u * 8u; i += BS) {
+            const uint32_t c = i & 7u, row = i >> 3, rA = row & 3u, rB = row >> 2;
+            const int xA = (int)(P.bm[rA * 4u] & 0xFFFFu), xB = (int)(P.bm[rB * 4u] & 0xFFFFu);
+            const int yA = (int)(P.bm[rA * 4u + 2u] & 0xFFFFu), yB = (int)(P.bm[rB * 4u + 2u] & 0xFFFFu);
+            const uint32_t d0 = ((uint32_t)((2 - 2 * xA) * 128) & 0xFFFFu) | ((uint32_t)((2 - 2 * xB) * 128) << 16);
+            const uint32_t d1 = ((uint32_t)((2 - 2 * yA) * 128) & 0xFFFFu) | ((uint32_t)((2 - 2 * yB) * 128) << 16);
+            const uint32_t z = (uint32_t)((yA - xA) * 128 + (yB - xB) * 128 * 65536);
+            *reinterpret_cast<uint4*>(g + a_bm + (rA << 7) + (rB << 9) + (c << 4)) = make_uint4(d0, d1, z, 0u);
         }
     }
     for (uint32_t i = ANTI ? 16u * 8u * 8u : threadIdx.x; i < 16u * 8u * 8u; i += BS) {
@@ -751,9 +769,9 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
     __syncthreads();
 
     PairEngine eng;
-    eng.Q0 = eng.Q1 = eng.Q2 = eng.Q3 = 0u;
+    eng.Q0 = eng.Q1 = eng.Q2 = eng.Q3 = PAIR_BASE2;       // D_0 = 0 (plus the base)
     eng.sxA = eng.sxB = a_ll + ((lane & 7u) << 4);            // state 0 = the all-zero vector
-    eng.kbm = ANTI ? a_bm + ((lane & 15u) << 3) : a_bm + ((lane & 7u) << 4);
+    eng.kbm = a_bm + ((lane & 7u) << 4);
     eng.kst = a_st + lane * 4u;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
     eng.km1 = P.fma_km1;
@@ -835,41 +853,43 @@ __global__ void __launch_bounds__(DET2P_BLOCK, 3) detect2p_kernel(const __grid_c
             }
             UA = make_uint4(UA.y, UA.z, UA.w, 0u);
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
-            // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob); the last one
-            // normalises (Eq. 5) if NORM8
-            auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob, auto norm8) {
-                constexpr bool NORM8 = decltype(norm8)::value;
-                eng.step<false, ANTI != 0>(ea << 7, eb << 9, eb << 7, P);
-                eng.step<false, ANTI != 0>(oa << 7, ob << 9, ob << 7, P);
-                eng.step<false, ANTI != 0>(ea << 5, eb << 7, eb << 5, P);
-                eng.step<false, ANTI != 0>(oa << 5, ob << 7, ob << 5, P);
-                eng.step<false, ANTI != 0>(ea << 3, eb << 5, eb << 3, P);
-                eng.step<false, ANTI != 0>(oa << 3, ob << 5, ob << 3, P);
-                eng.step<false, ANTI != 0>(ea << 1, eb << 3, eb << 1, P);
-                eng.step<NORM8, ANTI != 0>(oa << 1, ob << 3, ob << 1, P);
-            };
+            // steps t = 4 i + k of both trials in word q_k, field i = bits 4 i .. 4 i + 3 = (r_A, r_B): one shift puts
+            // a step's pair at bits 7..10, the row offset of the branch-metric table and (bits 7..8) of trial A's log row
+            uint32_t q0 = bitsel(wev[0], wev[1] << 2, 0x33333333u), q2 = bitsel(wev[0] >> 2, wev[1], 0x33333333u);
+            uint32_t q1 = bitsel(wod[0], wod[1] << 2, 0x33333333u), q3 = bitsel(wod[0] >> 2, wod[1], 0x33333333u);
             if (valid == 32u) {
-                uint32_t ea = wev[0], oa = wod[0], eb = wev[1], ob = wod[1];
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {                                  // 16 steps per iteration (measured: 8 -> 6.98e11, 16 -> 7.07e11, 32 -> 6.92e11 steps/s)
-                    oct(ea, oa, eb, ob, std::false_type{});
-                    oct(ea >> 8, oa >> 8, eb >> 8, ob >> 8, std::true_type{});
-                    ea >>= 16; oa >>= 16; eb >>= 16; ob >>= 16;
+                    eng.step<false, ANTI != 0>(q0 << 7, q0 << 5, P);
+                    eng.step<false, ANTI != 0>(q1 << 7, q1 << 5, P);
+                    eng.step<false, ANTI != 0>(q2 << 7, q2 << 5, P);
+                    eng.step<false, ANTI != 0>(q3 << 7, q3 << 5, P);
+                    eng.step<false, ANTI != 0>(q0 << 3, q0 << 1, P);
+                    eng.step<false, ANTI != 0>(q1 << 3, q1 << 1, P);
+                    eng.step<false, ANTI != 0>(q2 << 3, q2 << 1, P);
+                    eng.step<false, ANTI != 0>(q3 << 3, q3 << 1, P);
+                    eng.step<false, ANTI != 0>(q0 >> 1, q0 >> 3, P);
+                    eng.step<false, ANTI != 0>(q1 >> 1, q1 >> 3, P);
+                    eng.step<false, ANTI != 0>(q2 >> 1, q2 >> 3, P);
+                    eng.step<false, ANTI != 0>(q3 >> 1, q3 >> 3, P);
+                    eng.step<false, ANTI != 0>(q0 >> 5, q0 >> 7, P);
+                    eng.step<false, ANTI != 0>(q1 >> 5, q1 >> 7, P);
+                    eng.step<false, ANTI != 0>(q2 >> 5, q2 >> 7, P);
+                    eng.step<true, ANTI != 0>(q3 >> 5, q3 >> 7, P);
+                    q0 >>= 16; q1 >>= 16; q2 >>= 16; q3 >>= 16;
                 }
-            } else {
+            } else {                                                           // the last block of a trial: four steps at a time
 #pragma unroll 1
-                for (uint32_t c = 0; c < valid; c += 8u) {
-                    const uint32_t ea = wev[0] >> c, oa = wod[0] >> c, eb = wev[1] >> c, ob = wod[1] >> c;
-                    if (c + 8u <= valid) {
-                        oct(ea, oa, eb, ob, std::true_type{});
-                    } else {
-                        for (uint32_t j = 0; j < valid - c; ++j) {
-                            const uint32_t sh = j & ~1u;
-                            const uint32_t wa = ((j & 1u) ? oa : ea) >> sh, wb = ((j & 1u) ? ob : eb) >> sh;
-                            eng.step<true, ANTI != 0>(wa << 7, wb << 9, wb << 7, P);
-                        }
-                    }
+                for (uint32_t c = 0; c < valid; c += 4u) {
+                    const uint32_t left = valid - c;
+                    eng.step<false, ANTI != 0>(q0 << 7, q0 << 5, P);
+                    if (left > 1u) eng.step<false, ANTI != 0>(q1 << 7, q1 << 5, P);
+                    if (left > 2u) eng.step<false, ANTI != 0>(q2 << 7, q2 << 5, P);
+                    if (left > 3u) eng.step<false, ANTI != 0>(q3 << 7, q3 << 5, P);
+                    q0 >>= 4; q1 >>= 4; q2 >>= 4; q3 >>= 4;
+                    if ((c & 12u) == 12u) eng.normalise();
                 }
+                eng.normalise();
             }
         }
     }
