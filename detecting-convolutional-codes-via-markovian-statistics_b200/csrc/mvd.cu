@@ -60,6 +60,13 @@ struct mvd_ctx {
     std::vector<uint32_t> bfs_levels;   // level sizes of the last GPU enumeration
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
     uint64_t h2d_bytes = 0, d2h_bytes = 0;   // counted at every host<->device copy this context issues (mvd_copy_stats)
+    // asynchronous detection launches (MVD_OPT_ASYNC_DETECT): mvd_detect with a device tally destination only returns
+    // once the work is queued; mvd_synchronize drains: waits, reads the error flag, adds up the kernel times
+    bool async_detect = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> async_ev;   // event pairs of the launches in flight (ring, <= 64)
+    uint32_t async_pending = 0;
+    double async_ms_sum = 0.0;
+    uint64_t async_launches = 0;
     uint32_t learn_warm = LEARN_WARM;
     bool learn_warm_set = false;    // MVD_OPT_LEARN_WARM given: mvd_set_code keeps it
 
@@ -477,6 +484,30 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
     return false;
 }
 
+// Wait for the asynchronous detection launches in flight, add up their kernel times, read and clear the error flag.
+int drain_async(mvd_ctx* ctx) {
+    if (!ctx->async_pending) return MVD_OK;
+    int herr = 0;
+    CK(d2h(ctx, &herr, ctx->d_err.p, sizeof(int)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < ctx->async_pending; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->async_ev[i].first, ctx->async_ev[i].second));
+        ctx->async_ms_sum += ms;
+        ctx->last_ms = ms;
+    }
+    ctx->async_launches += ctx->async_pending;
+    ctx->async_pending = 0;
+    if (herr) {
+        CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (herr & 1) return fail(ctx, MVD_E_UNKNOWN_STATE, "a relative-metric vector was not in the state table (KeyError)");
+    if (herr & 2) return fail(ctx, MVD_E_UNKNOWN_STATE, "relative metric exceeded 15 (hash key overflow)");
+    if (herr & 4) return fail(ctx, MVD_E_CUDA, "pair kernel: the dynamic shared window does not start where the host's layout assumed");
+    return MVD_OK;
+}
+
 int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segment* segs, uint32_t nsegs,
         const LaunchOut& out) {
     if (!ctx) return MVD_E_INVALID;
@@ -616,8 +647,14 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     P.hvals = ctx->d_hvals.as<uint32_t>();
     P.hcap = ctx->hcap;
     P.burn = out.burn;
+    // asynchronous launch: device tallies only, nothing for the host to read; the error flag accumulates until the drain
+    const bool async = ctx->async_detect && mode == MODE_DETECT && out.d_tallies && !out.tallies && !out.logp;
+    if (ctx->async_pending && (!async || ctx->async_pending >= 64)) {
+        const int rc = drain_async(ctx);
+        if (rc != MVD_OK) return rc;
+    }
     CK(ctx->d_err.reserve(sizeof(int)));
-    CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
+    if (!ctx->async_pending) CK(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), ctx->stream));
     P.error_flag = ctx->d_err.as<int>();
     P.fp = fplan;
     P.fp.dstate2 = ctx->d_dstate2.as<uint16_t>();
@@ -728,7 +765,19 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const dim3 grid((unsigned)blocks);
     const bool n2 = (n == 2);
     cudaError_t le = cudaErrorInvalidValue;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const bool go_async = async && !split;
+    cudaEvent_t ev0 = ctx->ev0, ev1 = ctx->ev1;
+    if (go_async) {
+        if (ctx->async_ev.size() <= ctx->async_pending) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            ctx->async_ev.emplace_back(a, b);
+        }
+        ev0 = ctx->async_ev[ctx->async_pending].first;
+        ev1 = ctx->async_ev[ctx->async_pending].second;
+    }
+    CK(cudaEventRecord(ev0, ctx->stream));
     bool plearn = mode == MODE_LEARN && engine == MVD_ENGINE_FSM && !ctx->force_generic && src->mode == MVD_SRC_PHILOX;
     uint32_t maxL = 0;
     for (uint32_t i = 0; i < nsegs && plearn; ++i) {
@@ -831,9 +880,17 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     if (!fast && !split && !(plearn && maxL > 0)) ctx->last_fast = 0;
     if (le != cudaSuccess) return fail(ctx, MVD_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     ctx->launches += 1;
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ev1, ctx->stream));
     if (mode == MODE_DETECT && out.d_tallies)
         CK(cudaMemcpyAsync(out.d_tallies, ctx->d_tallies.p, 8 * (size_t)nsegs, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (go_async) {
+        ctx->async_pending += 1;
+        return MVD_OK;
+    }
+    if (ctx->async_pending) {                      // (a split launch among asynchronous ones)
+        const int rc = drain_async(ctx);
+        if (rc != MVD_OK) return rc;
+    }
 
     // ---- read back
     int herr = 0;
@@ -920,6 +977,10 @@ int mvd_destroy(mvd_ctx* ctx) {
                       &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
                       &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot};
     for (DevBuf* b : bufs) b->release();
+    for (auto& pr : ctx->async_ev) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -932,6 +993,8 @@ const char* mvd_last_error(const mvd_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int mvd_set_stream(mvd_ctx* ctx, void* cuda_stream) {
     if (!ctx) return MVD_E_INVALID;
     cudaSetDevice(ctx->device);
+    const int rc = drain_async(ctx);
+    if (rc != MVD_OK) return rc;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
@@ -942,7 +1005,18 @@ int mvd_set_stream(mvd_ctx* ctx, void* cuda_stream) {
 int mvd_synchronize(mvd_ctx* ctx) {
     if (!ctx) return MVD_E_INVALID;
     CK(cudaSetDevice(ctx->device));
+    const int rc = drain_async(ctx);
+    if (rc != MVD_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    return MVD_OK;
+}
+
+int mvd_async_stats(mvd_ctx* ctx, double* kernel_ms_sum, uint64_t* launches) {
+    if (!ctx) return MVD_E_INVALID;
+    if (kernel_ms_sum) *kernel_ms_sum = ctx->async_ms_sum;
+    if (launches) *launches = ctx->async_launches;
+    ctx->async_ms_sum = 0.0;
+    ctx->async_launches = 0;
     return MVD_OK;
 }
 
@@ -1566,6 +1640,14 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
     }
     if (option == MVD_OPT_NO_ANTIPODAL) {
         ctx->no_antipodal = value != 0;
+        return MVD_OK;
+    }
+    if (option == MVD_OPT_ASYNC_DETECT) {
+        if (!value) {
+            const int rc = drain_async(ctx);
+            if (rc != MVD_OK) return rc;
+        }
+        ctx->async_detect = value != 0;
         return MVD_OK;
     }
     if (option == MVD_OPT_SPLIT) {

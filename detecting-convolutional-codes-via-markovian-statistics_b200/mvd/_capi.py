@@ -11,7 +11,7 @@ import os
 
 MAX_N = 4
 MAX_M = 6
-ABI_VERSION = 2          # must equal MVD_ABI_VERSION of include/mvd.h: the struct layouts below mirror that header
+ABI_VERSION = 3          # must equal MVD_ABI_VERSION of include/mvd.h: the struct layouts below mirror that header
 
 SRC_PHILOX, SRC_BITSTREAM = 0, 1
 ENGINE_AUTO, ENGINE_ACS, ENGINE_FSM = 0, 1, 2
@@ -24,6 +24,7 @@ OPT_LEARN_WARM = 3
 OPT_NO_FSM1 = 4
 OPT_SPLIT = 5
 OPT_NO_ANTIPODAL = 6
+OPT_ASYNC_DETECT = 7
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 
@@ -33,7 +34,7 @@ EXPORTS = (
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
     "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table", "mvd_acs_final",
-    "mvd_copy_stats",
+    "mvd_copy_stats", "mvd_async_stats",
 )
 
 
@@ -116,6 +117,7 @@ def load():
     lib.mvd_last_kernel_ms.argtypes = [vp, P(C.c_float)]
     lib.mvd_launch_count.argtypes = [vp, P(u64)]
     lib.mvd_copy_stats.argtypes = [vp, P(u64), P(u64)]
+    lib.mvd_async_stats.argtypes = [vp, P(C.c_double), P(u64)]
     lib.mvd_int_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
     lib.mvd_set_option.argtypes = [vp, i32, C.c_int64]
     lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]

@@ -319,6 +319,25 @@ class Detector:
         self._ck(self.lib.mvd_launch_count(self.ctx, C.byref(v)))
         return int(v.value)
 
+    def async_detect(self, on: bool = True):
+        """``detect(..., d_tallies_ptr=..., host_tallies=False)`` calls only queue their work (``MVD_OPT_ASYNC_DETECT``);
+        :meth:`synchronize` waits for them.  Switching it off drains what is in flight."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_ASYNC_DETECT, 1 if on else 0))
+
+    def synchronize(self):
+        """Wait for everything queued on the context's stream; raises the KeyError analogue of any asynchronous launch."""
+        self._ck(self.lib.mvd_synchronize(self.ctx))
+
+    def async_stats(self):
+        """(summed kernel ms, launches) of the asynchronous detection launches drained since the last call."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self.lib.mvd_async_stats(self.ctx, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def set_stream(self, cuda_stream_ptr: int):
+        """Run this context's work on the caller's CUDA stream (``mvd_set_stream``), e.g. a torch stream's ``cuda_stream``."""
+        self._ck(self.lib.mvd_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
+
     def force_generic(self, on: bool = True):
         """Route detection through the generic (checked) kernels instead of the fast ones."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_FORCE_GENERIC, 1 if on else 0))

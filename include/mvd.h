@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MVD_ABI_VERSION 2
+#define MVD_ABI_VERSION 3
 #define MVD_MAX_N 4   /* outputs per step (R = 2^n <= 16)            */
 #define MVD_MAX_M 6   /* encoder memory  (2^m <= 64 trellis states)  */
 
@@ -218,6 +218,9 @@ int mvd_launch_count(mvd_ctx* ctx, uint64_t* launches);
  * cudaMemcpyAsync call sites of the library (tables, segment descriptors, bit streams in; tallies, counts,
  * log-likelihoods, error flags out).  bench.py reports the per-step difference as e2e.h2d/d2h_bytes_per_step. */
 int mvd_copy_stats(mvd_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Kernel time (CUDA events around each launch, summed) and number of the asynchronous detection launches
+ * (MVD_OPT_ASYNC_DETECT) drained since the last call of this function; both counters are reset. */
+int mvd_async_stats(mvd_ctx* ctx, double* kernel_ms_sum, uint64_t* launches);
 
 /* Options.  MVD_OPT_FORCE_GENERIC (value 0/1): 1 = never take the fast detection kernels
  * (mvd_detect2.cuh), always the generic checked ones -- used by the parity tests to cover both.
@@ -236,9 +239,16 @@ enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one t
        MVD_OPT_SPLIT = 5,          /* few long trials (NEXT-table engine, on-device bits) are split along the time axis
                                       (csrc/mvd_split.cuh; identical results): 0 = when it fills the GPU better,
                                       1 = whenever possible, 2 = never.  The warm-up is MVD_OPT_LEARN_WARM's. */
-       MVD_OPT_NO_ANTIPODAL = 6 }; /* 1 = the two-trials-per-thread m = 2 kernel reads the general branch-metric table even
+       MVD_OPT_NO_ANTIPODAL = 6,   /* 1 = the two-trials-per-thread m = 2 kernel reads the general branch-metric table even
                                       when every decoder generator has its first and last tap set (the complement-label
                                       short cut; identical results) */
+       MVD_OPT_ASYNC_DETECT = 7 }; /* 1 = mvd_detect calls that ask for device tallies only (tallies == NULL, logp == NULL,
+                                      d_tallies != NULL) return as soon as their work is queued on the context's stream;
+                                      mvd_synchronize (or any call that reads results, or setting the option back to 0)
+                                      waits for them and reports a KeyError of any of them.  At most 64 are kept in
+                                      flight.  The segment records and tally words of a sweep stay on the device, so a
+                                      loop of sweeps needs no host round trip between them (Pd_plotter.py:210-223
+                                      repeated; bench.py's resident leg) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);

@@ -751,6 +751,43 @@ def test_engines_and_sources_agree_at_scale(codes_spec, dets):
     assert int(tb[0]) == int(tq[0]) and np.array_equal(lpb, lpq)
 
 
+def test_async_detect_queue_matches_synchronous_calls(codes_spec, dets):
+    """MVD_OPT_ASYNC_DETECT: five sweeps queued without a host round trip (two alternating device tally buffers, more
+    launches than the in-flight ring holds on a second run) give the tallies of five synchronous calls; the kernel
+    times of all of them are accounted; a call that reads results drains the queue."""
+    import torch
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec["c75"]
+    det = dets("c75")
+    _, P1, _ = _oracle_models(det, spec, 0.1, 8000, 5)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(0.1)
+    mk = lambda i: [Seg(N=200, threshold=T, stream=7 * i + d, enc_taps=_taps(codes_spec[("c75", "c65")[d]]), decide=d,
+                        trial_begin=0, trial_end=5000) for d in (0, 1)]
+    want = [det.detect(mk(i), seed=77, engine="acs") for i in range(5)]
+    bufs = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(5)]
+    torch.cuda.synchronize()
+    det.async_detect(True)
+    try:
+        det.async_stats()
+        for i in range(5):
+            assert det.detect(mk(i), seed=77, engine="acs", d_tallies_ptr=bufs[i].data_ptr(), host_tallies=False) is None
+        det.synchronize()
+        ms, n = det.async_stats()
+        assert n == 5 and ms > 0
+        for i in range(5):
+            assert bufs[i].cpu().numpy().astype(np.uint64).tolist() == want[i].tolist()
+        for i in range(70):                                   # more than the 64 launches kept in flight
+            det.detect(mk(i % 5), seed=77, engine="acs", d_tallies_ptr=bufs[i % 5].data_ptr(), host_tallies=False)
+        got = det.detect(mk(0), seed=77, engine="acs")        # a synchronous call drains the queue first
+        assert got.tolist() == want[0].tolist()
+        assert det.async_stats()[1] == 70
+        assert bufs[4].cpu().numpy().astype(np.uint64).tolist() == want[4].tolist()
+    finally:
+        det.async_detect(False)
+
+
 def test_edge_cases(codes_spec, dets):
     from mvd import bitsource
     from mvd.engine import Seg
