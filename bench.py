@@ -535,6 +535,9 @@ def main():
             "peak_alu_pipe_only": alu_gops, "frac_alu_pipe_only": ach / alu_gops,
             "peak_nominal": nominal, "frac_of_nominal": ach / nominal,
             "frac_core_plus_rng": (OPS_CORE + rng_ops) * rate_kernel * 1e-9 / mixed_gops if rng_ops else None,
+            # issued warp-instructions (ncu source page) x measured rate / issue-rate peak: what the schedulers actually did;
+            # below frac because the 16x2 instructions do two of the survey's scalar ops each
+            "issue_utilisation": mix.get("instr_per_step") * rate_kernel * 1e-9 / mixed_gops if mix.get("instr_per_step") else None,
             "ops_per_step": {"core": OPS_CORE, "f64_adds": 2, "rng_executed": rng_ops,
                              "instr_issued_per_step": mix.get("instr_per_step"), "instr_mix_source": mix.get("source"),
                              "note": "core = SURVEY 8(d): 2^(m+k+1) + 2^m + 3n + 5 at m=2, k=1, n=2; rng_executed = thread "

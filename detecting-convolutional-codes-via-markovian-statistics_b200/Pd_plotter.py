@@ -145,7 +145,7 @@ def _learn_edge_tables(det, p_list, learn_len, learn_burn, laplace, seed, engine
     segs = [Seg(N=L, threshold=bitsource.bsc_threshold(float(p)), stream=bitsource.LEARN_STREAM,
                 enc_taps=det.dec_taps, trial_begin=0, trial_end=1) for p in p_list]
     counts = det.learn_counts(segs, burn=int(learn_burn), seed=int(seed), engine=engine)
-    tables = [codes.p1_from_edge_counts(det.table, counts[i], laplace) for i in range(len(p_list))]
+    tables = codes.p1_tables_from_edge_counts(det.table, counts, laplace)      # [len(p_list), S, R]
     return counts, tables
 
 

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -59,6 +60,8 @@ struct mvd_ctx {
     double tref_unit = 0.0;
     std::vector<uint32_t> bfs_levels;   // level sizes of the last GPU enumeration
     uint32_t last_dirty = 0;        // chunk-parallel learning: chunks that needed the fix-up pass
+    void* pin[2] = {nullptr, nullptr};      // pinned staging halves of the large copies (h2d / d2h)
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0, d2h_bytes = 0;   // counted at every host<->device copy this context issues (mvd_copy_stats)
     // asynchronous detection launches (MVD_OPT_ASYNC_DETECT): mvd_detect with a device tally destination only returns
     // once the work is queued; mvd_synchronize drains: waits, reads the error flag, adds up the kernel times
@@ -93,7 +96,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot;
 };
 
 namespace {
@@ -109,13 +112,93 @@ int fail(mvd_ctx* c, int code, const char* fmt, ...) {
 }
 
 // every host<->device copy of the library goes through these two: the byte counters are what bench.py reports
+// Large copies (edge counts and log-likelihood tables of an m = 4 code: 34 MB each way) go through two pinned 8 MB
+// buffers of the context: DMA at link speed into / out of pinned memory while host threads move the other half to /
+// from the caller's pageable array (a plain cudaMemcpyAsync on pageable memory ran at ~4 GB/s: 8.5 ms per table set).
+constexpr size_t PIN_CHUNK = (size_t)8 << 20;
+constexpr size_t PIN_MIN = (size_t)2 << 20;
+
+// fn(lo, hi) over [0, count) on up to 16 host threads (ranges of at least `grain`); the element-wise work of the
+// table helpers below does not depend on how the range is cut
+template <class F>
+void host_parallel(uint64_t count, uint64_t grain, F fn) {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt == 0 ? 1u : (nt > 16u ? 16u : nt);
+    const uint64_t want = (count + grain - 1) / grain;
+    if (want < nt) nt = (unsigned)(want ? want : 1);
+    if (nt <= 1) {
+        fn(0, count);
+        return;
+    }
+    std::vector<std::thread> th;
+    const uint64_t per = (count + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const uint64_t lo = (uint64_t)t * per, hi = lo + per < count ? lo + per : count;
+        if (lo < hi) th.emplace_back([=, &fn] { fn(lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+inline cudaError_t pin_ready(mvd_ctx* c) {
+    if (c->pin[0]) return cudaSuccess;
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaHostAlloc(&c->pin[i], PIN_CHUNK, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+inline void host_copy(void* dst, const void* src, size_t bytes) {
+    host_parallel(bytes, (size_t)1 << 20, [&](uint64_t lo, uint64_t hi) {
+        memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+    });
+}
+
 inline cudaError_t h2d(mvd_ctx* c, void* dst, const void* src, size_t bytes) {
     c->h2d_bytes += bytes;
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (bytes < PIN_MIN || pin_ready(c) != cudaSuccess) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    int half = 0;
+    bool used[2] = {false, false};
+    for (size_t off = 0; off < bytes; off += PIN_CHUNK, half ^= 1) {
+        const size_t len = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+        if (used[half]) {
+            cudaError_t e = cudaEventSynchronize(c->pin_ev[half]);     // the DMA that last read this half
+            if (e != cudaSuccess) return e;
+        }
+        host_copy(c->pin[half], static_cast<const char*>(src) + off, len);
+        cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst) + off, c->pin[half], len, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->pin_ev[half], c->stream);
+        if (e != cudaSuccess) return e;
+        used[half] = true;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (used[i]) {
+            cudaError_t e = cudaEventSynchronize(c->pin_ev[i]);        // the pinned halves are free again on return
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
 }
 inline cudaError_t d2h(mvd_ctx* c, void* dst, const void* src, size_t bytes) {
     c->d2h_bytes += bytes;
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (bytes < PIN_MIN || pin_ready(c) != cudaSuccess) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    // chunk i + 1 is on the wire while chunk i is copied out of its pinned half; complete on return
+    const size_t nchunks = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * PIN_CHUNK, len = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+        cudaError_t e = cudaMemcpyAsync(c->pin[i & 1], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->pin_ev[i & 1], c->stream);
+        return e;
+    };
+    cudaError_t e = issue(0);
+    if (e != cudaSuccess) return e;
+    for (size_t i = 0; i < nchunks; ++i) {
+        if (i + 1 < nchunks && (e = issue(i + 1)) != cudaSuccess) return e;
+        if ((e = cudaEventSynchronize(c->pin_ev[i & 1])) != cudaSuccess) return e;
+        const size_t off = i * PIN_CHUNK, len = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+        host_copy(static_cast<char*>(dst) + off, c->pin[i & 1], len);
+    }
+    return cudaSuccess;
 }
 
 #define CK(call)                                                                                      \
@@ -974,9 +1057,13 @@ int mvd_destroy(mvd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
-                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
+                      &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_stage, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
                       &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
+        if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]);
+    }
     for (auto& pr : ctx->async_ev) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -1201,15 +1288,17 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
     if (!logP1 || !logTref || ntables == 0) return fail(ctx, MVD_E_INVALID, "null / empty log-likelihood tables");
     CK(cudaSetDevice(ctx->device));
     const size_t SR = (size_t)ctx->S << ctx->n;
-    std::vector<double> inter(2 * SR * ntables);
-    for (uint32_t t = 0; t < ntables; ++t)
-        for (size_t e = 0; e < SR; ++e) {
-            inter[2 * (t * SR + e)] = logP1[t * SR + e];
-            inter[2 * (t * SR + e) + 1] = logTref[e];
-        }
-    CK(ctx->d_ll.reserve(inter.size() * 8));
-    CK(h2d(ctx, ctx->d_ll.p, inter.data(), inter.size() * 8));
+    // the tables go up as they are (log P1 [ntables][SR], log Tref [SR]); the interleaved rows the kernels read and the
+    // packed NEXT-walk entries are written on the device (pack_ll_kernel) -- at S = 150 743 the host loops that used to
+    // do this took 84 ms per call, 94 % of run_experiment's wall time together with the P1 / log tables
+    CK(ctx->d_stage.reserve((SR * ntables + SR) * 8));
+    double* d_lp1 = ctx->d_stage.as<double>();
+    double* d_ltref = d_lp1 + SR * ntables;
+    CK(h2d(ctx, d_lp1, logP1, SR * ntables * 8));
+    CK(h2d(ctx, d_ltref, logTref, SR * 8));
+    CK(ctx->d_ll.reserve(2 * SR * ntables * 8));
     // log Tref[e] == c[e] * unit exactly, c = 0 or a power of two?  (unit = the non-zero value of least magnitude)
+    bool large = false;
     {
         double unit = 0.0;
         for (size_t e = 0; e < SR; ++e)
@@ -1234,26 +1323,15 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
         if (ok) {
             CK(ctx->d_tcode.reserve(SR * 4));
             CK(h2d(ctx, ctx->d_tcode.p, code.data(), SR * 4));
-            if (128 + (SR << 7) + 64 > ctx->prop.sharedMemPerBlockOptin && SR < (1ull << 28)) {
-                // large S: packed NEXT-walk entries {log P1, next row byte offset, c} stay in global memory
-                std::vector<uint32_t> pk(4 * SR * ntables);
-                for (uint32_t t = 0; t < ntables; ++t)
-                    for (size_t e = 0; e < SR; ++e) {
-                        uint64_t bits;
-                        memcpy(&bits, &logP1[t * SR + e], 8);
-                        uint32_t* o = pk.data() + 4 * (t * SR + e);
-                        o[0] = (uint32_t)bits;
-                        o[1] = (uint32_t)(bits >> 32);
-                        o[2] = (ctx->h_next[e] << ctx->n) << 4;
-                        o[3] = code[e];
-                    }
-                CK(ctx->d_gfsm1.reserve(pk.size() * 4));
-                CK(h2d(ctx, ctx->d_gfsm1.p, pk.data(), pk.size() * 4));
-                CK(cudaStreamSynchronize(ctx->stream));
-                ctx->have_gfsm1 = true;
-            }
+            // large S: packed NEXT-walk entries {log P1, next row byte offset, c} stay in global memory
+            large = 128 + (SR << 7) + 64 > ctx->prop.sharedMemPerBlockOptin && SR < (1ull << 28);
+            if (large) CK(ctx->d_gfsm1.reserve(16 * SR * ntables));
         }
     }
+    CK(mvd_launch_pack_ll(d_lp1, d_ltref, ctx->d_nxt.as<uint32_t>(), ctx->d_tcode.as<uint32_t>(), (uint32_t)SR, ntables,
+                          ctx->d_ll.as<double2>(), large ? ctx->d_gfsm1.as<uint4>() : nullptr, ctx->stream));
+    ctx->launches += 1;
+    ctx->have_gfsm1 = large;
     // m = 4 two-trials-per-thread ACS kernel: the same rows in hash-slot order (64 B per slot and table)
     ctx->have_llslot = false;
     if (ctx->ph_slots && ctx->m == 4 && (size_t)ctx->ph_slots * 64 * ntables <= ((size_t)24 << 30)) {
@@ -1600,7 +1678,33 @@ int mvd_parity_detect(mvd_ctx* ctx, const mvd_src* src, const mvd_parity_segment
 
 int mvd_host_log_table(const double* values, double* out, uint64_t count) {
     if (!values || !out) return MVD_E_INVALID;
-    for (uint64_t i = 0; i < count; ++i) out[i] = std::log(values[i] > 1e-300 ? values[i] : 1e-300);
+    // the same libm call per element whatever the thread count (bit-equal to the single-threaded loop)
+    host_parallel(count, 1u << 15, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) out[i] = std::log(values[i] > 1e-300 ? values[i] : 1e-300);
+    });
+    return MVD_OK;
+}
+
+int mvd_host_p1_edge_tables(const uint64_t* edge_counts, const uint32_t* next, uint32_t S, uint32_t R, uint32_t ntables,
+                            double laplace, double* P1) {
+    if (!edge_counts || !next || !P1 || S == 0 || R == 0 || R > 16) return MVD_E_INVALID;
+    const double lapS = laplace * (double)S;                       // one rounding, as `laplace * S` in Python
+    host_parallel((uint64_t)S * ntables, 1u << 13, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t q = lo; q < hi; ++q) {
+            const uint64_t i = q % S;
+            const uint64_t* c = edge_counts + q * R;
+            const uint32_t* nx = next + i * R;
+            double row = 0.0;
+            for (uint32_t r = 0; r < R; ++r) row += (double)c[r];  // integers: exact in any order
+            const double denom = row + lapS;
+            for (uint32_t r = 0; r < R; ++r) {
+                double cij = 0.0;
+                for (uint32_t r2 = 0; r2 < R; ++r2)
+                    if (nx[r2] == nx[r]) cij += (double)c[r2];
+                P1[q * R + r] = (cij + laplace) / denom;
+            }
+        }
+    });
     return MVD_OK;
 }
 

@@ -99,6 +99,21 @@ __global__ void slot_rows_kernel(const double2* __restrict__ ll, const uint32_t*
         out[(size_t)t * slots * 4u + idx] = st == MVD_EMPTY ? make_double2(0.0, 0.0) : ll[(size_t)t * SR + st + (idx & 3u)];
 }
 
+// Device-side packing of the log-likelihood tables (mvd_set_loglik): the host uploads log P1 [ntables][SR] and
+// log Tref [SR] as they are; the interleaved {log P1, log Tref} rows and (large S) the 16-byte entries of the one-load
+// NEXT walk {log P1, next row byte offset, c} are written here instead of by single-threaded host loops.
+__global__ void pack_ll_kernel(const double* __restrict__ lp1, const double* __restrict__ ltref, const uint32_t* __restrict__ nxt,
+                               const uint32_t* __restrict__ tcode, uint32_t SR, uint32_t ntables, double2* __restrict__ ll,
+                               uint4* __restrict__ gfsm1) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)SR * ntables) return;
+    const uint32_t e = (uint32_t)(idx % SR);
+    const double a = lp1[idx];
+    ll[idx] = make_double2(a, ltref[e]);
+    if (gfsm1)
+        gfsm1[idx] = make_uint4((uint32_t)__double2loint(a), (uint32_t)__double2hiint(a), nxt[e] << 4, tcode[e]);
+}
+
 template <int M, bool GT, int PHILOX, bool DS = false>
 __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(const __grid_constant__ Params P,
                                                                                const __grid_constant__ SegBatch B) {

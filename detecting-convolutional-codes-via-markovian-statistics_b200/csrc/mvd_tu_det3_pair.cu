@@ -31,3 +31,10 @@ cudaError_t mvd_launch_slot_rows(const double2* ll, const uint32_t* pht, uint32_
     slot_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ll, pht, slots, SR, ntables, out);
     return cudaGetLastError();
 }
+
+cudaError_t mvd_launch_pack_ll(const double* lp1, const double* ltref, const uint32_t* nxt, const uint32_t* tcode, uint32_t SR,
+                               uint32_t ntables, double2* ll, uint4* gfsm1, cudaStream_t st) {
+    const size_t n = (size_t)SR * ntables;
+    pack_ll_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lp1, ltref, nxt, tcode, SR, ntables, ll, gfsm1);
+    return cudaGetLastError();
+}

@@ -34,7 +34,7 @@ EXPORTS = (
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
     "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table", "mvd_acs_final",
-    "mvd_copy_stats", "mvd_async_stats",
+    "mvd_copy_stats", "mvd_async_stats", "mvd_host_p1_edge_tables",
 )
 
 
@@ -118,6 +118,7 @@ def load():
     lib.mvd_launch_count.argtypes = [vp, P(u64)]
     lib.mvd_copy_stats.argtypes = [vp, P(u64), P(u64)]
     lib.mvd_async_stats.argtypes = [vp, P(C.c_double), P(u64)]
+    lib.mvd_host_p1_edge_tables.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, vp]
     lib.mvd_int_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
     lib.mvd_set_option.argtypes = [vp, i32, C.c_int64]
     lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]

@@ -220,10 +220,13 @@ class Detector:
 
     def set_models(self, p1_edge_tables: Iterable[np.ndarray], tref_edge: Optional[np.ndarray] = None):
         """Upload ``log P1`` (one table per distinct p) and ``log T(1/2)``, edge-indexed [S, R]."""
-        tabs = [np.asarray(t, dtype=np.float64).reshape(self.S, self.R) for t in p1_edge_tables]
+        if isinstance(p1_edge_tables, np.ndarray) and p1_edge_tables.ndim == 3:
+            tabs = np.ascontiguousarray(p1_edge_tables, dtype=np.float64).reshape(-1, self.S, self.R)    # one threaded log pass
+        else:
+            tabs = np.stack([np.asarray(t, dtype=np.float64).reshape(self.S, self.R) for t in p1_edge_tables])
         if tref_edge is None:
             tref_edge = codes.tref_half_table(self.table)
-        self.logP1 = np.ascontiguousarray(np.stack([_log_table(t) for t in tabs]))
+        self.logP1 = _log_table(tabs)
         self.logTref = np.ascontiguousarray(_log_table(np.asarray(tref_edge, dtype=np.float64).reshape(self.S, self.R)))
         self._ck(self.lib.mvd_set_loglik(self.ctx, len(tabs), self.logP1.ctypes.data, self.logTref.ctypes.data))
         self.ntables = len(tabs)

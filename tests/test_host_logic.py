@@ -143,6 +143,32 @@ def test_numeric_T_edges_match_reference_symbolic(golden, name, pv):
         np.testing.assert_allclose(dense[np.arange(g["S"])[:, None], tab.nxt], got, rtol=0, atol=0)
 
 
+def test_host_p1_edge_tables_equal_the_numpy_closed_form():
+    """mvd_host_p1_edge_tables (C, host threads) == the numpy statements of the closed form, bit for bit, on a state
+    table above DENSE_LIMIT (random successor structure with merging edges, zero rows, counts up to 2^40) for a
+    dyadic and a non-dyadic Laplace constant; and the threaded log table == math.log element by element."""
+    import math
+    from mvd import codes, engine
+    rng = np.random.default_rng(3)
+    S, R, T = codes.DENSE_LIMIT + 1500, 4, 3
+    nxt = rng.integers(0, S, size=(S, R), dtype=np.uint32)
+    nxt[::3, 1] = nxt[::3, 0]                          # edges that share a successor
+    nxt[::7, 3] = nxt[::7, 2]
+    tab = codes.StateTable(k=1, n=2, m=4, metrics=np.zeros((S, 16), dtype=np.uint8), nxt=nxt)
+    counts = rng.integers(0, 1 << 40, size=(T, S, R), dtype=np.uint64)
+    counts[0, ::5] = 0                                 # unvisited rows
+    counts[1] = rng.integers(0, 3, size=(S, R))
+    for laplace in (1.0, 0.3):
+        got = codes.p1_tables_from_edge_counts(tab, counts, laplace)
+        for t in range(T):
+            assert np.array_equal(got[t], codes.p1_closed_form_numpy(tab, counts[t], laplace))
+        assert np.array_equal(codes.p1_from_edge_counts(tab, counts[2], laplace), got[2])
+    big = rng.random(300000) ** 8
+    big[::1000] = 0.0
+    logs = engine._log_table(big)
+    assert logs.tolist() == [math.log(max(float(v), 1e-300)) for v in big]
+
+
 def test_host_log_table_is_math_log():
     """The C helper behind large log-likelihood tables returns math.log(max(v, 1e-300)) bit for bit
     (Pd_plotter.py:114-115) -- and _log_table switches to it without changing a single value."""
