@@ -55,6 +55,9 @@ struct mvd_ctx {
     int last_fast = 0;              // 0 = generic kernel, else 1 + lookup kind + 16 * log2(log-row stride)
     bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false, no_antipodal = false;
     int split_mode = 0;             // 0 = automatic, 1 = always split long trials along the time axis, 2 = never
+    bool split_sequential = false;  // MVD_OPT_SPLIT_SEQUENTIAL: the split path adds every term one by one (no re-association)
+    bool split_tables_ready = false;// tie binades / float32 terms of the current log-likelihood tables are on the device
+    unsigned long long last_split_sub = 0, last_split_seq = 0;   // sub-chunks of the last split launch / of them added term by term
     bool have_gfsm1 = false;
     bool tref_packed = false;       // log Tref = c * unit with c in {0, 2^j}: one-load NEXT walk possible
     double tref_unit = 0.0;
@@ -96,7 +99,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot, d_sapx, d_splan, d_sres, d_stie, d_sapxtab, d_sflags;
 };
 
 namespace {
@@ -889,16 +892,18 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     } else if (split) {
         // few long trials: one thread per (trial, chunk) walks the states, one per trial adds the log-likelihoods
         // in step order (mvd_split.cuh)
-        std::vector<unsigned long long> meta(2 * (size_t)nsegs + 1);
-        unsigned long long w = 0, ew = 0;
+        std::vector<unsigned long long> meta(3 * (size_t)nsegs + 1);
+        unsigned long long w = 0, ew = 0, subs = 0;
         const int eb = SR <= 256u ? 1 : (SR <= 65536u ? 2 : 4);
         const unsigned long long spg = 16 / eb;
         for (uint32_t i = 0; i < nsegs; ++i) {
             const unsigned long long ntr = ds[i].trial_end - ds[i].trial_begin;
             meta[i] = w;
             meta[nsegs + 1 + i] = ew;
+            meta[2 * (size_t)nsegs + 1 + i] = subs;
             w += ntr * (((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
             ew += ntr * (((unsigned long long)ds[i].N + spg - 1) / spg) * 4ull;      // 16-byte groups, in 32-bit words
+            subs += ntr * (((unsigned long long)ds[i].N + SPLIT_SUB - 1ull) / SPLIT_SUB);
         }
         meta[nsegs] = w;
         SplitParams SP{};
@@ -910,30 +915,62 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         SP.warm = ctx->learn_warm;
         SP.nchains = (uint32_t)trials;
         SP.nwork = w;
+        SP.sequential = ctx->split_sequential ? 1 : 0;
         CK(ctx->d_smeta.reserve(meta.size() * 8 + 16));
         CK(h2d(ctx, ctx->d_smeta.p, meta.data(), meta.size() * 8));
         SP.work_begin = ctx->d_smeta.as<unsigned long long>();
         SP.edge_begin = SP.work_begin + nsegs + 1;
+        SP.sub_begin = SP.work_begin + 2 * (size_t)nsegs + 1;
         CK(ctx->d_lspec.reserve((size_t)w * 4));
         CK(ctx->d_lend.reserve((size_t)w * 4));
         CK(ctx->d_ldirty.reserve(4));
         CK(cudaMemsetAsync(ctx->d_ldirty.p, 0, 4, ctx->stream));
         CK(ctx->d_sedges.reserve((size_t)ew * 4));
+        CK(ctx->d_sapx.reserve((size_t)subs * 8));
+        CK(ctx->d_splan.reserve((size_t)subs * 4));
+        CK(ctx->d_sres.reserve((size_t)subs * 16));
+        // per (table, edge): the binade in which each term is a round-half-even tie, the terms in float32, "some term > 0"
+        CK(ctx->d_sflags.reserve(16));                          // [0] flags (u32), [8] sub-chunks added term by term (u64)
+        if (!ctx->split_tables_ready) {
+            const size_t cells = (size_t)SR * ctx->ntables;
+            CK(ctx->d_stie.reserve(cells * 8));
+            CK(ctx->d_sapxtab.reserve(cells * 8));
+            CK(mvd_launch_split_tables(ctx->d_ll.as<double2>(), cells, ctx->d_stie.as<uint2>(), ctx->d_sapxtab.as<float2>(),
+                                       ctx->d_sflags.as<uint32_t>(), ctx->stream));
+            ctx->launches += 1;
+            ctx->split_tables_ready = true;
+        }
+        CK(cudaMemsetAsync(ctx->d_sflags.as<unsigned char>() + 8, 0, 8, ctx->stream));
         SP.spec_start = ctx->d_lspec.as<uint32_t>();
         SP.end = ctx->d_lend.as<uint32_t>();
         SP.ndirty = ctx->d_ldirty.as<uint32_t>();
         SP.edges = ctx->d_sedges.as<uint32_t>();
+        SP.apx = ctx->d_sapx.as<float2>();
+        SP.plan = ctx->d_splan.as<uint32_t>();
+        SP.res = ctx->d_sres.as<double2>();
+        SP.tietab = ctx->d_stie.as<uint2>();
+        SP.apxtab = ctx->d_sapxtab.as<float2>();
+        SP.flags = ctx->d_sflags.as<uint32_t>();
+        SP.nseq = reinterpret_cast<unsigned long long*>(ctx->d_sflags.as<unsigned char>() + 8);
+        // shared memory: log-likelihood rows 8 x replicated (16-byte pitch), tie / float32 rows 16 x (8-byte pitch), when they fit
         SP.ll_rep_shift = (size_t)SR * 128 <= 64 * 1024 ? 3 : 0;
-        const size_t nb = (size_t)SR * 4, lb = ((size_t)SR * 16) << SP.ll_rep_shift;
-        SP.nxt_in_smem = nb <= 64 * 1024;
-        SP.ll_in_smem = lb <= 64 * 1024;
-        SP.ring_offset = SP.ll_in_smem ? (uint32_t)((lb + 127) & ~(size_t)127) : 0u;   // the scoring kernel's cp.async ring follows its table
-        SP.chain_block = SPLIT_BLOCK;                            // per-chain kernels: spread few chains over all SMs
+        SP.apx_rep_shift = (size_t)SR * 128 <= 64 * 1024 ? 4 : 0;
+        const size_t nb = ((size_t)SR * 4 + 15) & ~(size_t)15, lb = ((size_t)SR * 16) << SP.ll_rep_shift;
+        const size_t ab = ((size_t)SR * 8) << SP.apx_rep_shift, tb = ((size_t)SR * 8) << (SP.ll_rep_shift ? SP.ll_rep_shift + 1 : 0);
+        SP.nxt_in_smem = nb + ab <= 96 * 1024;
+        SP.ll_in_smem = lb + tb <= 128 * 1024;
+        SP.walk_apx_offset = (uint32_t)nb;
+        SP.isum_tie_offset = (uint32_t)lb;
+        SP.chain_block = SPLIT_BLOCK;                            // scoring kernel: spread few chains over all SMs
         while (SP.chain_block > 32 && (trials + SP.chain_block - 1) / SP.chain_block < 2 * sms) SP.chain_block >>= 1;
+        SP.score_ring_offset = SP.ll_in_smem ? (uint32_t)((lb + 127) & ~(size_t)127) : 0u;
+        const size_t ring_bytes = 2 * (size_t)SPLIT_RB_HOST * SP.chain_block * 20;   // two batches of {partial sums 16 B, plan 4 B} per thread
         CK(cudaStreamSynchronize(ctx->stream));                 // meta is a stack-lifetime vector
-        le = mvd_launch_split(SP.nxt_in_smem, nb, SP.ll_in_smem, lb, ctx->stream, P, SP);
-        ctx->launches += 2;
+        le = mvd_launch_split(SP.nxt_in_smem ? (SP.fast_walk ? nb + ab : nb) : 0, SP.ll_in_smem ? lb + tb : 0,
+                              SP.score_ring_offset + ring_bytes, ctx->stream, P, SP);
+        ctx->launches += SP.sequential ? 2 : 3;
         ctx->last_fast = 16384;
+        ctx->last_split_sub = subs;
     } else if (fast) {
         // segments travel as kernel parameters, DET2_MAXSEG per launch; grid.y = segment
         le = cudaSuccess;
@@ -983,6 +1020,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         if (split) {
             hdirty.assign(1, 0u);
             CK(d2h(ctx, hdirty.data(), ctx->d_ldirty.p, 4));
+            CK(d2h(ctx, &ctx->last_split_seq, ctx->d_sflags.as<unsigned char>() + 8, 8));
         }
         if (out.tallies) CK(d2h(ctx, out.tallies, ctx->d_tallies.p, 8 * (size_t)nsegs));
         if (out.logp) CK(d2h(ctx, out.logp, ctx->d_logp.p, 16 * (size_t)trials));
@@ -1058,7 +1096,8 @@ int mvd_destroy(mvd_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_bm, &ctx->d_nxt, &ctx->d_ll, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_segs, &ctx->d_tallies,
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
                       &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_stage, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
-                      &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot};
+                      &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot, &ctx->d_sapx, &ctx->d_splan,
+                      &ctx->d_sres, &ctx->d_stie, &ctx->d_sapxtab, &ctx->d_sflags};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
@@ -1343,6 +1382,7 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ntables = ntables;
+    ctx->split_tables_ready = false;
     return MVD_OK;
 }
 
@@ -1754,6 +1794,10 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
         ctx->async_detect = value != 0;
         return MVD_OK;
     }
+    if (option == MVD_OPT_SPLIT_SEQUENTIAL) {
+        ctx->split_sequential = value != 0;
+        return MVD_OK;
+    }
     if (option == MVD_OPT_SPLIT) {
         if (value < 0 || value > 2) return fail(ctx, MVD_E_INVALID, "MVD_OPT_SPLIT takes 0, 1 or 2");
         ctx->split_mode = (int)value;
@@ -1777,6 +1821,13 @@ int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind) {
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks) {
     if (!ctx || !dirty_chunks) return MVD_E_INVALID;
     *dirty_chunks = ctx->last_dirty;
+    return MVD_OK;
+}
+
+int mvd_split_stats(mvd_ctx* ctx, uint64_t* subchunks, uint64_t* sequential) {
+    if (!ctx) return MVD_E_INVALID;
+    if (subchunks) *subchunks = ctx->last_split_sub;
+    if (sequential) *sequential = ctx->last_split_seq;
     return MVD_OK;
 }
 

@@ -75,9 +75,11 @@ cudaError_t mvd_launch_chernoff_dense(const ChernoffParams& P, cudaStream_t st);
 // parity-template baseline (mvd_tu_parity.cu, mvd_parity.cuh)
 cudaError_t mvd_launch_parity(dim3 grid, cudaStream_t st, const Params& P, const ParityBatch& B, uint32_t* satisfied);
 
-// detection trials split along the time axis (mvd_split.cuh, in mvd_tu_learn.cu)
-cudaError_t mvd_launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
-                             const SplitParams& SP);
+// detection trials split along the time axis (mvd_split.cuh, in mvd_tu_learn.cu): walk, repair + predict, partial sums, score --
+// four kernels in a row on `st`; the *_bytes are their dynamic shared memory
+cudaError_t mvd_launch_split(size_t walk_bytes, size_t isum_bytes, size_t score_bytes, cudaStream_t st, const Params& P, const SplitParams& SP);
+// per (table, edge): tie binades, float32 terms, "some term is positive" flag
+cudaError_t mvd_launch_split_tables(const double2* ll, size_t cells, uint2* tie, float2* apx, uint32_t* flags, cudaStream_t st);
 
 // Eq. 4-5 at m = 2..6, two trials per thread, final metric vectors only (mvd_tu_acsp.cu)
 cudaError_t mvd_launch_acsp(int m, dim3 grid, unsigned threads, cudaStream_t st, const Params& P, const DevSeg& sg,

@@ -2,21 +2,41 @@
 // BASELINE config 3: N up to 10^5 at the reference's 10^4 iterations per point, divided over 8 GPUs).
 //
 // One thread per trial leaves the GPU empty when there are only a few thousand trials, and the chain of one
-// trial is sequential.  But only two things in Pd_plotter.py:210-223 are order-dependent: the Markov-state
-// trajectory (integers) and the two float64 sums of log_prob_sequence (:106-116).  So:
-//   1. split_walk_kernel  -- one thread per (trial, chunk of SPLIT_CH steps): the position-addressed bit
-//      source lets any chunk be generated on its own; the thread starts `warm` steps early from state 0 (the
-//      relative-metric recursion forgets its start), records the state it has at the chunk start and
-//      writes the edge index e_t = state * R + r_t of every step of its chunk;
-//   2. split_fix_kernel   -- one thread per trial: a chunk whose speculated start differs from the previous
-//      chunk's end is re-walked from the true state until both trajectories meet (exactly the
-//      speculate / check / fix scheme of the learning chains, mvd_learn2.cuh); after it the edge list is the
-//      sequential trajectory, bit for bit;
-//   3. split_score_kernel -- one thread per trial adds log P1[e_t] and log Tref[e_t] in step order, so both
-//      sums -- and the decision -- are the ones of the one-thread-per-trial kernels.
+// trial is sequential.  Two things in Pd_plotter.py:210-223 are order-dependent: the Markov-state trajectory
+// (integers) and the two float64 sums of log_prob_sequence (:106-116).  Both are cut into pieces here that are
+// worked on in parallel and still give the reference's bits:
+//   1. split_walk_kernel / split_walk2_kernel -- one thread per (trial, chunk of SPLIT_CH steps): the
+//      position-addressed bit source lets any chunk be generated on its own; the thread starts `warm` steps early
+//      from state 0 (the relative-metric recursion forgets its start), records the state it has at the chunk
+//      start, writes the edge index e_t = state * R + r_t of every step of its chunk and a float32 estimate of the
+//      two sums over every SPLIT_SUB steps;
+//   2. split_plan_kernel -- one warp per trial: chunks whose speculated start differs from the previous chunk's
+//      end are re-walked from the true state until both trajectories meet (the speculate / check / fix scheme of
+//      the learning chains, mvd_learn2.cuh), after which the edge list is the sequential trajectory, bit for bit;
+//      a prefix sum of the estimates predicts, for every sub-chunk, the binade [2^k, 2^(k+1)) in which each of the
+//      two running sums will be while it crosses that sub-chunk;
+//   3. split_isum_kernel -- one thread per (trial, chunk): for every sub-chunk with a prediction it runs the
+//      float64 recurrence r <- r + v_t from r = -2^k instead of from the (unknown) running sum;
+//   4. split_score_kernel -- one thread per trial goes through the sub-chunks in order: where the running sum
+//      really is in the predicted binade and stays there, a + (r_end + 2^k) IS the value the step-by-step
+//      recurrence reaches (see below); everywhere else it adds the sub-chunk's terms one by one.
+//
+// Why step 4 is exact.  All terms are log-probabilities, v_t <= 0 (checked on the device when the tables are
+// installed; a table with a positive entry switches the predictions off), so |a| never decreases.  While |a| is in
+// [2^k, 2^(k+1)) every sum a + v_t is rounded to a multiple of u = 2^(k-52), and because a itself is such a multiple
+// the rounded result is a + rnd_u(v_t), rnd_u = nearest multiple of u -- unless v_t / u has fractional part exactly
+// 1/2, where round-half-even looks at the parity of a (a "tie"; every v has exactly one binade in which that happens,
+// k* = exponent(v) + 1 + trailing zeros of its mantissa, tabulated per edge).  So as long as the sum stays inside the
+// binade and no tie term occurs, the recurrence adds the FIXED integers rnd_u(v_t) / u, whatever its starting point:
+// started from -2^k it ends at -2^k + sum rnd_u(v_t), and that sum moves to the true starting value without any
+// rounding.  The scoring thread checks exactly the two premises (exponent of a before, exponent of a + S after; a tie
+// makes S a NaN), which also covers a recurrence from -2^k that left the binade: it ends at or beyond -2^(k+1), so
+// |a + S| >= 2^(k+1) and the check fails.  Predictions only decide how often the cheap case applies.
 #pragma once
 #include "mvd_detect2.cuh"
 #include "mvd_learn2.cuh"
+
+#define SPLIT_PLAN_FAST (1u << 22)      // plan word of a sub-chunk: bits 0-10 / 11-21 biased exponents of the two sums
 
 __device__ __forceinline__ uint32_t split_find(const unsigned long long* begin, uint32_t n, unsigned long long x) {
     uint32_t lo = 0, hi = n;
@@ -42,6 +62,39 @@ __device__ __forceinline__ uint32_t split_get(const uint4& grp, uint32_t pos) {
     return EB == 4 ? word : ((word >> sh) & ((1u << (EB * 8)) - 1u));
 }
 
+// ---- tables of the exact re-association, one entry per (log-likelihood table, edge); built once per mvd_set_loglik
+// tie[e] = {bit k set: log P1[e] is a tie term in binade 2^k, the same for log Tref[e]} (k = 0 .. 31),
+// apx[e] = the two terms in float32; flags bit 0: some term is positive or not a number (no predictions then)
+__device__ __forceinline__ uint32_t split_tie_bit(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v) & 0x7FFFFFFFFFFFFFFFull;
+    if (b == 0ull || (b >> 52) == 0x7FFull) return 0u;
+    int ev = (int)(b >> 52) - 1023;
+    unsigned long long mant = b & 0xFFFFFFFFFFFFFull;
+    if ((b >> 52) == 0ull) ev = -1022; else mant |= 1ull << 52;
+    const int k = ev + 1 + (__ffsll((long long)mant) - 1);
+    return (k >= 0 && k < 32) ? (1u << k) : 0u;
+}
+
+__global__ void split_tables_kernel(const double2* __restrict__ ll, size_t cells, uint2* __restrict__ tie, float2* __restrict__ apx,
+                                    uint32_t* __restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const double2 v = ll[i];
+    tie[i] = make_uint2(split_tie_bit(v.x), split_tie_bit(v.y));
+    apx[i] = make_float2((float)v.x, (float)v.y);
+    if (!(v.x <= 0.0) || !(v.y <= 0.0)) atomicOr(flags, 1u);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ float2 split_apx(const float2* g, uint32_t abase, uint32_t sh, uint32_t e) {
+    if (SMEM) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(abase + (e << sh)));
+        return v;
+    }
+    return __ldg(g + e);
+}
+
 template <bool SMEM, int EB>
 __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,12 +116,15 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
     const unsigned long long tl = local % ntr;
     const unsigned long long trial = sg.trial_begin + tl;
     // edge of (trial tl, step t): 16-byte group (t / SPG) * ntr + tl, position t % SPG -- groups are trial-minor,
-    // so that the stores here and the loads of the scoring pass are coalesced across trials
+    // so that the stores here and the loads of the later passes are coalesced across trials
     constexpr uint32_t SPG = 16 / EB;
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    float2* AX = SP.apx + SP.sub_begin[seg] + tl;                 // estimate of sub-chunk s: AX[s * ntr]
+    const float2* gapx = SP.apxtab + (size_t)sg.table * P.SR;
     const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
     const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
     uint32_t sx = 0;                                              // state 0 (exact when w_begin == 0)
+    float s1 = 0.f, s0 = 0.f;
     uint32_t Rw[MVD_MAX_N];
     for (uint32_t b = w_begin >> 5; b * 32u < t_end; ++b) {
         const uint32_t t0 = b * 32u;
@@ -86,10 +142,17 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
                     if (u < cnt) {
                         const uint32_t e = sx + word_of_step(Rw, P.n, q * SPG + u);
                         split_put<EB>(grp, u, e);
+                        const float2 f = __ldg(gapx + e);
+                        s1 += f.x;
+                        s0 += f.y;
                         sx = SMEM ? nxt[e] : __ldg(nxt + e);
                     }
                 }
                 E4[(unsigned long long)(t0 / SPG + q) * ntr] = grp;
+            }
+            if (((t0 + 32u) % SPLIT_SUB) == 0u || t0 + 32u >= t_end) {
+                AX[(unsigned long long)(t0 / SPLIT_SUB) * ntr] = make_float2(s1, s0);
+                s1 = s0 = 0.f;
             }
         } else {
             for (uint32_t t = 0; t < nst; ++t) {
@@ -106,25 +169,33 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
 // uniform), bit-parallel encoder, received words interleaved once per 32 steps, 16 steps per straight-line stretch.
 // grid (ceil(nch * ntr32 / SPLIT_BLOCK), segments), ntr32 = trials rounded up to a multiple of 32.
 // Needs n = 2 and a warm-up that is a multiple of 128 steps; anything else takes split_walk_kernel.
+// SMEM: NEXT and the float32 terms (replicated 2^SP.apx_rep_shift times at 8-byte pitch: one copy per lane of a half
+// warp, LDS.64 is served per half warp) sit in shared memory.
 template <bool SMEM, int EB>
 __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint4 tbm[8];
     constexpr uint32_t SPG = 16 / EB;
-    const uint32_t seg = blockIdx.y;
+    const uint32_t seg = blockIdx.y, bx = blockIdx.x;
     const DevSeg sg = P.segs[seg];
     const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
     const unsigned long long ntr = sg.trial_end - sg.trial_begin, ntr32 = (ntr + 31ull) & ~31ull;
-    if ((unsigned long long)blockIdx.x * SPLIT_BLOCK >= nch * ntr32) return;      // uniform: shorter segment
+    if ((unsigned long long)bx * SPLIT_BLOCK >= nch * ntr32) return;              // uniform: shorter segment
     const uint32_t* nxt = P.nxt;
+    const float2* gapx = SP.apxtab + (size_t)sg.table * P.SR;
+    const uint32_t as = (uint32_t)SP.apx_rep_shift, ash = as + 3u;
+    uint32_t abase = 0;
     if (SMEM) {
         uint32_t* s_nx = reinterpret_cast<uint32_t*>(smem_raw);
         for (uint32_t i = threadIdx.x; i < P.SR; i += SPLIT_BLOCK) s_nx[i] = P.nxt[i];
         nxt = s_nx;
+        float2* s_apx = reinterpret_cast<float2*>(smem_raw + SP.walk_apx_offset);
+        for (uint32_t i = threadIdx.x; i < (P.SR << as); i += SPLIT_BLOCK) s_apx[i] = gapx[i >> as];
+        abase = (uint32_t)__cvta_generic_to_shared(s_apx) + ((threadIdx.x & ((1u << as) - 1u)) << 3);
     }
     if (threadIdx.x < 32u) reinterpret_cast<uint32_t*>(tbm)[threadIdx.x] = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
     __syncthreads();
-    const unsigned long long local = (unsigned long long)blockIdx.x * SPLIT_BLOCK + threadIdx.x;
+    const unsigned long long local = (unsigned long long)bx * SPLIT_BLOCK + threadIdx.x;
     const uint32_t c = (uint32_t)(local / ntr32);
     if (c >= nch) return;                                          // whole warps (ntr32 is a multiple of 32)
     const unsigned long long tl = local % ntr32;
@@ -132,6 +203,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
     const unsigned long long trial = sg.trial_begin + tl;
     const unsigned long long wid = SP.work_begin[seg] + (unsigned long long)c * ntr + tl;
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    float2* AX = SP.apx + SP.sub_begin[seg] + tl;                  // estimate of sub-chunk s: AX[s * ntr]
     const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
     const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
@@ -139,6 +211,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
     const int m = P.m;
     uint32_t sx = 0;                                               // state 0 (exact when w_begin == 0)
+    float s1 = 0.f, s0 = 0.f;                                      // float32 estimate of the two sums over the current sub-chunk
     const uint32_t sb0 = w_begin >> 7;
     uint32_t prevU = 0;
     if (sb0 > 0u && sg.random_input) prevU = philox10(((4u * (sb0 - 1u)) << 6) | 32u, c1, c2, c3, P).w;
@@ -164,19 +237,19 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
             }
             prevU = U;
             const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1;
-            // received word of step t = bits (2t+1, 2t) of (whi:wlo); first output is the MSB
-            const uint32_t wlo = (spread16(R0 & 0xFFFFu) << 1) | spread16(R1 & 0xFFFFu);
-            const uint32_t whi = (spread16(R0 >> 16) << 1) | spread16(R1 >> 16);
+            // received word of step t = (R0 bit t, R1 bit t), first output is the MSB: two bit-selects put the pairs of the
+            // even steps into one word and those of the odd steps into another, at bits (t | 1, t & ~1) (see detect2p_kernel)
+            const uint32_t wev = bitsel(R1, R0 << 1, 0x55555555u), wod = bitsel(R1 >> 1, R0, 0x55555555u);
             if (t0 == t_begin && active) SP.spec_start[wid] = sx;
             const bool emit = t0 >= t_begin && active;
             if (valid == 32u) {
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t x = h ? whi : wlo;
+                    const uint32_t xe = wev >> (16 * h), xo = wod >> (16 * h);
                     uint32_t e[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        e[j] = sx + ((x >> (2 * j)) & 3u);
+                        e[j] = sx + ((((j & 1) ? xo : xe) >> (j & ~1)) & 3u);
                         sx = SMEM ? nxt[e[j]] : __ldg(nxt + e[j]);
                     }
                     if (emit) {
@@ -187,6 +260,17 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
                             for (int u = 0; u < (int)SPG; ++u) split_put<EB>(grp, (uint32_t)u, e[q * (int)SPG + u]);
                             E4[(unsigned long long)((t0 + 16u * (uint32_t)h) / SPG + (uint32_t)q) * ntr] = grp;
                         }
+                        float p1 = 0.f, p0 = 0.f;                   // a second pair of accumulators: two short chains instead of one
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float2 fa = split_apx<SMEM>(gapx, abase, ash, e[j]), fb = split_apx<SMEM>(gapx, abase, ash, e[j + 1]);
+                            s1 += fa.x;
+                            s0 += fa.y;
+                            p1 += fb.x;
+                            p0 += fb.y;
+                        }
+                        s1 += p1;
+                        s0 += p0;
                     }
                 }
             } else {
@@ -196,27 +280,40 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
                     const uint32_t cnt = min(SPG, nst - q * SPG);
                     for (uint32_t u = 0; u < cnt; ++u) {
                         const uint32_t t = q * SPG + u;
-                        const uint32_t r = ((t < 16u ? wlo : whi) >> (2u * (t & 15u))) & 3u;
+                        const uint32_t r = (((t & 1u) ? wod : wev) >> (t & ~1u)) & 3u;
                         const uint32_t e = sx + r;
 #pragma unroll
                         for (uint32_t z = 0; z < SPG; ++z)
                             if (z == u) split_put<EB>(grp, z, e);
+                        if (emit) {
+                            const float2 f = split_apx<SMEM>(gapx, abase, ash, e);
+                            s1 += f.x;
+                            s0 += f.y;
+                        }
                         sx = SMEM ? nxt[e] : __ldg(nxt + e);
                     }
                     if (emit) E4[(unsigned long long)(t0 / SPG + q) * ntr] = grp;
                 }
             }
         }
+        if (sb * 128u >= t_begin && active) {                       // SPLIT_SUB = 128 = one superblock
+            AX[(unsigned long long)sb * ntr] = make_float2(s1, s0);
+            s1 = s0 = 0.f;
+        }
     }
     if (active) SP.end[wid] = sx;
 }
 
-// one thread per chain: repair the chunks whose speculated start state was wrong, in order
+// ---- one warp per trial: repair the chunks whose speculated start state was wrong, then predict the binades
+__device__ __forceinline__ uint32_t split_bexp(double x) {          // biased exponent
+    return ((uint32_t)__double2hiint(x) >> 20) & 0x7FFu;
+}
+
 template <int EB>
-__global__ void __launch_bounds__(SPLIT_BLOCK) split_fix_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
+__global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
     constexpr uint32_t SPG = 16 / EB;
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= SP.nchains) return;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (q >= SP.nchains) return;                                   // whole warps
     // chain -> segment: out_offset = chains before the segment
     uint32_t lo = 0, hi = P.nsegs;
     while (hi - lo > 1) {
@@ -225,56 +322,108 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_fix_kernel(const __grid_con
     }
     const uint32_t seg = lo;
     const DevSeg sg = P.segs[seg];
-    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
+    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH, nsub = (N + SPLIT_SUB - 1u) / SPLIT_SUB;
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
     const unsigned long long tl = q - sg.out_offset;
     const unsigned long long trial = sg.trial_begin + tl;
     const unsigned long long w0 = SP.work_begin[seg] + tl;        // work item of chunk c: w0 + c * ntr
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+
+    // -- 1. the lanes compare chunk starts with the ends before them; a dirty chunk is rare and repaired by lane 0
+    uint32_t first_bad = 0xFFFFFFFFu;
+    for (uint32_t c = 1u + lane; c < nch; c += 32u)
+        if (first_bad == 0xFFFFFFFFu && __ldcg(SP.end + w0 + (unsigned long long)(c - 1u) * ntr) != __ldcg(SP.spec_start + w0 + (unsigned long long)c * ntr))
+            first_bad = c;
+    uint32_t c = __reduce_min_sync(0xFFFFFFFFu, first_bad);
     uint32_t fixed = 0;
-    for (uint32_t c = 1; c < nch; ++c) {
-        uint32_t st = SP.end[w0 + (unsigned long long)(c - 1u) * ntr], ss = SP.spec_start[w0 + (unsigned long long)c * ntr];
-        if (st == ss) continue;
-        ++fixed;
-        const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
-        uint32_t Rw[MVD_MAX_N];
-        bool merged = false;
-        for (uint32_t b = t_begin >> 5; b * 32u < t_end && !merged; ++b) {
-            const uint32_t t0 = b * 32u;
-            const uint32_t valid = min(32u, N - t0);
-            chain_block_words(P, sg, trial, b, valid, Rw);
-            const uint32_t nst = min(valid, t_end - t0);
-            for (uint32_t t = 0; t < nst; ++t) {
-                if (st == ss) {
-                    merged = true;
-                    break;
+    while (c != 0xFFFFFFFFu) {                                     // uniform
+        uint32_t carry = 0;                                        // chunk c + 1 has to be looked at again
+        if (lane == 0u) {
+            uint32_t st = __ldcg(SP.end + w0 + (unsigned long long)(c - 1u) * ntr), ss = __ldcg(SP.spec_start + w0 + (unsigned long long)c * ntr);
+            if (st != ss) {
+                ++fixed;
+                const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+                uint32_t Rw[MVD_MAX_N];
+                bool merged = false;
+                for (uint32_t b = t_begin >> 5; b * 32u < t_end && !merged; ++b) {
+                    const uint32_t t0 = b * 32u;
+                    const uint32_t valid = min(32u, N - t0);
+                    chain_block_words(P, sg, trial, b, valid, Rw);
+                    const uint32_t nst = min(valid, t_end - t0);
+                    for (uint32_t t = 0; t < nst; ++t) {
+                        if (st == ss) {
+                            merged = true;
+                            break;
+                        }
+                        const uint32_t r = word_of_step(Rw, P.n, t);
+                        unsigned char* gb = reinterpret_cast<unsigned char*>(E4 + (unsigned long long)((t0 + t) / SPG) * ntr) + ((t0 + t) % SPG) * EB;
+                        const uint32_t e = st + r;
+                        if (EB == 1) *gb = (unsigned char)e;
+                        else if (EB == 2) *reinterpret_cast<unsigned short*>(gb) = (unsigned short)e;
+                        else *reinterpret_cast<uint32_t*>(gb) = e;
+                        ss = __ldg(P.nxt + ss + r);
+                        st = __ldg(P.nxt + st + r);
+                    }
                 }
-                const uint32_t r = word_of_step(Rw, P.n, t);
-                {
-                    unsigned char* gb = reinterpret_cast<unsigned char*>(E4 + (unsigned long long)((t0 + t) / SPG) * ntr) + ((t0 + t) % SPG) * EB;
-                    const uint32_t e = st + r;
-                    if (EB == 1) *gb = (unsigned char)e;
-                    else if (EB == 2) *reinterpret_cast<unsigned short*>(gb) = (unsigned short)e;
-                    else *reinterpret_cast<uint32_t*>(gb) = e;
+                if (!merged && st != ss) {                         // the next chunk started from the wrong state too
+                    SP.end[w0 + (unsigned long long)c * ntr] = st;
+                    carry = 1u;
                 }
-                ss = __ldg(P.nxt + ss + r);
-                st = __ldg(P.nxt + st + r);
             }
         }
-        if (!merged && st != ss) SP.end[w0 + (unsigned long long)c * ntr] = st;   // the next chunk started from the wrong state too
+        __syncwarp();                                              // lane 0's stores before the other lanes' loads
+        carry = __shfl_sync(0xFFFFFFFFu, carry, 0);
+        uint32_t nextc = 0xFFFFFFFFu;
+        if (carry && c + 1u < nch) {
+            nextc = c + 1u;
+        } else {
+            // next chunk after c that the first comparison found dirty (later ones of this lane are found again here)
+            uint32_t mine = 0xFFFFFFFFu;
+            for (uint32_t cc = 1u + lane; cc < nch; cc += 32u)
+                if (cc > c && mine == 0xFFFFFFFFu && __ldcg(SP.end + w0 + (unsigned long long)(cc - 1u) * ntr) != __ldcg(SP.spec_start + w0 + (unsigned long long)cc * ntr))
+                    mine = cc;
+            nextc = __reduce_min_sync(0xFFFFFFFFu, mine);
+        }
+        c = nextc;
     }
-    if (fixed) atomicAdd(SP.ndirty, fixed);
+    if (lane == 0u && fixed) atomicAdd(SP.ndirty, fixed);
+
+    // -- 2. predicted binades: prefix sums of the float32 estimates (lanes = sub-chunks)
+    const float2* AX = SP.apx + SP.sub_begin[seg] + tl;
+    uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
+    const bool predict = SP.sequential == 0 && (__ldcg(SP.flags) & 1u) == 0u;
+    double c1 = 0.0, c0 = 0.0;                                     // magnitudes of the sums before the current 32 sub-chunks
+    for (uint32_t base = 0; base < nsub; base += 32u) {
+        const uint32_t s = base + lane;
+        float2 f = make_float2(0.f, 0.f);
+        if (s < nsub) f = __ldcg(AX + (unsigned long long)s * ntr);
+        const double own1 = -(double)f.x, own0 = -(double)f.y;
+        double x1 = own1, x0 = own0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d), y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d);
+            if ((int)lane >= d) {
+                x1 += y1;
+                x0 += y0;
+            }
+        }
+        const double e1 = c1 + x1, e0 = c0 + x0, b1 = e1 - own1, b0 = e0 - own0;   // sums after / before sub-chunk s
+        uint32_t plan = 0u;
+        if (predict && s < nsub) {
+            // the estimates are good to ~1e-5: no prediction where either sum is that close to a power of two
+            const uint32_t k1 = split_bexp(b1 * (1.0 - 1e-4)), k0 = split_bexp(b0 * (1.0 - 1e-4));
+            const bool ok = k1 == split_bexp(e1 * (1.0 + 1e-4)) && k0 == split_bexp(e0 * (1.0 + 1e-4)) && k1 >= 1023u && k1 < 1055u &&
+                            k0 >= 1023u && k0 < 1055u;
+            if (ok) plan = SPLIT_PLAN_FAST | k1 | (k0 << 11);
+        }
+        if (s < nsub) PL[(unsigned long long)s * ntr] = plan;
+        c1 = __shfl_sync(0xFFFFFFFFu, e1, 31);
+        c0 = __shfl_sync(0xFFFFFFFFu, e0, 31);
+    }
 }
 
-// one thread per chain: the two sums of log_prob_sequence in step order, decision, tallies
-// grid (chunks of blockDim.x chains, segments); blockDim.x <= SPLIT_BLOCK is chosen by the host so that a few
-// thousand chains still spread over all SMs.
-// SMEM: the {log P1, log Tref} rows of the segment's table are staged in shared memory, replicated
-// 2^SP.ll_rep_shift times at 16-byte pitch (one copy per lane of a quarter warp, as in mvd_detect2.cuh) so that
-// the random row reads of a warp are bank-conflict free; read with ld.shared (a generic pointer that may be
-// shared or global costs a slower LD per step).
-#define SPLIT_RING 32u                 // 16-byte groups of the edge stream in flight per scoring thread
-
+// ---- log-likelihood rows in shared memory, replicated 2^rs times at 16-byte pitch (one copy per lane of a quarter warp: the
+// random row reads of a warp are bank-conflict free), read with ld.shared (a generic pointer costs a slower LD per step)
 template <bool SMEM>
 __device__ __forceinline__ double2 split_ll(const double2* g, uint32_t sbase, uint32_t sh, uint32_t e) {
     if (SMEM) {
@@ -285,10 +434,117 @@ __device__ __forceinline__ double2 split_ll(const double2* g, uint32_t sbase, ui
     return __ldg(g + e);
 }
 
+template <bool SMEM>
+__device__ __forceinline__ uint2 split_tie(const uint2* g, uint32_t tbase, uint32_t sh, uint32_t e) {
+    if (SMEM) {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(tbase + (e << sh)));
+        return v;
+    }
+    return __ldg(g + e);
+}
+
+// ---- one thread per (trial, chunk): the recurrence of every predicted sub-chunk from -2^k
+// grid (ceil(chunks * trials / SPLIT_IBLOCK), segments)
+#define SPLIT_IBLOCK 256
+
+template <bool SMEM, int EB>
+__global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t SPG = 16 / EB;
+    const uint32_t seg = blockIdx.y;
+    const DevSeg sg = P.segs[seg];
+    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
+    const unsigned long long ntr = sg.trial_end - sg.trial_begin;
+    if ((unsigned long long)blockIdx.x * SPLIT_IBLOCK >= nch * ntr) return;       // uniform: shorter segment
+    const double2* ll = P.ll + (size_t)sg.table * P.SR;
+    const uint2* tie = SP.tietab + (size_t)sg.table * P.SR;
+    const uint32_t rs = (uint32_t)SP.ll_rep_shift, sh = rs + 4u, ts = rs ? rs + 1u : 0u, tsh = ts + 3u;
+    uint32_t sbase = 0, tbase = 0;
+    if (SMEM) {
+        double2* s_ll = reinterpret_cast<double2*>(smem_raw);
+        uint2* s_tie = reinterpret_cast<uint2*>(smem_raw + SP.isum_tie_offset);
+        for (uint32_t i = threadIdx.x; i < (P.SR << rs); i += SPLIT_IBLOCK) s_ll[i] = ll[i >> rs];
+        for (uint32_t i = threadIdx.x; i < (P.SR << ts); i += SPLIT_IBLOCK) s_tie[i] = tie[i >> ts];
+        __syncthreads();
+        sbase = (uint32_t)__cvta_generic_to_shared(s_ll) + ((threadIdx.x & ((1u << rs) - 1u)) << 4);
+        tbase = (uint32_t)__cvta_generic_to_shared(s_tie) + ((threadIdx.x & ((1u << ts) - 1u)) << 3);
+    }
+    const unsigned long long local = (unsigned long long)blockIdx.x * SPLIT_IBLOCK + threadIdx.x;
+    if (local >= nch * ntr) return;
+    const uint32_t c = (uint32_t)(local / ntr);
+    const unsigned long long tl = local % ntr;
+    const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    const uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
+    double2* RS = SP.res + SP.sub_begin[seg] + tl;
+#pragma unroll 1
+    for (uint32_t j = 0; j < SPLIT_CH / SPLIT_SUB; ++j) {
+        const uint32_t s = c * (SPLIT_CH / SPLIT_SUB) + j, t0 = s * SPLIT_SUB;
+        if (t0 >= N) break;
+        const uint32_t plan = __ldcg(PL + (unsigned long long)s * ntr);
+        if (!(plan & SPLIT_PLAN_FAST)) continue;
+        const uint32_t k1 = plan & 0x7FFu, k0 = (plan >> 11) & 0x7FFu;
+        const double m1 = __hiloint2double((int)(0x80000000u | (k1 << 20)), 0), m0 = __hiloint2double((int)(0x80000000u | (k0 << 20)), 0);   // -2^k
+        double r1 = m1, r0 = m0;
+        uint32_t tm1 = 0u, tm0 = 0u;
+        const uint32_t ns = min(SPLIT_SUB, N - t0), g0 = t0 / SPG, ng = ns / SPG, rem = ns - ng * SPG;
+        uint4 grp = make_uint4(0u, 0u, 0u, 0u);
+        if (ng) grp = __ldcg(E4 + (unsigned long long)g0 * ntr);
+#pragma unroll 1
+        for (uint32_t g = 0; g < ng; ++g) {
+            const uint4 cur = grp;
+            if (g + 1u < ng || rem) grp = __ldcg(E4 + (unsigned long long)(g0 + g + 1u) * ntr);
+#pragma unroll
+            for (uint32_t u = 0; u < SPG; ++u) {
+                const uint32_t e = split_get<EB>(cur, u);
+                const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
+                const uint2 t = split_tie<SMEM>(tie, tbase, tsh, e);
+                r1 += v.x;
+                r0 += v.y;
+                tm1 |= t.x;
+                tm0 |= t.y;
+            }
+        }
+        if (rem) {
+            if (!ng) grp = __ldcg(E4 + (unsigned long long)g0 * ntr);
+            for (uint32_t u = 0; u < rem; ++u) {
+                uint32_t e = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < SPG; ++w)
+                    if (w == u) e = split_get<EB>(grp, w);
+                const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
+                const uint2 t = split_tie<SMEM>(tie, tbase, tsh, e);
+                r1 += v.x;
+                r0 += v.y;
+                tm1 |= t.x;
+                tm0 |= t.y;
+            }
+        }
+        // what the sub-chunk adds: r_end + 2^k (exact when the recurrence stayed in its binade); a tie term voids it
+        double S1 = r1 - m1, S0 = r0 - m0;
+        if ((tm1 >> (k1 - 1023u)) & 1u) S1 = __longlong_as_double(0x7FF8000000000000ll);
+        if ((tm0 >> (k0 - 1023u)) & 1u) S0 = __longlong_as_double(0x7FF8000000000000ll);
+        RS[(unsigned long long)s * ntr] = make_double2(S1, S0);
+    }
+}
+
+// ---- one thread per trial: the two sums of log_prob_sequence (Pd_plotter.py:114-115), decision, tallies
+// grid (chunks of blockDim.x chains, segments); blockDim.x <= SPLIT_BLOCK is chosen by the host so that a few
+// thousand chains still spread over all SMs.
+// The sub-chunk records {plan, partial sums} come through a per-thread shared-memory ring (cp.async, one batch of
+// SPLIT_RB records ahead).  A thread runs through the records whose partial sums apply; at the first one that does not it
+// waits for the other lanes of its warp to reach theirs, and the warp adds those sub-chunks term by term TOGETHER (one
+// piece of code, one call site: lanes whose binade crossings fall into different sub-chunks of a batch still share the
+// pass -- per batch the warp pays for the most crossings of any lane, not for the union over its lanes).
+#define SPLIT_RB ((uint32_t)SPLIT_RB_HOST)   // records per batch
+
 template <bool SMEM, int EB>
 __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t SPG = 16 / EB;
+    constexpr uint32_t UR = SPG < 8u ? SPG : 8u;                   // rows per pipeline unit of the term-by-term pass
+    constexpr uint32_t UPG = SPG / UR;                             // units per 16-byte group
+    constexpr uint32_t GPS = SPLIT_SUB / SPG;                      // groups per full sub-chunk
     const uint32_t seg = blockIdx.y;
     const DevSeg sg = P.segs[seg];
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
@@ -303,59 +559,123 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
         sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + ((threadIdx.x & ((1u << rs) - 1u)) << 4);
     }
     const unsigned long long tl = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tl >= ntr) return;
+    const bool active = tl < ntr;                                  // idle lanes of the last warp stay for the votes
     const uint32_t q = (uint32_t)(sg.out_offset + tl);
-    const uint32_t N = sg.N;
+    const uint32_t N = sg.N, nsub = (N + SPLIT_SUB - 1u) / SPLIT_SUB, nbatch = (nsub + SPLIT_RB - 1u) / SPLIT_RB;
     const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
+    const uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
+    const double2* RS = SP.res + SP.sub_begin[seg] + tl;
+    // ring: [2 halves][SPLIT_RB slots][blockDim.x threads] partial sums (16 B), then the plan words (4 B)
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + SP.score_ring_offset;
+    const uint32_t rres = ring + threadIdx.x * 16u, rplan = ring + 2u * SPLIT_RB * blockDim.x * 16u + threadIdx.x * 4u;
+    auto fetch = [&](uint32_t b) {                                 // batch b -> half b & 1
+        if (active && b < nbatch) {
+            const uint32_t half = (b & 1u) * SPLIT_RB;
+#pragma unroll 4
+            for (uint32_t j = 0; j < SPLIT_RB; ++j) {
+                const uint32_t s = b * SPLIT_RB + j;
+                if (s < nsub) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rplan + (half + j) * blockDim.x * 4u), "l"(PL + (unsigned long long)s * ntr));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rres + (half + j) * blockDim.x * 16u), "l"(RS + (unsigned long long)s * ntr));
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
     double a1 = 0.0, a0 = 0.0;
-    // The adds are one dependent chain per sum (Pd_plotter.py:114-115 in step order): all that can overlap are the
-    // loads.  With one warp per SM a load sees the whole DRAM latency (~2 000 cycles = 13 groups at 9.5 cycles per
-    // step; measured: every group cost ~200 cycles of stall with a 12-deep register ring), so the edge stream goes
-    // through an asynchronous shared-memory ring of SPLIT_RING groups per thread (cp.async), refilled as it is consumed.
-    const uint32_t ngroups = N / SPG;
-    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(smem_raw) + SP.ring_offset + threadIdx.x * 16u;
-    const uint32_t rstride = blockDim.x * 16u;                    // slot s of this thread: ring0 + s * rstride
-#pragma unroll 1
-    for (uint32_t i = 0; i < SPLIT_RING; ++i) {
-        if (i < ngroups)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + i * rstride), "l"(E4 + (unsigned long long)i * ntr));
-        asm volatile("cp.async.commit_group;");
-    }
-    uint32_t slot = 0;
-#pragma unroll 1
-    for (uint32_t g = 0; g < ngroups; ++g) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(SPLIT_RING - 1));
-        uint4 grp;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(grp.x), "=r"(grp.y), "=r"(grp.z), "=r"(grp.w) : "r"(ring0 + slot * rstride));
-        double2 v[SPG];
+    uint32_t nseq = 0;                                             // sub-chunks added term by term (performance counter)
+    auto rows = [&](const uint4& g, uint32_t unit, double2 (&v)[UR]) {
 #pragma unroll
-        for (uint32_t u = 0; u < SPG; ++u) v[u] = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(grp, u));
-        if (g + SPLIT_RING < ngroups)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + slot * rstride), "l"(E4 + (unsigned long long)(g + SPLIT_RING) * ntr));
-        asm volatile("cp.async.commit_group;");
-        slot = slot + 1u == SPLIT_RING ? 0u : slot + 1u;
+        for (uint32_t u = 0; u < UR; ++u) v[u] = split_ll<SMEM>(ll, sbase, sh, split_get<EB>(g, unit * UR + u));
+    };
+    auto adds = [&](const double2 (&v)[UR]) {
 #pragma unroll
-        for (uint32_t u = 0; u < SPG; ++u) {
+        for (uint32_t u = 0; u < UR; ++u) {
             a1 += v[u].x;
             a0 += v[u].y;
         }
-    }
-    if (ngroups * SPG < N) {
-        const uint4 grp = __ldcs(E4 + (unsigned long long)ngroups * ntr);
-        for (uint32_t u = 0; u < N - ngroups * SPG; ++u) {
-            uint32_t e = 0;
+    };
+    fetch(0);
+#pragma unroll 1
+    for (uint32_t b = 0; b < nbatch; ++b) {
+        fetch(b + 1u);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const uint32_t half = (b & 1u) * SPLIT_RB;
+        const uint32_t cnt = active ? min(SPLIT_RB, nsub - b * SPLIT_RB) : 0u;
+        uint32_t j = 0;
+#pragma unroll 1
+        while (true) {
+            // the records whose partial sums apply: both sums in the predicted binade before and after
+#pragma unroll 1
+            while (j < cnt) {
+                uint32_t plan;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(plan) : "r"(rplan + (half + j) * blockDim.x * 4u));
+                if (!(plan & SPLIT_PLAN_FAST)) break;
+                double2 r;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(rres + (half + j) * blockDim.x * 16u));
+                const uint32_t k1 = plan & 0x7FFu, k0 = (plan >> 11) & 0x7FFu;
+                const double n1 = a1 + r.x, n0 = a0 + r.y;
+                if (!(split_bexp(a1) == k1 && split_bexp(n1) == k1 && split_bexp(a0) == k0 && split_bexp(n0) == k0)) break;
+                a1 = n1;
+                a0 = n0;
+                ++j;
+            }
+            const bool need = j < cnt;
+            if (!__any_sync(0xFFFFFFFFu, need)) break;
+            if (need) {
+                // sub-chunk s term by term, in step order
+                const uint32_t s = b * SPLIT_RB + j;
+                ++j;
+                ++nseq;
+                const uint32_t t0 = s * SPLIT_SUB, ns = min(SPLIT_SUB, N - t0), g0 = t0 / SPG;
+                if (ns == SPLIT_SUB) {
+                    // groups in batches of 8 loads; the rows of unit x + 1 are read while the terms of unit x are added
+#pragma unroll 1
+                    for (uint32_t gb = 0; gb < GPS; gb += 8u) {
+                        uint4 G[8];
 #pragma unroll
-            for (uint32_t w = 0; w < SPG; ++w)
-                if (w == u) e = split_get<EB>(grp, w);
-            const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
-            a1 += v.x;
-            a0 += v.y;
+                        for (uint32_t i = 0; i < 8u; ++i)
+                            if (i < GPS) G[i] = __ldcg(E4 + (unsigned long long)(g0 + gb + i) * ntr);
+                        constexpr uint32_t NU = (GPS < 8u ? GPS : 8u) * UPG;
+                        double2 va[UR], vb[UR];
+                        rows(G[0], 0u, va);
+#pragma unroll
+                        for (uint32_t x = 0; x < NU; x += 2u) {
+                            if (x + 1u < NU) rows(G[(x + 1u) / UPG], (x + 1u) % UPG, vb);
+                            adds(va);
+                            if (x + 2u < NU) rows(G[(x + 2u) / UPG], (x + 2u) % UPG, va);
+                            if (x + 1u < NU) adds(vb);
+                        }
+                    }
+                } else {
+                    // the ragged last sub-chunk of a trial
+                    const uint32_t ngall = (ns + SPG - 1u) / SPG;
+#pragma unroll 1
+                    for (uint32_t g = 0; g < ngall; ++g) {
+                        const uint4 grp = __ldcg(E4 + (unsigned long long)(g0 + g) * ntr);
+                        const uint32_t c2 = min(SPG, ns - g * SPG);
+#pragma unroll 1
+                        for (uint32_t u = 0; u < c2; ++u) {
+                            uint32_t e = 0;
+#pragma unroll
+                            for (uint32_t w = 0; w < SPG; ++w)
+                                if (w == u) e = split_get<EB>(grp, w);
+                            const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
+                            a1 += v.x;
+                            a0 += v.y;
+                        }
+                    }
+                }
+            }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!active) return;
     const bool win = sg.decide == 0 ? (a1 > a0) : (a1 <= a0);                    // Pd_plotter.py:215 / :222
     if (win) {
         atomicAdd(P.tallies + seg, 1ull);
         if (P.tallies2) atomicAdd(P.tallies2 + seg, 1ull);
     }
     if (P.logp) reinterpret_cast<double2*>(P.logp)[q] = make_double2(a1, a0);
+    if (nseq) atomicAdd(SP.nseq, (unsigned long long)nseq);
 }

@@ -23,58 +23,75 @@ cudaError_t mvd_launch_learn(bool smem_tables, size_t lsmem, uint32_t nsegs, cud
 // ---- detection trials split along the time axis (mvd_split.cuh)
 #include "mvd_split.cuh"
 
+cudaError_t mvd_launch_split_tables(const double2* ll, size_t cells, uint2* tie, float2* apx, uint32_t* flags, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(flags, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    split_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ll, cells, tie, apx, flags);
+    return cudaGetLastError();
+}
+
 namespace {
+template <class K>
+cudaError_t with_smem(K kern, size_t bytes) {
+    return bytes ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+}
+
 template <int EB>
-cudaError_t launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
-                         const SplitParams& SP) {
+cudaError_t launch_split(size_t walk_bytes, size_t isum_bytes, size_t score_bytes, cudaStream_t st, const Params& P, const SplitParams& SP) {
     const unsigned wblocks = (unsigned)((SP.nwork + SPLIT_BLOCK - 1) / SPLIT_BLOCK);
     const unsigned cb = SP.chain_block;
-    const unsigned cblocks = (SP.nchains + cb - 1) / cb;
     cudaError_t e;
+    // 1. walk: one thread per (trial, chunk)
     if (SP.fast_walk) {                                  // n = 2, warm-up a multiple of 128: the fast walk
-        unsigned long long mx = 0;
-        mx = ((SP.max_chunks * ((SP.max_trials + 31ull) & ~31ull)) + SPLIT_BLOCK - 1) / SPLIT_BLOCK;
+        const unsigned long long mx = ((SP.max_chunks * ((SP.max_trials + 31ull) & ~31ull)) + SPLIT_BLOCK - 1) / SPLIT_BLOCK;
         const dim3 wgrid((unsigned)mx, P.nsegs);
-        if (nxt_smem) {
+        if (SP.nxt_in_smem) {
             auto kern = split_walk2_kernel<true, EB>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nxt_bytes);
-            if (e != cudaSuccess) return e;
-            kern<<<wgrid, SPLIT_BLOCK, nxt_bytes, st>>>(P, SP);
+            if ((e = with_smem(kern, walk_bytes)) != cudaSuccess) return e;
+            kern<<<wgrid, SPLIT_BLOCK, walk_bytes, st>>>(P, SP);
         } else {
             split_walk2_kernel<false, EB><<<wgrid, SPLIT_BLOCK, 0, st>>>(P, SP);
         }
-    } else if (nxt_smem) {
+    } else if (SP.nxt_in_smem) {
         auto kern = split_walk_kernel<true, EB>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nxt_bytes);
-        if (e != cudaSuccess) return e;
-        kern<<<wblocks, SPLIT_BLOCK, nxt_bytes, st>>>(P, SP);
+        if ((e = with_smem(kern, walk_bytes)) != cudaSuccess) return e;
+        kern<<<wblocks, SPLIT_BLOCK, walk_bytes, st>>>(P, SP);
     } else {
         split_walk_kernel<false, EB><<<wblocks, SPLIT_BLOCK, 0, st>>>(P, SP);
     }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    split_fix_kernel<EB><<<cblocks, cb, 0, st>>>(P, SP);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // 2. repair + predictions: one warp per trial
+    split_plan_kernel<EB><<<(SP.nchains + (SPLIT_BLOCK / 32) - 1) / (SPLIT_BLOCK / 32), SPLIT_BLOCK, 0, st>>>(P, SP);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // 3. re-associated partial sums: one thread per (trial, chunk)
+    if (!SP.sequential) {
+        const dim3 igrid((unsigned)((SP.max_chunks * SP.max_trials + SPLIT_IBLOCK - 1) / SPLIT_IBLOCK), P.nsegs);
+        if (SP.ll_in_smem) {
+            auto kern = split_isum_kernel<true, EB>;
+            if ((e = with_smem(kern, isum_bytes)) != cudaSuccess) return e;
+            kern<<<igrid, SPLIT_IBLOCK, isum_bytes, st>>>(P, SP);
+        } else {
+            split_isum_kernel<false, EB><<<igrid, SPLIT_IBLOCK, 0, st>>>(P, SP);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    // 4. the sums in order, decisions: one thread per trial
     const dim3 sgrid((unsigned)((SP.max_trials + cb - 1) / cb), P.nsegs);
-    const size_t ring_bytes = (size_t)cb * 16 * 32;      // SPLIT_RING groups of 16 bytes per thread
-    const size_t sbytes = (size_t)SP.ring_offset + ring_bytes;
-    if (ll_smem) {
+    if (SP.ll_in_smem) {
         auto kern = split_score_kernel<true, EB>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
-        if (e != cudaSuccess) return e;
-        kern<<<sgrid, cb, sbytes, st>>>(P, SP);
+        if ((e = with_smem(kern, score_bytes)) != cudaSuccess) return e;
+        kern<<<sgrid, cb, score_bytes, st>>>(P, SP);
     } else {
         auto kern = split_score_kernel<false, EB>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
-        if (e != cudaSuccess) return e;
-        kern<<<sgrid, cb, sbytes, st>>>(P, SP);
+        if ((e = with_smem(kern, score_bytes)) != cudaSuccess) return e;
+        kern<<<sgrid, cb, score_bytes, st>>>(P, SP);
     }
     return cudaGetLastError();
 }
 }  // namespace
 
-cudaError_t mvd_launch_split(bool nxt_smem, size_t nxt_bytes, bool ll_smem, size_t ll_bytes, cudaStream_t st, const Params& P,
-                             const SplitParams& SP) {
-    if (SP.edge_bytes == 1) return launch_split<1>(nxt_smem, nxt_bytes, ll_smem, ll_bytes, st, P, SP);
-    if (SP.edge_bytes == 2) return launch_split<2>(nxt_smem, nxt_bytes, ll_smem, ll_bytes, st, P, SP);
-    return launch_split<4>(nxt_smem, nxt_bytes, ll_smem, ll_bytes, st, P, SP);
+cudaError_t mvd_launch_split(size_t walk_bytes, size_t isum_bytes, size_t score_bytes, cudaStream_t st, const Params& P, const SplitParams& SP) {
+    if (SP.edge_bytes == 1) return launch_split<1>(walk_bytes, isum_bytes, score_bytes, st, P, SP);
+    if (SP.edge_bytes == 2) return launch_split<2>(walk_bytes, isum_bytes, score_bytes, st, P, SP);
+    return launch_split<4>(walk_bytes, isum_bytes, score_bytes, st, P, SP);
 }

@@ -99,8 +99,10 @@ struct LearnParams {
 };
 
 // ---- detection trials split along the time axis (mvd_split.cuh)
-#define SPLIT_CH 512u
+#define SPLIT_CH 512u                       // steps per chunk (one walker thread)
+#define SPLIT_SUB 128u                      // steps per sub-chunk (one prediction / one re-associated partial sum)
 #define SPLIT_BLOCK 128
+#define SPLIT_RB_HOST 16                    // = SPLIT_RB of mvd_split.cuh: sub-chunk records per batch of the scoring kernel's ring
 
 struct SplitParams {
     uint32_t warm;                          // warm-up steps (multiple of 32)
@@ -108,17 +110,29 @@ struct SplitParams {
     unsigned long long nwork;               // (chain, chunk) pairs
     const unsigned long long* work_begin;   // [nsegs + 1] first work item of a segment (items: chunk-major, trial-minor)
     const unsigned long long* edge_begin;   // [nsegs] first 32-bit word of a segment's 16-byte edge groups
+    const unsigned long long* sub_begin;    // [nsegs] first sub-chunk record of a segment (records: sub-chunk-major, trial-minor)
     uint32_t* spec_start;                   // [nwork] state * R at the chunk start (speculated)
     uint32_t* end;                          // [nwork] state * R at the chunk end
     uint32_t* edges;
     uint32_t* ndirty;                       // [1] chunks repaired (performance counter)
+    unsigned long long* nseq;               // [1] sub-chunks whose terms were added one by one (performance counter)
+    float2* apx;                            // [sub-chunk records] float32 estimate of the two sums over the sub-chunk
+    uint32_t* plan;                         // [sub-chunk records] predicted binades (SPLIT_PLAN_FAST | k1 | k0 << 11) or 0
+    double2* res;                           // [sub-chunk records] what the sub-chunk adds to each sum inside the predicted binade
+    const float2* apxtab;                   // [ntables][SR] {log P1, log Tref} in float32
+    const uint2* tietab;                    // [ntables][SR] binades in which the two terms are round-half-even ties
+    const uint32_t* flags;                  // [1] bit 0: some term is positive / not a number (no predictions)
+    int sequential;                         // 1 = no predictions: every term added one by one (MVD_OPT_SPLIT_SEQUENTIAL)
     int nxt_in_smem, ll_in_smem;
     int ll_rep_shift;                       // log2 copies of a log-likelihood row in shared memory (0 or 3)
-    uint32_t chain_block;                   // threads per block of the per-chain kernels (fix, score)
+    int apx_rep_shift;                      // log2 copies of a float32 row in the fast walk's shared memory (0 or 4)
+    uint32_t walk_apx_offset;               // fast walk: byte offset of the float32 rows in dynamic shared memory
+    uint32_t isum_tie_offset;               // split_isum_kernel: byte offset of the tie rows in dynamic shared memory
+    uint32_t score_ring_offset;             // split_score_kernel: byte offset of the record ring in dynamic shared memory
+    uint32_t chain_block;                   // threads per block of the scoring kernel
     unsigned long long max_trials;          // most trials of any segment (x extent of the scoring grid)
     int edge_bytes;                         // bytes per stored edge index: 1 (S R <= 256), 2 (<= 65 536) or 4
     int fast_walk;                          // 1: split_walk2_kernel (n = 2, warm-up a multiple of 128)
-    uint32_t ring_offset;                   // scoring kernel: byte offset of the cp.async ring in dynamic shared memory
     unsigned long long max_chunks;          // most chunks of any segment
 };
 

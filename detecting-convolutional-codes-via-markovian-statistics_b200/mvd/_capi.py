@@ -25,6 +25,7 @@ OPT_NO_FSM1 = 4
 OPT_SPLIT = 5
 OPT_NO_ANTIPODAL = 6
 OPT_ASYNC_DETECT = 7
+OPT_SPLIT_SEQUENTIAL = 8
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 
@@ -34,7 +35,7 @@ EXPORTS = (
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
     "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table", "mvd_acs_final",
-    "mvd_copy_stats", "mvd_async_stats", "mvd_host_p1_edge_tables",
+    "mvd_copy_stats", "mvd_async_stats", "mvd_host_p1_edge_tables", "mvd_split_stats",
 )
 
 
@@ -123,6 +124,7 @@ def load():
     lib.mvd_set_option.argtypes = [vp, i32, C.c_int64]
     lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]
     lib.mvd_learn_stats.argtypes = [vp, P(u32)]
+    lib.mvd_split_stats.argtypes = [vp, P(u64), P(u64)]
     lib.mvd_device_info.argtypes = [vp, P(i32), P(i32), P(u64), C.c_char_p, i32]
     for name in EXPORTS:
         getattr(lib, name)            # AttributeError here = header / library mismatch

@@ -322,6 +322,17 @@ class Detector:
         self._ck(self.lib.mvd_launch_count(self.ctx, C.byref(v)))
         return int(v.value)
 
+    def split_sequential(self, on: bool = True):
+        """Split path: add every log-likelihood term one by one in step order (``MVD_OPT_SPLIT_SEQUENTIAL``) instead of
+        re-associating the float64 additions inside a binade -- identical results, the check of the re-association."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT_SEQUENTIAL, 1 if on else 0))
+
+    def split_stats(self):
+        """(sub-chunks of the last split launch, sub-chunks whose terms were added one by one)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.mvd_split_stats(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def async_detect(self, on: bool = True):
         """``detect(..., d_tallies_ptr=..., host_tallies=False)`` calls only queue their work (``MVD_OPT_ASYNC_DETECT``);
         :meth:`synchronize` waits for them.  Switching it off drains what is in flight."""

@@ -236,7 +236,8 @@ int mvd_async_stats(mvd_ctx* ctx, double* kernel_ms_sum, uint64_t* launches);
  * + 256 if the two-trials-per-thread kernel ran, + 512 if the tables stayed in global memory (large S);
  * 1024 = chunk-parallel learning chain, 2048 = GPU state enumeration, 4096 = Chernoff spectral radius, 8192 = parity-template trials,
  * 32768 = mvd_acs_final,
- * 16384 = detection trials split along the time axis (mvd_learn_stats then gives the chunks repaired).
+ * 16384 = detection trials split along the time axis (mvd_learn_stats then gives the chunks repaired, mvd_split_stats the
+ * share of the float64 additions that were re-associated).
  * mvd_learn_stats: chunks of the last chunk-parallel learning call whose speculated start state was
  * wrong and had to be repaired (results are exact either way; this is a performance counter). */
 enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one trial per thread, 2 = two per thread
@@ -249,16 +250,23 @@ enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one t
        MVD_OPT_NO_ANTIPODAL = 6,   /* 1 = the two-trials-per-thread m = 2 kernel reads the general branch-metric table even
                                       when every decoder generator has its first and last tap set (the complement-label
                                       short cut; identical results) */
-       MVD_OPT_ASYNC_DETECT = 7 }; /* 1 = mvd_detect calls that ask for device tallies only (tallies == NULL, logp == NULL,
+       MVD_OPT_ASYNC_DETECT = 7, /* 1 = mvd_detect calls that ask for device tallies only (tallies == NULL, logp == NULL,
                                       d_tallies != NULL) return as soon as their work is queued on the context's stream;
                                       mvd_synchronize (or any call that reads results, or setting the option back to 0)
                                       waits for them and reports a KeyError of any of them.  At most 64 are kept in
                                       flight.  The segment records and tally words of a sweep stay on the device, so a
                                       loop of sweeps needs no host round trip between them (Pd_plotter.py:210-223
                                       repeated; bench.py's resident leg) */
+       MVD_OPT_SPLIT_SEQUENTIAL = 8 };/* 1 = the split path adds every log-likelihood term one by one in step order instead of
+                                      re-associating the additions inside a binade (identical results; the check of that) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);
+/* Split path (few long trials, kind 16384; Pd_plotter.py:106-116 for N = 10^4 .. 10^5): the two float64 sums of a trial are formed
+ * from partial sums over 128-step sub-chunks wherever the running sum provably stays inside one binade (bit-identical to the
+ * step-by-step additions, see csrc/mvd_split.cuh) and term by term elsewhere.  subchunks = sub-chunks of the last split launch,
+ * sequential = those added term by term (performance counters). */
+int mvd_split_stats(mvd_ctx* ctx, uint64_t* subchunks, uint64_t* sequential);
 
 /* Integer roofline denominators, measured on this device (32-bit lane-ops/s over all SMs):
  * alu_gops     -- dependent-free LOP3 chains: the ALU pipe alone (min/shift/logic/permute issue only there);
