@@ -56,6 +56,7 @@ struct mvd_ctx {
     bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false, no_antipodal = false;
     int split_mode = 0;             // 0 = automatic, 1 = always split long trials along the time axis, 2 = never
     bool split_sequential = false;  // MVD_OPT_SPLIT_SEQUENTIAL: the split path adds every term one by one (no re-association)
+    uint32_t split_chunk = 0;       // MVD_OPT_SPLIT_CHUNK: 0 = automatic, else 256 / 512 / 1024 steps per chunk
     bool split_tables_ready = false;// tie binades / float32 terms of the current log-likelihood tables are on the device
     unsigned long long last_split_sub = 0, last_split_seq = 0;   // sub-chunks of the last split launch / of them added term by term
     bool have_gfsm1 = false;
@@ -99,7 +100,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot, d_sapx, d_splan, d_sres, d_stie, d_sapxtab, d_sflags;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot, d_sapx, d_splan, d_sres, d_stie, d_sapxtab, d_sflags, d_stiek;
 };
 
 namespace {
@@ -834,7 +835,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             if (ds[i].N == 0) split = false;
             steps += ntr * ds[i].N;
             ew += ntr * (((unsigned long long)ds[i].N + 3ull) & ~3ull);
-            work += ntr * (((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
+            work += ntr * (((unsigned long long)ds[i].N + 255ull) / 256ull);      // chunks at the smallest chunk size
         }
         split = split && ew * 4ull <= (6ull << 30) && work <= 0x7FFFFFFFull * (unsigned long long)SPLIT_BLOCK;
         if (ctx->split_mode == 0) {
@@ -845,7 +846,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             for (uint32_t i = 0; i < nsegs; ++i) maxN = std::max(maxN, ds[i].N);
             const double t_plain = std::max((double)maxN * 63e-9, (double)steps / 1.0e12);
             const double t_split = (double)steps / 7.5e11 + (double)maxN * 12.5e-9 + 15e-6;
-            split = split && maxN >= 4u * SPLIT_CH && t_split < 0.8 * t_plain;
+            split = split && maxN >= 2048u && t_split < 0.8 * t_plain;
         }
     }
     const dim3 grid((unsigned)blocks);
@@ -894,6 +895,15 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         // in step order (mvd_split.cuh)
         std::vector<unsigned long long> meta(3 * (size_t)nsegs + 1);
         unsigned long long w = 0, ew = 0, subs = 0;
+        // steps per chunk: the largest of 1024 / 512 / 256 that still gives the walk 1.5 x the threads the GPU holds at
+        // 64 registers (the warm-up before every chunk is overhead: 128 steps per chunk)
+        uint32_t chunk = SPLIT_CH_MAX;
+        for (; chunk > 256u; chunk >>= 1) {
+            unsigned long long items = 0;
+            for (uint32_t i = 0; i < nsegs; ++i) items += (ds[i].trial_end - ds[i].trial_begin) * (((unsigned long long)ds[i].N + chunk - 1ull) / chunk);
+            if (items * 2ull >= 3ull * 1024ull * sms) break;
+        }
+        if (ctx->split_chunk) chunk = ctx->split_chunk;
         const int eb = SR <= 256u ? 1 : (SR <= 65536u ? 2 : 4);
         const unsigned long long spg = 16 / eb;
         for (uint32_t i = 0; i < nsegs; ++i) {
@@ -901,7 +911,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             meta[i] = w;
             meta[nsegs + 1 + i] = ew;
             meta[2 * (size_t)nsegs + 1 + i] = subs;
-            w += ntr * (((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
+            w += ntr * (((unsigned long long)ds[i].N + chunk - 1ull) / chunk);
             ew += ntr * (((unsigned long long)ds[i].N + spg - 1) / spg) * 4ull;      // 16-byte groups, in 32-bit words
             subs += ntr * (((unsigned long long)ds[i].N + SPLIT_SUB - 1ull) / SPLIT_SUB);
         }
@@ -909,7 +919,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         SplitParams SP{};
         SP.edge_bytes = eb;
         SP.fast_walk = (n == 2 && ctx->learn_warm % 128u == 0u) ? 1 : 0;
-        for (uint32_t i = 0; i < nsegs; ++i) SP.max_chunks = std::max<unsigned long long>(SP.max_chunks, ((unsigned long long)ds[i].N + SPLIT_CH - 1ull) / SPLIT_CH);
+        SP.chunk = chunk;
+        for (uint32_t i = 0; i < nsegs; ++i) SP.max_chunks = std::max<unsigned long long>(SP.max_chunks, ((unsigned long long)ds[i].N + chunk - 1ull) / chunk);
         for (uint32_t i = 0; i < nsegs; ++i) SP.max_trials = std::max<unsigned long long>(SP.max_trials, ds[i].trial_end - ds[i].trial_begin);
         if (nsegs > 65535) return fail(ctx, MVD_E_INVALID, "too many segments for one call");
         SP.warm = ctx->learn_warm;
@@ -933,10 +944,11 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         CK(ctx->d_sflags.reserve(16));                          // [0] flags (u32), [8] sub-chunks added term by term (u64)
         if (!ctx->split_tables_ready) {
             const size_t cells = (size_t)SR * ctx->ntables;
-            CK(ctx->d_stie.reserve(cells * 8));
+            CK(ctx->d_stie.reserve(cells * 4));
             CK(ctx->d_sapxtab.reserve(cells * 8));
-            CK(mvd_launch_split_tables(ctx->d_ll.as<double2>(), cells, ctx->d_stie.as<uint2>(), ctx->d_sapxtab.as<float2>(),
-                                       ctx->d_sflags.as<uint32_t>(), ctx->stream));
+            CK(ctx->d_stiek.reserve(16 * (size_t)ctx->ntables));
+            CK(mvd_launch_split_tables(ctx->d_ll.as<double2>(), (uint32_t)SR, ctx->ntables, ctx->d_stie.as<uint32_t>(), ctx->d_sapxtab.as<float2>(),
+                                       ctx->d_sflags.as<uint32_t>(), ctx->d_stiek.as<unsigned long long>(), ctx->stream));
             ctx->launches += 1;
             ctx->split_tables_ready = true;
         }
@@ -948,15 +960,16 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         SP.apx = ctx->d_sapx.as<float2>();
         SP.plan = ctx->d_splan.as<uint32_t>();
         SP.res = ctx->d_sres.as<double2>();
-        SP.tietab = ctx->d_stie.as<uint2>();
+        SP.tietab = ctx->d_stie.as<uint32_t>();
         SP.apxtab = ctx->d_sapxtab.as<float2>();
         SP.flags = ctx->d_sflags.as<uint32_t>();
+        SP.tiek = ctx->d_stiek.as<unsigned long long>();
         SP.nseq = reinterpret_cast<unsigned long long*>(ctx->d_sflags.as<unsigned char>() + 8);
         // shared memory: log-likelihood rows 8 x replicated (16-byte pitch), tie / float32 rows 16 x (8-byte pitch), when they fit
         SP.ll_rep_shift = (size_t)SR * 128 <= 64 * 1024 ? 3 : 0;
         SP.apx_rep_shift = (size_t)SR * 128 <= 64 * 1024 ? 4 : 0;
         const size_t nb = ((size_t)SR * 4 + 15) & ~(size_t)15, lb = ((size_t)SR * 16) << SP.ll_rep_shift;
-        const size_t ab = ((size_t)SR * 8) << SP.apx_rep_shift, tb = ((size_t)SR * 8) << (SP.ll_rep_shift ? SP.ll_rep_shift + 1 : 0);
+        const size_t ab = ((size_t)SR * 8) << SP.apx_rep_shift, tb = ((size_t)SR * 4) << (SP.ll_rep_shift ? SP.ll_rep_shift + 2 : 0);
         SP.nxt_in_smem = nb + ab <= 96 * 1024;
         SP.ll_in_smem = lb + tb <= 128 * 1024;
         SP.walk_apx_offset = (uint32_t)nb;
@@ -1097,7 +1110,7 @@ int mvd_destroy(mvd_ctx* ctx) {
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
                       &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_stage, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
                       &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot, &ctx->d_sapx, &ctx->d_splan,
-                      &ctx->d_sres, &ctx->d_stie, &ctx->d_sapxtab, &ctx->d_sflags};
+                      &ctx->d_sres, &ctx->d_stie, &ctx->d_sapxtab, &ctx->d_sflags, &ctx->d_stiek};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
@@ -1792,6 +1805,11 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
             if (rc != MVD_OK) return rc;
         }
         ctx->async_detect = value != 0;
+        return MVD_OK;
+    }
+    if (option == MVD_OPT_SPLIT_CHUNK) {
+        if (value != 0 && value != 256 && value != 512 && value != 1024) return fail(ctx, MVD_E_INVALID, "MVD_OPT_SPLIT_CHUNK takes 0, 256, 512 or 1024");
+        ctx->split_chunk = (uint32_t)value;
         return MVD_OK;
     }
     if (option == MVD_OPT_SPLIT_SEQUENTIAL) {

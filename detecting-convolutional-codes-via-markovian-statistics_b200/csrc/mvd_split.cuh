@@ -5,7 +5,7 @@
 // trial is sequential.  Two things in Pd_plotter.py:210-223 are order-dependent: the Markov-state trajectory
 // (integers) and the two float64 sums of log_prob_sequence (:106-116).  Both are cut into pieces here that are
 // worked on in parallel and still give the reference's bits:
-//   1. split_walk_kernel / split_walk2_kernel -- one thread per (trial, chunk of SPLIT_CH steps): the
+//   1. split_walk_kernel / split_walk2_kernel -- one thread per (trial, chunk of SP.chunk steps): the
 //      position-addressed bit source lets any chunk be generated on its own; the thread starts `warm` steps early
 //      from state 0 (the relative-metric recursion forgets its start), records the state it has at the chunk
 //      start, writes the edge index e_t = state * R + r_t of every step of its chunk and a float32 estimate of the
@@ -35,7 +35,9 @@
 #pragma once
 #include "mvd_detect2.cuh"
 #include "mvd_learn2.cuh"
+#include <type_traits>
 
+// SP.chunk = steps per chunk (a multiple of SPLIT_SUB, chosen by the host so that the walk fills the GPU)
 #define SPLIT_PLAN_FAST (1u << 22)      // plan word of a sub-chunk: bits 0-10 / 11-21 biased exponents of the two sums
 
 __device__ __forceinline__ uint32_t split_find(const unsigned long long* begin, uint32_t n, unsigned long long x) {
@@ -63,24 +65,30 @@ __device__ __forceinline__ uint32_t split_get(const uint4& grp, uint32_t pos) {
 }
 
 // ---- tables of the exact re-association, one entry per (log-likelihood table, edge); built once per mvd_set_loglik
-// tie[e] = {bit k set: log P1[e] is a tie term in binade 2^k, the same for log Tref[e]} (k = 0 .. 31),
+// tie[e] = k1 | k0 << 8: the binade 2^k (k = 0 .. SPLIT_KMAX - 1, else 0xFF) in which log P1[e] / log Tref[e] is a tie term,
 // apx[e] = the two terms in float32; flags bit 0: some term is positive or not a number (no predictions then)
-__device__ __forceinline__ uint32_t split_tie_bit(double v) {
+#define SPLIT_KMAX 64u
+__device__ __forceinline__ uint32_t split_tie_code(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v) & 0x7FFFFFFFFFFFFFFFull;
-    if (b == 0ull || (b >> 52) == 0x7FFull) return 0u;
+    if (b == 0ull || (b >> 52) == 0x7FFull) return 0xFFu;
     int ev = (int)(b >> 52) - 1023;
     unsigned long long mant = b & 0xFFFFFFFFFFFFFull;
     if ((b >> 52) == 0ull) ev = -1022; else mant |= 1ull << 52;
     const int k = ev + 1 + (__ffsll((long long)mant) - 1);
-    return (k >= 0 && k < 32) ? (1u << k) : 0u;
+    return (k >= 0 && k < (int)SPLIT_KMAX) ? (uint32_t)k : 0xFFu;
 }
 
-__global__ void split_tables_kernel(const double2* __restrict__ ll, size_t cells, uint2* __restrict__ tie, float2* __restrict__ apx,
-                                    uint32_t* __restrict__ flags) {
+// tiek[table] = {binades in which some log P1 term of the table is a tie, the same for log Tref}: a sub-chunk predicted into a
+// binade without any reads no tie codes at all
+__global__ void split_tables_kernel(const double2* __restrict__ ll, size_t cells, uint32_t SR, uint32_t* __restrict__ tie,
+                                    float2* __restrict__ apx, uint32_t* __restrict__ flags, unsigned long long* __restrict__ tiek) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
     const double2 v = ll[i];
-    tie[i] = make_uint2(split_tie_bit(v.x), split_tie_bit(v.y));
+    const uint32_t t1 = split_tie_code(v.x), t0 = split_tie_code(v.y);
+    tie[i] = t1 | (t0 << 8);
+    if (t1 != 0xFFu) atomicOr(tiek + 2 * (i / SR), 1ull << t1);
+    if (t0 != 0xFFu) atomicOr(tiek + 2 * (i / SR) + 1, 1ull << t0);
     apx[i] = make_float2((float)v.x, (float)v.y);
     if (!(v.x <= 0.0) || !(v.y <= 0.0)) atomicOr(flags, 1u);
 }
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
     float2* AX = SP.apx + SP.sub_begin[seg] + tl;                 // estimate of sub-chunk s: AX[s * ntr]
     const float2* gapx = SP.apxtab + (size_t)sg.table * P.SR;
-    const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+    const uint32_t t_begin = c * SP.chunk, t_end = min(N, t_begin + SP.chunk);
     const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
     uint32_t sx = 0;                                              // state 0 (exact when w_begin == 0)
     float s1 = 0.f, s0 = 0.f;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
     constexpr uint32_t SPG = 16 / EB;
     const uint32_t seg = blockIdx.y, bx = blockIdx.x;
     const DevSeg sg = P.segs[seg];
-    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
+    const uint32_t N = sg.N, nch = (N + SP.chunk - 1u) / SP.chunk;
     const unsigned long long ntr = sg.trial_end - sg.trial_begin, ntr32 = (ntr + 31ull) & ~31ull;
     if ((unsigned long long)bx * SPLIT_BLOCK >= nch * ntr32) return;              // uniform: shorter segment
     const uint32_t* nxt = P.nxt;
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
     const unsigned long long wid = SP.work_begin[seg] + (unsigned long long)c * ntr + tl;
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
     float2* AX = SP.apx + SP.sub_begin[seg] + tl;                  // estimate of sub-chunk s: AX[s * ntr]
-    const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+    const uint32_t t_begin = c * SP.chunk, t_end = min(N, t_begin + SP.chunk);
     const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
     const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
     }
     const uint32_t seg = lo;
     const DevSeg sg = P.segs[seg];
-    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH, nsub = (N + SPLIT_SUB - 1u) / SPLIT_SUB;
+    const uint32_t N = sg.N, nch = (N + SP.chunk - 1u) / SP.chunk, nsub = (N + SPLIT_SUB - 1u) / SPLIT_SUB;
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
     const unsigned long long tl = q - sg.out_offset;
     const unsigned long long trial = sg.trial_begin + tl;
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
             uint32_t st = __ldcg(SP.end + w0 + (unsigned long long)(c - 1u) * ntr), ss = __ldcg(SP.spec_start + w0 + (unsigned long long)c * ntr);
             if (st != ss) {
                 ++fixed;
-                const uint32_t t_begin = c * SPLIT_CH, t_end = min(N, t_begin + SPLIT_CH);
+                const uint32_t t_begin = c * SP.chunk, t_end = min(N, t_begin + SP.chunk);
                 uint32_t Rw[MVD_MAX_N];
                 bool merged = false;
                 for (uint32_t b = t_begin >> 5; b * 32u < t_end && !merged; ++b) {
@@ -412,8 +420,8 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
         if (predict && s < nsub) {
             // the estimates are good to ~1e-5: no prediction where either sum is that close to a power of two
             const uint32_t k1 = split_bexp(b1 * (1.0 - 1e-4)), k0 = split_bexp(b0 * (1.0 - 1e-4));
-            const bool ok = k1 == split_bexp(e1 * (1.0 + 1e-4)) && k0 == split_bexp(e0 * (1.0 + 1e-4)) && k1 >= 1023u && k1 < 1055u &&
-                            k0 >= 1023u && k0 < 1055u;
+            const bool ok = k1 == split_bexp(e1 * (1.0 + 1e-4)) && k0 == split_bexp(e0 * (1.0 + 1e-4)) && k1 >= 1023u && k1 < 1023u + SPLIT_KMAX &&
+                            k0 >= 1023u && k0 < 1023u + SPLIT_KMAX;
             if (ok) plan = SPLIT_PLAN_FAST | k1 | (k0 << 11);
         }
         if (s < nsub) PL[(unsigned long long)s * ntr] = plan;
@@ -435,10 +443,10 @@ __device__ __forceinline__ double2 split_ll(const double2* g, uint32_t sbase, ui
 }
 
 template <bool SMEM>
-__device__ __forceinline__ uint2 split_tie(const uint2* g, uint32_t tbase, uint32_t sh, uint32_t e) {
+__device__ __forceinline__ uint32_t split_tie(const uint32_t* g, uint32_t tbase, uint32_t sh, uint32_t e) {
     if (SMEM) {
-        uint2 v;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(tbase + (e << sh)));
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tbase + (e << sh)));
         return v;
     }
     return __ldg(g + e);
@@ -454,21 +462,21 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
     constexpr uint32_t SPG = 16 / EB;
     const uint32_t seg = blockIdx.y;
     const DevSeg sg = P.segs[seg];
-    const uint32_t N = sg.N, nch = (N + SPLIT_CH - 1u) / SPLIT_CH;
+    const uint32_t N = sg.N, nch = (N + SP.chunk - 1u) / SP.chunk;
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
     if ((unsigned long long)blockIdx.x * SPLIT_IBLOCK >= nch * ntr) return;       // uniform: shorter segment
     const double2* ll = P.ll + (size_t)sg.table * P.SR;
-    const uint2* tie = SP.tietab + (size_t)sg.table * P.SR;
-    const uint32_t rs = (uint32_t)SP.ll_rep_shift, sh = rs + 4u, ts = rs ? rs + 1u : 0u, tsh = ts + 3u;
+    const uint32_t* tie = SP.tietab + (size_t)sg.table * P.SR;
+    const uint32_t rs = (uint32_t)SP.ll_rep_shift, sh = rs + 4u, ts = rs ? rs + 2u : 0u, tsh = ts + 2u;   // tie rows: one copy per lane
     uint32_t sbase = 0, tbase = 0;
     if (SMEM) {
         double2* s_ll = reinterpret_cast<double2*>(smem_raw);
-        uint2* s_tie = reinterpret_cast<uint2*>(smem_raw + SP.isum_tie_offset);
+        uint32_t* s_tie = reinterpret_cast<uint32_t*>(smem_raw + SP.isum_tie_offset);
         for (uint32_t i = threadIdx.x; i < (P.SR << rs); i += SPLIT_IBLOCK) s_ll[i] = ll[i >> rs];
         for (uint32_t i = threadIdx.x; i < (P.SR << ts); i += SPLIT_IBLOCK) s_tie[i] = tie[i >> ts];
         __syncthreads();
         sbase = (uint32_t)__cvta_generic_to_shared(s_ll) + ((threadIdx.x & ((1u << rs) - 1u)) << 4);
-        tbase = (uint32_t)__cvta_generic_to_shared(s_tie) + ((threadIdx.x & ((1u << ts) - 1u)) << 3);
+        tbase = (uint32_t)__cvta_generic_to_shared(s_tie) + ((threadIdx.x & ((1u << ts) - 1u)) << 2);
     }
     const unsigned long long local = (unsigned long long)blockIdx.x * SPLIT_IBLOCK + threadIdx.x;
     if (local >= nch * ntr) return;
@@ -477,53 +485,59 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
     const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
     const uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
     double2* RS = SP.res + SP.sub_begin[seg] + tl;
+    const unsigned long long tk1 = __ldg(SP.tiek + 2 * (size_t)sg.table), tk0 = __ldg(SP.tiek + 2 * (size_t)sg.table + 1);
+    const uint32_t spc = SP.chunk / SPLIT_SUB;
 #pragma unroll 1
-    for (uint32_t j = 0; j < SPLIT_CH / SPLIT_SUB; ++j) {
-        const uint32_t s = c * (SPLIT_CH / SPLIT_SUB) + j, t0 = s * SPLIT_SUB;
+    for (uint32_t j = 0; j < spc; ++j) {
+        const uint32_t s = c * spc + j, t0 = s * SPLIT_SUB;
         if (t0 >= N) break;
         const uint32_t plan = __ldcg(PL + (unsigned long long)s * ntr);
         if (!(plan & SPLIT_PLAN_FAST)) continue;
         const uint32_t k1 = plan & 0x7FFu, k0 = (plan >> 11) & 0x7FFu;
         const double m1 = __hiloint2double((int)(0x80000000u | (k1 << 20)), 0), m0 = __hiloint2double((int)(0x80000000u | (k0 << 20)), 0);   // -2^k
         double r1 = m1, r0 = m0;
-        uint32_t tm1 = 0u, tm0 = 0u;
+        bool tie1 = false, tie0 = false;
+        const uint32_t kc1 = k1 - 1023u, kc0 = (k0 - 1023u) << 8;
         const uint32_t ns = min(SPLIT_SUB, N - t0), g0 = t0 / SPG, ng = ns / SPG, rem = ns - ng * SPG;
-        uint4 grp = make_uint4(0u, 0u, 0u, 0u);
-        if (ng) grp = __ldcg(E4 + (unsigned long long)g0 * ntr);
+        const uint4* Eg = E4 + (unsigned long long)g0 * ntr;
+        // one term: r <- r + v in both recurrences; CHK: is it a tie term of the sub-chunk's binade?
+        auto term = [&](uint32_t e, auto chk) {
+            const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
+            r1 += v.x;
+            r0 += v.y;
+            if (decltype(chk)::value) {
+                const uint32_t t = split_tie<SMEM>(tie, tbase, tsh, e);
+                tie1 |= (t & 0xFFu) == kc1;
+                tie0 |= (t & 0xFF00u) == kc0;
+            }
+        };
+        auto groups = [&](auto chk) {
+            uint4 grp = make_uint4(0u, 0u, 0u, 0u);
+            if (ng) grp = __ldcg(Eg);
 #pragma unroll 1
-        for (uint32_t g = 0; g < ng; ++g) {
-            const uint4 cur = grp;
-            if (g + 1u < ng || rem) grp = __ldcg(E4 + (unsigned long long)(g0 + g + 1u) * ntr);
+            for (uint32_t g = 0; g < ng; ++g) {
+                const uint4 cur = grp;
+                if (g + 1u < ng || rem) grp = __ldcg(Eg + (unsigned long long)(g + 1u) * ntr);
 #pragma unroll
-            for (uint32_t u = 0; u < SPG; ++u) {
-                const uint32_t e = split_get<EB>(cur, u);
-                const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
-                const uint2 t = split_tie<SMEM>(tie, tbase, tsh, e);
-                r1 += v.x;
-                r0 += v.y;
-                tm1 |= t.x;
-                tm0 |= t.y;
+                for (uint32_t u = 0; u < SPG; ++u) term(split_get<EB>(cur, u), chk);
             }
-        }
-        if (rem) {
-            if (!ng) grp = __ldcg(E4 + (unsigned long long)g0 * ntr);
-            for (uint32_t u = 0; u < rem; ++u) {
-                uint32_t e = 0;
+            if (rem) {
+                if (!ng) grp = __ldcg(Eg);
+                for (uint32_t u = 0; u < rem; ++u) {
+                    uint32_t e = 0;
 #pragma unroll
-                for (uint32_t w = 0; w < SPG; ++w)
-                    if (w == u) e = split_get<EB>(grp, w);
-                const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
-                const uint2 t = split_tie<SMEM>(tie, tbase, tsh, e);
-                r1 += v.x;
-                r0 += v.y;
-                tm1 |= t.x;
-                tm0 |= t.y;
+                    for (uint32_t w = 0; w < SPG; ++w)
+                        if (w == u) e = split_get<EB>(grp, w);
+                    term(e, chk);
+                }
             }
-        }
+        };
+        if (((tk1 >> kc1) | (tk0 >> (k0 - 1023u))) & 1ull) groups(std::true_type{});   // the table has a tie term in one of the two binades
+        else groups(std::false_type{});
         // what the sub-chunk adds: r_end + 2^k (exact when the recurrence stayed in its binade); a tie term voids it
         double S1 = r1 - m1, S0 = r0 - m0;
-        if ((tm1 >> (k1 - 1023u)) & 1u) S1 = __longlong_as_double(0x7FF8000000000000ll);
-        if ((tm0 >> (k0 - 1023u)) & 1u) S0 = __longlong_as_double(0x7FF8000000000000ll);
+        if (tie1) S1 = __longlong_as_double(0x7FF8000000000000ll);
+        if (tie0) S0 = __longlong_as_double(0x7FF8000000000000ll);
         RS[(unsigned long long)s * ntr] = make_double2(S1, S0);
     }
 }
@@ -570,14 +584,18 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
     const uint32_t rres = ring + threadIdx.x * 16u, rplan = ring + 2u * SPLIT_RB * blockDim.x * 16u + threadIdx.x * 4u;
     auto fetch = [&](uint32_t b) {                                 // batch b -> half b & 1
         if (active && b < nbatch) {
-            const uint32_t half = (b & 1u) * SPLIT_RB;
+            const uint32_t half = (b & 1u) * SPLIT_RB, n = min(SPLIT_RB, nsub - b * SPLIT_RB);
+            const uint32_t* pl = PL + (unsigned long long)(b * SPLIT_RB) * ntr;
+            const double2* rs = RS + (unsigned long long)(b * SPLIT_RB) * ntr;
+            uint32_t dp = rplan + half * blockDim.x * 4u, dr = rres + half * blockDim.x * 16u;
 #pragma unroll 4
-            for (uint32_t j = 0; j < SPLIT_RB; ++j) {
-                const uint32_t s = b * SPLIT_RB + j;
-                if (s < nsub) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rplan + (half + j) * blockDim.x * 4u), "l"(PL + (unsigned long long)s * ntr));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rres + (half + j) * blockDim.x * 16u), "l"(RS + (unsigned long long)s * ntr));
-                }
+            for (uint32_t j = 0; j < n; ++j) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dp), "l"(pl));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dr), "l"(rs));
+                pl += ntr;
+                rs += ntr;
+                dp += blockDim.x * 4u;
+                dr += blockDim.x * 16u;
             }
         }
         asm volatile("cp.async.commit_group;");
@@ -609,13 +627,16 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
 #pragma unroll 1
             while (j < cnt) {
                 uint32_t plan;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(plan) : "r"(rplan + (half + j) * blockDim.x * 4u));
-                if (!(plan & SPLIT_PLAN_FAST)) break;
                 double2 r;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(plan) : "r"(rplan + (half + j) * blockDim.x * 4u));
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(rres + (half + j) * blockDim.x * 16u));
-                const uint32_t k1 = plan & 0x7FFu, k0 = (plan >> 11) & 0x7FFu;
+                if (!(plan & SPLIT_PLAN_FAST)) break;
+                // sign and exponent (the top 12 bits) of both sums, before and after, are those of -2^k
+                const uint32_t K1 = 0x80000000u | (plan << 20), K0 = 0x80000000u | ((plan >> 11) << 20);
                 const double n1 = a1 + r.x, n0 = a0 + r.y;
-                if (!(split_bexp(a1) == k1 && split_bexp(n1) == k1 && split_bexp(a0) == k0 && split_bexp(n0) == k0)) break;
+                const uint32_t bad = ((uint32_t)__double2hiint(a1) ^ K1) | ((uint32_t)__double2hiint(n1) ^ K1) |
+                                     ((uint32_t)__double2hiint(a0) ^ K0) | ((uint32_t)__double2hiint(n0) ^ K0);
+                if (bad >> 20) break;
                 a1 = n1;
                 a0 = n0;
                 ++j;

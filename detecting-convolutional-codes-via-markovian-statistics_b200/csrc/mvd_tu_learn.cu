@@ -23,10 +23,13 @@ cudaError_t mvd_launch_learn(bool smem_tables, size_t lsmem, uint32_t nsegs, cud
 // ---- detection trials split along the time axis (mvd_split.cuh)
 #include "mvd_split.cuh"
 
-cudaError_t mvd_launch_split_tables(const double2* ll, size_t cells, uint2* tie, float2* apx, uint32_t* flags, cudaStream_t st) {
+cudaError_t mvd_launch_split_tables(const double2* ll, uint32_t SR, uint32_t ntables, uint32_t* tie, float2* apx, uint32_t* flags,
+                                    unsigned long long* tiek, cudaStream_t st) {
+    const size_t cells = (size_t)SR * ntables;
     cudaError_t e = cudaMemsetAsync(flags, 0, 4, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(tiek, 0, 16 * (size_t)ntables, st);
     if (e != cudaSuccess) return e;
-    split_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ll, cells, tie, apx, flags);
+    split_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ll, cells, SR, tie, apx, flags, tiek);
     return cudaGetLastError();
 }
 

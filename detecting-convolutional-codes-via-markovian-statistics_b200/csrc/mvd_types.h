@@ -99,13 +99,14 @@ struct LearnParams {
 };
 
 // ---- detection trials split along the time axis (mvd_split.cuh)
-#define SPLIT_CH 512u                       // steps per chunk (one walker thread)
+#define SPLIT_CH_MAX 1024u                  // most steps per chunk (one walker thread); SplitParams.chunk = 256, 512 or 1024
 #define SPLIT_SUB 128u                      // steps per sub-chunk (one prediction / one re-associated partial sum)
 #define SPLIT_BLOCK 128
 #define SPLIT_RB_HOST 16                    // = SPLIT_RB of mvd_split.cuh: sub-chunk records per batch of the scoring kernel's ring
 
 struct SplitParams {
     uint32_t warm;                          // warm-up steps (multiple of 32)
+    uint32_t chunk;                         // steps per chunk (multiple of SPLIT_SUB)
     uint32_t nchains;
     unsigned long long nwork;               // (chain, chunk) pairs
     const unsigned long long* work_begin;   // [nsegs + 1] first work item of a segment (items: chunk-major, trial-minor)
@@ -120,7 +121,8 @@ struct SplitParams {
     uint32_t* plan;                         // [sub-chunk records] predicted binades (SPLIT_PLAN_FAST | k1 | k0 << 11) or 0
     double2* res;                           // [sub-chunk records] what the sub-chunk adds to each sum inside the predicted binade
     const float2* apxtab;                   // [ntables][SR] {log P1, log Tref} in float32
-    const uint2* tietab;                    // [ntables][SR] binades in which the two terms are round-half-even ties
+    const uint32_t* tietab;                 // [ntables][SR] k1 | k0 << 8: the binade in which each of the two terms is a round-half-even tie (0xFF: none)
+    const unsigned long long* tiek;         // [ntables][2] binades (bit k) in which some log P1 / log Tref term of the table is a tie
     const uint32_t* flags;                  // [1] bit 0: some term is positive / not a number (no predictions)
     int sequential;                         // 1 = no predictions: every term added one by one (MVD_OPT_SPLIT_SEQUENTIAL)
     int nxt_in_smem, ll_in_smem;

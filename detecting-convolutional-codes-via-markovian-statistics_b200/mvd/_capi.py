@@ -26,6 +26,7 @@ OPT_SPLIT = 5
 OPT_NO_ANTIPODAL = 6
 OPT_ASYNC_DETECT = 7
 OPT_SPLIT_SEQUENTIAL = 8
+OPT_SPLIT_CHUNK = 9
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmvd.so")
 

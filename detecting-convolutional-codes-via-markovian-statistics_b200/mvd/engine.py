@@ -231,6 +231,14 @@ class Detector:
         self._ck(self.lib.mvd_set_loglik(self.ctx, len(tabs), self.logP1.ctypes.data, self.logTref.ctypes.data))
         self.ntables = len(tabs)
 
+    def set_loglik(self, logP1: np.ndarray, logTref: np.ndarray):
+        """Upload the log tables themselves (``mvd_set_loglik``): ``logP1`` [ntables, S, R], ``logTref`` [S, R] -- what
+        :meth:`set_models` derives from probabilities with the reference's ``math.log(max(P, 1e-300))`` (Pd_plotter.py:114)."""
+        self.logP1 = np.ascontiguousarray(logP1, dtype=np.float64).reshape(-1, self.S, self.R)
+        self.logTref = np.ascontiguousarray(logTref, dtype=np.float64).reshape(self.S, self.R)
+        self._ck(self.lib.mvd_set_loglik(self.ctx, len(self.logP1), self.logP1.ctypes.data, self.logTref.ctypes.data))
+        self.ntables = len(self.logP1)
+
     def detect(self, segs, seed: Optional[int] = None, bits=None, engine: str = "auto",
                want_logp: bool = False, d_tallies_ptr: Optional[int] = None, bits_device_ptr=None, bits_words=0,
                host_tallies: bool = True):
@@ -326,6 +334,10 @@ class Detector:
         """Split path: add every log-likelihood term one by one in step order (``MVD_OPT_SPLIT_SEQUENTIAL``) instead of
         re-associating the float64 additions inside a binade -- identical results, the check of the re-association."""
         self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT_SEQUENTIAL, 1 if on else 0))
+
+    def split_chunk(self, steps: int = 0):
+        """Steps per chunk of the split path (``MVD_OPT_SPLIT_CHUNK``): 0 = chosen per call, else 256, 512 or 1024."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT_CHUNK, int(steps)))
 
     def split_stats(self):
         """(sub-chunks of the last split launch, sub-chunks whose terms were added one by one)."""

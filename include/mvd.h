@@ -257,8 +257,9 @@ enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one t
                                       flight.  The segment records and tally words of a sweep stay on the device, so a
                                       loop of sweeps needs no host round trip between them (Pd_plotter.py:210-223
                                       repeated; bench.py's resident leg) */
-       MVD_OPT_SPLIT_SEQUENTIAL = 8 };/* 1 = the split path adds every log-likelihood term one by one in step order instead of
+       MVD_OPT_SPLIT_SEQUENTIAL = 8, /* 1 = the split path adds every log-likelihood term one by one in step order instead of
                                       re-associating the additions inside a binade (identical results; the check of that) */
+       MVD_OPT_SPLIT_CHUNK = 9 };  /* steps per chunk of the split path: 0 = chosen per call, else 256, 512 or 1024 (identical results) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);
 int mvd_learn_stats(mvd_ctx* ctx, uint32_t* dirty_chunks);

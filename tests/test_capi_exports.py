@@ -60,7 +60,7 @@ def test_option_constants_match_header():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     opts = dict(re.findall(r"\bMVD_(OPT_[A-Z0-9_]+)\s*=\s*(\d+)", text))
-    assert set(opts) == {"OPT_FORCE_GENERIC", "OPT_NO_PAIR", "OPT_LEARN_WARM", "OPT_NO_FSM1", "OPT_SPLIT", "OPT_NO_ANTIPODAL", "OPT_ASYNC_DETECT", "OPT_SPLIT_SEQUENTIAL"}
+    assert set(opts) == {"OPT_FORCE_GENERIC", "OPT_NO_PAIR", "OPT_LEARN_WARM", "OPT_NO_FSM1", "OPT_SPLIT", "OPT_NO_ANTIPODAL", "OPT_ASYNC_DETECT", "OPT_SPLIT_SEQUENTIAL", "OPT_SPLIT_CHUNK"}
     for name, value in opts.items():
         assert getattr(_capi, name) == int(value), name
 

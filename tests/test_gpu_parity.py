@@ -408,7 +408,14 @@ def test_split_long_trials_vs_oracle(codes_spec, dets, dec, enc, Ns, p, warm):
         assert (det.last_kernel_kind() & 16384) != 0
         assert det.learn_dirty_chunks() == dirty
         assert det.split_stats() == (subs, subs)
+        det.split_sequential(False)
+        for chunk in (256, 512, 1024):                            # steps per walker thread (chosen per call otherwise)
+            det.split_chunk(chunk)
+            ct, clp = det.detect(segs, seed=77, engine="fsm", want_logp=True)
+            assert np.array_equal(ct, tallies) and np.array_equal(clp, lp), chunk
+            assert det.split_stats()[0] == subs        # (the share taken term by term may differ by a sub-chunk: the estimates of a repaired chunk come from its speculated trajectory)
     finally:
+        det.split_chunk(0)
         det.split_sequential(False)
         det.split_trials(0)
         det.learn_warm(128)
@@ -605,6 +612,66 @@ def test_m4_large_table_vs_oracle(codes_spec):
                 assert np.array_equal(lp[d * ntr:(d + 1) * ntr], want[d][1])
 
 
+def test_split_reassociation_with_tie_terms(codes_spec, dets):
+    """The split path re-associates the float64 additions of log_prob_sequence (Pd_plotter.py:106-116) inside a binade; a
+    term v with v / ulp ending in exactly one half is the one case in which the step-by-step rounding depends on the running
+    sum (round-half-even).  Log tables with such terms planted in the binades the sums pass through (2^8 .. 2^15), positive
+    terms (no monotone sum: every term is added in order) and an all-zero table: per-trial sums bit-identical to Python's own
+    float additions over the oracle's trajectory."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec["c75"]
+    det = dets("c75")
+    tab, P1, Tref = _oracle_models(det, spec, 0.1, 8000, 5)
+    T = bitsource.bsc_threshold(0.1)
+    ntr, N, seed = 5, 30011, 99
+    taps = _taps(spec)
+    trajs = []
+    for t in range(ntr):
+        U, E = co.trial_words(seed, 7, t, N, 2, T)
+        idx, rseq, _ = co.simulate(taps, taps, 2, spec["m"], N, U, E, tab)
+        trajs.append((np.asarray(idx[:N], dtype=np.int64), np.asarray(rseq[:N], dtype=np.int64)))
+    logP1 = np.log(np.maximum(np.asarray(P1, dtype=np.float64), 1e-300)).reshape(det.S, det.R)
+    logT = np.log(np.maximum(np.asarray(Tref, dtype=np.float64), 1e-300)).reshape(det.S, det.R)
+    visits = np.zeros((det.S, det.R), dtype=np.int64)
+    for idx, rseq in trajs:
+        np.add.at(visits, (idx, rseq), 1)
+    busy = np.dstack(np.unravel_index(np.argsort(-visits, axis=None)[:12], visits.shape))[0]
+    tie1, tie0 = logP1.copy(), logT.copy()
+    for j, (i, r) in enumerate(busy):                              # the most visited edges become tie terms of binade 2^k
+        k = 8 + j % 8
+        tie1[i, r] = -(0.5 + 2.0 ** (k - 53))
+        if j < 3:
+            tie0[i, r] = -(0.75 + 2.0 ** (k + 3 - 53))
+    pos1 = logP1.copy()
+    pos1[busy[0][0], busy[0][1]] = 0.25                            # a positive term: the sums are not monotone
+    seg = [Seg(N=N, threshold=T, stream=7, enc_taps=taps, decide=0, trial_begin=0, trial_end=ntr)]
+    det.split_trials(1)
+    try:
+        for name, l1, l0 in (("plain", logP1, logT), ("ties", tie1, tie0), ("positive", pos1, logT), ("zero", np.zeros_like(logP1), logT)):
+            det.set_loglik(l1[None], l0)
+            _, lp = det.detect(seg, seed=seed, engine="fsm", want_logp=True)
+            assert (det.last_kernel_kind() & 16384) != 0
+            subs, seq = det.split_stats()
+            for t, (idx, rseq) in enumerate(trajs):
+                a1 = a0 = 0.0
+                for v1, v0 in zip(l1[idx, rseq].tolist(), l0[idx, rseq].tolist()):
+                    a1 += v1
+                    a0 += v0
+                assert (a1, a0) == (lp[t, 0], lp[t, 1]), (name, t)
+            if name == "plain":
+                assert seq < 0.3 * subs
+                plain_seq = seq
+            elif name == "ties":
+                assert plain_seq < seq < subs, "the planted tie terms did not force any sub-chunk back to term-by-term additions"
+            elif name == "positive":
+                assert seq == subs
+    finally:
+        det.split_trials(0)
+        det.set_models([P1])
+
+
 @pytest.mark.parametrize("dec,enc,p", [("c75", "c65", 0.1), ("m3a", "m3b", 0.05)])
 def test_config3_blocklengths_vs_oracle(codes_spec, dets, dec, enc, p):
     """BASELINE config 3 (Pd vs blocklength, N = 10^2 .. 10^5): N = 10^4, 10^5 and the ragged 100 003 through the
@@ -629,6 +696,8 @@ def test_config3_blocklengths_vs_oracle(codes_spec, dets, dec, enc, p):
     try:
         runs.append(det.detect(segs, seed=77, engine="fsm", want_logp=True))
         assert (det.last_kernel_kind() & 16384) != 0
+        subs, seq = det.split_stats()
+        assert subs == ntr * 2 * sum(-(-N // 128) for N in Ns) and seq < 0.15 * subs    # most additions re-associated
         det.split_trials(0)
         runs.append(det.detect(segs, seed=77, engine="auto", want_logp=True))       # automatic choice: few long trials split
         assert (det.last_kernel_kind() & 16384) != 0
