@@ -840,12 +840,13 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         split = split && ew * 4ull <= (6ull << 30) && work <= 0x7FFFFFFFull * (unsigned long long)SPLIT_BLOCK;
         if (ctx->split_mode == 0) {
             // automatic: compare the two paths with measured rates (B200, m = 2).  One thread per trial: the chain of a
-            // trial costs ~63 ns per step until the GPU is full (~1e12 steps/s); split: the walk is work-bound at
-            // ~7.5e11 steps/s (warm-up included) and the in-order scoring costs ~12.5 ns per step of the longest trial.
+            // trial costs ~59 ns per step until the GPU is full (~1e12 steps/s); split: walk + partial sums are work-bound at
+            // ~5.5e11 steps/s (warm-up included), the in-order part costs ~2.2 ns per step of the longest trial (one record
+            // per 128 steps plus the binade crossings), four launches ~50 us.
             uint32_t maxN = 0;
             for (uint32_t i = 0; i < nsegs; ++i) maxN = std::max(maxN, ds[i].N);
-            const double t_plain = std::max((double)maxN * 63e-9, (double)steps / 1.0e12);
-            const double t_split = (double)steps / 7.5e11 + (double)maxN * 12.5e-9 + 15e-6;
+            const double t_plain = std::max((double)maxN * 59e-9, (double)steps / 1.0e12);
+            const double t_split = (double)steps / 5.5e11 + (double)maxN * 2.2e-9 + 50e-6;
             split = split && maxN >= 2048u && t_split < 0.8 * t_plain;
         }
     }
