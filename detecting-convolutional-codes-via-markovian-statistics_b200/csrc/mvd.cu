@@ -56,6 +56,9 @@ struct mvd_ctx {
     bool force_generic = false, no_pair = false, force_pair = false, no_fsm1 = false, no_antipodal = false;
     int split_mode = 0;             // 0 = automatic, 1 = always split long trials along the time axis, 2 = never
     bool split_sequential = false;  // MVD_OPT_SPLIT_SEQUENTIAL: the split path adds every term one by one (no re-association)
+    bool table_code = false;        // mvd_set_code_tables: trellis / encoders as tables (any k), generic NEXT-walk kernels only
+    std::vector<uint8_t> h_dec_prev, h_dec_lab;   // [2^m][2^k]
+    uint32_t nenc = 0;
     uint32_t split_chunk = 0;       // MVD_OPT_SPLIT_CHUNK: 0 = automatic, else 256 / 512 / 1024 steps per chunk
     bool split_tables_ready = false;// tie binades / float32 terms of the current log-likelihood tables are on the device
     unsigned long long last_split_sub = 0, last_split_seq = 0;   // sub-chunks of the last split launch / of them added term by term
@@ -100,7 +103,7 @@ struct mvd_ctx {
     uint32_t ntables = 0;
 
     DevBuf d_bm, d_nxt, d_ll, d_hkeys, d_hvals, d_segs, d_tallies, d_counts, d_logp, d_trace_idx, d_trace_met,
-        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot, d_sapx, d_splan, d_sres, d_stie, d_sapxtab, d_sflags, d_stiek;
+        d_hashes, d_final, d_err, d_bits, d_peak, d_dstate, d_dstate2, d_stage, d_lspec, d_lend, d_ldirty, d_tcode, d_gfsm1, d_smeta, d_sedges, d_phd, d_pht, d_llslot, d_sapx, d_splan, d_sres, d_stie, d_sapxtab, d_sflags, d_stiek, d_enc;
 };
 
 namespace {
@@ -298,9 +301,19 @@ int install_states(mvd_ctx* ctx) {
             for (int r = 0; r < R && closed; ++r) {
                 int tmp[64], lo = 1 << 30;
                 for (int ns = 0; ns < nstate; ++ns) {
-                    const int a = cur[ns >> 1] + __builtin_popcount((unsigned)(lab0[ns] ^ r));
-                    const int b = cur[(ns >> 1) + HALF] + __builtin_popcount((unsigned)(lab1[ns] ^ r));
-                    tmp[ns] = a < b ? a : b;
+                    if (ctx->table_code) {                       // 2^k incoming branches from the tables (viterbi_markov.py:150-155)
+                        const int nb = 1 << ctx->k;
+                        int best = 1 << 30;
+                        for (int b = 0; b < nb; ++b) {
+                            const int v = cur[ctx->h_dec_prev[(size_t)ns * nb + b]] + __builtin_popcount((unsigned)(ctx->h_dec_lab[(size_t)ns * nb + b] ^ r));
+                            best = v < best ? v : best;
+                        }
+                        tmp[ns] = best;
+                    } else {
+                        const int a = cur[ns >> 1] + __builtin_popcount((unsigned)(lab0[ns] ^ r));
+                        const int b = cur[(ns >> 1) + HALF] + __builtin_popcount((unsigned)(lab1[ns] ^ r));
+                        tmp[ns] = a < b ? a : b;
+                    }
                     lo = tmp[ns] < lo ? tmp[ns] : lo;
                 }
                 const uint8_t* nx = ctx->h_metrics.data() + (size_t)ctx->h_next[(size_t)i * R + r] * nstate;
@@ -610,6 +623,11 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
 
     if (engine == MVD_ENGINE_AUTO) engine = (mode == MODE_HASH) ? MVD_ENGINE_ACS : MVD_ENGINE_FSM;
     if (mode == MODE_HASH) engine = MVD_ENGINE_ACS;
+    if (ctx->table_code) {
+        if (engine != MVD_ENGINE_FSM) return fail(ctx, MVD_E_UNSUPPORTED, "a code given as tables runs on the Markov-state walk (MVD_ENGINE_FSM / AUTO) only");
+        if (ctx->nenc == 0) return fail(ctx, MVD_E_STATE, "no encoder tables (mvd_set_encoders)");
+        if (!ctx->closed) return fail(ctx, MVD_E_INVALID, "the state table is not closed under Eq. 4-5 on the given trellis");
+    }
     if (engine != MVD_ENGINE_ACS && engine != MVD_ENGINE_FSM) return fail(ctx, MVD_E_INVALID, "bad engine %d", engine);
     if (engine == MVD_ENGINE_ACS && mode != MODE_HASH && !ctx->acs_ok)
         return fail(ctx, MVD_E_UNSUPPORTED, "ACS engine needs relative metrics <= 15");
@@ -619,7 +637,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     int det2_lk = -1, det2_lls = 0;
     size_t det2_smem = 0;
     bool det2_gt = false;
-    const bool fast = mode == MODE_DETECT && !ctx->force_generic &&
+    const bool fast = mode == MODE_DETECT && !ctx->force_generic && !ctx->table_code &&
                       plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
     // (layout of detect2p_kernel: straggler queues, masks, branch metrics, log rows, then the state table at a 32 KB-aligned
@@ -668,12 +686,15 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         d.table = s.table;
         for (int j = 0; j < MVD_MAX_N; ++j) {
             d.enc_taps[j] = j < n ? s.enc_taps[j] : 0u;
-            if (j < n && (s.enc_taps[j] >> (m + 1))) return fail(ctx, MVD_E_INVALID, "segment %u: encoder tap beyond memory m=%d", i, m);
+            if (!ctx->table_code && j < n && (s.enc_taps[j] >> (m + 1))) return fail(ctx, MVD_E_INVALID, "segment %u: encoder tap beyond memory m=%d", i, m);
+        }
+        if (ctx->table_code) {
+            if (s.enc_taps[0] >= ctx->nenc) return fail(ctx, MVD_E_INVALID, "segment %u: encoder index %u >= %u (mvd_set_encoders)", i, s.enc_taps[0], ctx->nenc);
+            d.enc_taps[0] = s.enc_taps[0];
         }
         d.decide = s.decide;
         d.random_input = s.random_input ? 1u : 0u;
         d.dmin = s.threshold ? (uint32_t)__builtin_ctz(s.threshold) : 32u;
-        if (getenv("MVD_HACK_NCALLS2") && d.dmin < 24u) d.dmin = 24u;     // TIMING EXPERIMENT ONLY (wrong bits): at most 2 calls per flip word
         const uint64_t ntr = s.trial_end - s.trial_begin;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one call");
         d.block_begin = (uint32_t)blocks;
@@ -685,7 +706,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         trials += ntr;
         if (src->mode == MVD_SRC_BITSTREAM) {
             const uint64_t nsb = ((uint64_t)s.N + 127) / 128;
-            need_words = std::max<uint64_t>(need_words, s.bits_offset + nsb * (uint64_t)(1 + n) * ntr);
+            need_words = std::max<uint64_t>(need_words, s.bits_offset + nsb * (uint64_t)(ctx->k + n) * ntr);
         }
     }
     if (blocks > 0x7FFFFFFFull) return fail(ctx, MVD_E_INVALID, "too many trials in one call");
@@ -694,6 +715,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     Params P{};
     P.n = n;
     P.m = m;
+    P.k = ctx->k;
+    P.enc_tab = ctx->table_code ? ctx->d_enc.as<uint16_t>() : nullptr;
     P.R = R;
     P.nstate = nstate;
     P.S = S;
@@ -826,7 +849,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         return MVD_OK;
     }
     // few long trials (Pd-vs-N sweeps): split them along the time axis when that fills the GPU better
-    bool split = mode == MODE_DETECT && engine == MVD_ENGINE_FSM && !ctx->force_generic && ctx->split_mode != 2 &&
+    bool split = mode == MODE_DETECT && engine == MVD_ENGINE_FSM && !ctx->force_generic && !ctx->table_code && ctx->split_mode != 2 &&
                  src->mode == MVD_SRC_PHILOX && ctx->closed && trials > 0 && trials <= 0x7FFFFFFFull;
     if (split) {
         unsigned long long steps = 0, ew = 0, work = 0;
@@ -866,7 +889,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         ev1 = ctx->async_ev[ctx->async_pending].second;
     }
     CK(cudaEventRecord(ev0, ctx->stream));
-    bool plearn = mode == MODE_LEARN && engine == MVD_ENGINE_FSM && !ctx->force_generic && src->mode == MVD_SRC_PHILOX;
+    bool plearn = mode == MODE_LEARN && engine == MVD_ENGINE_FSM && !ctx->force_generic && !ctx->table_code && src->mode == MVD_SRC_PHILOX;
     uint32_t maxL = 0;
     for (uint32_t i = 0; i < nsegs && plearn; ++i) {
         plearn = (segs[i].trial_end - segs[i].trial_begin) == 1;
@@ -1111,7 +1134,7 @@ int mvd_destroy(mvd_ctx* ctx) {
                       &ctx->d_counts, &ctx->d_logp, &ctx->d_trace_idx, &ctx->d_trace_met, &ctx->d_hashes, &ctx->d_final,
                       &ctx->d_err, &ctx->d_bits, &ctx->d_peak, &ctx->d_dstate, &ctx->d_dstate2, &ctx->d_stage, &ctx->d_lspec, &ctx->d_lend, &ctx->d_ldirty, &ctx->d_tcode, &ctx->d_gfsm1,
                       &ctx->d_smeta, &ctx->d_sedges, &ctx->d_phd, &ctx->d_pht, &ctx->d_llslot, &ctx->d_sapx, &ctx->d_splan,
-                      &ctx->d_sres, &ctx->d_stie, &ctx->d_sapxtab, &ctx->d_sflags, &ctx->d_stiek};
+                      &ctx->d_sres, &ctx->d_stie, &ctx->d_sapxtab, &ctx->d_sflags, &ctx->d_stiek, &ctx->d_enc};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
@@ -1171,6 +1194,8 @@ int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps) {
     ctx->k = k;
     ctx->n = n;
     ctx->m = m;
+    ctx->table_code = false;
+    ctx->nenc = 0;
     for (int j = 0; j < MVD_MAX_N; ++j) ctx->dec_taps[j] = j < n ? dec_taps[j] : 0u;
     // branch metrics, 16x2 packed: low half = input 0 (ns = 2g), high half = input 1 (ns = 2g+1)
     const int nstate = 1 << m, NP = nstate / 2, HALF = nstate / 2, R = 1 << n;
@@ -1194,6 +1219,51 @@ int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps) {
     return MVD_OK;
 }
 
+int mvd_set_code_tables(mvd_ctx* ctx, int k, int n, int m, const uint8_t* dec_prev, const uint8_t* dec_label) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!dec_prev || !dec_label) return fail(ctx, MVD_E_INVALID, "null trellis tables");
+    if (k < 1 || k > MVD_MAX_K) return fail(ctx, MVD_E_UNSUPPORTED, "k=%d outside [1,%d]", k, MVD_MAX_K);
+    if (n < 1 || n > MVD_MAX_N) return fail(ctx, MVD_E_UNSUPPORTED, "n=%d outside [1,%d]", n, MVD_MAX_N);
+    if (m < 1 || m > MVD_MAX_M) return fail(ctx, MVD_E_UNSUPPORTED, "m=%d outside [1,%d]", m, MVD_MAX_M);
+    const size_t cells = (size_t)1 << (m + k);
+    for (size_t i = 0; i < cells; ++i) {
+        if (dec_prev[i] >> m) return fail(ctx, MVD_E_INVALID, "dec_prev[%zu]=%u is not a trellis state (m=%d)", i, dec_prev[i], m);
+        if (dec_label[i] >> n) return fail(ctx, MVD_E_INVALID, "dec_label[%zu]=%u has more than n=%d bits", i, dec_label[i], n);
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->k = k;
+    ctx->n = n;
+    ctx->m = m;
+    ctx->table_code = true;
+    ctx->nenc = 0;
+    ctx->h_dec_prev.assign(dec_prev, dec_prev + cells);
+    ctx->h_dec_lab.assign(dec_label, dec_label + cells);
+    for (int j = 0; j < MVD_MAX_N; ++j) ctx->dec_taps[j] = 0u;
+    ctx->have_code = true;
+    ctx->have_states = false;
+    ctx->ntables = 0;
+    return MVD_OK;
+}
+
+int mvd_set_encoders(mvd_ctx* ctx, uint32_t nenc, const uint8_t* enc_next, const uint8_t* enc_out) {
+    if (!ctx) return MVD_E_INVALID;
+    if (!ctx->have_code || !ctx->table_code) return fail(ctx, MVD_E_STATE, "mvd_set_code_tables first");
+    if (!enc_next || !enc_out || nenc == 0 || nenc > 65536u) return fail(ctx, MVD_E_INVALID, "null / empty encoder tables");
+    const size_t cells = (size_t)1 << (ctx->m + ctx->k);
+    std::vector<uint16_t> packed((size_t)nenc * cells);
+    for (size_t i = 0; i < packed.size(); ++i) {
+        if (enc_next[i] >> ctx->m) return fail(ctx, MVD_E_INVALID, "enc_next[%zu]=%u is not an encoder state (m=%d)", i, enc_next[i], ctx->m);
+        if (enc_out[i] >> ctx->n) return fail(ctx, MVD_E_INVALID, "enc_out[%zu]=%u has more than n=%d bits", i, enc_out[i], ctx->n);
+        packed[i] = (uint16_t)((uint16_t)enc_next[i] << 8 | enc_out[i]);
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_enc.reserve(packed.size() * 2));
+    CK(h2d(ctx, ctx->d_enc.p, packed.data(), packed.size() * 2));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nenc = nenc;
+    return MVD_OK;
+}
+
 int mvd_set_states(mvd_ctx* ctx, uint32_t S, const uint8_t* metrics, const uint32_t* next) {
     if (!ctx) return MVD_E_INVALID;
     if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code first");
@@ -1209,6 +1279,7 @@ int mvd_enumerate_states(mvd_ctx* ctx, uint32_t max_states, uint32_t* S_out) {
     if (!ctx) return MVD_E_INVALID;
     if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code first");
     if (max_states == 0) return fail(ctx, MVD_E_INVALID, "max_states = 0");
+    if (ctx->table_code) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_enumerate_states needs the tap-mask form of the code (mvd_set_code)");
     const int n = ctx->n, m = ctx->m, nstate = 1 << m, R = 1 << n, HALF = nstate / 2;
     // branch labels of the butterfly
     std::vector<int> lab0(nstate), lab1(nstate);   // label of branch into ns from ps0 / ps1
@@ -1283,6 +1354,7 @@ int mvd_enumerate_states_gpu(mvd_ctx* ctx, uint32_t max_states, uint32_t flags, 
     if (!ctx) return MVD_E_INVALID;
     if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code first");
     if ((flags & MVD_BFS_INSTALL) && (flags & MVD_BFS_COUNT_ONLY)) return fail(ctx, MVD_E_INVALID, "INSTALL and COUNT_ONLY exclude each other");
+    if (ctx->table_code) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_enumerate_states_gpu needs the tap-mask form of the code (mvd_set_code)");
     CK(cudaSetDevice(ctx->device));
     MvdBfsConfig cfg;
     cfg.n = ctx->n;
@@ -1443,6 +1515,7 @@ int mvd_acs_final(mvd_ctx* ctx, const mvd_src* src, const mvd_segment* seg, uint
     if (!ctx) return MVD_E_INVALID;
     if (!src || !seg || !final_metrics) return fail(ctx, MVD_E_INVALID, "null argument");
     if (!ctx->have_code) return fail(ctx, MVD_E_STATE, "mvd_set_code has not been called");
+    if (ctx->table_code) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final needs the tap-mask form of the code (mvd_set_code)");
     if (ctx->n != 2 || ctx->m < 2) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final supports n = 2, m = 2..6 (use mvd_acs_hash)");
     if (src->mode != MVD_SRC_PHILOX) return fail(ctx, MVD_E_UNSUPPORTED, "mvd_acs_final takes the on-device bit source (use mvd_acs_hash)");
     if (seg->N >= 0x80000000u) return fail(ctx, MVD_E_INVALID, "N = %u >= 2^31 overflows the position-addressed Philox counter", seg->N);

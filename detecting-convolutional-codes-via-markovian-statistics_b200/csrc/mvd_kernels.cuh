@@ -161,6 +161,81 @@ __device__ __forceinline__ void run_trial(const Params& P, const DevSeg& sg, boo
     }
 }
 
+// The same driver for codes given as tables (mvd_set_code_tables / mvd_set_encoders: any k <= MVD_MAX_K inputs per step,
+// viterbi_markov.py:82-106 is generic in k): the encoder of the segment's hypothesis is the table
+// enc[(state << k) | u] = next state << 8 | output label, u = (u_0 .. u_{k-1}) with u_0 the most significant bit (the position
+// of the tuple in itertools.product([0,1], repeat=k)); the info word of input i comes from slot 32 + i of the superblock's first
+// block (bit streams: 128-bit word c = i of the k + n per superblock).
+template <class Eng>
+__device__ __forceinline__ void run_trial_tab(const Params& P, const DevSeg& sg, bool active, unsigned long long trial,
+                                              unsigned long long tl, unsigned long long ntr, Eng& eng) {
+    const int n = P.n, k = P.k;
+    const uint32_t N = sg.N;
+    const uint32_t T = sg.threshold;
+    const int dmin = (int)sg.dmin;
+    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    const uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream;
+    const uint16_t* enc = P.enc_tab + ((size_t)sg.enc_taps[0] << (P.m + k));
+    uint32_t es = 0;                                              // encoder state 0 (alpha_exponent.py:123)
+    const uint32_t nsb = (N + 127u) >> 7;
+    for (uint32_t sb = 0; sb < nsb; ++sb) {
+        uint4 Uw[MVD_MAX_K], Ew[MVD_MAX_N];
+#pragma unroll
+        for (int i = 0; i < MVD_MAX_K; ++i) Uw[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < MVD_MAX_N; ++j) Ew[j] = make_uint4(0, 0, 0, 0);
+        if (philox) {
+#pragma unroll
+            for (int i = 0; i < MVD_MAX_K; ++i)
+                if (i < k) Uw[i] = philox10(((4u * sb) << 6) | (32u + (uint32_t)i), c1, c2, c3, P);
+        } else if (active) {
+            const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * (unsigned)(k + n) * ntr + tl;
+#pragma unroll
+            for (int i = 0; i < MVD_MAX_K; ++i)
+                if (i < k) Uw[i] = __ldg(base + (unsigned long long)i * ntr);
+#pragma unroll
+            for (int j = 0; j < MVD_MAX_N; ++j)
+                if (j < n) Ew[j] = __ldg(base + (unsigned long long)(k + j) * ntr);
+        }
+        if (!sg.random_input) {
+#pragma unroll
+            for (int i = 0; i < MVD_MAX_K; ++i) Uw[i] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t0 = sb * 128u + (uint32_t)w * 32u;
+            if (t0 >= N) break;
+            const uint32_t valid = min(32u, N - t0);
+            const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+            uint32_t Ui[MVD_MAX_K], Ej[MVD_MAX_N];
+#pragma unroll
+            for (int i = 0; i < MVD_MAX_K; ++i) Ui[i] = i < k ? pick(Uw[i], w) : 0u;
+#pragma unroll
+            for (int j = 0; j < MVD_MAX_N; ++j) {
+                Ej[j] = 0u;
+                if (j < n) {
+                    if (philox) Ej[j] = lazy_bernoulli(((4u * sb + (uint32_t)w) << 6) | (8u * (uint32_t)j), c1, c2, c3, T, dmin,
+                                                       active ? vmask : 0u, P);
+                    else Ej[j] = pick(Ew[j], w);
+                }
+            }
+#pragma unroll 1
+            for (uint32_t t = 0; t < valid; ++t) {
+                uint32_t u = 0, f = 0;
+#pragma unroll
+                for (int i = 0; i < MVD_MAX_K; ++i)
+                    if (i < k) u = (u << 1) | ((Ui[i] >> t) & 1u);
+#pragma unroll
+                for (int j = 0; j < MVD_MAX_N; ++j)
+                    if (j < n) f = (f << 1) | ((Ej[j] >> t) & 1u);
+                const uint32_t br = __ldg(enc + ((es << k) | u));
+                es = br >> 8;
+                eng.step(t0 + t, (br & 0xFFu) ^ f);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ FSM engine
 template <int MODE, bool SMEM>
 struct FsmEngine {
@@ -196,7 +271,8 @@ struct FsmEngine {
 };
 
 // grid: one block per (segment, chunk of MVD_BLOCK trials)
-template <int MODE, int NOUT, bool SMEM>
+// TAB: the code was given as tables (run_trial_tab)
+template <int MODE, int NOUT, bool SMEM, bool TAB = false>
 __global__ void __launch_bounds__(MVD_BLOCK) fsm_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t seg = find_segment(P, blockIdx.x);
@@ -238,7 +314,8 @@ __global__ void __launch_bounds__(MVD_BLOCK) fsm_kernel(const __grid_constant__ 
     }
     if (MODE == MODE_TRACE && active) eng.tr_idx[0] = 0;
 
-    run_trial<NOUT>(P, sg, active, trial, tl, ntr, eng);
+    if (TAB) run_trial_tab(P, sg, active, trial, tl, ntr, eng);
+    else run_trial<NOUT>(P, sg, active, trial, tl, ntr, eng);
 
     if (MODE == MODE_DETECT) {
         const bool win = active && (sg.decide == 0 ? (eng.a1 > eng.a0) : (eng.a1 <= eng.a0));

@@ -44,9 +44,9 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters,
 }
 
 namespace {
-template <int MODE, int NOUT, bool SMEM>
+template <int MODE, int NOUT, bool SMEM, bool TAB = false>
 cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
-    auto kern = fsm_kernel<MODE, NOUT, SMEM>;
+    auto kern = fsm_kernel<MODE, NOUT, SMEM, TAB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, MVD_BLOCK, smem, st>>>(P);
@@ -55,6 +55,11 @@ cudaError_t launch_fsm(dim3 grid, size_t smem, cudaStream_t st, const Params& P)
 }  // namespace
 
 cudaError_t mvd_launch_generic_fsm(int mode, bool n2, bool in_smem, dim3 grid, size_t smem, cudaStream_t st, const Params& P) {
+    if (P.enc_tab) {                                     // code given as tables (any k)
+        if (mode == MODE_DETECT) return in_smem ? launch_fsm<MODE_DETECT, 0, true, true>(grid, smem, st, P) : launch_fsm<MODE_DETECT, 0, false, true>(grid, smem, st, P);
+        if (mode == MODE_LEARN) return in_smem ? launch_fsm<MODE_LEARN, 0, true, true>(grid, smem, st, P) : launch_fsm<MODE_LEARN, 0, false, true>(grid, smem, st, P);
+        return in_smem ? launch_fsm<MODE_TRACE, 0, true, true>(grid, smem, st, P) : launch_fsm<MODE_TRACE, 0, false, true>(grid, smem, st, P);
+    }
     if (mode == MODE_DETECT) {
         if (in_smem) return n2 ? launch_fsm<MODE_DETECT, 2, true>(grid, smem, st, P) : launch_fsm<MODE_DETECT, 0, true>(grid, smem, st, P);
         return n2 ? launch_fsm<MODE_DETECT, 2, false>(grid, smem, st, P) : launch_fsm<MODE_DETECT, 0, false>(grid, smem, st, P);

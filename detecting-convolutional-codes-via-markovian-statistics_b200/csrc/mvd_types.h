@@ -39,6 +39,8 @@ struct FastPlan {
 
 struct Params {
     int n, m, R, nstate;
+    int k;                          // inputs per step (1 unless the code was given as tables)
+    const uint16_t* enc_tab;        // codes given as tables: [nenc][2^m][2^k] next state << 8 | output label, else NULL
     uint32_t S, SR;                 // SR = S * R
     int src_mode;
     uint32_t rk0[10], rk1[10];      // Philox round keys (key + r * Weyl), shared by every thread

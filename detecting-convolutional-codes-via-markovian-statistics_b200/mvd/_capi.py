@@ -11,6 +11,7 @@ import os
 
 MAX_N = 4
 MAX_M = 6
+MAX_K = 3
 ABI_VERSION = 3          # must equal MVD_ABI_VERSION of include/mvd.h: the struct layouts below mirror that header
 
 SRC_PHILOX, SRC_BITSTREAM = 0, 1
@@ -36,7 +37,7 @@ EXPORTS = (
     "mvd_learn_counts", "mvd_detect", "mvd_trace", "mvd_acs_hash", "mvd_last_kernel_ms", "mvd_launch_count",
     "mvd_int_peak", "mvd_device_info", "mvd_set_option", "mvd_last_kernel_kind", "mvd_learn_stats",
     "mvd_enumerate_states_gpu", "mvd_bfs_levels", "mvd_chernoff_rho", "mvd_chernoff_rho_dense", "mvd_parity_detect", "mvd_host_log_table", "mvd_acs_final",
-    "mvd_copy_stats", "mvd_async_stats", "mvd_host_p1_edge_tables", "mvd_split_stats",
+    "mvd_copy_stats", "mvd_async_stats", "mvd_host_p1_edge_tables", "mvd_split_stats", "mvd_set_code_tables", "mvd_set_encoders",
 )
 
 
@@ -126,6 +127,8 @@ def load():
     lib.mvd_last_kernel_kind.argtypes = [vp, P(i32)]
     lib.mvd_learn_stats.argtypes = [vp, P(u32)]
     lib.mvd_split_stats.argtypes = [vp, P(u64), P(u64)]
+    lib.mvd_set_code_tables.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.mvd_set_encoders.argtypes = [vp, C.c_uint32, vp, vp]
     lib.mvd_device_info.argtypes = [vp, P(i32), P(i32), P(u64), C.c_char_p, i32]
     for name in EXPORTS:
         getattr(lib, name)            # AttributeError here = header / library mismatch

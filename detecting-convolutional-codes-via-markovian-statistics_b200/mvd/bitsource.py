@@ -14,7 +14,9 @@ MVD-PHILOX-2
   block of any trial can be generated independently (chunk-parallel learning chains, several
   threads per long trial) and skipping a call never moves the rest of the stream.
 * info bits: the four info words of the superblock of blocks 4s..4s+3 come from ONE call with
-  ``b = 4s, slot = 32``; bit t of word w is the info bit of step 128 s + 32 w + t.
+  ``b = 4s, slot = 32``; bit t of word w is the info bit of step 128 s + 32 w + t.  Codes with k > 1 inputs per step
+  (viterbi_markov.py:89-104 is generic in k) take the words of input i from ``slot = 32 + i`` of the same block
+  (i < k <= 3; input 0 is the k = 1 definition), and the step's input tuple is (u_0, ..., u_{k-1}).
 * BSC flips: for block b and output j (0 <= j < n <= 4) a *lazy Bernoulli word* E_j (bit t = flip of
   output j at step 32 b + t), whose k-th call (k = 0..7) has ``slot = 8 j + k``.
 * lazy Bernoulli word for threshold T (P(flip) = T / 2^32), restricted to the valid lanes
@@ -31,8 +33,8 @@ of lazy calls made every block's position depend on all earlier blocks.)
 Bitstream layout (verification mode, also the HBM-bound path)
 -------------------------------------------------------------
 ``bits`` is an array of 128-bit words (4 x uint32, little-endian lanes x,y,z,w), indexed
-``[(sb * (1 + n) + c) * ntrials + trial]`` where c = 0 is the info stream and c = 1 + j the flip
-stream of output j: consecutive trials are adjacent, so a warp reads 512 contiguous bytes.
+``[(sb * (k + n) + c) * ntrials + trial]`` where c = i < k is the info stream of input i (k = 1: c = 0) and
+c = k + j the flip stream of output j: consecutive trials are adjacent, so a warp reads 512 contiguous bytes.
 """
 from __future__ import annotations
 
@@ -152,6 +154,21 @@ def trial_words(seed: int, stream: int, trial: int, N: int, n: int, T: int) -> T
     return U, E
 
 
+def trial_words_k(seed: int, stream: int, trial: int, N: int, k: int, n: int, T: int) -> Tuple[np.ndarray, np.ndarray]:
+    """:func:`trial_words` for k inputs per step: ``U`` uint32 [k, nblk] (input i from slot 32 + i), ``E`` uint32 [n, nblk]."""
+    nblk = (N + 31) // 32
+    U0, E = trial_words(seed, stream, trial, N, n, T)
+    U = np.zeros((k, nblk), dtype=np.uint32)
+    U[0] = U0
+    for i in range(1, k):
+        for sb in range((N + 127) // 128):
+            uw = stream_call(seed, stream, trial, 4 * sb, INFO_SLOT + i)
+            for w in range(4):
+                if 32 * (4 * sb + w) < N:
+                    U[i, 4 * sb + w] = uw[w]
+    return U, E
+
+
 def words_to_bits(words: np.ndarray, N: int) -> np.ndarray:
     """uint32 [..., nblk] -> uint8 bits [..., N], LSB-first inside each word."""
     w = np.ascontiguousarray(words, dtype="<u4")
@@ -173,21 +190,23 @@ def bits_to_words(bits: np.ndarray) -> np.ndarray:
 def pack_bitstreams(u_bits: np.ndarray, e_bits: np.ndarray) -> np.ndarray:
     """Host bit arrays -> device layout.
 
-    ``u_bits`` uint8 [ntrials, N]; ``e_bits`` uint8 [ntrials, n, N].
-    Returns uint32 [nsb, 1 + n, ntrials, 4] (C-contiguous) == 128-bit words indexed
-    ``(sb * (1 + n) + c) * ntrials + trial``.
+    ``u_bits`` uint8 [ntrials, N] (k = 1) or [ntrials, k, N]; ``e_bits`` uint8 [ntrials, n, N].
+    Returns uint32 [nsb, k + n, ntrials, 4] (C-contiguous) == 128-bit words indexed
+    ``(sb * (k + n) + c) * ntrials + trial``.
     """
     u_bits = np.asarray(u_bits, dtype=np.uint8)
     e_bits = np.asarray(e_bits, dtype=np.uint8)
-    ntr, N = u_bits.shape
+    if u_bits.ndim == 2:
+        u_bits = u_bits[:, None, :]
+    ntr, k, N = u_bits.shape
     n = e_bits.shape[1]
     assert e_bits.shape == (ntr, n, N)
-    uw = bits_to_words(u_bits)                      # [ntr, nsb*4]
+    uw = bits_to_words(u_bits)                      # [ntr, k, nsb*4]
     ew = bits_to_words(e_bits)                      # [ntr, n, nsb*4]
     nsb = uw.shape[-1] // 4
-    out = np.empty((nsb, 1 + n, ntr, 4), dtype=np.uint32)
-    out[:, 0] = uw.reshape(ntr, nsb, 4).transpose(1, 0, 2)
-    out[:, 1:] = ew.reshape(ntr, n, nsb, 4).transpose(2, 1, 0, 3)
+    out = np.empty((nsb, k + n, ntr, 4), dtype=np.uint32)
+    out[:, :k] = uw.reshape(ntr, k, nsb, 4).transpose(2, 1, 0, 3)
+    out[:, k:] = ew.reshape(ntr, n, nsb, 4).transpose(2, 1, 0, 3)
     return np.ascontiguousarray(out)
 
 

@@ -72,12 +72,24 @@ class Detector:
         if rc != 0:
             _capi.check(self.lib, None, rc)
         self.device = int(device)
-        if self.k != 1:
-            self.close()
-            raise _capi.MvdError(-3, "the device path supports k = 1 codes only")
-        self.dec_taps = codes.tap_masks(self.gen1, self.m, self.k)
-        taps = (C.c_uint32 * len(self.dec_taps))(*self.dec_taps)
-        self._ck(self.lib.mvd_set_code(self.ctx, self.k, self.n, self.m, taps))
+        self.table_code = self.k != 1
+        if self.table_code:
+            # k > 1 inputs per step: the reference's trellis / branch functions are generic in k (viterbi_markov.py:82-132);
+            # their results go to the device as tables (mvd_set_code_tables), hypotheses are encoder-table indices
+            if self.k > _capi.MAX_K:
+                self.close()
+                raise _capi.MvdError(-3, f"the device path supports k <= {_capi.MAX_K} inputs per step")
+            prev, blab = codes.trellis_arrays(self.gen1, self.m, self.k, self.n)
+            self._ck(self.lib.mvd_set_code_tables(self.ctx, self.k, self.n, self.m, np.ascontiguousarray(prev, dtype=np.uint8).ctypes.data,
+                                                  np.ascontiguousarray(blab, dtype=np.uint8).ctypes.data))
+            self._enc_index, self._enc_next, self._enc_out = {}, [], []
+            self.dec_taps = self.taps_of(self.gen1)               # encoder 0 = the decoder's own code
+            if table is None and enumerate_with != "python":
+                enumerate_with = "python"                         # the C++ / GPU enumerations need the tap-mask form
+        else:
+            self.dec_taps = codes.tap_masks(self.gen1, self.m, self.k)
+            taps = (C.c_uint32 * len(self.dec_taps))(*self.dec_taps)
+            self._ck(self.lib.mvd_set_code(self.ctx, self.k, self.n, self.m, taps))
         if table is not None:
             self.table = table
             self._upload_states()
@@ -156,7 +168,19 @@ class Detector:
         return self.table.S
 
     def taps_of(self, gen) -> List[int]:
-        return codes.tap_masks(codes.freeze_generator(gen), self.m, self.k)
+        """What goes into ``Seg.enc_taps`` for the encoder ``gen``: its tap masks (k = 1), or -- for a code given as tables --
+        ``[index]`` of its (enc_next, enc_out) tables, registered with ``mvd_set_encoders`` on first use."""
+        gen = codes.freeze_generator(gen)
+        if not self.table_code:
+            return codes.tap_masks(gen, self.m, self.k)
+        if gen not in self._enc_index:
+            enc_out, enc_next = codes.encoder_tables(gen, self.m, self.k)
+            self._enc_index[gen] = len(self._enc_next)
+            self._enc_next.append(np.asarray(enc_next, dtype=np.uint8))
+            self._enc_out.append(np.asarray(enc_out, dtype=np.uint8))
+            nx, ou = np.ascontiguousarray(np.stack(self._enc_next)), np.ascontiguousarray(np.stack(self._enc_out))
+            self._ck(self.lib.mvd_set_encoders(self.ctx, len(self._enc_next), nx.ctypes.data, ou.ctypes.data))
+        return [self._enc_index[gen]]
 
     def segment_array(self, N, threshold, stream, table, enc_taps, decide, trial_begin, trial_end, random_input=1,
                       bits_offset=0) -> np.ndarray:

@@ -133,11 +133,17 @@ def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_in
 
     dec = generator_matrix if decoder_matrix is None else decoder_matrix
     det = _detector(codes.freeze_generator(dec), k, n, m, device)
+    if k != 1:
+        engine = "fsm"      # codes with k > 1 inputs go to the device as tables and run the Markov-state walk (mvd_set_code_tables)
     seg = Seg(N=int(length), threshold=bitsource.bsc_threshold(float(p_val)), stream=stream,
               enc_taps=det.taps_of(generator_matrix), random_input=bool(random_input),
               trial_begin=int(trial), trial_end=int(trial) + 1)
     if u_bits is not None or e_bits is not None:
-        u = np.zeros((1, length), dtype=np.uint8) if u_bits is None else np.asarray(u_bits, dtype=np.uint8).reshape(1, length)
+        if k == 1:
+            u = np.zeros((1, length), dtype=np.uint8) if u_bits is None else np.asarray(u_bits, dtype=np.uint8).reshape(1, length)
+        else:                                                     # input tuples per step -> [1, k, length]
+            u = np.zeros((1, k, length), dtype=np.uint8) if u_bits is None else \
+                np.asarray(u_bits, dtype=np.uint8).reshape(length, k).T.reshape(1, k, length)
         e = np.zeros((1, n, length), dtype=np.uint8) if e_bits is None else \
             np.asarray(e_bits, dtype=np.uint8).reshape(length, n).T.reshape(1, n, length)
         idx, met = det.trace(seg, bits=bitsource.pack_bitstreams(u, e), engine=engine)

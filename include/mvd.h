@@ -28,12 +28,13 @@ extern "C" {
 #define MVD_ABI_VERSION 3
 #define MVD_MAX_N 4   /* outputs per step (R = 2^n <= 16)            */
 #define MVD_MAX_M 6   /* encoder memory  (2^m <= 64 trellis states)  */
+#define MVD_MAX_K 3   /* inputs per step of a code given as tables   */
 
 enum {
     MVD_OK = 0,
     MVD_E_INVALID = -1,       /* bad argument                                             */
     MVD_E_CUDA = -2,          /* CUDA runtime error (no device, launch failure, ...)      */
-    MVD_E_UNSUPPORTED = -3,   /* outside the device envelope (k != 1, n > 4, m > 6, ...)  */
+    MVD_E_UNSUPPORTED = -3,   /* outside the device envelope (k > 3, n > 4, m > 6, ...)   */
     MVD_E_STATE = -4,         /* call order: tables not set                               */
     MVD_E_NOMEM = -5,
     MVD_E_UNKNOWN_STATE = -6  /* a metric vector was not in the state table: the KeyError of
@@ -49,7 +50,8 @@ typedef struct mvd_ctx mvd_ctx;
  * PHILOX: generated on the device, stream spec MVD-PHILOX-2 (mvd/bitsource.py), key = seed.
  * BITSTREAM: read from `bits`, an array of 128-bit words indexed
  *   seg.bits_offset + (sb * (1 + n) + c) * ntrials + (trial - seg.trial_begin)
- * (sb = step / 128, c = 0 info stream, c = 1 + j flips of output j, ntrials = trial_end - trial_begin;
+ * (sb = step / 128, c = 0 info stream, c = 1 + j flips of output j -- k + n words per superblock, inputs first, for a code
+ * given as tables --, ntrials = trial_end - trial_begin;
  * bit b of 32-bit lane w of a word is step 128*sb + 32*w + b). */
 typedef struct mvd_src {
     int32_t mode;             /* MVD_SRC_*                                              */
@@ -89,6 +91,21 @@ int mvd_synchronize(mvd_ctx* ctx);
  * (viterbi_markov.py:118-132) + branch_output_and_next_state (:82-106) for k = 1.
  * dec_taps[j] bit t = generator_matrix[j][0][t]. */
 int mvd_set_code(mvd_ctx* ctx, int k, int n, int m, const uint32_t* dec_taps);
+
+/* The same for codes GIVEN AS TABLES, any k <= MVD_MAX_K inputs per step: branch_output_and_next_state
+ * (viterbi_markov.py:82-106) and build_trellis (:118-132) are generic in k in the reference -- including the register
+ * [u_i, s_0, ..] that every input i sees -- and whatever they produce can be handed over as it is:
+ *   dec_prev / dec_label [2^m][2^k]: predecessor state and branch label (first output = MSB) of the incoming branches of
+ *   every trellis state, in the reference's insertion order (ps ascending, inputs in itertools.product order);
+ *   mvd_set_encoders: enc_next / enc_out [nenc][2^m][2^k] for the encoders of the hypotheses, input tuple (u_0 .. u_{k-1})
+ *   at index u_0 2^(k-1) + .. + u_{k-1}; a segment's enc_taps[0] is then the INDEX of its encoder.
+ * The device path of such a code is the Markov-state walk (MVD_ENGINE_FSM, what MVD_ENGINE_AUTO selects): learning chains,
+ * detection trials and traces run on the generic kernels with a table-driven encoder; the info bits of input i come from
+ * Philox slot 32 + i (mvd/bitsource.py) or from info stream c = i of the k + n per superblock.  mvd_set_states checks the
+ * table against Eq. 4-5 on this trellis (closure).  MVD_ENGINE_ACS, mvd_enumerate_states(_gpu) and mvd_acs_hash need the
+ * tap-mask form (k = 1) and return MVD_E_UNSUPPORTED. */
+int mvd_set_code_tables(mvd_ctx* ctx, int k, int n, int m, const uint8_t* dec_prev, const uint8_t* dec_label);
+int mvd_set_encoders(mvd_ctx* ctx, uint32_t nenc, const uint8_t* enc_next, const uint8_t* enc_out);
 
 /* Markov-state table: replaces the `states` list and the `state_index` dict
  * (viterbi_markov.py:166-195, Pd_plotter.py:136-139).  metrics: S x 2^m bytes, next: S x 2^n. */

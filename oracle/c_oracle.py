@@ -48,6 +48,12 @@ def lib():
         L.mvdo_run_trials.argtypes = [vp, vp, i32, i32, u32, u32, u64, u32, u64, u64, vp, vp, vp, i32, vp]
         L.mvdo_run_trials.restype = C.c_int64
         L.mvdo_learn_chain.argtypes = [vp, vp, i32, i32, u32, u32, u32, u64, u32, u64, vp, vp, vp]
+        L.mvdo_trial_words_k.argtypes = [u64, u32, u64, u32, i32, i32, u32, vp, vp]
+        L.mvdo_metric_step_tab.argtypes = [vp, vp, i32, i32, vp, i32, vp]
+        L.mvdo_simulate_tab.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, vp, vp, vp, vp, vp, vp]
+        L.mvdo_run_trials_tab.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, u32, u64, u32, u64, u64, vp, vp, vp, i32, vp]
+        L.mvdo_run_trials_tab.restype = C.c_int64
+        L.mvdo_learn_chain_tab.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, u32, u32, u64, u32, u64, vp, vp]
         _lib = L
     return _lib
 
@@ -174,3 +180,62 @@ def acs_hash(dec_taps, enc_taps, n, m, N, U, E):
     if rc != 0:
         raise OverflowError("relative metric exceeded 15")
     return int(h.value), fin
+
+
+# ---- codes given as tables (k <= 3): prev / blab / enc_next / enc_out uint8 [2^m, 2^k] (mvd.codes.trellis_arrays / encoder_tables)
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def trial_words_k(seed, stream, trial, N, k, n, T):
+    nblk = (N + 31) // 32
+    U = np.zeros((k, nblk), dtype=np.uint32)
+    E = np.zeros((n, nblk), dtype=np.uint32)
+    lib().mvdo_trial_words_k(seed, stream, trial, N, k, n, T, U.ctypes.data, E.ctypes.data)
+    return U, E
+
+
+def metric_step_tab(prev, blab, m, k, D, r):
+    p, b = _u8(prev), _u8(blab)
+    d = np.ascontiguousarray(D, dtype=np.int32)
+    o = np.zeros(1 << m, dtype=np.int32)
+    lib().mvdo_metric_step_tab(p.ctypes.data, b.ctypes.data, m, k, d.ctypes.data, int(r), o.ctypes.data)
+    return tuple(int(v) for v in o)
+
+
+def simulate_tab(prev, blab, enc_next, enc_out, k, n, m, N, U, E, table, want_metrics=False):
+    p, b, en, eo = _u8(prev), _u8(blab), _u8(enc_next), _u8(enc_out)
+    U, E = _u32(U), _u32(E)
+    idx = np.zeros(N + 1, dtype=np.int32)
+    rseq = np.zeros(N + 1, dtype=np.uint8)
+    met = np.zeros((N + 1, 1 << m), dtype=np.uint8) if want_metrics else None
+    rc = lib().mvdo_simulate_tab(p.ctypes.data, b.ctypes.data, en.ctypes.data, eo.ctypes.data, k, n, m, N, U.ctypes.data,
+                                 E.ctypes.data, table.h, idx.ctypes.data, rseq.ctypes.data,
+                                 met.ctypes.data if want_metrics else None)
+    if rc != 0:
+        raise KeyError(f"metric vector at step {-rc - 1} not in the state table")
+    return idx, rseq[:N], met
+
+
+def run_trials_tab(prev, blab, enc_next, enc_out, k, n, m, N, T, seed, stream, trial_begin, trial_end, table, P1edge, Tref_edge,
+                   decide, want_logp=False):
+    p, b, en, eo = _u8(prev), _u8(blab), _u8(enc_next), _u8(enc_out)
+    p1 = np.ascontiguousarray(P1edge, dtype=np.float64)
+    tr = np.ascontiguousarray(Tref_edge, dtype=np.float64)
+    lp = np.zeros((trial_end - trial_begin, 2), dtype=np.float64) if want_logp else None
+    s = lib().mvdo_run_trials_tab(p.ctypes.data, b.ctypes.data, en.ctypes.data, eo.ctypes.data, k, n, m, N, T, seed, stream,
+                                  trial_begin, trial_end, table.h, p1.ctypes.data, tr.ctypes.data, decide,
+                                  lp.ctypes.data if want_logp else None)
+    if s < 0:
+        raise KeyError("a metric vector was not in the state table")
+    return (int(s), lp) if want_logp else int(s)
+
+
+def learn_chain_tab(prev, blab, enc_next, enc_out, k, n, m, length, burn, T, seed, stream, trial, table):
+    p, b, en, eo = _u8(prev), _u8(blab), _u8(enc_next), _u8(enc_out)
+    edge = np.zeros((table.S, 1 << n), dtype=np.uint64)
+    rc = lib().mvdo_learn_chain_tab(p.ctypes.data, b.ctypes.data, en.ctypes.data, eo.ctypes.data, k, n, m, length, burn, T, seed,
+                                    stream, trial, table.h, edge.ctypes.data)
+    if rc != 0:
+        raise KeyError("a metric vector was not in the state table")
+    return edge

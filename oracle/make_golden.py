@@ -18,6 +18,7 @@ Usage:  python oracle/make_golden.py [--ref /root/reference] [--out tests/golden
 from __future__ import annotations
 
 import argparse
+import itertools
 import hashlib
 import json
 import os
@@ -42,6 +43,15 @@ CODES = {
 M4_CODES = {
     "m4a": dict(k=1, n=2, m=4, gen=[[[1, 1, 0, 0, 1]], [[1, 1, 0, 1, 1]]]),   # (31,33)
     "m4c": dict(k=1, n=2, m=4, gen=[[[1, 0, 0, 1, 1]], [[1, 1, 1, 0, 1]]]),   # (23,35)
+}
+
+
+# k = 2 inputs per step (viterbi_markov.py:82-132 is generic in k; every input sees the same register [u_i, s_0 ..]):
+# the table-driven device path (mvd_set_code_tables) is pinned by these
+K2_CODES = {
+    "k2b": dict(k=2, n=3, m=2, gen=[[[1, 0, 1], [0, 1, 1]], [[1, 1, 0], [1, 0, 1]], [[0, 1, 1], [1, 1, 1]]]),             # S = 5
+    "k2c": dict(k=2, n=3, m=3, gen=[[[1, 1, 0, 1], [0, 1, 1, 0]], [[1, 0, 1, 1], [1, 1, 0, 0]], [[0, 1, 1, 1], [1, 0, 1, 0]]]),   # S = 235
+    "k2d": dict(k=2, n=3, m=3, gen=[[[1, 0, 1, 1], [0, 1, 1, 0]], [[1, 1, 0, 1], [1, 0, 1, 0]], [[0, 1, 1, 1], [1, 1, 0, 0]]]),
 }
 
 
@@ -101,7 +111,7 @@ def kat_for_code(vm, pdp, name, spec, symbolic=True):
                trellis={str(ns): [[ps, list(u), list(o)] for ps, u, o in lst] for ns, lst in trellis.items()},
                branches=[[s, list(u), list(vm.branch_output_and_next_state(s, u, gen, m, k)[0]),
                           vm.branch_output_and_next_state(s, u, gen, m, k)[1]]
-                         for s in range(1 << m) for u in ([(0,), (1,)] if k == 1 else [])])
+                         for s in range(1 << m) for u in itertools.product([0, 1], repeat=k)])
     if S <= 500:
         out["states"] = [list(s) for s in states]
         out["next"] = nxt
@@ -141,7 +151,7 @@ def sim_kat(vm, name, spec, enc_spec, N, p, seed, stream, trial):
                                             step=vm.viterbi_metric_step,
                                             branch_fn=vm.branch_output_and_next_state,
                                             trellis_fn=vm.build_trellis)
-    u, e = ref_port.philox_bits(seed, stream, trial, N, n, ref_port.threshold_of(p))
+    u, e = ref_port.philox_bits(seed, stream, trial, N, n, ref_port.threshold_of(p), k)
     return dict(N=N, p=p, seed=seed, stream=stream, trial=trial, u_bits=u, e_bits=e,
                 metrics=[list(d) for d in sim["metrics"]], received=[list(r) for r in sim["received"]])
 
@@ -355,6 +365,7 @@ def main():
     ap.add_argument("--m4-only", action="store_true", help="only (re)write m4_kats.json")
     ap.add_argument("--alpha-only", action="store_true", help="only (re)write alpha_kats.json")
     ap.add_argument("--parity-only", action="store_true", help="only (re)write parity_kats.json")
+    ap.add_argument("--k2-only", action="store_true", help="only (re)write k2_kats.json (k = 2 codes)")
     ap.add_argument("--add-experiments", action="store_true",
                     help="only add the experiments missing from experiments.json (existing entries are kept byte for byte)")
     args = ap.parse_args()
@@ -371,6 +382,23 @@ def main():
                 print("[exp]", name, exps[name]["reference_seconds"], "s", flush=True)
         with open(path, "w") as f:
             json.dump(exps, f, separators=(",", ":"))
+        return
+
+    if args.k2_only:
+        k2 = dict(codes={}, sims={}, experiments={})
+        for name, spec in K2_CODES.items():
+            k2["codes"][name] = kat_for_code(vm, pdp, name, spec, symbolic=(name == "k2b"))
+            print(f"[k2] {name}: S={k2['codes'][name]['S']}", flush=True)
+        k2["sims"] = {
+            "k2c_self": sim_kat(vm, "k2c", K2_CODES["k2c"], K2_CODES["k2c"], 300, 0.1, 12345, 0, 7),
+            "k2c_vs_d": sim_kat(vm, "k2c", K2_CODES["k2c"], K2_CODES["k2d"], 260, 0.05, 99, 1, (1 << 33) + 5),
+            "k2b_self": sim_kat(vm, "k2b", K2_CODES["k2b"], K2_CODES["k2b"], 129, 0.3, 5, 2, 3),
+        }
+        k2["experiments"]["k2c_k2d"] = experiment_golden(vm, pdp, K2_CODES["k2c"], K2_CODES["k2d"], num_iter=10, p_vec=[0.05, 0.2],
+                                                         N_list=[64, 150], seed=7)
+        print("[k2] experiment", k2["experiments"]["k2c_k2d"]["reference_seconds"], "s", flush=True)
+        with open(os.path.join(args.out, "k2_kats.json"), "w") as f:
+            json.dump(k2, f, separators=(",", ":"))
         return
 
     with open(os.path.join(args.out, "parity_kats.json"), "w") as f:

@@ -123,9 +123,9 @@ def threshold_of(p):
     return min(int(math.floor(p * 4294967296.0 + 0.5)), M32)
 
 
-def philox_bits(seed, stream, trial, N, n, T):
-    """MVD-PHILOX-2 (mvd/bitsource.py docstring): info bits u[N] and flips e[N][n] of one trial.
-    Every Philox call is addressed by position: c0 = (block << 6) | slot."""
+def philox_bits(seed, stream, trial, N, n, T, k=1):
+    """MVD-PHILOX-2 (mvd/bitsource.py docstring): info bits u[N] (k = 1) or input tuples u[N][k] (k > 1: input i from
+    slot 32 + i) and flips e[N][n] of one trial.  Every Philox call is addressed by position: c0 = (block << 6) | slot."""
     key = (seed & M32, (seed >> 32) & M32)
 
     def call(block, slot):
@@ -150,10 +150,11 @@ def philox_bits(seed, stream, trial, N, n, T):
             k += 1
         return e
 
-    u = [0] * N
+    u = [0] * N if k == 1 else [[0] * k for _ in range(N)]
     e = [[0] * n for _ in range(N)]
     for sb in range((N + 127) // 128):
         uw = call(4 * sb, 32)
+        uk = [uw] + [call(4 * sb, 32 + i) for i in range(1, k)]
         for w in range(4):
             t0 = 128 * sb + 32 * w
             if t0 >= N:
@@ -162,7 +163,10 @@ def philox_bits(seed, stream, trial, N, n, T):
             vmask = M32 if valid == 32 else (1 << valid) - 1
             ew = [lazy(4 * sb + w, j, vmask) for j in range(n)]
             for b in range(valid):
-                u[t0 + b] = (uw[w] >> b) & 1
+                if k == 1:
+                    u[t0 + b] = (uw[w] >> b) & 1
+                else:
+                    u[t0 + b] = [(uk[i][w] >> b) & 1 for i in range(k)]
                 for j in range(n):
                     e[t0 + b][j] = (ew[j] >> b) & 1
     return u, e
@@ -184,9 +188,7 @@ def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_in
     dec = generator_matrix if decoder_matrix is None else decoder_matrix
     trellis = trellis_fn(dec, m, k)
     if u_bits is None or e_bits is None:
-        if k != 1:
-            raise NotImplementedError("MVD-PHILOX-2 is defined for k = 1")
-        gu, ge = philox_bits(0 if seed is None else int(seed), stream, trial, length, n, threshold_of(p_val))
+        gu, ge = philox_bits(0 if seed is None else int(seed), stream, trial, length, n, threshold_of(p_val), k)
         u_bits = gu if u_bits is None else u_bits
         e_bits = ge if e_bits is None else e_bits
     D = tuple([0] * (1 << m))
@@ -194,7 +196,7 @@ def simulate_markov_sequence(generator_matrix, m, k, n, length, p_val, random_in
     received = []
     enc = 0
     for t in range(length):
-        u = (int(u_bits[t]) if random_input else 0,) if k == 1 else tuple(int(b) for b in u_bits[t])
+        u = (int(u_bits[t]) if random_input else 0,) if k == 1 else tuple(int(b) if random_input else 0 for b in u_bits[t])
         out, enc = branch_fn(enc, u, generator_matrix, m, k)
         r = tuple(int(o) ^ int(f) for o, f in zip(out, e_bits[t]))
         D = step(list(D), trellis, r)

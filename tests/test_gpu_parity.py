@@ -2,6 +2,8 @@
 and against the CPU oracle on identical bit streams.  Integer results are compared bit-exactly;
 float64 log-likelihoods bit-exactly too (tolerance stated where it is looser).  All calls go through
 the C ABI (ctypes -> libmvd.so)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -919,8 +921,11 @@ def test_abi_argument_errors(codes_spec, dets):
         det.detect([Seg(N=10, trial_begin=5, trial_end=1)], seed=1)                     # end < begin
     with pytest.raises(_capi.MvdError):
         det.detect([Seg(N=300, trial_begin=0, trial_end=4)], bits=np.zeros((1, 3, 4, 4), dtype=np.uint32))  # short
-    with pytest.raises(_capi.MvdError):
-        Detector([[[1, 1, 1], [1, 0, 1]], [[1, 0, 1], [1, 1, 1]]], 2, 2, 2)              # k = 2 unsupported on device
+    with pytest.raises(_capi.MvdError) as exc:
+        Detector([[[1, 1, 1]] * 4, [[1, 0, 1]] * 4], 4, 2, 2)                            # k = 4 > MVD_MAX_K inputs per step
+    assert exc.value.code == -3
+    with pytest.raises(_capi.MvdError):                                                 # tap-mask form is k = 1 (tables: test_k2_codes.py)
+        det._ck(det.lib.mvd_set_code(det.ctx, 2, 2, 2, (C.c_uint32 * 2)(7, 5)))
 
 
 def test_int_peak_and_info(dets):
