@@ -500,8 +500,9 @@ struct LaunchOut {
 // Shared-memory plan of the fast detection kernels; returns false if they do not apply.
 bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPlan* fp, size_t* smem_out, bool* gt_out) {
     *gt_out = false;
-    if (ctx->n != 2 || !ctx->closed) return false;
-    const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 4;
+    // n = 2: every engine; n = 3 (rate 1/3): the NEXT-walk engines, which take any number of received words
+    if (!(ctx->n == 2 || (ctx->n == 3 && engine == MVD_ENGINE_FSM)) || !ctx->closed) return false;
+    const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 1 << ctx->n;
     const size_t SR = (size_t)ctx->S * R;
     int lk;
     if (engine == MVD_ENGINE_FSM && ctx->tref_packed && !ctx->no_fsm1 && 128 + (SR << 4) + 64 <= ctx->prop.sharedMemPerBlockOptin) {

@@ -334,6 +334,85 @@ __device__ __forceinline__ void run_trial_n2(const Params& P, const DevSeg& sg, 
     }
 }
 
+// ------------------------------------------------------------------------------------------ driver (n = 3)
+// Rate-1/3 codes on the NEXT-walk engines (which do not care how many received words there are: a step takes r << LLS).
+// Same bit source, same encoder; the received word of step t is (R0 bit t, R1 bit t, R2 bit t), first output = MSB,
+// assembled with three shifts and three LOP3 per step (8 steps straight-line, shift counts as immediates).
+template <int LLS, class Eng>
+__device__ __forceinline__ void run_trial_n3(const Params& P, const DevSeg& sg, bool active, unsigned long long trial,
+                                             unsigned long long tl, unsigned long long ntr, const uint4* tbm, Eng& eng) {
+    const int m = P.m;
+    const uint32_t N = sg.N;
+    const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
+    const bool philox = P.src_mode == MVD_SRC_PHILOX;
+    uint32_t c1 = (uint32_t)trial, c2 = (uint32_t)(trial >> 32), c3 = sg.stream, am = active ? 0xFFFFFFFFu : 0u;
+    uint32_t a_tbp = (uint32_t)__cvta_generic_to_shared(tbm);
+    asm volatile("" : "+r"(c1), "+r"(c2), "+r"(am));
+    const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1], taps2 = sg.enc_taps[2];
+    uint32_t prevU = 0;
+    const uint32_t nsb = (N + 127u) >> 7;
+    for (uint32_t sb = 0; sb < nsb; ++sb) {
+        uint4 Uw = make_uint4(0, 0, 0, 0), E0 = Uw, E1 = Uw, E2 = Uw;
+        if (philox) {
+            Uw = philox10(((4u * sb) << 6) | 32u, c1, c2, c3, P);
+        } else if (active) {
+            const uint4* base = P.bits + sg.bits_offset + (unsigned long long)sb * 4ull * ntr + tl;
+            Uw = __ldg(base);
+            E0 = __ldg(base + ntr);
+            E1 = __ldg(base + 2ull * ntr);
+            E2 = __ldg(base + 3ull * ntr);
+        }
+        if (!sg.random_input) Uw = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t t0 = sb * 128u + (uint32_t)w * 32u;
+            if (t0 >= N) break;
+            const uint32_t valid = min(32u, N - t0);
+            const uint32_t vmask = valid == 32u ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+            const uint32_t U = pick(Uw, w);
+            uint32_t e0, e1, e2;
+            if (philox) {
+                uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask & am;
+                asm volatile("" : "+r"(vm));
+                e0 = e1 = e2 = 0u;
+#pragma unroll 1
+                for (int j = 0; j < 3; ++j) {                               // one copy of the lazy loop for the three outputs
+                    e0 = e1;
+                    e1 = e2;
+                    e2 = lazy_bernoulli_a(cb | ((uint32_t)j << 3), c1, c2, c3, a_tbp, ncalls, vm, P);
+                }
+            } else {
+                e0 = pick(E0, w);
+                e1 = pick(E1, w);
+                e2 = pick(E2, w);
+            }
+            uint32_t o0 = U & (0u - (taps0 & 1u)), o1 = U & (0u - (taps1 & 1u)), o2 = U & (0u - (taps2 & 1u));
+#pragma unroll 1
+            for (int i = 1; i <= m; ++i) {
+                const uint32_t sh = __funnelshift_l(prevU, U, i);
+                o0 ^= sh & (0u - ((taps0 >> i) & 1u));
+                o1 ^= sh & (0u - ((taps1 >> i) & 1u));
+                o2 ^= sh & (0u - ((taps2 >> i) & 1u));
+            }
+            prevU = U;
+            const uint32_t R0 = o0 ^ e0, R1 = o1 ^ e1, R2 = o2 ^ e2;        // BSC
+            if (valid == 32u) {
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {                               // 8 steps per iteration
+                    // bits 0..7 of the three words moved to where step J wants them: output 0 at LLS + 2, 1 at LLS + 1, 2 at LLS
+                    const uint32_t x0 = (R0 >> (8 * h)) << (LLS + 2), x1 = (R1 >> (8 * h)) << (LLS + 1), x2 = (R2 >> (8 * h)) << LLS;
+#pragma unroll
+                    for (int J = 0; J < 8; ++J)
+                        eng.step(((x0 >> J) & (4u << LLS)) | ((x1 >> J) & (2u << LLS)) | ((x2 >> J) & (1u << LLS)));
+                }
+            } else {
+                for (uint32_t t = 0; t < valid; ++t)
+                    eng.step(((((R0 >> t) & 1u) << 2) | (((R1 >> t) & 1u) << 1) | ((R2 >> t) & 1u)) << LLS);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ engines
 // ACS: Eq. 4-5 in registers (AcsCore), then metric vector -> Markov state.
 //   sx = shared-memory byte address of this lane's copy of the log-likelihood row of the current state.
@@ -461,9 +540,11 @@ struct Fsm1Engine {
 // GT = true: the state / log-likelihood tables stay in global memory (L2-resident; S too large for
 // shared memory, e.g. m = 4 with S = 25 751 ... 232 567): nothing but the threshold masks and the
 // branch metrics is staged, LLS = 4 (no replicas).
-template <int LK, int M, int LLS, bool GT = false>
+// NOUT = 3: rate-1/3 codes (NEXT-walk engines only).
+template <int LK, int M, int LLS, bool GT = false, int NOUT = 2>
 __global__ void __launch_bounds__(DET2_BLOCK, (LK == LK_FSM1 || LK == LK_FSM) ? 3 : 2) detect2_kernel(const __grid_constant__ Params P,
                                                                 const __grid_constant__ SegBatch B) {
+    static_assert(NOUT == 2 || (NOUT == 3 && (LK == LK_FSM1 || LK == LK_FSM)), "n = 3 runs on the NEXT-walk engines");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REP = 1 << (LLS - 4);
     const DevSeg& sg = B.s[blockIdx.y];
@@ -551,7 +632,8 @@ __global__ void __launch_bounds__(DET2_BLOCK, (LK == LK_FSM1 || LK == LK_FSM) ? 
         eng.unit = P.fp.tref_unit;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS, 0>(P, sg, active, trial, tl, ntr, tbm, eng);
+        if (NOUT == 3) run_trial_n3<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
+        else run_trial_n2<LLS, 0>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     } else if (LK == LK_FSM) {
@@ -562,7 +644,8 @@ __global__ void __launch_bounds__(DET2_BLOCK, (LK == LK_FSM1 || LK == LK_FSM) ? 
         eng.nx_lane = LLS == 7 ? (P.fp.off_st + lane * 4u) - ll_lane : P.fp.off_st;
         eng.a1 = 0.0;
         eng.a0 = 0.0;
-        run_trial_n2<LLS, 0>(P, sg, active, trial, tl, ntr, tbm, eng);
+        if (NOUT == 3) run_trial_n3<LLS>(P, sg, active, trial, tl, ntr, tbm, eng);
+        else run_trial_n2<LLS, 0>(P, sg, active, trial, tl, ntr, tbm, eng);
         a1 = eng.a1;
         a0 = eng.a0;
     } else {

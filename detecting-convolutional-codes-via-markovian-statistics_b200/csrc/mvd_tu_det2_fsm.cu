@@ -3,9 +3,9 @@
 #include "mvd_launch.h"
 
 namespace {
-template <int LK, int M, int LLS, bool GT>
+template <int LK, int M, int LLS, bool GT, int NOUT = 2>
 cudaError_t launch_one(dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
-    auto kern = detect2_kernel<LK, M, LLS, GT>;
+    auto kern = detect2_kernel<LK, M, LLS, GT, NOUT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, threads, smem, st>>>(P, B);
@@ -15,6 +15,25 @@ cudaError_t launch_one(dim3 grid, unsigned threads, size_t smem, cudaStream_t st
 
 cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned threads, size_t smem, cudaStream_t st,
                                 const Params& P, const SegBatch& B) {
+    if (P.n == 3) {                                      // rate-1/3: the same engines behind the n = 3 driver
+        if (lk == LK_FSM1) {
+            if (gt) return launch_one<LK_FSM1, 1, 4, true, 3>(grid, threads, smem, st, P, B);
+            switch (lls) {
+                case 4: return launch_one<LK_FSM1, 1, 4, false, 3>(grid, threads, smem, st, P, B);
+                case 5: return launch_one<LK_FSM1, 1, 5, false, 3>(grid, threads, smem, st, P, B);
+                case 6: return launch_one<LK_FSM1, 1, 6, false, 3>(grid, threads, smem, st, P, B);
+                default: return launch_one<LK_FSM1, 1, 7, false, 3>(grid, threads, smem, st, P, B);
+            }
+        }
+        if (lk != LK_FSM || gt) return cudaErrorInvalidValue;
+        switch (lls) {
+            case 4: return launch_one<LK_FSM, 1, 4, false, 3>(grid, threads, smem, st, P, B);
+            case 5: return launch_one<LK_FSM, 1, 5, false, 3>(grid, threads, smem, st, P, B);
+            case 6: return launch_one<LK_FSM, 1, 6, false, 3>(grid, threads, smem, st, P, B);
+            case 7: return launch_one<LK_FSM, 1, 7, false, 3>(grid, threads, smem, st, P, B);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     if (lk == LK_FSM1) {
         if (gt) return launch_one<LK_FSM1, 1, 4, true>(grid, threads, smem, st, P, B);
         switch (lls) {

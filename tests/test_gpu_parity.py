@@ -254,8 +254,11 @@ def test_detect_vs_oracle(codes_spec, dets, engine, dec, enc, N, p, path):
         det.no_antipodal(False)
     if path == "fastg":
         path = "fast"
-    if path == "generic" or spec["n"] != 2:
+    if path == "generic" or (spec["n"] != 2 and engine == "acs"):
         assert kind == 0
+    elif spec["n"] != 2:
+        # rate 1/3 on the NEXT-walk engines (run_trial_n3): the one-load walk when log T(1/2) packs, else the two-load one
+        assert kind != 0 and (kind - 1) % 16 in ((2,) if path == "fast1" else (2, 3))
     else:
         want_lookup = (2 if path == "fast1" else 3) if engine == "fsm" else (0 if spec["m"] <= 2 else 1)
         assert kind != 0 and (kind - 1) % 16 == want_lookup
@@ -371,6 +374,52 @@ def test_detect_fast_bitstream_vs_generic(codes_spec, dets, engine, dec, enc, pa
         idx, rseq, _ = co.simulate(_taps(spec), taps2, 2, spec["m"], N, U, E, tab)
         assert co.log_prob(idx, rseq, N, 2, P1) == lp_fast[t, 0]
         assert co.log_prob(idx, rseq, N, 2, Tref) == lp_fast[t, 1]
+
+
+@pytest.mark.parametrize("no_fsm1", [False, True])
+def test_rate13_fast_walk_bitstream(codes_spec, dets, no_fsm1):
+    """Rate 1/3 (n = 3, R = 8 received words) through the fast NEXT-walk kernels (run_trial_n3) on host-supplied bit streams and
+    on the device bit source: == the generic kernels == the oracle, ragged N, both walk variants."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec["r13"]
+    det = dets("r13")
+    tab, P1, Tref = _oracle_models(det, spec, 0.12, 8000, 7)
+    det.set_models([P1])
+    rng = np.random.default_rng(5)
+    ntr, N = 600, 203
+    u = rng.integers(0, 2, (ntr, N), dtype=np.uint8)
+    e = (rng.random((ntr, 3, N)) < 0.12).astype(np.uint8)
+    bits = bitsource.pack_bitstreams(u, e)
+    taps = _taps(spec)
+    seg = Seg(N=N, enc_taps=taps, decide=1, trial_begin=0, trial_end=ntr)
+    det.no_fsm1(no_fsm1)
+    try:
+        t_fast, lp_fast = det.detect([seg], bits=bits, engine="fsm", want_logp=True)
+        kind = det.last_kernel_kind()
+        T = bitsource.bsc_threshold(0.12)
+        pseg = Seg(N=N, threshold=T, stream=4, enc_taps=taps, decide=0, trial_begin=9, trial_end=9 + ntr)
+        t_ph, lp_ph = det.detect([pseg], seed=77, engine="fsm", want_logp=True)
+        assert det.last_kernel_kind() == kind
+    finally:
+        det.no_fsm1(False)
+    assert kind != 0 and (kind - 1) % 16 in ((2,) if no_fsm1 else (2, 3))
+    det.force_generic(True)
+    try:
+        t_gen, lp_gen = det.detect([seg], bits=bits, engine="fsm", want_logp=True)
+        assert det.last_kernel_kind() == 0
+    finally:
+        det.force_generic(False)
+    assert int(t_fast[0]) == int(t_gen[0]) and np.array_equal(lp_fast, lp_gen)
+    for t in range(30):
+        U = bitsource.bits_to_words(u[t])[:(N + 31) // 32]
+        E = bitsource.bits_to_words(e[t])[:, :(N + 31) // 32]
+        idx, rseq, _ = co.simulate(taps, taps, 3, spec["m"], N, U, E, tab)
+        assert co.log_prob(idx, rseq, N, 3, P1) == lp_fast[t, 0]
+        assert co.log_prob(idx, rseq, N, 3, Tref) == lp_fast[t, 1]
+    want, wlp = co.run_trials(taps, taps, 3, spec["m"], N, T, 77, 4, 9, 9 + ntr, tab, P1, Tref, 0, want_logp=True)
+    assert int(t_ph[0]) == want and np.array_equal(lp_ph, wlp)
 
 
 @pytest.mark.parametrize("warm", [128, 0])
