@@ -495,6 +495,11 @@ def main():
             ps[eng] = {"pd_vs_p_ms": 1e3 * tp, "pd_vs_p_kernel_ms": dp["detect_kernel_ms"], "pd_vs_p_steps": dp["steps"],
                        "pd_vs_n_ms": 1e3 * tn, "pd_vs_n_kernel_ms": dn["detect_kernel_ms"], "pd_vs_n_steps": dn["steps"],
                        "pd_vs_p_sha": _sha(dp["tallies"]), "pd_vs_n_sha": _sha(dn["tallies"])}
+        # BASELINE config 3 as the reference runs it: 10^4 iterations per point in total (few long trials per GPU: the time-split
+        # path with exactly re-associated float64 sums, csrc/mvd_split.cuh)
+        t3, d3 = sweep(10000, SWEEP_N_PS, SWEEP_N_NS, "auto")
+        ps["config3_ref_iters"] = {"trials_per_point": 10000, "pd_vs_n_ms": 1e3 * t3, "pd_vs_n_kernel_ms": d3["detect_kernel_ms"],
+                                   "pd_vs_n_steps": d3["steps"], "pd_vs_n_sha": _sha(d3["tallies"])}
         line["paper_sweep"] = ps
 
         # ---- sustained: the resident loop for >= sustain_s seconds, clocks and power sampled throughout

@@ -197,3 +197,49 @@ def test_gpu_k2_vs_oracle_and_envelope(k2):
         assert det.lib.mvd_set_states(det.ctx, det.table.S, met.ctypes.data, np.ascontiguousarray(bad, dtype=np.uint32).ctypes.data) == 0
         with pytest.raises(_capi.MvdError):
             det.detect(segs, seed=31, engine="fsm")
+
+
+@pytest.mark.gpu
+def test_integration_md_table_stub_runs_as_written(k2):
+    """The k > 1 stub of INTEGRATION.md (tables from the reference-named trellis / branch functions -> mvd_set_code_tables /
+    mvd_set_encoders) executed verbatim, then one detection call through the raw C ABI == the Detector path."""
+    import ctypes as C
+    import re
+    import viterbi_markov as vm
+    from mvd import _capi, bitsource, codes
+    from mvd.engine import Detector, Seg
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    snippet = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "mvd_set_code_tables" in b][0]
+    spec, espec = k2["codes"]["k2c"], k2["codes"]["k2d"]
+    k, n, m = spec["k"], spec["n"], spec["m"]
+    lib = C.CDLL(_capi.LIB_PATH)
+    lib.mvd_last_error.restype = C.c_char_p
+    ctx = C.c_void_p()
+    assert lib.mvd_create(C.byref(ctx), 0) == 0
+    env = dict(vm=vm, np=np, lib=lib, ctx=ctx, k=k, n=n, m=m, gen1=spec["gen"], gen2=espec["gen"],
+               ptr=lambda a: a.ctypes.data_as(C.c_void_p))
+    exec(compile(snippet, "INTEGRATION.md#tables", "exec"), env)
+    with Detector(spec["gen"], k, n, m) as det:
+        T = bitsource.bsc_threshold(0.1)
+        counts = det.learn_counts([Seg(N=20000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=det.dec_taps)], burn=200, seed=3)[0]
+        P1 = codes.p1_from_edge_counts(det.table, counts, 1.0)
+        det.set_models([P1])
+        segs = [Seg(N=120, threshold=T, stream=h, enc_taps=det.taps_of((spec, espec)[h]["gen"]), decide=h, trial_begin=0, trial_end=2000)
+                for h in (0, 1)]
+        want = det.detect(segs, seed=3)
+        met = np.ascontiguousarray(det.table.metrics, dtype=np.uint8)
+        nxt = np.ascontiguousarray(det.table.nxt, dtype=np.uint32)
+        assert lib.mvd_set_states(ctx, det.table.S, env["ptr"](met), env["ptr"](nxt)) == 0, lib.mvd_last_error(ctx)
+        assert lib.mvd_set_loglik(ctx, 1, env["ptr"](det.logP1), env["ptr"](det.logTref)) == 0
+        raw = (_capi.Segment * 2)()
+        for h in (0, 1):
+            raw[h].N, raw[h].threshold, raw[h].stream, raw[h].table, raw[h].decide, raw[h].random_input = 120, T, h, 0, h, 1
+            raw[h].enc_taps[0] = h                                  # encoder INDEX: 0 = gen1, 1 = gen2
+            raw[h].trial_begin, raw[h].trial_end = 0, 2000
+        src = _capi.Src()
+        src.mode, src.seed = _capi.SRC_PHILOX, 3
+        tallies = np.zeros(2, dtype=np.uint64)
+        assert lib.mvd_detect(ctx, C.byref(src), raw, 2, 0, env["ptr"](tallies), None, None) == 0, lib.mvd_last_error(ctx)
+        assert tallies.tolist() == want.tolist()
+    lib.mvd_destroy(ctx)
