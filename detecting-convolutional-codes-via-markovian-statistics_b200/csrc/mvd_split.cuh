@@ -623,13 +623,21 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
         uint32_t j = 0;
 #pragma unroll 1
         while (true) {
-            // the records whose partial sums apply: both sums in the predicted binade before and after
+            // the records whose partial sums apply: both sums in the predicted binade before and after.  Record j + 1 is read
+            // while record j is tested (its slot always exists in the ring; what it holds past the batch is never used)
+            uint32_t plan = 0u;
+            double2 r = make_double2(0.0, 0.0);
+            auto record = [&](uint32_t jj, uint32_t& pl, double2& rr) {
+                const uint32_t slot = half + min(jj, SPLIT_RB - 1u);
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pl) : "r"(rplan + slot * blockDim.x * 4u));
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rr.x), "=d"(rr.y) : "r"(rres + slot * blockDim.x * 16u));
+            };
+            if (j < cnt) record(j, plan, r);
 #pragma unroll 1
             while (j < cnt) {
-                uint32_t plan;
-                double2 r;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(plan) : "r"(rplan + (half + j) * blockDim.x * 4u));
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(rres + (half + j) * blockDim.x * 16u));
+                uint32_t plan_n;
+                double2 r_n;
+                record(j + 1u, plan_n, r_n);
                 if (!(plan & SPLIT_PLAN_FAST)) break;
                 // sign and exponent (the top 12 bits) of both sums, before and after, are those of -2^k
                 const uint32_t K1 = 0x80000000u | (plan << 20), K0 = 0x80000000u | ((plan >> 11) << 20);
@@ -640,6 +648,8 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
                 a1 = n1;
                 a0 = n0;
                 ++j;
+                plan = plan_n;
+                r = r_n;
             }
             const bool need = j < cnt;
             if (!__any_sync(0xFFFFFFFFu, need)) break;
