@@ -52,6 +52,11 @@ K2_CODES = {
     "k2b": dict(k=2, n=3, m=2, gen=[[[1, 0, 1], [0, 1, 1]], [[1, 1, 0], [1, 0, 1]], [[0, 1, 1], [1, 1, 1]]]),             # S = 5
     "k2c": dict(k=2, n=3, m=3, gen=[[[1, 1, 0, 1], [0, 1, 1, 0]], [[1, 0, 1, 1], [1, 1, 0, 0]], [[0, 1, 1, 1], [1, 0, 1, 0]]]),   # S = 235
     "k2d": dict(k=2, n=3, m=3, gen=[[[1, 0, 1, 1], [0, 1, 1, 0]], [[1, 1, 0, 1], [1, 0, 1, 0]], [[0, 1, 1, 1], [1, 1, 0, 0]]]),
+    # k = 3 inputs, n = 4 outputs, m = 2 < k (the next state is the first two inputs): S = 89 and S = 15
+    "k3a": dict(k=3, n=4, m=2, gen=[[[1, 1, 1], [1, 1, 1], [0, 1, 0]], [[1, 0, 1], [1, 0, 1], [0, 0, 0]],
+                                    [[1, 1, 1], [0, 0, 1], [0, 0, 1]], [[0, 1, 1], [1, 0, 1], [0, 1, 1]]]),
+    "k3b": dict(k=3, n=4, m=2, gen=[[[0, 0, 1], [1, 1, 0], [0, 1, 0]], [[0, 0, 0], [0, 1, 0], [0, 1, 0]],
+                                    [[0, 1, 0], [0, 1, 0], [0, 1, 0]], [[1, 1, 0], [1, 0, 0], [0, 0, 0]]]),
 }
 
 
@@ -387,12 +392,14 @@ def main():
     if args.k2_only:
         k2 = dict(codes={}, sims={}, experiments={})
         for name, spec in K2_CODES.items():
-            k2["codes"][name] = kat_for_code(vm, pdp, name, spec, symbolic=(name == "k2b"))
+            k2["codes"][name] = kat_for_code(vm, pdp, name, spec, symbolic=(name in ("k2b", "k3b")))
             print(f"[k2] {name}: S={k2['codes'][name]['S']}", flush=True)
         k2["sims"] = {
             "k2c_self": sim_kat(vm, "k2c", K2_CODES["k2c"], K2_CODES["k2c"], 300, 0.1, 12345, 0, 7),
             "k2c_vs_d": sim_kat(vm, "k2c", K2_CODES["k2c"], K2_CODES["k2d"], 260, 0.05, 99, 1, (1 << 33) + 5),
             "k2b_self": sim_kat(vm, "k2b", K2_CODES["k2b"], K2_CODES["k2b"], 129, 0.3, 5, 2, 3),
+            "k3a_self": sim_kat(vm, "k3a", K2_CODES["k3a"], K2_CODES["k3a"], 200, 0.1, 77, 0, 1),
+            "k3a_vs_b": sim_kat(vm, "k3a", K2_CODES["k3a"], K2_CODES["k3b"], 161, 0.2, 77, 1, 2),
         }
         k2["experiments"]["k2c_k2d"] = experiment_golden(vm, pdp, K2_CODES["k2c"], K2_CODES["k2d"], num_iter=10, p_vec=[0.05, 0.2],
                                                          N_list=[64, 150], seed=7)

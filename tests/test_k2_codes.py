@@ -1,4 +1,4 @@
-"""Codes with k = 2 inputs per step: viterbi_markov.py:82-132 is generic in k (every input sees the register
+"""Codes with k = 2 and k = 3 inputs per step: viterbi_markov.py:82-132 is generic in k (every input sees the register
 [u_i, s_0, ..]).  The device takes such codes as tables (mvd_set_code_tables / mvd_set_encoders) and runs the Markov-state
 walk with a table-driven encoder.  Golden vectors: tests/golden/k2_kats.json, written by `oracle/make_golden.py --k2-only`
 from the reference's own functions (branch / trellis / step / BFS, and run_experiment unmodified with the injected simulator).
@@ -27,7 +27,7 @@ def _tables(spec):
 
 
 # ------------------------------------------------------------------------------------------------ CPU: host tables + oracle
-@pytest.mark.parametrize("name", ["k2b", "k2c", "k2d"])
+@pytest.mark.parametrize("name", ["k2b", "k2c", "k2d", "k3a", "k3b"])
 def test_host_tables_match_reference(k2, name):
     """encoder_tables / trellis_arrays / enumerate_states for k = 2 == the reference's branch_output_and_next_state,
     build_trellis and enumerate_markov_states_allzero (state list, BFS order, NEXT)."""
@@ -51,7 +51,11 @@ def test_host_tables_match_reference(k2, name):
         assert np.array_equal(codes.tref_half_table(tab), np.array(g["T_edge"]["0.5"]))
 
 
-@pytest.mark.parametrize("sim,dec,enc", [("k2c_self", "k2c", "k2c"), ("k2c_vs_d", "k2c", "k2d"), ("k2b_self", "k2b", "k2b")])
+SIMS = [("k2c_self", "k2c", "k2c"), ("k2c_vs_d", "k2c", "k2d"), ("k2b_self", "k2b", "k2b"), ("k3a_self", "k3a", "k3a"),
+        ("k3a_vs_b", "k3a", "k3b")]
+
+
+@pytest.mark.parametrize("sim,dec,enc", SIMS)
 def test_oracle_tab_trajectories(k2, sim, dec, enc):
     """mvdo_trial_words_k + mvdo_simulate_tab == the reference's branch + step functions under MVD-PHILOX-2 with k = 2
     (info bits of input i from slot 32 + i): bits, received words and metric vectors."""
@@ -112,7 +116,7 @@ def test_oracle_tab_experiment(k2):
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("sim,dec,enc", [("k2c_self", "k2c", "k2c"), ("k2c_vs_d", "k2c", "k2d"), ("k2b_self", "k2b", "k2b")])
+@pytest.mark.parametrize("sim,dec,enc", SIMS)
 @pytest.mark.parametrize("source", ["philox", "bitstream"])
 def test_gpu_trace_k2(k2, sim, dec, enc, source):
     """simulate_markov_sequence (drop-in) for k = 2 on the device: the metric trajectory of the reference's own functions,
