@@ -764,6 +764,42 @@ def test_config3_blocklengths_vs_oracle(codes_spec, dets, dec, enc, p):
             assert np.array_equal(lp[j * ntr:(j + 1) * ntr], wlp)
 
 
+def test_config3_full_size_paths_agree(codes_spec, dets):
+    """BASELINE config 3 at full size (N = 10^5, 2 000 trials per hypothesis, 4e8 trellis steps): the split path with
+    re-associated sums == the same path adding every term in order == one thread per trial -- tallies and all 4 000 pairs of
+    float64 sums; 8 of the trials against the C oracle over their whole length."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    spec = codes_spec["c75"]
+    det = dets("c75")
+    tab, P1, Tref = _oracle_models(det, spec, 0.1, 8000, 5)
+    det.set_models([P1])
+    T = bitsource.bsc_threshold(0.1)
+    N, ntr = 100000, 2000
+    segs = [Seg(N=N, threshold=T, stream=60 + d, enc_taps=_taps(codes_spec["c65" if d else "c75"]), decide=d, trial_begin=0,
+                trial_end=ntr) for d in (0, 1)]
+    runs = []
+    try:
+        for split, seq in ((1, False), (1, True), (2, False)):
+            det.split_trials(split)
+            det.split_sequential(seq)
+            runs.append(det.detect(segs, seed=5, engine="fsm", want_logp=True))
+            assert bool(det.last_kernel_kind() & 16384) == (split == 1)
+            if split == 1 and not seq:
+                subs, nseq = det.split_stats()
+                assert subs == 2 * ntr * 782 and nseq < 0.05 * subs
+    finally:
+        det.split_trials(0)
+        det.split_sequential(False)
+    for t, lp in runs[1:]:
+        assert np.array_equal(t, runs[0][0]) and np.array_equal(lp, runs[0][1])
+    for d in (0, 1):
+        want, wlp = co.run_trials(_taps(spec), _taps(codes_spec["c65" if d else "c75"]), 2, 2, N, T, 5, 60 + d, 0, 4, tab, P1, Tref, d,
+                                  want_logp=True)
+        assert np.array_equal(runs[0][1][d * ntr:d * ntr + 4], wlp)
+
+
 _BENCH_GEOMETRY_WANT = {}
 
 
