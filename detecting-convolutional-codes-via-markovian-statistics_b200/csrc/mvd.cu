@@ -60,6 +60,8 @@ struct mvd_ctx {
     std::vector<uint8_t> h_dec_prev, h_dec_lab;   // [2^m][2^k]
     uint32_t nenc = 0;
     uint32_t split_chunk = 0;       // MVD_OPT_SPLIT_CHUNK: 0 = automatic, else 256 / 512 / 1024 steps per chunk
+    SplitClasses split_cls{};       // log Tref has <= 3 distinct non-zero values: the split path counts them (class mode)
+    bool no_split_classes = false;  // MVD_OPT_SPLIT_SEQUENTIAL = 2: re-association without the class mode (both sums as recurrences)
     bool split_tables_ready = false;// tie binades / float32 terms of the current log-likelihood tables are on the device
     unsigned long long last_split_sub = 0, last_split_seq = 0;   // sub-chunks of the last split launch / of them added term by term
     bool have_gfsm1 = false;
@@ -952,6 +954,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
         SP.nchains = (uint32_t)trials;
         SP.nwork = w;
         SP.sequential = ctx->split_sequential ? 1 : 0;
+        SP.cls = ctx->no_split_classes ? SplitClasses{} : ctx->split_cls;
         CK(ctx->d_smeta.reserve(meta.size() * 8 + 16));
         CK(h2d(ctx, ctx->d_smeta.p, meta.data(), meta.size() * 8));
         SP.work_begin = ctx->d_smeta.as<unsigned long long>();
@@ -973,7 +976,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             CK(ctx->d_sapxtab.reserve(cells * 8));
             CK(ctx->d_stiek.reserve(16 * (size_t)ctx->ntables));
             CK(mvd_launch_split_tables(ctx->d_ll.as<double2>(), (uint32_t)SR, ctx->ntables, ctx->d_stie.as<uint32_t>(), ctx->d_sapxtab.as<float2>(),
-                                       ctx->d_sflags.as<uint32_t>(), ctx->d_stiek.as<unsigned long long>(), ctx->stream));
+                                       ctx->d_sflags.as<uint32_t>(), ctx->d_stiek.as<unsigned long long>(),
+                                       ctx->no_split_classes ? SplitClasses{} : ctx->split_cls, ctx->stream));
             ctx->launches += 1;
             ctx->split_tables_ready = true;
         }
@@ -1429,6 +1433,20 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
         double unit = 0.0;
         for (size_t e = 0; e < SR; ++e)
             if (logTref[e] != 0.0 && (unit == 0.0 || std::fabs(logTref[e]) < std::fabs(unit))) unit = logTref[e];
+        // the distinct non-zero values of log Tref, if there are at most three (class mode of the split path, mvd_split.cuh)
+        SplitClasses cls{};
+        for (size_t e = 0; e < SR && cls.n >= 0; ++e) {
+            const double v = logTref[e];
+            if (v == 0.0) continue;
+            int j = 0;
+            while (j < cls.n && cls.val[j] != v) ++j;
+            if (j == cls.n) {
+                if (cls.n == 3 || !(v < 0.0)) cls.n = -1;           // a fourth value, a positive one or a NaN: no class mode
+                else cls.val[cls.n++] = v;
+            }
+        }
+        if (cls.n < 0) cls = SplitClasses{};
+        ctx->split_cls = cls;
         bool ok = true;
         std::vector<uint32_t> code(SR, 0u);
         for (size_t e = 0; e < SR && ok; ++e) {
@@ -1888,7 +1906,10 @@ int mvd_set_option(mvd_ctx* ctx, int option, int64_t value) {
         return MVD_OK;
     }
     if (option == MVD_OPT_SPLIT_SEQUENTIAL) {
-        ctx->split_sequential = value != 0;
+        if (value < 0 || value > 2) return fail(ctx, MVD_E_INVALID, "MVD_OPT_SPLIT_SEQUENTIAL takes 0, 1 or 2");
+        ctx->split_sequential = value == 1;
+        if (ctx->no_split_classes != (value == 2)) ctx->split_tables_ready = false;    // the float32 rows differ between the modes
+        ctx->no_split_classes = value == 2;
         return MVD_OK;
     }
     if (option == MVD_OPT_SPLIT) {

@@ -80,7 +80,7 @@ cudaError_t mvd_launch_parity(dim3 grid, cudaStream_t st, const Params& P, const
 cudaError_t mvd_launch_split(size_t walk_bytes, size_t isum_bytes, size_t score_bytes, cudaStream_t st, const Params& P, const SplitParams& SP);
 // per (table, edge): tie binades, float32 terms, "some term is positive" flag
 cudaError_t mvd_launch_split_tables(const double2* ll, uint32_t SR, uint32_t ntables, uint32_t* tie, float2* apx, uint32_t* flags,
-                                    unsigned long long* tiek, cudaStream_t st);
+                                    unsigned long long* tiek, const SplitClasses& cls, cudaStream_t st);
 
 // Eq. 4-5 at m = 2..6, two trials per thread, final metric vectors only (mvd_tu_acsp.cu)
 cudaError_t mvd_launch_acsp(int m, dim3 grid, unsigned threads, cudaStream_t st, const Params& P, const DevSeg& sg,

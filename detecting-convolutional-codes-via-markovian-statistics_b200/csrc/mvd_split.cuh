@@ -80,13 +80,29 @@ __device__ __forceinline__ uint32_t split_tie_code(double v) {
 
 // tiek[table] = {binades in which some log P1 term of the table is a tie, the same for log Tref}: a sub-chunk predicted into a
 // binade without any reads no tie codes at all
+// Class mode (cls.n > 0): log Tref takes at most three distinct non-zero values (rate-1/2 codes: T(1/2) entries are 1/4, 1/2, 3/4, 1),
+// so the second sum of a sub-chunk is determined by how often each value occurs.  apx[e].y is then not the term but a float32
+// COUNTER INCREMENT 256^j for class j (0 for a zero term): the walk's float additions count exactly (at most 128 terms per
+// sub-chunk: every partial sum is an integer below 2^24), and split_plan_kernel turns the counts into the exact partial sum.
 __global__ void split_tables_kernel(const double2* __restrict__ ll, size_t cells, uint32_t SR, uint32_t* __restrict__ tie,
-                                    float2* __restrict__ apx, uint32_t* __restrict__ flags, unsigned long long* __restrict__ tiek) {
+                                    float2* __restrict__ apx, uint32_t* __restrict__ flags, unsigned long long* __restrict__ tiek,
+                                    const SplitClasses cls) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
     const double2 v = ll[i];
     const uint32_t t1 = split_tie_code(v.x), t0 = split_tie_code(v.y);
     tie[i] = t1 | (t0 << 8);
+    if (cls.n > 0) {
+        float inc = 0.f;
+        if (v.y == cls.val[0]) inc = 1.f;
+        else if (cls.n > 1 && v.y == cls.val[1]) inc = 256.f;
+        else if (cls.n > 2 && v.y == cls.val[2]) inc = 65536.f;
+        else if (v.y != 0.0) atomicOr(flags, 1u);                 // not one of the classes (cannot happen: the host built them from this table)
+        apx[i] = make_float2((float)v.x, inc);
+        if (t1 != 0xFFu) atomicOr(tiek + 2 * (i / SR), 1ull << t1);
+        if (!(v.x <= 0.0) || !(v.y <= 0.0)) atomicOr(flags, 1u);
+        return;
+    }
     if (t1 != 0xFFu) atomicOr(tiek + 2 * (i / SR), 1ull << t1);
     if (t0 != 0xFFu) atomicOr(tiek + 2 * (i / SR) + 1, 1ull << t0);
     apx[i] = make_float2((float)v.x, (float)v.y);
@@ -369,6 +385,12 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
                         if (EB == 1) *gb = (unsigned char)e;
                         else if (EB == 2) *reinterpret_cast<unsigned short*>(gb) = (unsigned short)e;
                         else *reinterpret_cast<uint32_t*>(gb) = e;
+                        if (SP.cls.n > 0) {
+                            // class mode: the counts of the sub-chunk are exact data, not an estimate -- move this step's
+                            const float2* gapx = SP.apxtab + (size_t)sg.table * P.SR;
+                            float* cy = &(SP.apx + SP.sub_begin[seg] + tl + (unsigned long long)((t0 + t) / SPLIT_SUB) * ntr)->y;
+                            *cy += __ldg(gapx + e).y - __ldg(gapx + ss + r).y;
+                        }
                         ss = __ldg(P.nxt + ss + r);
                         st = __ldg(P.nxt + st + r);
                     }
@@ -400,12 +422,18 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
     const float2* AX = SP.apx + SP.sub_begin[seg] + tl;
     uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
     const bool predict = SP.sequential == 0 && (__ldcg(SP.flags) & 1u) == 0u;
+    uint32_t ctie[3];                                              // class mode: the binade in which each value is a tie term
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ctie[j] = j < SP.cls.n ? split_tie_code(SP.cls.val[j]) : 0xFFu;
     double c1 = 0.0, c0 = 0.0;                                     // magnitudes of the sums before the current 32 sub-chunks
     for (uint32_t base = 0; base < nsub; base += 32u) {
         const uint32_t s = base + lane;
         float2 f = make_float2(0.f, 0.f);
         if (s < nsub) f = __ldcg(AX + (unsigned long long)s * ntr);
-        const double own1 = -(double)f.x, own0 = -(double)f.y;
+        const uint32_t cnt = SP.cls.n > 0 ? (uint32_t)f.y : 0u;      // class mode: 8-bit counts of the three values, exact
+        double own1 = -(double)f.x, own0 = -(double)f.y;
+        if (SP.cls.n > 0)
+            own0 = -((double)(cnt & 0xFFu) * SP.cls.val[0] + (double)((cnt >> 8) & 0xFFu) * SP.cls.val[1] + (double)((cnt >> 16) & 0xFFu) * SP.cls.val[2]);
         double x1 = own1, x0 = own0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -423,6 +451,26 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
             const bool ok = k1 == split_bexp(e1 * (1.0 + 1e-4)) && k0 == split_bexp(e0 * (1.0 + 1e-4)) && k1 >= 1023u && k1 < 1023u + SPLIT_KMAX &&
                             k0 >= 1023u && k0 < 1023u + SPLIT_KMAX;
             if (ok) plan = SPLIT_PLAN_FAST | k1 | (k0 << 11);
+            if (ok && SP.cls.n > 0) {
+                // class mode: what the sub-chunk adds to the second sum inside binade 2^kk, exactly: every term equal to val_j adds
+                // rnd_u(val_j) = (-2^kk + val_j) + 2^kk, a multiple of u = 2^(kk-52) below 2^52 u.  count x that in float64 is exact
+                // unless it reaches 2^53 u = 2^(kk+1) -- and then the scoring thread's binade test fails whatever the rounding was.
+                const uint32_t kk = k0 - 1023u;
+                const double m0 = __hiloint2double((int)(0x80000000u | (k0 << 20)), 0);                       // -2^kk
+                double S0 = 0.0;
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t nj = (cnt >> (8 * j)) & 0xFFu;
+                    if (j < SP.cls.n && nj) {
+                        const double aq = (m0 + SP.cls.val[j]) - m0;                                          // <= 0
+                        if (!(aq > m0) || ctie[j] == kk) bad = true;  // a term of 2^kk or more, or a round-half-even tie in this binade
+                        S0 += (double)nj * aq;
+                    }
+                }
+                if (bad) S0 = __longlong_as_double(0x7FF8000000000000ll);
+                reinterpret_cast<double*>(SP.res + SP.sub_begin[seg] + tl + (unsigned long long)s * ntr)[1] = S0;
+            }
         }
         if (s < nsub) PL[(unsigned long long)s * ntr] = plan;
         c1 = __shfl_sync(0xFFFFFFFFu, e1, 31);
@@ -456,7 +504,9 @@ __device__ __forceinline__ uint32_t split_tie(const uint32_t* g, uint32_t tbase,
 // grid (ceil(chunks * trials / SPLIT_IBLOCK), segments)
 #define SPLIT_IBLOCK 256
 
-template <bool SMEM, int EB>
+// CLS: class mode -- the second sum comes from the walk's counts (split_plan_kernel); only log P1 is read here, 8 bytes per step
+// from 16 copies at 8-byte pitch (LDS.64 is served per half warp) instead of 16 bytes from 8 copies.
+template <bool SMEM, int EB, bool CLS = false>
 __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_constant__ Params P, const __grid_constant__ SplitParams SP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t SPG = 16 / EB;
@@ -467,15 +517,22 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
     if ((unsigned long long)blockIdx.x * SPLIT_IBLOCK >= nch * ntr) return;       // uniform: shorter segment
     const double2* ll = P.ll + (size_t)sg.table * P.SR;
     const uint32_t* tie = SP.tietab + (size_t)sg.table * P.SR;
-    const uint32_t rs = (uint32_t)SP.ll_rep_shift, sh = rs + 4u, ts = rs ? rs + 2u : 0u, tsh = ts + 2u;   // tie rows: one copy per lane
+    // copies: log rows 2^rs (16-byte pitch; class mode 2^(rs + 1) at 8-byte pitch), tie rows one per lane
+    const uint32_t rs = (uint32_t)SP.ll_rep_shift, vs = CLS ? (rs ? rs + 1u : 0u) : rs, sh = CLS ? vs + 3u : rs + 4u;
+    const uint32_t ts = rs ? rs + 2u : 0u, tsh = ts + 2u;
     uint32_t sbase = 0, tbase = 0;
     if (SMEM) {
-        double2* s_ll = reinterpret_cast<double2*>(smem_raw);
         uint32_t* s_tie = reinterpret_cast<uint32_t*>(smem_raw + SP.isum_tie_offset);
-        for (uint32_t i = threadIdx.x; i < (P.SR << rs); i += SPLIT_IBLOCK) s_ll[i] = ll[i >> rs];
+        if (CLS) {
+            double* s_v1 = reinterpret_cast<double*>(smem_raw);
+            for (uint32_t i = threadIdx.x; i < (P.SR << vs); i += SPLIT_IBLOCK) s_v1[i] = ll[i >> vs].x;
+        } else {
+            double2* s_ll = reinterpret_cast<double2*>(smem_raw);
+            for (uint32_t i = threadIdx.x; i < (P.SR << rs); i += SPLIT_IBLOCK) s_ll[i] = ll[i >> rs];
+        }
         for (uint32_t i = threadIdx.x; i < (P.SR << ts); i += SPLIT_IBLOCK) s_tie[i] = tie[i >> ts];
         __syncthreads();
-        sbase = (uint32_t)__cvta_generic_to_shared(s_ll) + ((threadIdx.x & ((1u << rs) - 1u)) << 4);
+        sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + ((threadIdx.x & ((1u << vs) - 1u)) << (CLS ? 3 : 4));
         tbase = (uint32_t)__cvta_generic_to_shared(s_tie) + ((threadIdx.x & ((1u << ts) - 1u)) << 2);
     }
     const unsigned long long local = (unsigned long long)blockIdx.x * SPLIT_IBLOCK + threadIdx.x;
@@ -502,27 +559,33 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
         const uint4* Eg = E4 + (unsigned long long)g0 * ntr;
         // one term: r <- r + v in both recurrences; CHK: is it a tie term of the sub-chunk's binade?
         auto term = [&](uint32_t e, auto chk) {
-            const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
-            r1 += v.x;
-            r0 += v.y;
+            if (CLS) {
+                double v1;
+                if (SMEM) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(sbase + (e << sh)));
+                else v1 = __ldg(&ll[e].x);
+                r1 += v1;
+            } else {
+                const double2 v = split_ll<SMEM>(ll, sbase, sh, e);
+                r1 += v.x;
+                r0 += v.y;
+            }
             if (decltype(chk)::value) {
                 const uint32_t t = split_tie<SMEM>(tie, tbase, tsh, e);
                 tie1 |= (t & 0xFFu) == kc1;
-                tie0 |= (t & 0xFF00u) == kc0;
+                if (!CLS) tie0 |= (t & 0xFF00u) == kc0;
             }
         };
         auto groups = [&](auto chk) {
             uint4 grp = make_uint4(0u, 0u, 0u, 0u);
-            if (ng) grp = __ldcg(Eg);
+            if (ng || rem) grp = __ldcg(Eg);
 #pragma unroll 1
             for (uint32_t g = 0; g < ng; ++g) {
                 const uint4 cur = grp;
-                if (g + 1u < ng || rem) grp = __ldcg(Eg + (unsigned long long)(g + 1u) * ntr);
+                if (g + 1u < ng || rem) grp = __ldcg(Eg + (unsigned long long)(g + 1u) * ntr);   // (three ahead measured: no faster)
 #pragma unroll
                 for (uint32_t u = 0; u < SPG; ++u) term(split_get<EB>(cur, u), chk);
             }
             if (rem) {
-                if (!ng) grp = __ldcg(Eg);
                 for (uint32_t u = 0; u < rem; ++u) {
                     uint32_t e = 0;
 #pragma unroll
@@ -532,13 +595,14 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
                 }
             }
         };
-        if (((tk1 >> kc1) | (tk0 >> (k0 - 1023u))) & 1ull) groups(std::true_type{});   // the table has a tie term in one of the two binades
+        if (((tk1 >> kc1) | (CLS ? 0ull : tk0 >> (k0 - 1023u))) & 1ull) groups(std::true_type{});   // the table has a tie term in one of the binades
         else groups(std::false_type{});
         // what the sub-chunk adds: r_end + 2^k (exact when the recurrence stayed in its binade); a tie term voids it
         double S1 = r1 - m1, S0 = r0 - m0;
         if (tie1) S1 = __longlong_as_double(0x7FF8000000000000ll);
         if (tie0) S0 = __longlong_as_double(0x7FF8000000000000ll);
-        RS[(unsigned long long)s * ntr] = make_double2(S1, S0);
+        if (CLS) reinterpret_cast<double*>(RS + (unsigned long long)s * ntr)[0] = S1;    // the second sum is split_plan_kernel's
+        else RS[(unsigned long long)s * ntr] = make_double2(S1, S0);
     }
 }
 

@@ -24,12 +24,12 @@ cudaError_t mvd_launch_learn(bool smem_tables, size_t lsmem, uint32_t nsegs, cud
 #include "mvd_split.cuh"
 
 cudaError_t mvd_launch_split_tables(const double2* ll, uint32_t SR, uint32_t ntables, uint32_t* tie, float2* apx, uint32_t* flags,
-                                    unsigned long long* tiek, cudaStream_t st) {
+                                    unsigned long long* tiek, const SplitClasses& cls, cudaStream_t st) {
     const size_t cells = (size_t)SR * ntables;
     cudaError_t e = cudaMemsetAsync(flags, 0, 4, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(tiek, 0, 16 * (size_t)ntables, st);
     if (e != cudaSuccess) return e;
-    split_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ll, cells, SR, tie, apx, flags, tiek);
+    split_tables_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ll, cells, SR, tie, apx, flags, tiek, cls);
     return cudaGetLastError();
 }
 
@@ -70,11 +70,13 @@ cudaError_t launch_split(size_t walk_bytes, size_t isum_bytes, size_t score_byte
     if (!SP.sequential) {
         const dim3 igrid((unsigned)((SP.max_chunks * SP.max_trials + SPLIT_IBLOCK - 1) / SPLIT_IBLOCK), P.nsegs);
         if (SP.ll_in_smem) {
-            auto kern = split_isum_kernel<true, EB>;
+            auto kern = SP.cls.n > 0 ? split_isum_kernel<true, EB, true> : split_isum_kernel<true, EB, false>;
             if ((e = with_smem(kern, isum_bytes)) != cudaSuccess) return e;
             kern<<<igrid, SPLIT_IBLOCK, isum_bytes, st>>>(P, SP);
+        } else if (SP.cls.n > 0) {
+            split_isum_kernel<false, EB, true><<<igrid, SPLIT_IBLOCK, 0, st>>>(P, SP);
         } else {
-            split_isum_kernel<false, EB><<<igrid, SPLIT_IBLOCK, 0, st>>>(P, SP);
+            split_isum_kernel<false, EB, false><<<igrid, SPLIT_IBLOCK, 0, st>>>(P, SP);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

@@ -106,7 +106,13 @@ struct LearnParams {
 #define SPLIT_BLOCK 128
 #define SPLIT_RB_HOST 16                    // = SPLIT_RB of mvd_split.cuh: sub-chunk records per batch of the scoring kernel's ring
 
+struct SplitClasses {                        // class mode of the split path (mvd_split.cuh): log Tref has <= 3 distinct non-zero values
+    int n;                                  // 0 = no class mode
+    double val[3];
+};
+
 struct SplitParams {
+    SplitClasses cls;
     uint32_t warm;                          // warm-up steps (multiple of 32)
     uint32_t chunk;                         // steps per chunk (multiple of SPLIT_SUB)
     uint32_t nchains;

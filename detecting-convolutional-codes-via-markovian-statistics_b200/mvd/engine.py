@@ -356,8 +356,9 @@ class Detector:
 
     def split_sequential(self, on: bool = True):
         """Split path: add every log-likelihood term one by one in step order (``MVD_OPT_SPLIT_SEQUENTIAL``) instead of
-        re-associating the float64 additions inside a binade -- identical results, the check of the re-association."""
-        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT_SEQUENTIAL, 1 if on else 0))
+        re-associating the float64 additions inside a binade -- identical results, the check of the re-association.  ``on=2``:
+        re-association without the class counting of the second sum (both sums as recurrences)."""
+        self._ck(self.lib.mvd_set_option(self.ctx, _capi.OPT_SPLIT_SEQUENTIAL, int(on)))
 
     def split_chunk(self, steps: int = 0):
         """Steps per chunk of the split path (``MVD_OPT_SPLIT_CHUNK``): 0 = chosen per call, else 256, 512 or 1024."""

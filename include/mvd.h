@@ -275,7 +275,9 @@ enum { MVD_OPT_FORCE_GENERIC = 1, MVD_OPT_NO_PAIR = 2,     /* NO_PAIR: 1 = one t
                                       loop of sweeps needs no host round trip between them (Pd_plotter.py:210-223
                                       repeated; bench.py's resident leg) */
        MVD_OPT_SPLIT_SEQUENTIAL = 8, /* 1 = the split path adds every log-likelihood term one by one in step order instead of
-                                      re-associating the additions inside a binade (identical results; the check of that) */
+                                      re-associating the additions inside a binade; 2 = re-association with both sums as
+                                      recurrences even when log Tref has <= 3 distinct values (no class counting); identical
+                                      results either way: the checks of 0 */
        MVD_OPT_SPLIT_CHUNK = 9 };  /* steps per chunk of the split path: 0 = chosen per call, else 256, 512 or 1024 (identical results) */
 int mvd_set_option(mvd_ctx* ctx, int option, int64_t value);
 int mvd_last_kernel_kind(mvd_ctx* ctx, int* kind);

@@ -459,6 +459,10 @@ def test_split_long_trials_vs_oracle(codes_spec, dets, dec, enc, Ns, p, warm):
         assert (det.last_kernel_kind() & 16384) != 0
         assert det.learn_dirty_chunks() == dirty
         assert det.split_stats() == (subs, subs)
+        det.split_sequential(2)                                   # re-association without the class counting of the second sum
+        gt, glp = det.detect(segs, seed=77, engine="fsm", want_logp=True)
+        assert np.array_equal(gt, tallies) and np.array_equal(glp, lp)
+        assert det.split_stats()[0] == subs
         det.split_sequential(False)
         for chunk in (256, 512, 1024):                            # steps per walker thread (chosen per call otherwise)
             det.split_chunk(chunk)
@@ -695,12 +699,16 @@ def test_split_reassociation_with_tie_terms(codes_spec, dets):
         tie1[i, r] = -(0.5 + 2.0 ** (k - 53))
         if j < 3:
             tie0[i, r] = -(0.75 + 2.0 ** (k + 3 - 53))
+    vals, cnts = np.unique(logT[logT != 0.0], return_counts=True)
+    cls0 = logT.copy()                                             # still three distinct values (class mode), the commonest one a tie
+    cls0[logT == vals[np.argmax(cnts)]] = -(0.5 + 2.0 ** (12 - 53))    # term of binade 2^12
     pos1 = logP1.copy()
     pos1[busy[0][0], busy[0][1]] = 0.25                            # a positive term: the sums are not monotone
     seg = [Seg(N=N, threshold=T, stream=7, enc_taps=taps, decide=0, trial_begin=0, trial_end=ntr)]
     det.split_trials(1)
     try:
-        for name, l1, l0 in (("plain", logP1, logT), ("ties", tie1, tie0), ("positive", pos1, logT), ("zero", np.zeros_like(logP1), logT)):
+        for name, l1, l0 in (("plain", logP1, logT), ("ties", tie1, tie0), ("class_tie", logP1, cls0), ("positive", pos1, logT),
+                             ("zero", np.zeros_like(logP1), logT)):
             det.set_loglik(l1[None], l0)
             _, lp = det.detect(seg, seed=seed, engine="fsm", want_logp=True)
             assert (det.last_kernel_kind() & 16384) != 0
@@ -714,7 +722,7 @@ def test_split_reassociation_with_tie_terms(codes_spec, dets):
             if name == "plain":
                 assert seq < 0.3 * subs
                 plain_seq = seq
-            elif name == "ties":
+            elif name in ("ties", "class_tie"):
                 assert plain_seq < seq < subs, "the planted tie terms did not force any sub-chunk back to term-by-term additions"
             elif name == "positive":
                 assert seq == subs
