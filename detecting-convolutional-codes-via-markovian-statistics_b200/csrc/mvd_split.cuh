@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
     // so that the stores here and the loads of the later passes are coalesced across trials
     constexpr uint32_t SPG = 16 / EB;
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
-    float2* AX = SP.apx + SP.sub_begin[seg] + tl;                 // estimate of sub-chunk s: AX[s * ntr]
+    float2* AX = SP.apx + SP.sub_begin[seg] + tl * ((N + SPLIT_SUB - 1u) / SPLIT_SUB);   // sub-chunk records are trial-major: AX[s]
     const float2* gapx = SP.apxtab + (size_t)sg.table * P.SR;
     const uint32_t t_begin = c * SP.chunk, t_end = min(N, t_begin + SP.chunk);
     const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk_kernel(const __grid_co
                 E4[(unsigned long long)(t0 / SPG + q) * ntr] = grp;
             }
             if (((t0 + 32u) % SPLIT_SUB) == 0u || t0 + 32u >= t_end) {
-                AX[(unsigned long long)(t0 / SPLIT_SUB) * ntr] = make_float2(s1, s0);
+                AX[t0 / SPLIT_SUB] = make_float2(s1, s0);
                 s1 = s0 = 0.f;
             }
         } else {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
     const unsigned long long trial = sg.trial_begin + tl;
     const unsigned long long wid = SP.work_begin[seg] + (unsigned long long)c * ntr + tl;
     uint4* E4 = reinterpret_cast<uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
-    float2* AX = SP.apx + SP.sub_begin[seg] + tl;                  // estimate of sub-chunk s: AX[s * ntr]
+    float2* AX = SP.apx + SP.sub_begin[seg] + tl * ((N + SPLIT_SUB - 1u) / SPLIT_SUB);    // sub-chunk records are trial-major: AX[s]
     const uint32_t t_begin = c * SP.chunk, t_end = min(N, t_begin + SP.chunk);
     const uint32_t w_begin = t_begin >= SP.warm ? t_begin - SP.warm : 0u;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_walk2_kernel(const __grid_c
             }
         }
         if (sb * 128u >= t_begin && active) {                       // SPLIT_SUB = 128 = one superblock
-            AX[(unsigned long long)sb * ntr] = make_float2(s1, s0);
+            AX[sb] = make_float2(s1, s0);
             s1 = s0 = 0.f;
         }
     }
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
                         if (SP.cls.n > 0) {
                             // class mode: the counts of the sub-chunk are exact data, not an estimate -- move this step's
                             const float2* gapx = SP.apxtab + (size_t)sg.table * P.SR;
-                            float* cy = &(SP.apx + SP.sub_begin[seg] + tl + (unsigned long long)((t0 + t) / SPLIT_SUB) * ntr)->y;
+                            float* cy = &(SP.apx + SP.sub_begin[seg] + tl * nsub + (t0 + t) / SPLIT_SUB)->y;
                             *cy += __ldg(gapx + e).y - __ldg(gapx + ss + r).y;
                         }
                         ss = __ldg(P.nxt + ss + r);
@@ -419,17 +419,22 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
     if (lane == 0u && fixed) atomicAdd(SP.ndirty, fixed);
 
     // -- 2. predicted binades: prefix sums of the float32 estimates (lanes = sub-chunks)
-    const float2* AX = SP.apx + SP.sub_begin[seg] + tl;
-    uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
+    // the records of a trial are consecutive in memory (trial-major): the lanes of this warp read and write whole sectors
+    const float2* AX = SP.apx + SP.sub_begin[seg] + tl * nsub;
+    uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl * nsub;
+    double2* RSP = SP.res + SP.sub_begin[seg] + tl * nsub;
     const bool predict = SP.sequential == 0 && (__ldcg(SP.flags) & 1u) == 0u;
     uint32_t ctie[3];                                              // class mode: the binade in which each value is a tie term
 #pragma unroll
     for (int j = 0; j < 3; ++j) ctie[j] = j < SP.cls.n ? split_tie_code(SP.cls.val[j]) : 0xFFu;
     double c1 = 0.0, c0 = 0.0;                                     // magnitudes of the sums before the current 32 sub-chunks
+    float2 fnext = make_float2(0.f, 0.f);                         // the records of the next 32 sub-chunks are read one round ahead
+    if (lane < nsub) fnext = __ldcg(AX + lane);
     for (uint32_t base = 0; base < nsub; base += 32u) {
         const uint32_t s = base + lane;
-        float2 f = make_float2(0.f, 0.f);
-        if (s < nsub) f = __ldcg(AX + (unsigned long long)s * ntr);
+        const float2 f = fnext;
+        fnext = make_float2(0.f, 0.f);
+        if (s + 32u < nsub) fnext = __ldcg(AX + s + 32u);
         const uint32_t cnt = SP.cls.n > 0 ? (uint32_t)f.y : 0u;      // class mode: 8-bit counts of the three values, exact
         double own1 = -(double)f.x, own0 = -(double)f.y;
         if (SP.cls.n > 0)
@@ -469,10 +474,10 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_plan_kernel(const __grid_co
                     }
                 }
                 if (bad) S0 = __longlong_as_double(0x7FF8000000000000ll);
-                reinterpret_cast<double*>(SP.res + SP.sub_begin[seg] + tl + (unsigned long long)s * ntr)[1] = S0;
+                reinterpret_cast<double*>(RSP + s)[1] = S0;
             }
         }
-        if (s < nsub) PL[(unsigned long long)s * ntr] = plan;
+        if (s < nsub) PL[s] = plan;
         c1 = __shfl_sync(0xFFFFFFFFu, e1, 31);
         c0 = __shfl_sync(0xFFFFFFFFu, e0, 31);
     }
@@ -540,15 +545,16 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
     const uint32_t c = (uint32_t)(local / ntr);
     const unsigned long long tl = local % ntr;
     const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
-    const uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
-    double2* RS = SP.res + SP.sub_begin[seg] + tl;
+    const unsigned long long rec0 = SP.sub_begin[seg] + tl * ((N + SPLIT_SUB - 1u) / SPLIT_SUB);   // trial-major records
+    const uint32_t* PL = SP.plan + rec0;
+    double2* RS = SP.res + rec0;
     const unsigned long long tk1 = __ldg(SP.tiek + 2 * (size_t)sg.table), tk0 = __ldg(SP.tiek + 2 * (size_t)sg.table + 1);
     const uint32_t spc = SP.chunk / SPLIT_SUB;
 #pragma unroll 1
     for (uint32_t j = 0; j < spc; ++j) {
         const uint32_t s = c * spc + j, t0 = s * SPLIT_SUB;
         if (t0 >= N) break;
-        const uint32_t plan = __ldcg(PL + (unsigned long long)s * ntr);
+        const uint32_t plan = __ldcg(PL + s);
         if (!(plan & SPLIT_PLAN_FAST)) continue;
         const uint32_t k1 = plan & 0x7FFu, k0 = (plan >> 11) & 0x7FFu;
         const double m1 = __hiloint2double((int)(0x80000000u | (k1 << 20)), 0), m0 = __hiloint2double((int)(0x80000000u | (k0 << 20)), 0);   // -2^k
@@ -601,8 +607,8 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
         double S1 = r1 - m1, S0 = r0 - m0;
         if (tie1) S1 = __longlong_as_double(0x7FF8000000000000ll);
         if (tie0) S0 = __longlong_as_double(0x7FF8000000000000ll);
-        if (CLS) reinterpret_cast<double*>(RS + (unsigned long long)s * ntr)[0] = S1;    // the second sum is split_plan_kernel's
-        else RS[(unsigned long long)s * ntr] = make_double2(S1, S0);
+        if (CLS) reinterpret_cast<double*>(RS + s)[0] = S1;    // the second sum is split_plan_kernel's
+        else RS[s] = make_double2(S1, S0);
     }
 }
 
@@ -641,23 +647,23 @@ __global__ void __launch_bounds__(SPLIT_BLOCK) split_score_kernel(const __grid_c
     const uint32_t q = (uint32_t)(sg.out_offset + tl);
     const uint32_t N = sg.N, nsub = (N + SPLIT_SUB - 1u) / SPLIT_SUB, nbatch = (nsub + SPLIT_RB - 1u) / SPLIT_RB;
     const uint4* E4 = reinterpret_cast<const uint4*>(SP.edges + SP.edge_begin[seg]) + tl;
-    const uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl;
-    const double2* RS = SP.res + SP.sub_begin[seg] + tl;
+    const uint32_t* PL = SP.plan + SP.sub_begin[seg] + tl * nsub;     // trial-major records: a batch is 16 consecutive ones
+    const double2* RS = SP.res + SP.sub_begin[seg] + tl * nsub;
     // ring: [2 halves][SPLIT_RB slots][blockDim.x threads] partial sums (16 B), then the plan words (4 B)
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + SP.score_ring_offset;
     const uint32_t rres = ring + threadIdx.x * 16u, rplan = ring + 2u * SPLIT_RB * blockDim.x * 16u + threadIdx.x * 4u;
     auto fetch = [&](uint32_t b) {                                 // batch b -> half b & 1
         if (active && b < nbatch) {
             const uint32_t half = (b & 1u) * SPLIT_RB, n = min(SPLIT_RB, nsub - b * SPLIT_RB);
-            const uint32_t* pl = PL + (unsigned long long)(b * SPLIT_RB) * ntr;
-            const double2* rs = RS + (unsigned long long)(b * SPLIT_RB) * ntr;
+            const uint32_t* pl = PL + b * SPLIT_RB;
+            const double2* rs = RS + b * SPLIT_RB;
             uint32_t dp = rplan + half * blockDim.x * 4u, dr = rres + half * blockDim.x * 16u;
 #pragma unroll 4
             for (uint32_t j = 0; j < n; ++j) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dp), "l"(pl));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dr), "l"(rs));
-                pl += ntr;
-                rs += ntr;
+                pl += 1;
+                rs += 1;
                 dp += blockDim.x * 4u;
                 dr += blockDim.x * 16u;
             }

@@ -119,7 +119,7 @@ struct SplitParams {
     unsigned long long nwork;               // (chain, chunk) pairs
     const unsigned long long* work_begin;   // [nsegs + 1] first work item of a segment (items: chunk-major, trial-minor)
     const unsigned long long* edge_begin;   // [nsegs] first 32-bit word of a segment's 16-byte edge groups
-    const unsigned long long* sub_begin;    // [nsegs] first sub-chunk record of a segment (records: sub-chunk-major, trial-minor)
+    const unsigned long long* sub_begin;    // [nsegs] first sub-chunk record of a segment (records: trial-major, a trial's sub-chunks consecutive)
     uint32_t* spec_start;                   // [nwork] state * R at the chunk start (speculated)
     uint32_t* end;                          // [nwork] state * R at the chunk end
     uint32_t* edges;
