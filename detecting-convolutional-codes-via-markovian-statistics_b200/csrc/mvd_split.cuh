@@ -550,11 +550,22 @@ __global__ void __launch_bounds__(SPLIT_IBLOCK) split_isum_kernel(const __grid_c
     double2* RS = SP.res + rec0;
     const unsigned long long tk1 = __ldg(SP.tiek + 2 * (size_t)sg.table), tk0 = __ldg(SP.tiek + 2 * (size_t)sg.table + 1);
     const uint32_t spc = SP.chunk / SPLIT_SUB;
+    // the plan words of the chunk's sub-chunks (consecutive in memory), all requested before the first is needed
+    constexpr uint32_t SPC_MAX = SPLIT_CH_MAX / SPLIT_SUB;
+    uint32_t plans[SPC_MAX];
+#pragma unroll
+    for (uint32_t j = 0; j < SPC_MAX; ++j) {
+        plans[j] = 0u;
+        if (j < spc && (c * spc + j) * SPLIT_SUB < N) plans[j] = __ldcg(PL + c * spc + j);
+    }
 #pragma unroll 1
     for (uint32_t j = 0; j < spc; ++j) {
         const uint32_t s = c * spc + j, t0 = s * SPLIT_SUB;
         if (t0 >= N) break;
-        const uint32_t plan = __ldcg(PL + s);
+        uint32_t plan = 0u;
+#pragma unroll
+        for (uint32_t z = 0; z < SPC_MAX; ++z)
+            if (z == j) plan = plans[z];
         if (!(plan & SPLIT_PLAN_FAST)) continue;
         const uint32_t k1 = plan & 0x7FFu, k0 = (plan >> 11) & 0x7FFu;
         const double m1 = __hiloint2double((int)(0x80000000u | (k1 << 20)), 0), m0 = __hiloint2double((int)(0x80000000u | (k0 << 20)), 0);   // -2^k
