@@ -392,14 +392,18 @@ int install_states(mvd_ctx* ctx) {
         }
     }
     // ---- perfect hash for m = 3 / 4, n = 2 (two-trials-per-thread ACS kernels, mvd_detect3p.cuh): hash, displace.
-    // w0 = k0 | k1 << 16 (and w1 = k2 | k3 << 16 for m = 4) with k_i = D[4i] + 8 D[4i+1] + 64 D[4i+2] + 512 D[4i+3]
-    // (metrics <= 7); bucket = (w0 C1 + w1 C3) >> bshift, slot = (((w0 C2 + w1 C4) >> h2shift) + disp[bucket]) &
+    // w0 = k0 | k1 << 16 (and w1 = k2 | k3 << 16 for m = 4) with the OFFSET-INVARIANT digits
+    // k_q = sum_i 16^i (D[4q+i] - D[0] + 8)   (metrics <= 7, so every digit is in 1..15): the kernel forms the same words
+    // from un-normalised metrics; bucket = (w0 C1 + w1 C3) >> bshift, slot = (((w0 C2 + w1 C4) >> h2shift) + disp[bucket]) &
     // (slots - 1).  Buckets are placed largest first, each with the smallest displacement that lands all its keys
-    // on free slots (single keys take the next free slot).
+    // on free slots (single keys take the next free slot).  m = 3 (tables in shared memory) first tries the smallest
+    // power of two >= S / 0.85 slots, then twice that.
     ctx->ph_slots = 0;
     if (ctx->closed && (ctx->m == 3 || ctx->m == 4) && ctx->n == 2 && ctx->max_metric <= 7 && (ctx->m == 4 || S <= 1024) && S <= (1u << 20)) {
-        uint32_t slots = 256, nb = 256;
-        while (slots < 2 * S) slots <<= 1;
+      uint32_t slots0 = 256;
+      if (ctx->m == 3) { while (slots0 * 0.85 < S) slots0 <<= 1; } else { while (slots0 < 2 * S) slots0 <<= 1; }
+      for (uint32_t slots = slots0; slots <= (ctx->m == 3 ? 2 * slots0 : slots0) && !ctx->ph_slots; slots <<= 1) {
+        uint32_t nb = 256;
         if (ctx->m == 4) while (nb < S / 4) nb <<= 1;
         uint32_t lb = 0;
         while ((1u << lb) < nb) ++lb;
@@ -410,7 +414,8 @@ int install_states(mvd_ctx* ctx) {
             const uint8_t* v = ctx->h_metrics.data() + (size_t)i * nstate;
             uint32_t w[2] = {0u, 0u};
             for (int q = 0; q < nstate / 4; ++q) {
-                const uint32_t kq = v[4 * q] + 8u * v[4 * q + 1] + 64u * v[4 * q + 2] + 512u * v[4 * q + 3];
+                uint32_t kq = 0;
+                for (int i = 0; i < 4; ++i) kq |= (uint32_t)((int)v[4 * q + i] - (int)v[0] + 8) << (4 * i);
                 w[q >> 1] |= kq << (16 * (q & 1));
             }
             w0[i] = w[0];
@@ -477,8 +482,9 @@ int install_states(mvd_ctx* ctx) {
             ctx->ph_slots = slots;
             ctx->ph_bshift = bshift;
             ctx->ph_nb = nb;
-            ctx->ph_slot0 = disp[0] & (slots - 1);          // the all-zero vector: w0 = w1 = 0, bucket 0, second hash 0
+            ctx->ph_slot0 = (h2[0] + disp[h1[0]]) & (slots - 1);   // Markov state 0 = the all-zero vector
         }
+      }
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_states = true;
@@ -655,7 +661,11 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && ctx->linkey_ok && pair_smem <= 110 * 1024 &&
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
     // m = 3: two trials per thread with the perfect-hash lookup (2 blocks of 256 pair-threads per SM)
-    const size_t pair3_smem = 2 * (size_t)ctx->ph_slots * 8 + 1024 + 128 + 128 + ((size_t)ctx->S * 4 << 5) + 64;
+    // (layout of detect3p_kernel: straggler queues, masks, branch table, displacements at a 1 KB-aligned and the slot table at a
+    // (slots x 8)-aligned absolute shared address, log rows; the dynamic window starts after the 1 KB the system reserves)
+    const size_t pair3_tb = (size_t)ctx->ph_slots * 8;
+    const size_t pair3_T = pair3_tb ? (((pair_sbase + DET2P_QUEUES + 128 + 128 + 1023) & ~(size_t)1023) + 1024 + pair3_tb - 1) & ~(pair3_tb - 1) : 0;
+    const size_t pair3_smem = pair3_T + pair3_tb + ((size_t)ctx->S * 4 << 5) - pair_sbase;
     const bool pair3s = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && !det2_gt && ctx->m == 3 &&
                         ctx->ph_slots && pair3_smem <= 75 * 1024 &&
                         (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
@@ -781,6 +791,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     P.fp.ph_c4 = ctx->ph_c4;
     P.fp.ph_nb = ctx->ph_nb;
     P.fp.ph_slot0 = ctx->ph_slot0;
+    P.fp.kq[0] = 16u; P.fp.kq[1] = 256u; P.fp.kq[2] = 4096u; P.fp.kq[3] = 0u - 4369u; P.fp.kq[4] = 1u; P.fp.kq[5] = 0u - 4368u;
     P.fp.ll_slot = ctx->d_llslot.as<double2>();
 
     // ---- outputs
@@ -1029,8 +1040,9 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             if (maxblocks == 0) continue;
             const dim3 g2((unsigned)maxblocks, cnt);
             // m = 4: the bucket displacements ride in shared memory when they fit beside two resident blocks
-            const size_t pair4_smem = 4096 + ((size_t)ctx->ph_nb * 4 <= 64 * 1024 ? (size_t)ctx->ph_nb * 4 : 0);
-            if (pair3) le = mvd_launch_det3_pair(m, g2, threads, pair4 ? pair4_smem : pair3_smem, ctx->stream, P, B);
+            const bool pair4_ds = (size_t)ctx->ph_nb * 4 <= 64 * 1024;       // bucket displacements in shared memory
+            const size_t pair4_smem = ((pair_sbase + DET2P_QUEUES + 128 + 128 + 1023) & ~(size_t)1023) + (pair4_ds ? (size_t)ctx->ph_nb * 4 : 0) - pair_sbase;
+            if (pair3) le = mvd_launch_det3_pair(m, g2, threads, pair4 ? pair4_smem : pair3_smem, ctx->stream, P, B, pair4 && pair4_ds, P.bm_antipodal != 0);
             else le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
             extra_launches += 1;
         }

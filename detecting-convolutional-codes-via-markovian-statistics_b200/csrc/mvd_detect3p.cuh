@@ -3,9 +3,16 @@
 // run across the two trials as in detect2p_kernel (mvd_detect2.cuh), and the metric-vector -> Markov-state
 // lookup (the state_index dict of Pd_plotter.py:139) is a *perfect hash* built on the host for the closed set:
 //
-//     w0   = k0 | k1 << 16,  k_i = D[4i] + 8 D[4i+1] + 64 D[4i+2] + 512 D[4i+3]   (metrics <= 7; m = 4: w1 from k2, k3)
+//     w0   = k0 | k1 << 16,  k_q = sum_i 16^i (D[4q+i] - D[0] + 8)          (|D[s] - D[0]| <= 7; m = 4: w1 from k2, k3)
 //     slot = (((w0 c2 + w1 c4) >> 11) + disp[(w0 C1 + w1 C3) >> bshift]) & (slots - 1)        (hash, displace;
 //                                                     c2, c4: odd multipliers the host build settles on)
+//
+// The key is OFFSET-INVARIANT (differences to D[0]), so it is the same for the un-normalised vector D' of Eq. 4 and for
+// D' - min D' of Eq. 5: the minimum is not needed to find the Markov state, and Eq. 5 is applied once per 32-step block
+// (it only keeps the 16-bit lanes small).  k_q is a linear form, sum_i 16^i Q[4q+i] - 4369 Q[0] + 0x8888, evaluated on
+// the packed pair by IMADs (FMA pipe) with multipliers taken from the kernel parameters; both lanes' true results are in
+// [0, 2^16), so the 32-bit arithmetic is exact whatever the low lane carries in between.  Round 1 packed the
+// normalised metrics (base 8) and paid a VIMNMX3 tree plus a correction of 585 min per step, all on the ALU pipe.
 //
 // m = 3 keeps every table in shared memory.  m = 4 (template GT; S = 25 751 ... 232 567) cannot: there the log rows are
 // stored BY SLOT in global memory (FastPlan::ll_slot, built once per mvd_set_loglik by slot_rows_kernel), so the slot
@@ -14,13 +21,12 @@
 // displacement, slot and row from L2 -- three dependent gathers per trial-step, L1 wavefront-bound at 74 % with
 // `long_scoreboard` the top stall (profiles/r02a_m4_pair_ncu_full.txt).
 //
-// two dependent shared-memory reads and no probe loop, against ~1.3 probes of an open-addressing table with
-// key compares and a divergent loop in detect2_kernel<LK_HASH, 3> (66 warp-instructions per trellis step instead of
-// 107 at m = 3).  Results are the same bit for bit (same Eq. 4-5 arithmetic, same sums in step order).
+// Results are the same bit for bit as the one-trial kernels and the oracle (same Eq. 4-5 arithmetic, same sums in
+// step order).
 //
 // Shared memory (absolute addresses; alignment lets one LOP3 form an address):
-//   [hash slots: slots x 2 copies x 4 B, aligned to its size][displacements 256 x 4 B, 1 KB aligned]
-//   [threshold masks 128 B][V(r) 16 B (+ pad)][log rows S x 4 x 2 copies x 16 B, 128 B aligned]
+//   [straggler queues 1 KB per warp][threshold masks 128 B][branch table 128 B, 128 B aligned][displacements, 1 KB aligned]
+//   [hash slots: slots x 2 copies x 4 B, aligned to its size][log rows S x 4 x 2 copies x 16 B, 128 B aligned]
 #pragma once
 #include "mvd_detect2.cuh"
 
@@ -28,20 +34,32 @@
 #define PH3_C3 0xC2B2AE35u
 
 // Branch metrics without a table read per branch: for a rate-1/2 code the metric of a branch with label L
-// against received word r is popc(L ^ r), so the 16 branch words of a step are 16 picks from the four
-// bytes V(r) = (d(0,r), d(1,r), d(2,r), d(3,r)).  One 4-byte read per trial gives V(r_A), V(r_B); branch
-// (ns, b) is PRMT(V_A, V_B, sel[ns][b]) = V_A[L] | V_B[L] << 16 with a kernel-constant selector (selector
-// nibbles with bit 3 set yield the replicated sign bit = 0).  16 PRMTs replace four LDS.128 (16 shared-memory
-// wavefronts per step pair): this kernel is shared-memory bound, the ALU pipe has room.
-template <int M, bool GT, bool DS = false>
+// against received word r is popc(L ^ r).
+//   ANTI (every generator has its first and its last tap set, e.g. the demo pair (17,13) / (13,17)): the four branches of
+//   butterfly g carry the labels X, ~X, ~X, X, so with x_g = d(X, r) the step is
+//       D'[2g] = min(D[g] + x_g, D[g+H] + n - x_g),   D'[2g+1] = min(D[g] + n - x_g, D[g+H] + x_g):
+//   the block stages, per received word r, the bytes x_g of all 2^(m-1) butterflies (one LDS.32 / LDS.64 per trial, rows
+//   at 32-byte pitch like the log rows; n - x_g byte by byte = one IMAD per word); PRMT(row_A, row_B, constant selector)
+//   packs (x_g | r_A, x_g | r_B) -- ONE pick per butterfly and operand instead of one per branch; the two additions per butterfly are IMADs (multiplier 1 from the kernel parameters,
+//   FMA pipe), the VIADDMNMX pair stays on the ALU pipe.
+//   General decoders: the 2^(m+1) branch words of a step are picks from the four bytes V(r) = (d(0,r), d(1,r), d(2,r),
+//   d(3,r)) with per-decoder selectors held in registers (selector nibbles with bit 3 set yield the replicated sign = 0).
+// PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the selected byte (0 for the small bytes used
+// here).  __byte_perm with a compile-time selector is folded with bit 3 masked off, so the constant picks go through this.
+__device__ __forceinline__ uint32_t prmt_s(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+template <int M, bool GT, bool DS, bool ANTI>
 struct PairEngineN {
     static constexpr int NS = 1 << M, HALF = NS / 2;
     uint32_t Q[NS];                   // (trial A, trial B) metrics of the trellis states
     uint32_t sxA, sxB;                // smem: absolute address of this lane's copy of the current log row; GT: state * R
-    uint32_t kV, kD, kT, tmask;       // V(r) table (16 B) ; smem: displacement table ; slot table | copy * 4 ; (slots - 1) << 3
-    uint32_t sel[2 * NS];             // PRMT selector of branch (ns, b) at [2 ns + b]
+    uint32_t kV, kD, kT, tmask;       // branch table (32-byte rows) ; smem: displacement table ; slot table | copy * 4 ; (slots - 1) << 3
+    uint32_t sel[ANTI ? 1 : 2 * NS];  // general decoders: PRMT selector of branch (ns, b) at [2 ns + b]
     const uint32_t* gD;               // GT: displacements, slots and log rows in global memory
-    const uint32_t* gT;
     const double2* gll;
     uint32_t bshift, gmask, c2, c4;   // c2, c4: multipliers of the second hash, chosen by the host build
     double a1A, a0A, a1B, a0B;
@@ -56,36 +74,72 @@ struct PairEngineN {
         return lds_u32(kT | ((((w0 * c2) >> 18) + d8) & tmask));
     }
 
-    // sA5 / sB5: r_A / r_B at bits 5..6 (log rows, 32-byte entries); sA2 / sB2: r_A / r_B at bits 2..3 (V table).
-    // NORM = false defers Eq. 5 (as PairEngine::step of the m = 2 kernel): the key words are corrected by
-    // 585 min (585 = 1 + 8 + 64 + 512) instead of subtracting the minimum from all 2^m metrics; the last step
-    // of every 8-step stretch normalises, so a lane grows by at most 16 in between.
-    template <bool NORM>
-    __device__ __forceinline__ void step(uint32_t sA5, uint32_t sB5, uint32_t sA2, uint32_t sB2) {
-        const double2 vA = GT ? __ldg(gll + sxA + ((sA5 >> 5) & 3u)) : lds_d2(sxA | (sA5 & 0x60u));
-        const double2 vB = GT ? __ldg(gll + sxB + ((sB5 >> 5) & 3u)) : lds_d2(sxB | (sB5 & 0x60u));
+    // fA / fB: r_A / r_B at bits 5..6 (log rows and branch table: 32-byte entries; other bits arbitrary).
+    // Eq. 5 is deferred (see the header): the caller normalises once per 32-step block.
+    __device__ __forceinline__ void step(uint32_t fA, uint32_t fB, const Params& P) {
+        const double2 vA = GT ? __ldg(gll + sxA + ((fA >> 5) & 3u)) : lds_d2(sxA | (fA & 0x60u));
+        const double2 vB = GT ? __ldg(gll + sxB + ((fB >> 5) & 3u)) : lds_d2(sxB | (fB & 0x60u));
         a1A += vA.x;
         a0A += vA.y;
         a1B += vB.x;
         a0B += vB.y;
-        const uint32_t VA = lds_u32(kV | (sA2 & 0xCu)), VB = lds_u32(kV | (sB2 & 0xCu));
         uint32_t n[NS];
+        if (ANTI) {
+            // row r of the branch table: bytes x_g; n - x_g = 2 - x_g byte by byte (no borrow), one IMAD by -1 per word
+            uint32_t xa[2], na[2], xb[2], nb[2];
+            if (M == 3) {
+                xa[0] = lds_u32(kV | (fA & 0x60u));
+                xb[0] = lds_u32(kV | (fB & 0x60u));
+                xa[1] = xb[1] = 0u;
+            } else {
+                const uint2 ra = lds_v2(kV | (fA & 0x60u)), rb = lds_v2(kV | (fB & 0x60u));
+                xa[0] = ra.x; xa[1] = ra.y;
+                xb[0] = rb.x; xb[1] = rb.y;
+            }
 #pragma unroll
-        for (int ns = 0; ns < NS; ++ns)                 // new state ns from predecessors ns >> 1 and (ns >> 1) + HALF: Eq. 4, both trials
-            n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, sel[2 * ns + 1]));
-        uint32_t mn = __vimin3_u16x2(__vimin3_u16x2(n[0], n[1], n[2]), __vimin3_u16x2(n[3], n[4], n[5]), __vminu2(n[6], n[7]));
-        if (NS == 16) mn = __vimin3_u16x2(mn, __vimin3_u16x2(n[8], n[9], n[10]), __vimin3_u16x2(__vimin3_u16x2(n[11], n[12], n[13]), n[14], n[15]));
+            for (int j = 0; j < (M == 3 ? 1 : 2); ++j) {
+                na[j] = madlo(xa[j], P.fma_km1, 0x02020202u);
+                nb[j] = madlo(xb[j], P.fma_km1, 0x02020202u);
+            }
+            if (M == 3) na[1] = nb[1] = 0u;
+            const uint32_t one = P.fp.kq[4];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) Q[s] = NORM ? n[s] - mn : n[s];            // Eq. 5 (or deferred)
+            for (int g = 0; g < HALF; ++g) {
+                const uint32_t s4 = (uint32_t)(g & 3) | 0x80u | ((4u + (uint32_t)(g & 3)) << 8) | 0x8000u;
+                const uint32_t x = prmt_s(xa[g >> 2], xb[g >> 2], s4), nx = prmt_s(na[g >> 2], nb[g >> 2], s4);
+                const uint32_t t0 = madlo(Q[g], one, x), t1 = madlo(Q[g + HALF], one, x);
+                n[2 * g] = __viaddmin_u16x2(Q[g + HALF], nx, t0);              // Eq. 4, both trials
+                n[2 * g + 1] = __viaddmin_u16x2(Q[g], nx, t1);
+            }
+        } else {
+            const uint32_t VA = lds_u32(kV | (fA & 0x60u)), VB = lds_u32(kV | (fB & 0x60u));
+#pragma unroll
+            for (int ns = 0; ns < NS; ++ns)             // new state ns from predecessors ns >> 1 and (ns >> 1) + HALF: Eq. 4, both trials
+                n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, sel[2 * ns + 1]));
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) Q[s] = n[s];
+        // offset-invariant key words: low halves = trial A, high halves = trial B
         uint32_t k[NS / 4];
 #pragma unroll
-        for (int i = 0; i < NS / 4; ++i) {
-            k[i] = ((Q[4 * i + 3] * 8u + Q[4 * i + 2]) * 8u + Q[4 * i + 1]) * 8u + Q[4 * i];
-            if (!NORM) k[i] -= 585u * mn;
+        for (int q = 0; q < NS / 4; ++q) {
+            uint32_t acc = madlo(Q[0], q == 0 ? P.fp.kq[5] : P.fp.kq[3], 0x88888888u);      // - 4369 D[0] (q = 0: - 4368 D[0]) + 8 per digit
+            if (q > 0) acc = madlo(Q[4 * q], one_(P), acc);
+            acc = madlo(Q[4 * q + 1], P.fp.kq[0], acc);
+            acc = madlo(Q[4 * q + 2], P.fp.kq[1], acc);
+            k[q] = madlo(Q[4 * q + 3], P.fp.kq[2], acc);
         }
-        // low halves = trial A, high halves = trial B
         sxA = lookup(__byte_perm(k[0], k[1], 0x5410), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x5410) : 0u);
         sxB = lookup(__byte_perm(k[0], k[1], 0x7632), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x7632) : 0u);
+    }
+    static __device__ __forceinline__ uint32_t one_(const Params& P) { return P.fp.kq[4]; }
+
+    // Eq. 5 (keeps the lanes small; the key does not see it)
+    __device__ __forceinline__ void normalise() {
+        uint32_t mn = __vimin3_u16x2(__vimin3_u16x2(Q[0], Q[1], Q[2]), __vimin3_u16x2(Q[3], Q[4], Q[5]), __vminu2(Q[6], Q[7]));
+        if (NS == 16) mn = __vimin3_u16x2(mn, __vimin3_u16x2(Q[8], Q[9], Q[10]), __vimin3_u16x2(__vimin3_u16x2(Q[11], Q[12], Q[13]), Q[14], Q[15]));
+#pragma unroll
+        for (int s = 0; s < NS; ++s) Q[s] -= mn;
     }
 };
 
@@ -114,10 +168,10 @@ __global__ void pack_ll_kernel(const double* __restrict__ lp1, const double* __r
         gfsm1[idx] = make_uint4((uint32_t)__double2loint(a), (uint32_t)__double2hiint(a), nxt[e] << 4, tcode[e]);
 }
 
-template <int M, bool GT, int PHILOX, bool DS = false>
+template <int M, bool GT, int PHILOX, bool DS, bool ANTI>
 __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(const __grid_constant__ Params P,
                                                                                const __grid_constant__ SegBatch B) {
-    constexpr int NS = 1 << M;
+    constexpr int NS = 1 << M, HALF = NS / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevSeg& sg = B.s[blockIdx.y];
     const unsigned long long ntr = sg.trial_end - sg.trial_begin;
@@ -131,12 +185,22 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     const uint32_t SR = P.SR;
     const uint32_t slots = P.fp.ph_slots, tbytes = GT ? 0u : slots * 8u;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t a_T = GT ? ((sbase + 1023u) & ~1023u) : ((sbase + tbytes - 1u) & ~(tbytes - 1u));
-    const uint32_t a_D = a_T + tbytes;                       // tbytes >= 2 KB keeps the 1 KB alignment
-    const uint32_t a_tb = a_D + 1024u;
-    const uint32_t a_V = a_tb + 128u;                        // 16-byte table V(r), 16 B aligned
-    const uint32_t a_ll = a_V + 128u;
+    uint32_t a_sq = sbase + (threadIdx.x >> 5) * 1024u;      // this warp's straggler queue (flip_words4)
+    const uint32_t a_tb = (sbase + (uint32_t)DET2P_QUEUES + 127u) & ~127u;
+    const uint32_t a_V = a_tb + 128u;                        // branch table: 4 rows x 32 B, 128 B aligned
+    const uint32_t a_D = (a_V + 128u + 1023u) & ~1023u;      // m = 3: 256 displacements; m = 4 (DS): ph_nb of them
+    const uint32_t a_T = GT ? 0u : ((a_D + 1024u + tbytes - 1u) & ~(tbytes - 1u));
+    const uint32_t a_ll = a_T + tbytes;                      // log rows (m = 3), 128 B aligned
     unsigned char* g = smem_raw - sbase;                     // generic pointer of shared address 0
+    {
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        const uint32_t need = GT ? (DS ? a_D + 4u * P.fp.ph_nb : a_V + 128u) : a_ll + (SR << 5);
+        if (need - sbase > dyn) {                             // the host sized the window for another base address
+            if (threadIdx.x == 0) atomicOr(P.error_flag, 4);
+            return;
+        }
+    }
 
     if (threadIdx.x < 32u)
         *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
@@ -145,14 +209,23 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
         for (uint32_t i = threadIdx.x; i < SR * 2u; i += BS)
             *reinterpret_cast<double2*>(g + a_ll + ((i >> 1) << 5) + ((i & 1u) << 4)) = __ldg(llg + (i >> 1));
     }
-    if (threadIdx.x < 4u) {                                  // V(r) = bytes popc(L ^ r), L = 0..3
+    if (threadIdx.x < 4u) {
         const uint32_t r = threadIdx.x;
-        uint32_t v = 0;
-        for (uint32_t L = 0; L < 4u; ++L) v |= (uint32_t)__popc(L ^ r) << (8u * L);
-        *reinterpret_cast<uint32_t*>(g + a_V + 4u * r) = v;
+        uint32_t* row = reinterpret_cast<uint32_t*>(g + a_V + 32u * r);
+        if (ANTI) {
+            // bytes x_g = d(g -> 2g | r) of the butterflies g = 0 .. 2^(m-1) - 1 (P.bm[r][2 g + b]: low half = d(g + HALF b -> 2g))
+            uint32_t x[2] = {0u, 0u};
+            for (uint32_t gg = 0; gg < (uint32_t)HALF; ++gg) x[gg >> 2] |= (P.bm[r * NS + 2u * gg] & 0xFFFFu) << (8u * (gg & 3u));
+            row[0] = x[0];
+            row[1] = x[1];
+        } else {                                             // V(r) = bytes popc(L ^ r), L = 0..3
+            uint32_t v = 0;
+            for (uint32_t L = 0; L < 4u; ++L) v |= (uint32_t)__popc(L ^ r) << (8u * L);
+            row[0] = v;
+        }
     }
-    if (GT && DS)                                            // bucket displacements: ph_nb x 4 B after the V table
-        for (uint32_t i = threadIdx.x; i < P.fp.ph_nb; i += BS) *reinterpret_cast<uint32_t*>(g + a_ll + 4u * i) = P.fp.ph_d[i];
+    if (GT && DS)                                            // bucket displacements
+        for (uint32_t i = threadIdx.x; i < P.fp.ph_nb; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i];
     if (!GT) {
         for (uint32_t i = threadIdx.x; i < 256u; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i] << 3;
         for (uint32_t i = threadIdx.x; i < slots * 2u; i += BS) {
@@ -162,30 +235,32 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     }
     __syncthreads();
 
-    PairEngineN<M, GT, DS> eng;
+    PairEngineN<M, GT, DS, ANTI> eng;
 #pragma unroll
     for (int s = 0; s < NS; ++s) eng.Q[s] = 0u;
-    eng.sxA = eng.sxB = GT ? P.fp.ph_slot0 << 2 : a_ll + ((lane & 1u) << 4); // state 0 = the all-zero vector
+    // state 0 = the all-zero vector
+    eng.sxA = eng.sxB = GT ? P.fp.ph_slot0 << 2 : a_ll + ((lane & 1u) << 4);
     eng.gD = P.fp.ph_d;
-    eng.gT = P.fp.ph_t;
     eng.gll = GT ? P.fp.ll_slot + (size_t)sg.table * slots * 4u : P.ll + (size_t)sg.table * SR;
     eng.bshift = P.fp.ph_bshift;
     eng.gmask = slots - 1u;
     eng.c2 = P.fp.ph_c2;
     eng.c4 = P.fp.ph_c4;
     eng.kV = a_V;
-    eng.kD = (GT && DS) ? a_ll : a_D;
-    // label of branch (ns, b) from the branch-metric table of the decoder (P.bm[r][2 g + b] = distances to ns = 2g and
-    // 2g + 1 from predecessor g + 4 b): (d(L,0), d(L,1)) = (0,1), (1,0), (1,2), (2,1) for L = 0, 1, 2, 3
+    eng.kD = a_D;
+    if (!ANTI) {
+        // label of branch (ns, b) from the branch-metric table of the decoder (P.bm[r][2 g + b] = distances to ns = 2g and
+        // 2g + 1 from predecessor g + HALF b): (d(L,0), d(L,1)) = (0,1), (1,0), (1,2), (2,1) for L = 0, 1, 2, 3
 #pragma unroll
-    for (int ns = 0; ns < NS; ++ns)
+        for (int ns = 0; ns < NS; ++ns)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const uint32_t w0 = P.bm[0 * NS + 2 * (ns >> 1) + b], w1 = P.bm[1 * NS + 2 * (ns >> 1) + b];
-            const uint32_t d0 = (ns & 1) ? (w0 >> 16) : (w0 & 0xFFFFu), d1 = (ns & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
-            const uint32_t L = d0 == 0u ? 0u : (d0 == 2u ? 3u : (d1 == 0u ? 1u : 2u));
-            eng.sel[2 * ns + b] = L | 0x80u | ((4u + L) << 8) | 0x8000u;
-        }
+            for (int b = 0; b < 2; ++b) {
+                const uint32_t w0 = P.bm[0 * NS + 2 * (ns >> 1) + b], w1 = P.bm[1 * NS + 2 * (ns >> 1) + b];
+                const uint32_t d0 = (ns & 1) ? (w0 >> 16) : (w0 & 0xFFFFu), d1 = (ns & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
+                const uint32_t L = d0 == 0u ? 0u : (d0 == 2u ? 3u : (d1 == 0u ? 1u : 2u));
+                eng.sel[ANTI ? 0 : 2 * ns + b] = L | 0x80u | ((4u + L) << 8) | 0x8000u;
+            }
+    }
     eng.kT = a_T + ((lane & 1u) << 2);
     eng.tmask = (slots - 1u) << 3;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
@@ -194,10 +269,11 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
     constexpr bool philox = PHILOX != 0;              // bit source as a template parameter (see detect2p_kernel)
     const unsigned long long trA = sg.trial_begin + tlA, trB = sg.trial_begin + tlB;
-    // Philox counter words, activity masks, stream id and mask-table address pinned in registers (see detect2p_kernel)
+    // Philox counter words, stream id and mask-table address pinned in registers (see detect2p_kernel); an inactive trial of
+    // the last block draws bits like any other, nothing of it is counted or stored
     uint32_t c1A = (uint32_t)trA, c2A = (uint32_t)(trA >> 32), c1B = (uint32_t)trB, c2B = (uint32_t)(trB >> 32);
-    uint32_t mA = actA ? 0xFFFFFFFFu : 0u, mB = actB ? 0xFFFFFFFFu : 0u, c3 = sg.stream, a_tbp = a_tb;
-    asm volatile("" : "+r"(c1A), "+r"(c2A), "+r"(c1B), "+r"(c2B), "+r"(mA), "+r"(mB), "+r"(c3), "+r"(a_tbp));
+    uint32_t c3 = sg.stream, a_tbp = a_tb;
+    asm volatile("" : "+r"(c1A), "+r"(c2A), "+r"(c1B), "+r"(c2B), "+r"(c3), "+r"(a_tbp), "+r"(a_sq));
     const uint32_t taps0 = sg.enc_taps[0], taps1 = sg.enc_taps[1];
     uint32_t tm0[M + 1], tm1[M + 1];
 #pragma unroll
@@ -235,20 +311,15 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
             uint32_t wev[2], wod[2];                    // received pairs of the even / odd steps
             uint32_t eA0, eA1, eB0, eB1;
             if (philox) {
-                // four flip words (2 trials x 2 outputs) through one copy of the lazy loop, results rotate
+                // the four flip words of this 32-step block (2 trials x 2 outputs): two calls each by everybody, the
+                // undecided rest through the warp's straggler queue (flip_words4, mvd_detect2.cuh)
                 uint32_t cb = (4u * sb + (uint32_t)w) << 6, vm = vmask;
                 asm volatile("" : "+r"(cb), "+r"(vm));
-                eA0 = eA1 = eB0 = eB1 = 0u;
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    const bool second = j >= 2;
-                    const uint32_t e = lazy_bernoulli_a(cb | (((uint32_t)j & 1u) << 3), second ? c1B : c1A, second ? c2B : c2A, c3, a_tbp,
-                                                        ncalls, (second ? mB : mA) & vm, P);
-                    eA0 = eA1;
-                    eA1 = eB0;
-                    eB0 = eB1;
-                    eB1 = e;
-                }
+                const FlipWords f = flip_words4(cb, c1A, c2A, c1B, c2B, c3, vm, a_tbp, ncalls, a_sq, lane, BS, P);
+                eA0 = f.e0;
+                eA1 = f.e1;
+                eB0 = f.e2;
+                eB1 = f.e3;
             } else {
                 eA0 = pick(EA0, w);
                 eA1 = pick(EA1, w);
@@ -277,14 +348,14 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
             // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
             auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
-                eng.step<false>(ea << 5, eb << 5, ea << 2, eb << 2);
-                eng.step<false>(oa << 5, ob << 5, oa << 2, ob << 2);
-                eng.step<false>(ea << 3, eb << 3, ea, eb);
-                eng.step<false>(oa << 3, ob << 3, oa, ob);
-                eng.step<false>(ea << 1, eb << 1, ea >> 2, eb >> 2);
-                eng.step<false>(oa << 1, ob << 1, oa >> 2, ob >> 2);
-                eng.step<false>(ea >> 1, eb >> 1, ea >> 4, eb >> 4);
-                eng.step<true>(oa >> 1, ob >> 1, oa >> 4, ob >> 4);
+                eng.step(ea << 5, eb << 5, P);
+                eng.step(oa << 5, ob << 5, P);
+                eng.step(ea << 3, eb << 3, P);
+                eng.step(oa << 3, ob << 3, P);
+                eng.step(ea << 1, eb << 1, P);
+                eng.step(oa << 1, ob << 1, P);
+                eng.step(ea >> 1, eb >> 1, P);
+                eng.step(oa >> 1, ob >> 1, P);
             };
 #pragma unroll 1
             for (uint32_t c = 0; c < valid; c += 8u) {
@@ -295,10 +366,11 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
                     for (uint32_t j = 0; j < valid - c; ++j) {
                         const uint32_t sh = j & ~1u;
                         const uint32_t ra = (((j & 1u) ? oa : ea) >> sh) & 3u, rb = (((j & 1u) ? ob : eb) >> sh) & 3u;
-                        eng.step<true>(ra << 5, rb << 5, ra << 2, rb << 2);
+                        eng.step(ra << 5, rb << 5, P);
                     }
                 }
             }
+            eng.normalise();                            // Eq. 5 once per block: a lane grows by at most n = 2 per step
         }
     }
 

@@ -16,7 +16,8 @@ cudaError_t mvd_launch_det2_acs(int lk, int m, int lls, bool gt, dim3 grid, unsi
 cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned threads, size_t smem, cudaStream_t st,
                                 const Params& P, const SegBatch& B);
 cudaError_t mvd_launch_det2_pair(dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B);
-cudaError_t mvd_launch_det3_pair(int m, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B);
+cudaError_t mvd_launch_det3_pair(int m, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B,
+                                 bool ds, bool anti);
 cudaError_t mvd_launch_slot_rows(const double2* ll, const uint32_t* pht, uint32_t slots, uint32_t SR, uint32_t ntables, double2* out,
                                  cudaStream_t st);
 cudaError_t mvd_launch_pack_ll(const double* lp1, const double* ltref, const uint32_t* nxt, const uint32_t* tcode, uint32_t SR,

@@ -2,27 +2,28 @@
 #include "mvd_detect3p.cuh"
 #include "mvd_launch.h"
 
-cudaError_t mvd_launch_det3_pair(int m, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
-    const bool ph = P.src_mode == MVD_SRC_PHILOX;
-    if (m == 3) {
-        auto kern = ph ? detect3p_kernel<3, false, 1> : detect3p_kernel<3, false, 0>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, threads, smem, st>>>(P, B);
-    } else if (m == 4) {
-        // log rows by slot in global memory (L2); bucket displacements in shared memory when smem says so (> 4 KB)
-        const bool ds = smem > 4096;
-        auto kern = ds ? (ph ? detect3p_kernel<4, true, 1, true> : detect3p_kernel<4, true, 0, true>)
-                       : (ph ? detect3p_kernel<4, true, 1, false> : detect3p_kernel<4, true, 0, false>);
-        if (ds) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        kern<<<grid, threads, smem, st>>>(P, B);
-    } else {
-        return cudaErrorInvalidValue;
-    }
+template <class K>
+static cudaError_t launch_det3(K kern, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, threads, smem, st>>>(P, B);
     return cudaGetLastError();
+}
+
+// ds: (m = 4) bucket displacements in shared memory; anti: complement-label decoder (branch table of x_g, n - x_g bytes)
+cudaError_t mvd_launch_det3_pair(int m, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B,
+                                 bool ds, bool anti) {
+    const bool ph = P.src_mode == MVD_SRC_PHILOX;
+#define DET3_PICK(M, GT, DS)                                                                                              \
+    (anti ? (ph ? launch_det3(detect3p_kernel<M, GT, 1, DS, true>, grid, threads, smem, st, P, B)                          \
+                : launch_det3(detect3p_kernel<M, GT, 0, DS, true>, grid, threads, smem, st, P, B))                         \
+          : (ph ? launch_det3(detect3p_kernel<M, GT, 1, DS, false>, grid, threads, smem, st, P, B)                         \
+                : launch_det3(detect3p_kernel<M, GT, 0, DS, false>, grid, threads, smem, st, P, B)))
+    if (m == 3) return DET3_PICK(3, false, false);
+    // m = 4: log rows by slot in global memory (L2)
+    if (m == 4) return ds ? DET3_PICK(4, true, true) : DET3_PICK(4, true, false);
+#undef DET3_PICK
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t mvd_launch_slot_rows(const double2* ll, const uint32_t* pht, uint32_t slots, uint32_t SR, uint32_t ntables, double2* out,

@@ -34,6 +34,8 @@ struct FastPlan {
     uint32_t ph_c2, ph_c4;             //   multipliers of the second hash (chosen by the host build)
     uint32_t ph_nb;                    //   number of buckets (= entries of ph_d)
     uint32_t ph_slot0;                 //   slot of Markov state 0 (the all-zero vector)
+    uint32_t kq[6];                    //   16, 256, 4096, -4369, 1, -4368: multipliers of the offset-invariant key words, handed over as
+                                       //   launch-time values so that the key is formed by IMADs on the FMA pipe, not by ALU-pipe shifts
     const double2* ll_slot;            // m = 4: log-likelihood rows indexed by hash SLOT, [ntables][ph_slots * R] (no slot -> state read)
 };
 
