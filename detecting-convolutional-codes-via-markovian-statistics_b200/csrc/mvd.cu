@@ -661,23 +661,26 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && ctx->linkey_ok && pair_smem <= 110 * 1024 &&
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
     // m = 3: two trials per thread with the perfect-hash lookup (2 blocks of 256 pair-threads per SM)
-    // (layout of detect3p_kernel: straggler queues, masks, branch table, displacements at a 1 KB-aligned and the slot table at a
-    // (slots x 8)-aligned absolute shared address, log rows; the dynamic window starts after the 1 KB the system reserves)
-    const size_t pair3_tb = (size_t)ctx->ph_slots * 8;
-    const size_t pair3_T = pair3_tb ? (((pair_sbase + DET2P_QUEUES + 128 + 128 + 1023) & ~(size_t)1023) + 1024 + pair3_tb - 1) & ~(pair3_tb - 1) : 0;
-    const size_t pair3_smem = pair3_T + pair3_tb + ((size_t)ctx->S * 4 << 5) - pair_sbase;
+    // (layout of detect3p_kernel, m = 3: straggler queues of 24 warps, masks, branch table, lane-replicated displacements at a
+    // 32 KB-aligned and the 16-copy slot table at a (slots x 64)-aligned absolute shared address, log rows in 4 copies; the dynamic
+    // window starts after the 1 KB the system reserves; one block of 768 pair-threads per SM)
+    const size_t pair3_tb = (size_t)ctx->ph_slots * 64;
+    const size_t pair3_D = (((pair_sbase + DET3P_QUEUES + 255) & ~(size_t)255) + 256 + 256 + 32767) & ~(size_t)32767;
+    const size_t pair3_T = pair3_tb ? (pair3_D + 32768 + pair3_tb - 1) & ~(pair3_tb - 1) : 0;
+    const size_t pair3_smem = pair3_T + pair3_tb + ((size_t)ctx->S * 4 << 6) - pair_sbase;
     const bool pair3s = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && !det2_gt && ctx->m == 3 &&
-                        ctx->ph_slots && pair3_smem <= 75 * 1024 &&
-                        (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
+                        ctx->ph_slots && pair3_smem <= 227 * 1024 &&
+                        (ctx->force_pair || all_trials >= 2ull * DET3P_BLOCK * sms);
     // m = 4: the same kernel with displacements, slots and log rows in global memory
     const bool pair4 = fast && !pair && !ctx->no_pair && engine == MVD_ENGINE_ACS && det2_lk == LK_HASH && det2_gt && ctx->m == 4 &&
                        ctx->ph_slots && ctx->have_llslot && (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
     const bool pair3 = pair3s || pair4;
     // few trials: smaller blocks so that every SM gets work (the kernels read blockDim.x)
-    uint32_t threads = (pair || pair3) ? DET2P_BLOCK : DET2_BLOCK;
+    uint32_t threads = pair3s ? DET3P_BLOCK : (pair || pair3) ? DET2P_BLOCK : DET2_BLOCK;
     if (fast) {
         const uint64_t per_thread = (pair || pair3) ? 2 : 1;
-        while (threads > 64 && (all_trials + threads * per_thread - 1) / (threads * per_thread) < 4 * sms) threads >>= 1;
+        const uint32_t least = pair3s ? 96 : 64;             // 768 halves to 384, 192, 96: whole warps
+        while (threads > least && (all_trials + threads * per_thread - 1) / (threads * per_thread) < (pair3s ? 1 : 4) * sms) threads >>= 1;
     }
     const uint32_t block = fast ? threads * ((pair || pair3) ? 2u : 1u) : MVD_BLOCK;
 
@@ -1041,7 +1044,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
             const dim3 g2((unsigned)maxblocks, cnt);
             // m = 4: the bucket displacements ride in shared memory when they fit beside two resident blocks
             const bool pair4_ds = (size_t)ctx->ph_nb * 4 <= 64 * 1024;       // bucket displacements in shared memory
-            const size_t pair4_smem = ((pair_sbase + DET2P_QUEUES + 128 + 128 + 1023) & ~(size_t)1023) + (pair4_ds ? (size_t)ctx->ph_nb * 4 : 0) - pair_sbase;
+            const size_t pair4_smem = ((((pair_sbase + DET2P_QUEUES + 255) & ~(size_t)255) + 256 + 256 + 1023) & ~(size_t)1023) + (pair4_ds ? (size_t)ctx->ph_nb * 4 : 0) - pair_sbase;
             if (pair3) le = mvd_launch_det3_pair(m, g2, threads, pair4 ? pair4_smem : pair3_smem, ctx->stream, P, B, pair4 && pair4_ds, P.bm_antipodal != 0);
             else le = mvd_launch_det2(det2_lk, m, det2_lls, det2_gt, pair, g2, threads, pair ? pair_smem : det2_smem, ctx->stream, P, B);
             extra_launches += 1;

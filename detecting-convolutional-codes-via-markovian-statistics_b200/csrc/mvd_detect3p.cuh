@@ -24,9 +24,14 @@
 // Results are the same bit for bit as the one-trial kernels and the oracle (same Eq. 4-5 arithmetic, same sums in
 // step order).
 //
-// Shared memory (absolute addresses; alignment lets one LOP3 form an address):
-//   [straggler queues 1 KB per warp][threshold masks 128 B][branch table 128 B, 128 B aligned][displacements, 1 KB aligned]
-//   [hash slots: slots x 2 copies x 4 B, aligned to its size][log rows S x 4 x 2 copies x 16 B, 128 B aligned]
+// Shared memory, m = 3 (absolute addresses; alignment lets one LOP3 form an address).  The kernel is bound by shared-memory
+// wavefronts (ncu: 93 % of the LSU data pipe, 56 % of the wavefronts bank conflicts with two row copies and plain hash tables,
+// profiles/r03d_m3_pair_ncu_full.txt), so ONE block of 768 threads per SM shares conflict-poor replicas of every table:
+//   [straggler queues 1 KB per warp][threshold masks 128 B][branch table 4 x 64 B, 256 B aligned]
+//   [displacements 256 x 32 lanes x 4 B at a 32 KB-aligned address: one copy per lane = per bank, no conflicts]
+//   [hash slots: slots x 16 copies x 4 B, aligned to its size: two lanes per copy]
+//   [log rows S x 4 x 4 copies x 16 B, 256 B aligned]
+// m = 4 keeps blocks of 256 threads: [queues][masks][branch table][displacements ph_nb x 4 B, 1 KB aligned].
 #pragma once
 #include "mvd_detect2.cuh"
 
@@ -57,7 +62,7 @@ struct PairEngineN {
     static constexpr int NS = 1 << M, HALF = NS / 2;
     uint32_t Q[NS];                   // (trial A, trial B) metrics of the trellis states
     uint32_t sxA, sxB;                // smem: absolute address of this lane's copy of the current log row; GT: state * R
-    uint32_t kV, kD, kT, tmask;       // branch table (32-byte rows) ; smem: displacement table ; slot table | copy * 4 ; (slots - 1) << 3
+    uint32_t kV, kD, kT, tmask;       // branch table (64-byte rows) ; smem: displacement table | lane * 4 ; slot table | copy * 4 ; (slots - 1) << 6
     uint32_t sel[ANTI ? 1 : 2 * NS];  // general decoders: PRMT selector of branch (ns, b) at [2 ns + b]
     const uint32_t* gD;               // GT: displacements, slots and log rows in global memory
     const double2* gll;
@@ -70,15 +75,22 @@ struct PairEngineN {
             const uint32_t d = DS ? lds_u32(kD + (b << 2)) : __ldg(gD + b);
             return ((((w0 * c2 + w1 * c4) >> 11) + d) & gmask) << 2;           // slot * R: the row index of ll_slot
         }
-        const uint32_t d8 = lds_u32(kD | (((w0 * PH3_C1) >> 22) & 0x3FCu));           // displacement * 8
-        return lds_u32(kT | ((((w0 * c2) >> 18) + d8) & tmask));
+        const uint32_t d6 = lds_u32(kD | (((w0 * PH3_C1) >> 17) & 0x7F80u));          // displacement * 64, this lane's copy
+        return lds_u32(kT | ((((w0 * c2) >> 15) + d6) & tmask));
     }
 
-    // fA / fB: r_A / r_B at bits 5..6 (log rows and branch table: 32-byte entries; other bits arbitrary).
+    // (f & 0xC0) | base as ONE LOP3 (left to itself the compiler shares the AND between the two tables of a trial: three)
+    static __device__ __forceinline__ uint32_t radr(uint32_t f, uint32_t base) {
+        uint32_t d;
+        asm("lop3.b32 %0, %1, 0xC0, %2, 0xEA;" : "=r"(d) : "r"(f), "r"(base));
+        return d;
+    }
+
+    // fA / fB: r_A / r_B at bits 6..7 (log rows and branch table: 64-byte entries; other bits arbitrary).
     // Eq. 5 is deferred (see the header): the caller normalises once per 32-step block.
     __device__ __forceinline__ void step(uint32_t fA, uint32_t fB, const Params& P) {
-        const double2 vA = GT ? __ldg(gll + sxA + ((fA >> 5) & 3u)) : lds_d2(sxA | (fA & 0x60u));
-        const double2 vB = GT ? __ldg(gll + sxB + ((fB >> 5) & 3u)) : lds_d2(sxB | (fB & 0x60u));
+        const double2 vA = GT ? __ldg(gll + sxA + ((fA >> 6) & 3u)) : lds_d2(radr(fA, sxA));
+        const double2 vB = GT ? __ldg(gll + sxB + ((fB >> 6) & 3u)) : lds_d2(radr(fB, sxB));
         a1A += vA.x;
         a0A += vA.y;
         a1B += vB.x;
@@ -88,11 +100,11 @@ struct PairEngineN {
             // row r of the branch table: bytes x_g; n - x_g = 2 - x_g byte by byte (no borrow), one IMAD by -1 per word
             uint32_t xa[2], na[2], xb[2], nb[2];
             if (M == 3) {
-                xa[0] = lds_u32(kV | (fA & 0x60u));
-                xb[0] = lds_u32(kV | (fB & 0x60u));
+                xa[0] = lds_u32(radr(fA, kV));
+                xb[0] = lds_u32(radr(fB, kV));
                 xa[1] = xb[1] = 0u;
             } else {
-                const uint2 ra = lds_v2(kV | (fA & 0x60u)), rb = lds_v2(kV | (fB & 0x60u));
+                const uint2 ra = lds_v2(radr(fA, kV)), rb = lds_v2(radr(fB, kV));
                 xa[0] = ra.x; xa[1] = ra.y;
                 xb[0] = rb.x; xb[1] = rb.y;
             }
@@ -112,7 +124,7 @@ struct PairEngineN {
                 n[2 * g + 1] = __viaddmin_u16x2(Q[g], nx, t1);
             }
         } else {
-            const uint32_t VA = lds_u32(kV | (fA & 0x60u)), VB = lds_u32(kV | (fB & 0x60u));
+            const uint32_t VA = lds_u32(radr(fA, kV)), VB = lds_u32(radr(fB, kV));
 #pragma unroll
             for (int ns = 0; ns < NS; ++ns)             // new state ns from predecessors ns >> 1 and (ns >> 1) + HALF: Eq. 4, both trials
                 n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, sel[2 * ns + 1]));
@@ -169,8 +181,8 @@ __global__ void pack_ll_kernel(const double* __restrict__ lp1, const double* __r
 }
 
 template <int M, bool GT, int PHILOX, bool DS, bool ANTI>
-__global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(const __grid_constant__ Params P,
-                                                                               const __grid_constant__ SegBatch B) {
+__global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1 : 2) detect3p_kernel(const __grid_constant__ Params P,
+                                                                                                      const __grid_constant__ SegBatch B) {
     constexpr int NS = 1 << M, HALF = NS / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevSeg& sg = B.s[blockIdx.y];
@@ -183,19 +195,20 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     const bool actA = tlA < ntr, actB = tlB < ntr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t SR = P.SR;
-    const uint32_t slots = P.fp.ph_slots, tbytes = GT ? 0u : slots * 8u;
+    const uint32_t slots = P.fp.ph_slots, tbytes = GT ? 0u : slots * 64u;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     uint32_t a_sq = sbase + (threadIdx.x >> 5) * 1024u;      // this warp's straggler queue (flip_words4)
-    const uint32_t a_tb = (sbase + (uint32_t)DET2P_QUEUES + 127u) & ~127u;
-    const uint32_t a_V = a_tb + 128u;                        // branch table: 4 rows x 32 B, 128 B aligned
-    const uint32_t a_D = (a_V + 128u + 1023u) & ~1023u;      // m = 3: 256 displacements; m = 4 (DS): ph_nb of them
-    const uint32_t a_T = GT ? 0u : ((a_D + 1024u + tbytes - 1u) & ~(tbytes - 1u));
-    const uint32_t a_ll = a_T + tbytes;                      // log rows (m = 3), 128 B aligned
+    const uint32_t a_tb = (sbase + (GT ? (uint32_t)DET2P_QUEUES : (uint32_t)DET3P_QUEUES) + 255u) & ~255u;
+    const uint32_t a_V = a_tb + 256u;                        // branch table: 4 rows x 64 B, 256 B aligned
+    // m = 3: 256 displacements x 32 lanes (32 KB, 32 KB aligned); m = 4 (DS): ph_nb of them (1 KB aligned)
+    const uint32_t a_D = GT ? ((a_V + 256u + 1023u) & ~1023u) : ((a_V + 256u + 32767u) & ~32767u);
+    const uint32_t a_T = GT ? 0u : ((a_D + 32768u + tbytes - 1u) & ~(tbytes - 1u));
+    const uint32_t a_ll = a_T + tbytes;                      // log rows (m = 3), 256 B aligned
     unsigned char* g = smem_raw - sbase;                     // generic pointer of shared address 0
     {
         uint32_t dyn;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-        const uint32_t need = GT ? (DS ? a_D + 4u * P.fp.ph_nb : a_V + 128u) : a_ll + (SR << 5);
+        const uint32_t need = GT ? (DS ? a_D + 4u * P.fp.ph_nb : a_V + 256u) : a_ll + (SR << 6);
         if (need - sbase > dyn) {                             // the host sized the window for another base address
             if (threadIdx.x == 0) atomicOr(P.error_flag, 4);
             return;
@@ -206,12 +219,15 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
         *reinterpret_cast<uint32_t*>(g + a_tb + 4u * threadIdx.x) = 0u - ((sg.threshold >> (31u - threadIdx.x)) & 1u);
     if (!GT) {
         const double2* llg = P.ll + (size_t)sg.table * SR;
-        for (uint32_t i = threadIdx.x; i < SR * 2u; i += BS)
-            *reinterpret_cast<double2*>(g + a_ll + ((i >> 1) << 5) + ((i & 1u) << 4)) = __ldg(llg + (i >> 1));
+        for (uint32_t i = threadIdx.x; i < SR; i += BS) {   // one global read per entry, four shared copies
+            const double2 v = __ldg(llg + i);
+#pragma unroll
+            for (uint32_t c = 0; c < 4u; ++c) *reinterpret_cast<double2*>(g + a_ll + (i << 6) + (c << 4)) = v;
+        }
     }
     if (threadIdx.x < 4u) {
         const uint32_t r = threadIdx.x;
-        uint32_t* row = reinterpret_cast<uint32_t*>(g + a_V + 32u * r);
+        uint32_t* row = reinterpret_cast<uint32_t*>(g + a_V + 64u * r);
         if (ANTI) {
             // bytes x_g = d(g -> 2g | r) of the butterflies g = 0 .. 2^(m-1) - 1 (P.bm[r][2 g + b]: low half = d(g + HALF b -> 2g))
             uint32_t x[2] = {0u, 0u};
@@ -227,10 +243,15 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     if (GT && DS)                                            // bucket displacements
         for (uint32_t i = threadIdx.x; i < P.fp.ph_nb; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i];
     if (!GT) {
-        for (uint32_t i = threadIdx.x; i < 256u; i += BS) *reinterpret_cast<uint32_t*>(g + a_D + 4u * i) = P.fp.ph_d[i] << 3;
-        for (uint32_t i = threadIdx.x; i < slots * 2u; i += BS) {
-            const uint32_t row = P.fp.ph_t[i >> 1];          // state * 4, or MVD_EMPTY (never looked up)
-            *reinterpret_cast<uint32_t*>(g + a_T + 4u * i) = a_ll + ((row == MVD_EMPTY ? 0u : row) << 5) + ((i & 1u) << 4);
+        for (uint32_t i = threadIdx.x; i < 256u * 4u; i += BS) {              // a quarter of a bucket's 32 lane copies per thread
+            const uint4 d = make_uint4(P.fp.ph_d[i >> 2] << 6, P.fp.ph_d[i >> 2] << 6, P.fp.ph_d[i >> 2] << 6, P.fp.ph_d[i >> 2] << 6);
+            *reinterpret_cast<uint4*>(g + a_D + 32u * i) = d;
+            *reinterpret_cast<uint4*>(g + a_D + 32u * i + 16u) = d;
+        }
+        for (uint32_t i = threadIdx.x; i < slots * 4u; i += BS) {             // four of a slot's 16 copies per thread
+            const uint32_t row = P.fp.ph_t[i >> 2];          // state * 4, or MVD_EMPTY (never looked up)
+            const uint32_t a = a_ll + ((row == MVD_EMPTY ? 0u : row) << 6);
+            *reinterpret_cast<uint4*>(g + a_T + 16u * i) = make_uint4(a, a + 16u, a + 32u, a + 48u);
         }
     }
     __syncthreads();
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
 #pragma unroll
     for (int s = 0; s < NS; ++s) eng.Q[s] = 0u;
     // state 0 = the all-zero vector
-    eng.sxA = eng.sxB = GT ? P.fp.ph_slot0 << 2 : a_ll + ((lane & 1u) << 4);
+    eng.sxA = eng.sxB = GT ? P.fp.ph_slot0 << 2 : a_ll + ((lane & 3u) << 4);
     eng.gD = P.fp.ph_d;
     eng.gll = GT ? P.fp.ll_slot + (size_t)sg.table * slots * 4u : P.ll + (size_t)sg.table * SR;
     eng.bshift = P.fp.ph_bshift;
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
     eng.c2 = P.fp.ph_c2;
     eng.c4 = P.fp.ph_c4;
     eng.kV = a_V;
-    eng.kD = a_D;
+    eng.kD = GT ? a_D : a_D + (lane << 2);
     if (!ANTI) {
         // label of branch (ns, b) from the branch-metric table of the decoder (P.bm[r][2 g + b] = distances to ns = 2g and
         // 2g + 1 from predecessor g + HALF b): (d(L,0), d(L,1)) = (0,1), (1,0), (1,2), (2,1) for L = 0, 1, 2, 3
@@ -261,8 +282,8 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
                 eng.sel[ANTI ? 0 : 2 * ns + b] = L | 0x80u | ((4u + L) << 8) | 0x8000u;
             }
     }
-    eng.kT = a_T + ((lane & 1u) << 2);
-    eng.tmask = (slots - 1u) << 3;
+    eng.kT = a_T + ((lane & 15u) << 2);
+    eng.tmask = (slots - 1u) << 6;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
 
     const uint32_t N = sg.N;
@@ -348,14 +369,14 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
             // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
             auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
-                eng.step(ea << 5, eb << 5, P);
-                eng.step(oa << 5, ob << 5, P);
-                eng.step(ea << 3, eb << 3, P);
-                eng.step(oa << 3, ob << 3, P);
-                eng.step(ea << 1, eb << 1, P);
-                eng.step(oa << 1, ob << 1, P);
-                eng.step(ea >> 1, eb >> 1, P);
-                eng.step(oa >> 1, ob >> 1, P);
+                eng.step(ea << 6, eb << 6, P);
+                eng.step(oa << 6, ob << 6, P);
+                eng.step(ea << 4, eb << 4, P);
+                eng.step(oa << 4, ob << 4, P);
+                eng.step(ea << 2, eb << 2, P);
+                eng.step(oa << 2, ob << 2, P);
+                eng.step(ea, eb, P);
+                eng.step(oa, ob, P);
             };
 #pragma unroll 1
             for (uint32_t c = 0; c < valid; c += 8u) {
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(DET2P_BLOCK, M == 3 ? 3 : 2) detect3p_kernel(c
                     for (uint32_t j = 0; j < valid - c; ++j) {
                         const uint32_t sh = j & ~1u;
                         const uint32_t ra = (((j & 1u) ? oa : ea) >> sh) & 3u, rb = (((j & 1u) ? ob : eb) >> sh) & 3u;
-                        eng.step(ra << 5, rb << 5, P);
+                        eng.step(ra << 6, rb << 6, P);
                     }
                 }
             }

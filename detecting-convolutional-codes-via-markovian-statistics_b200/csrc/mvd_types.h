@@ -80,6 +80,8 @@ struct Params {
 #define DET2_BLOCK 512
 #define DET2P_BLOCK 256
 #define DET2P_QUEUES ((DET2P_BLOCK / 32) * 1024)   // straggler queues of the pair kernel: 128 items x 8 bytes per warp
+#define DET3P_BLOCK 768         // m = 3 pair kernel: one block per SM shares conflict-poor table replicas (mvd_detect3p.cuh)
+#define DET3P_QUEUES ((DET3P_BLOCK / 32) * 1024)
 #define DET2_MAXSEG 96          // segments per launch: they travel in the kernel parameters (uniform registers)
 
 struct SegBatch {
