@@ -306,6 +306,45 @@ def test_pair_kernel_every_m2_decoder_vs_oracle(g0, g1):
             assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
 
 
+M3_DECODERS = [(g0, g1) for g0 in range(9, 16) for g1 in range(9, 16) if g0 != g1]
+
+
+@pytest.mark.parametrize("g0,g1", M3_DECODERS)
+def test_pair_kernel_every_m3_decoder_vs_oracle(g0, g1):
+    """The two-trials-per-thread kernel of memory-3 codes (mvd_detect3p.cuh) over every rate-1/2 decoder whose two
+    generators both reach back three steps (S = 5 .. 987 Markov states; those with S <= 435 fit its shared-memory
+    layout, the others take the one-trial kernel): offset-invariant perfect-hash key, Eq. 5 once per 32-step block,
+    byte-row butterflies of the complement-label decoders and selector picks of the others, a full block of 768
+    pair-threads plus a partly filled one, a ragged N (4 blocks + 3 steps) -- tallies and per-trial float64 sums
+    against the oracle, bit for bit."""
+    import c_oracle as co
+    from mvd import bitsource, codes
+    from mvd.engine import Detector, Seg
+    bits = lambda g: [(g >> 3) & 1, (g >> 2) & 1, (g >> 1) & 1, g & 1]
+    gen, enc_gen = [[bits(g0)], [bits(g1)]], [[[1, 1, 1, 1]], [[1, 0, 1, 1]]]
+    p, N, ntr, seed = 0.08, 131, 1700, 99
+    T = bitsource.bsc_threshold(p)
+    with Detector(gen, 1, 2, 3) as det:
+        taps, etaps = det.taps_of(gen), det.taps_of(enc_gen)
+        tab = co.Table(det.table.metrics, 3)
+        edge, _ = co.learn_chain(taps, taps, 2, 3, 6000, 200, T, seed, bitsource.LEARN_STREAM, 0, tab)
+        P1 = codes.p1_from_edge_counts(det.table, edge, 1.0)
+        Tref = codes.tref_half_table(det.table)
+        det.set_models([P1])
+        segs = [Seg(N=N, threshold=T, stream=3 + d, enc_taps=(taps, etaps)[d], decide=d, trial_begin=5, trial_end=5 + ntr)
+                for d in (0, 1)]
+        det.no_pair(2)
+        tallies, lp = det.detect(segs, seed=seed, engine="acs", want_logp=True)
+        kind = det.last_kernel_kind()
+        assert kind != 0, "generic kernel ran instead of a fast one"
+        if det.S <= 435:
+            assert kind >= 256, "the pair kernel did not run"
+        for d in (0, 1):
+            want, wlp = co.run_trials(taps, (taps, etaps)[d], 2, 3, N, T, seed, 3 + d, 5, 5 + ntr, tab, P1, Tref, d, want_logp=True)
+            assert int(tallies[d]) == want
+            assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("dec,enc", [("c75", "c65"), ("m3a", "m3b")])
 def test_detect_against_numeric_T_of_any_p(codes_spec, dets, engine, dec, enc):
