@@ -68,6 +68,17 @@ struct PairEngineN {
     const double2* gll;
     uint32_t bshift, gmask, c2, c4;   // c2, c4: multipliers of the second hash, chosen by the host build
     double a1A, a0A, a1B, a0B;
+    double2 pA, pB;                   // GT: the terms read by the previous step, not yet added
+
+    // GT: add the terms of the last step
+    __device__ __forceinline__ void flush() {
+        if (GT) {
+            a1A += pA.x;
+            a0A += pA.y;
+            a1B += pB.x;
+            a0B += pB.y;
+        }
+    }
 
     __device__ __forceinline__ uint32_t lookup(uint32_t w0, uint32_t w1) const {
         if (GT) {
@@ -89,12 +100,23 @@ struct PairEngineN {
     // fA / fB: r_A / r_B at bits 6..7 (log rows and branch table: 64-byte entries; other bits arbitrary).
     // Eq. 5 is deferred (see the header): the caller normalises once per 32-step block.
     __device__ __forceinline__ void step(uint32_t fA, uint32_t fB, const Params& P) {
-        const double2 vA = GT ? __ldg(gll + sxA + ((fA >> 6) & 3u)) : lds_d2(radr(fA, sxA));
-        const double2 vB = GT ? __ldg(gll + sxB + ((fB >> 6) & 3u)) : lds_d2(radr(fB, sxB));
-        a1A += vA.x;
-        a0A += vA.y;
-        a1B += vB.x;
-        a0B += vB.y;
+        if (GT) {
+            // the rows come from L2 (~300 cycles): the terms of a step are added one step later (same order of additions, so the
+            // same sums bit for bit), which takes the read off the path of the DADD chain (long_scoreboard was the top stall)
+            const double2 vA = __ldg(gll + sxA + ((fA >> 6) & 3u)), vB = __ldg(gll + sxB + ((fB >> 6) & 3u));
+            a1A += pA.x;
+            a0A += pA.y;
+            a1B += pB.x;
+            a0B += pB.y;
+            pA = vA;
+            pB = vB;
+        } else {
+            const double2 vA = lds_d2(radr(fA, sxA)), vB = lds_d2(radr(fB, sxB));
+            a1A += vA.x;
+            a0A += vA.y;
+            a1B += vB.x;
+            a0B += vB.y;
+        }
         uint32_t n[NS];
         if (ANTI) {
             // row r of the branch table: bytes x_g; n - x_g = 2 - x_g byte by byte (no borrow), one IMAD by -1 per word
@@ -285,6 +307,7 @@ __global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1
     eng.kT = a_T + ((lane & 15u) << 2);
     eng.tmask = (slots - 1u) << 6;
     eng.a1A = eng.a0A = eng.a1B = eng.a0B = 0.0;
+    eng.pA = eng.pB = make_double2(0.0, 0.0);
 
     const uint32_t N = sg.N;
     const int ncalls = sg.dmin > 31u ? 0 : (int)((31u - sg.dmin) / 4u + 1u);
@@ -395,6 +418,7 @@ __global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1
         }
     }
 
+    eng.flush();
     const bool winA = actA && (sg.decide == 0 ? (eng.a1A > eng.a0A) : (eng.a1A <= eng.a0A));
     const bool winB = actB && (sg.decide == 0 ? (eng.a1B > eng.a0B) : (eng.a1B <= eng.a0B));
     const int cnt = __syncthreads_count(winA ? 1 : 0) + __syncthreads_count(winB ? 1 : 0);
