@@ -600,14 +600,19 @@ def test_m4_global_tables_vs_oracle(codes_spec):
                 assert int(t[0]) == want
                 assert np.array_equal(lp, wlp)
         # ACS engine, two trials per thread with the perfect-hash lookup (mvd_detect3p.cuh, m = 4 variant)
-        det.no_pair(2)
-        try:
-            t, lp = det.detect([seg], seed=8, engine="acs", want_logp=True)
-            kind = det.last_kernel_kind()
-        finally:
-            det.no_pair(False)
-        assert kind & 256 and kind & 512
-        assert int(t[0]) == want and np.array_equal(lp, wlp)
+        # (both instances: byte-row butterflies of a complement-label decoder -- (31,33) is one -- and the selector picks
+        # every other decoder takes)
+        for general in (False, True):
+            det.no_pair(2)
+            det.no_antipodal(general)
+            try:
+                t, lp = det.detect([seg], seed=8, engine="acs", want_logp=True)
+                kind = det.last_kernel_kind()
+            finally:
+                det.no_pair(False)
+                det.no_antipodal(False)
+            assert kind & 256 and kind & 512
+            assert int(t[0]) == want and np.array_equal(lp, wlp)
         # learning chain through the global-memory histogram
         got = det.learn_counts([Seg(N=60000, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=_taps(spec))],
                                burn=200, seed=3)[0]
