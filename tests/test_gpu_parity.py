@@ -306,6 +306,27 @@ def test_pair_kernel_every_m2_decoder_vs_oracle(g0, g1):
             assert np.array_equal(lp[d * ntr:(d + 1) * ntr], wlp)
 
 
+def test_m3_pair_kernel_full_blocks_vs_oracle(codes_spec):
+    """The memory-3 pair kernel at its production geometry: enough trials that the dispatcher keeps blocks of 768 threads
+    (one per SM, 204 KB of shared tables) instead of shrinking them, last block ragged, N = 37 (one 32-step block + 5
+    steps) -- tallies and every per-trial float64 sum against the oracle."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Detector, Seg
+    spec = codes_spec["m3a"]
+    with Detector(spec["gen"], 1, 2, 3) as det:
+        tab, P1, Tref = _oracle_models(det, spec, 0.05, 20000, 3)
+        det.set_models([P1])
+        T = bitsource.bsc_threshold(0.05)
+        taps, taps2 = _taps(spec), _taps(codes_spec["m3b"])
+        ntr = 160 * 2 * 768 + 301
+        seg = Seg(N=37, threshold=T, stream=1, enc_taps=taps2, decide=1, trial_begin=3, trial_end=3 + ntr)
+        t, lp = det.detect([seg], seed=8, engine="acs", want_logp=True)
+        assert det.last_kernel_kind() & 256, "detect3p_kernel did not run"
+        want, wlp = co.run_trials(taps, taps2, 2, 3, 37, T, 8, 1, 3, 3 + ntr, tab, P1, Tref, 1, want_logp=True)
+        assert int(t[0]) == want and np.array_equal(lp, wlp)
+
+
 M3_DECODERS = [(g0, g1) for g0 in range(9, 16) for g1 in range(9, 16) if g0 != g1]
 
 
