@@ -169,6 +169,30 @@ def test_host_p1_edge_tables_equal_the_numpy_closed_form():
     assert logs.tolist() == [math.log(max(float(v), 1e-300)) for v in big]
 
 
+def test_small_tables_closed_form_equals_the_dense_replay():
+    """Small state tables (S <= DENSE_LIMIT): with integer counts and a dyadic Laplace constant the closed form in C
+    gives the same bits as replaying the reference's dense ``P = counts + laplace; P /= P.sum(axis=1)``
+    (Pd_plotter.py:166-167) -- real tables of the m = 2 / m = 3 codes, learned-count-sized and huge counts, zero rows;
+    a non-dyadic constant still takes the dense replay."""
+    from mvd import codes
+    rng = np.random.default_rng(11)
+    for gen, m in (([[[1, 1, 1]], [[1, 0, 1]]], 2), ([[[1, 1, 1, 1]], [[1, 0, 1, 1]]], 3)):
+        tab = codes.enumerate_states(gen, m, 1, 2)
+        S, R = tab.S, tab.R
+        counts = rng.integers(0, 5000, size=(4, S, R), dtype=np.uint64)
+        counts[1, ::4] = 0
+        counts[2] = rng.integers(0, 1 << 35, size=(S, R), dtype=np.uint64)
+        counts[3] = 0
+        for laplace in (1.0, 0.5, 2.0, 0.0009765625, 0.3):
+            assert codes._exact_row_sums(counts, laplace, S) == (laplace != 0.3)
+            got = codes.p1_tables_from_edge_counts(tab, counts, laplace)
+            for t in range(4):
+                dense = codes.p1_dense(tab, counts[t], laplace)
+                assert np.array_equal(got[t], dense[np.arange(S)[:, None], tab.nxt]), (m, laplace, t)
+    assert not codes._exact_row_sums(np.zeros((1, 3, 4)), 1.0, 3)                  # float counts: not taken for exact
+    assert not codes._exact_row_sums(np.full((1, 3, 4), 1 << 37, dtype=np.uint64), 1.0, 3)
+
+
 def test_host_log_table_is_math_log():
     """The C helper behind large log-likelihood tables returns math.log(max(v, 1e-300)) bit for bit
     (Pd_plotter.py:114-115) -- and _log_table switches to it without changing a single value."""
