@@ -660,7 +660,7 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     // pairing halves the thread count: only when the GPU stays full (3 blocks of 256 pair-threads per SM)
     const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && ctx->linkey_ok && pair_smem <= 110 * 1024 &&
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
-    // m = 3: two trials per thread with the perfect-hash lookup (2 blocks of 256 pair-threads per SM)
+    // m = 3: two trials per thread with the perfect-hash lookup
     // (layout of detect3p_kernel, m = 3: straggler queues of 24 warps, masks, branch table, lane-replicated displacements at a
     // 32 KB-aligned and the 16-copy slot table at a (slots x 64)-aligned absolute shared address, log rows in 4 copies; the dynamic
     // window starts after the 1 KB the system reserves; one block of 768 pair-threads per SM)
