@@ -27,7 +27,7 @@
 // Shared memory, m = 3 (absolute addresses; alignment lets one LOP3 form an address).  The kernel is bound by shared-memory
 // wavefronts (ncu: 93 % of the LSU data pipe, 56 % of the wavefronts bank conflicts with two row copies and plain hash tables,
 // profiles/r03d_m3_pair_ncu_full.txt), so ONE block of 768 threads per SM shares conflict-poor replicas of every table:
-//   [straggler queues 1 KB per warp][threshold masks 128 B][branch table 4 x 64 B, 256 B aligned]
+//   [straggler queues 1 KB per warp][threshold masks 128 B][branch table 4 x 16 B (four banks), 256 B aligned]
 //   [displacements 256 x 32 lanes x 4 B at a 32 KB-aligned address: one copy per lane = per bank, no conflicts]
 //   [hash slots: slots x 16 copies x 4 B, aligned to its size: two lanes per copy]
 //   [log rows S x 4 x 4 copies x 16 B, 256 B aligned]
@@ -44,7 +44,7 @@
 //   butterfly g carry the labels X, ~X, ~X, X, so with x_g = d(X, r) the step is
 //       D'[2g] = min(D[g] + x_g, D[g+H] + n - x_g),   D'[2g+1] = min(D[g] + n - x_g, D[g+H] + x_g):
 //   the block stages, per received word r, the bytes x_g of all 2^(m-1) butterflies (one LDS.32 / LDS.64 per trial, rows
-//   at 32-byte pitch like the log rows; n - x_g byte by byte = one IMAD per word); PRMT(row_A, row_B, constant selector)
+//   at 16-byte pitch; n - x_g byte by byte = one IMAD per word); PRMT(row_A, row_B, constant selector)
 //   packs (x_g | r_A, x_g | r_B) -- ONE pick per butterfly and operand instead of one per branch; the two additions per butterfly are IMADs (multiplier 1 from the kernel parameters,
 //   FMA pipe), the VIADDMNMX pair stays on the ALU pipe.
 //   General decoders: the 2^(m+1) branch words of a step are picks from the four bytes V(r) = (d(0,r), d(1,r), d(2,r),
@@ -97,9 +97,17 @@ struct PairEngineN {
         return d;
     }
 
-    // fA / fB: r_A / r_B at bits 6..7 (log rows and branch table: 64-byte entries; other bits arbitrary).
+    // the branch table has 16-byte rows (r at bits 4..5): its four rows lie in four different banks, where rows at the 64-byte
+    // pitch of the log rows put r = 0, 2 (and 1, 3) into the same bank -- two wavefronts per read
+    static __device__ __forceinline__ uint32_t xadr(uint32_t x, uint32_t base) {
+        uint32_t d;
+        asm("lop3.b32 %0, %1, 0x30, %2, 0xEA;" : "=r"(d) : "r"(x), "r"(base));
+        return d;
+    }
+
+    // fA / fB: r_A / r_B at bits 6..7 (log rows: 64-byte entries); xA / xB: the same at bits 4..5 (branch table); other bits arbitrary.
     // Eq. 5 is deferred (see the header): the caller normalises once per 32-step block.
-    __device__ __forceinline__ void step(uint32_t fA, uint32_t fB, const Params& P) {
+    __device__ __forceinline__ void step(uint32_t fA, uint32_t fB, uint32_t xA, uint32_t xB, const Params& P) {
         if (GT) {
             // the rows come from L2 (~300 cycles): the terms of a step are added one step later (same order of additions, so the
             // same sums bit for bit), which takes the read off the path of the DADD chain (long_scoreboard was the top stall)
@@ -122,11 +130,11 @@ struct PairEngineN {
             // row r of the branch table: bytes x_g; n - x_g = 2 - x_g byte by byte (no borrow), one IMAD by -1 per word
             uint32_t xa[2], na[2], xb[2], nb[2];
             if (M == 3) {
-                xa[0] = lds_u32(radr(fA, kV));
-                xb[0] = lds_u32(radr(fB, kV));
+                xa[0] = lds_u32(xadr(xA, kV));
+                xb[0] = lds_u32(xadr(xB, kV));
                 xa[1] = xb[1] = 0u;
             } else {
-                const uint2 ra = lds_v2(radr(fA, kV)), rb = lds_v2(radr(fB, kV));
+                const uint2 ra = lds_v2(xadr(xA, kV)), rb = lds_v2(xadr(xB, kV));
                 xa[0] = ra.x; xa[1] = ra.y;
                 xb[0] = rb.x; xb[1] = rb.y;
             }
@@ -146,7 +154,7 @@ struct PairEngineN {
                 n[2 * g + 1] = __viaddmin_u16x2(Q[g], nx, t1);
             }
         } else {
-            const uint32_t VA = lds_u32(radr(fA, kV)), VB = lds_u32(radr(fB, kV));
+            const uint32_t VA = lds_u32(xadr(xA, kV)), VB = lds_u32(xadr(xB, kV));
 #pragma unroll
             for (int ns = 0; ns < NS; ++ns)             // new state ns from predecessors ns >> 1 and (ns >> 1) + HALF: Eq. 4, both trials
                 n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, sel[2 * ns + 1]));
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     uint32_t a_sq = sbase + (threadIdx.x >> 5) * 1024u;      // this warp's straggler queue (flip_words4)
     const uint32_t a_tb = (sbase + (GT ? (uint32_t)DET2P_QUEUES : (uint32_t)DET3P_QUEUES) + 255u) & ~255u;
-    const uint32_t a_V = a_tb + 256u;                        // branch table: 4 rows x 64 B, 256 B aligned
+    const uint32_t a_V = a_tb + 256u;                        // branch table: 4 rows x 16 B, 256 B aligned
     // m = 3: 256 displacements x 32 lanes (32 KB, 32 KB aligned); m = 4 (DS): ph_nb of them (1 KB aligned)
     const uint32_t a_D = GT ? ((a_V + 256u + 1023u) & ~1023u) : ((a_V + 256u + 32767u) & ~32767u);
     const uint32_t a_T = GT ? 0u : ((a_D + 32768u + tbytes - 1u) & ~(tbytes - 1u));
@@ -249,7 +257,7 @@ __global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1
     }
     if (threadIdx.x < 4u) {
         const uint32_t r = threadIdx.x;
-        uint32_t* row = reinterpret_cast<uint32_t*>(g + a_V + 64u * r);
+        uint32_t* row = reinterpret_cast<uint32_t*>(g + a_V + 16u * r);
         if (ANTI) {
             // bytes x_g = d(g -> 2g | r) of the butterflies g = 0 .. 2^(m-1) - 1 (P.bm[r][2 g + b]: low half = d(g + HALF b -> 2g))
             uint32_t x[2] = {0u, 0u};
@@ -392,14 +400,17 @@ __global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1
             UB = make_uint4(UB.y, UB.z, UB.w, 0u);
             // 8 steps = bits 0..7 of the even-step words (ea, eb) and of the odd-step words (oa, ob)
             auto oct = [&](uint32_t ea, uint32_t oa, uint32_t eb, uint32_t ob) {
-                eng.step(ea << 6, eb << 6, P);
-                eng.step(oa << 6, ob << 6, P);
-                eng.step(ea << 4, eb << 4, P);
-                eng.step(oa << 4, ob << 4, P);
-                eng.step(ea << 2, eb << 2, P);
-                eng.step(oa << 2, ob << 2, P);
-                eng.step(ea, eb, P);
-                eng.step(oa, ob, P);
+                // (the branch-table field of a step is the log-row field of the step after next: one more shift per word and oct)
+                const uint32_t ea6 = ea << 6, eb6 = eb << 6, oa6 = oa << 6, ob6 = ob << 6, ea4 = ea << 4, eb4 = eb << 4, oa4 = oa << 4, ob4 = ob << 4;
+                const uint32_t ea2 = ea << 2, eb2 = eb << 2, oa2 = oa << 2, ob2 = ob << 2;
+                eng.step(ea6, eb6, ea4, eb4, P);
+                eng.step(oa6, ob6, oa4, ob4, P);
+                eng.step(ea4, eb4, ea2, eb2, P);
+                eng.step(oa4, ob4, oa2, ob2, P);
+                eng.step(ea2, eb2, ea, eb, P);
+                eng.step(oa2, ob2, oa, ob, P);
+                eng.step(ea, eb, ea >> 2, eb >> 2, P);
+                eng.step(oa, ob, oa >> 2, ob >> 2, P);
             };
 #pragma unroll 1
             for (uint32_t c = 0; c < valid; c += 8u) {
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(M == 3 ? DET3P_BLOCK : DET2P_BLOCK, M == 3 ? 1
                     for (uint32_t j = 0; j < valid - c; ++j) {
                         const uint32_t sh = j & ~1u;
                         const uint32_t ra = (((j & 1u) ? oa : ea) >> sh) & 3u, rb = (((j & 1u) ? ob : eb) >> sh) & 3u;
-                        eng.step(ra << 6, rb << 6, P);
+                        eng.step(ra << 6, rb << 6, ra << 4, rb << 4, P);
                     }
                 }
             }
