@@ -44,9 +44,9 @@
 //   butterfly g carry the labels X, ~X, ~X, X, so with x_g = d(X, r) the step is
 //       D'[2g] = min(D[g] + x_g, D[g+H] + n - x_g),   D'[2g+1] = min(D[g] + n - x_g, D[g+H] + x_g):
 //   the block stages, per received word r, the bytes x_g of all 2^(m-1) butterflies (one LDS.32 / LDS.64 per trial, rows
-//   at 16-byte pitch; n - x_g byte by byte = one IMAD per word); PRMT(row_A, row_B, constant selector)
-//   packs (x_g | r_A, x_g | r_B) -- ONE pick per butterfly and operand instead of one per branch; the two additions per butterfly are IMADs (multiplier 1 from the kernel parameters,
-//   FMA pipe), the VIADDMNMX pair stays on the ALU pipe.
+//   at 16-byte pitch); PRMT(row_A, row_B, constant selector) packs (x_g | r_A, x_g | r_B) -- ONE pick per butterfly instead of
+//   one per branch; n - x_g of the pair is 0x00020002 - pair, and that and the two additions per butterfly are IMADs
+//   (multipliers -1 / 1 from the kernel parameters, FMA pipe); the VIADDMNMX pair stays on the ALU pipe.
 //   General decoders: the 2^(m+1) branch words of a step are picks from the four bytes V(r) = (d(0,r), d(1,r), d(2,r),
 //   d(3,r)) with per-decoder selectors held in registers (selector nibbles with bit 3 set yield the replicated sign = 0).
 // PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the selected byte (0 for the small bytes used
@@ -127,8 +127,9 @@ struct PairEngineN {
         }
         uint32_t n[NS];
         if (ANTI) {
-            // row r of the branch table: bytes x_g; n - x_g = 2 - x_g byte by byte (no borrow), one IMAD by -1 per word
-            uint32_t xa[2], na[2], xb[2], nb[2];
+            // row r of the branch table: bytes x_g; the packed pair (n - x_g | r_A, n - x_g | r_B) = 0x00020002 - (x_g pair), one IMAD by -1
+            // (no borrow: x_g <= 2) instead of a second PRMT
+            uint32_t xa[2], xb[2];
             if (M == 3) {
                 xa[0] = lds_u32(xadr(xA, kV));
                 xb[0] = lds_u32(xadr(xB, kV));
@@ -138,17 +139,11 @@ struct PairEngineN {
                 xa[0] = ra.x; xa[1] = ra.y;
                 xb[0] = rb.x; xb[1] = rb.y;
             }
-#pragma unroll
-            for (int j = 0; j < (M == 3 ? 1 : 2); ++j) {
-                na[j] = madlo(xa[j], P.fma_km1, 0x02020202u);
-                nb[j] = madlo(xb[j], P.fma_km1, 0x02020202u);
-            }
-            if (M == 3) na[1] = nb[1] = 0u;
             const uint32_t one = P.fp.kq[4];
 #pragma unroll
             for (int g = 0; g < HALF; ++g) {
                 const uint32_t s4 = (uint32_t)(g & 3) | 0x80u | ((4u + (uint32_t)(g & 3)) << 8) | 0x8000u;
-                const uint32_t x = prmt_s(xa[g >> 2], xb[g >> 2], s4), nx = prmt_s(na[g >> 2], nb[g >> 2], s4);
+                const uint32_t x = prmt_s(xa[g >> 2], xb[g >> 2], s4), nx = madlo(x, P.fma_km1, 0x00020002u);
                 const uint32_t t0 = madlo(Q[g], one, x), t1 = madlo(Q[g + HALF], one, x);
                 n[2 * g] = __viaddmin_u16x2(Q[g + HALF], nx, t0);              // Eq. 4, both trials
                 n[2 * g + 1] = __viaddmin_u16x2(Q[g], nx, t1);
