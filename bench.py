@@ -566,6 +566,36 @@ def main():
             line["alt_engine"] = {"engine": other, "value": steps_per_pass * max(3, args.steps // 2) / dto,
                                   "kernel_ms_per_step": float(np.mean(kmo)),
                                   "tallies_equal": bool(np.array_equal(last_tallies().cpu().numpy(), final_tallies))}
+            # ---- the other BASELINE code pairs through the same public API (kernel time of the detection launch, median of 3):
+            # the demo's m = 3 pair (S = 435, tables in shared memory) and an m = 4 full detector (S = 25 751, tables in L2)
+            oc = {}
+            for name, g1, g2, mm, its, pv, ll in (
+                    ("m3_demo_pair_17_13_vs_13_17", [[[1, 1, 1, 1]], [[1, 0, 1, 1]]], [[[1, 0, 1, 1]], [[1, 1, 1, 1]]], 3, 200000,
+                     [0.01, 0.05, 0.1, 0.2, 0.3], None),
+                    ("m4_31_33_vs_33_31", [[[1, 1, 0, 0, 1]], [[1, 1, 0, 1, 1]]], [[[1, 1, 0, 1, 1]], [[1, 1, 0, 0, 1]]], 4, 100000,
+                     [0.05, 0.1], 200000)):
+                try:
+                    ent = {"trials_per_point": its, "N": N_BLOCK, "p_vec": pv}
+                    for eng in ("acs", "auto"):
+                        dd, ms = {}, []
+                        for it in range(4):
+                            pdp.run_experiment(1, 2, mm, g1, g2, its, pv, ll, 200, 1.0, SEED, N_spectrum=[N_BLOCK], engine=eng,
+                                               device=local_rank, details=dd, shard=False)
+                            if it:
+                                ms.append(dd["detect_kernel_ms"])
+                        km = float(np.median(ms))
+                        ent[eng] = {"kernel_ms": km, "steps_per_s": dd["steps"] / (km * 1e-3), "kernel_kind": dd["kernel_kind"],
+                                    "tallies_sha": _sha(dd["tallies"])}
+                    ops = 5 * 2 ** mm + 11                                   # SURVEY 8(d) at k = 1, n = 2
+                    ent.update(S=dd["S"], ops_per_step_core=ops, tallies_equal=ent["acs"]["tallies_sha"] == ent["auto"]["tallies_sha"],
+                               frac_issue_peak_acs=ops * ent["acs"]["steps_per_s"] * 1e-9 / mixed_gops)
+                    oc[name] = ent
+                except Exception as exc:                                     # an extra leg must not take the bench line down
+                    oc[name] = {"error": str(exc)[:200]}
+            oc["note"] = ("acs = Eq. 4-5 in registers, two trials per thread (detect3p_kernel): m = 3 bound by shared-memory wavefronts / issue / "
+                          "ALU pipe alike, m = 4 by the L1TEX gather rate (one 32-byte sector per trial-step); auto = NEXT-table walk; profiles/r03*")
+            line["other_configs"] = oc
+            install_bench_models()
             # bit-stream (verification-mode) kernel: HBM view.  10^5 trials/point -> 3 bits/step from HBM.
             bt = min(trials, 100_000)
             nsb = (N_BLOCK + 127) // 128
