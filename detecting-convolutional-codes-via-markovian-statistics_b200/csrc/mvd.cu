@@ -506,8 +506,10 @@ struct LaunchOut {
 };
 
 // Shared-memory plan of the fast detection kernels; returns false if they do not apply.
-bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPlan* fp, size_t* smem_out, bool* gt_out) {
+bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPlan* fp, size_t* smem_out, bool* gt_out,
+               bool allow_big = false, bool* big_out = nullptr) {
     *gt_out = false;
+    if (big_out) *big_out = false;
     // n = 2: every engine; n = 3 (rate 1/3): the NEXT-walk engines, which take any number of received words
     if (!(ctx->n == 2 || (ctx->n == 3 && engine == MVD_ENGINE_FSM)) || !ctx->closed) return false;
     const int m = ctx->m, nstate = 1 << m, NP = nstate / 2, R = 1 << ctx->n;
@@ -519,7 +521,13 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
         // (measured at S = 435: 8 / 4 / 2 / 1 copies = 7.06e11 / 8.46e11 / 8.44e11 / 8.17e11 steps/s)
         int lls = 7;
         const char* force = getenv("MVD_FSM1_LLS");                 // experiments only
-        if (force && *force >= '4' && *force <= '7') lls = *force - '0';
+        // ... unless the launch is large enough for TWO blocks of 768 threads per SM around a 4-copy table (n = 2)
+        const bool big = !force && allow_big && big_out && ctx->n == 2 && 128 + (SR << 6) + 64 > 75 * 1024 &&
+                         128 + (SR << 6) + 64 <= 112 * 1024;
+        if (big) {
+            *big_out = true;
+            lls = 6;
+        } else if (force && *force >= '4' && *force <= '7') lls = *force - '0';
         else while (lls > 4 && 128 + (SR << lls) + 64 > 75 * 1024) --lls;
         while (lls > 4 && 128 + (SR << lls) + 64 > ctx->prop.sharedMemPerBlockOptin) --lls;
         fp->off_tb = 0;
@@ -646,17 +654,19 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     int det2_lk = -1, det2_lls = 0;
     size_t det2_smem = 0;
     bool det2_gt = false;
+    uint64_t all_trials = 0;
+    for (uint32_t i = 0; i < nsegs; ++i) all_trials += segs[i].trial_end >= segs[i].trial_begin ? segs[i].trial_end - segs[i].trial_begin : 0;
+    const uint64_t sms = (uint64_t)ctx->prop.multiProcessorCount;
+    bool det2_big = false;
     const bool fast = mode == MODE_DETECT && !ctx->force_generic && !ctx->table_code &&
-                      plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt);
+                      plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt,
+                                all_trials >= 2ull * DET2_BIG_BLOCK * sms && !getenv("MVD_NO_BIG_BLOCK"), &det2_big);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
     // (layout of detect2p_kernel: straggler queues, masks, branch metrics, log rows, then the state table at a 32 KB-aligned
     // absolute shared address; the dynamic window starts after the 1 KB the system reserves)
     const size_t pair_sbase = 1024;
     const size_t pair_st = (pair_sbase + DET2P_QUEUES + 128 + 2048 + 4096 + ((size_t)ctx->S * 4 << 7) + 32767) & ~(size_t)32767;
     const size_t pair_smem = pair_st + 32768 - pair_sbase;
-    uint64_t all_trials = 0;
-    for (uint32_t i = 0; i < nsegs; ++i) all_trials += segs[i].trial_end >= segs[i].trial_begin ? segs[i].trial_end - segs[i].trial_begin : 0;
-    const uint64_t sms = (uint64_t)ctx->prop.multiProcessorCount;
     // pairing halves the thread count: only when the GPU stays full (3 blocks of 256 pair-threads per SM)
     const bool pair = fast && !ctx->no_pair && det2_lk == LK_DIRECT && ctx->m == 2 && ctx->linkey_ok && pair_smem <= 110 * 1024 &&
                       (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 3ull * sms);
@@ -676,8 +686,8 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
                        ctx->ph_slots && ctx->have_llslot && (ctx->force_pair || all_trials >= 2ull * DET2P_BLOCK * 2ull * sms);
     const bool pair3 = pair3s || pair4;
     // few trials: smaller blocks so that every SM gets work (the kernels read blockDim.x)
-    uint32_t threads = pair3s ? DET3P_BLOCK : (pair || pair3) ? DET2P_BLOCK : DET2_BLOCK;
-    if (fast) {
+    uint32_t threads = pair3s ? DET3P_BLOCK : (pair || pair3) ? DET2P_BLOCK : det2_big ? DET2_BIG_BLOCK : DET2_BLOCK;
+    if (fast && !(det2_big && !pair && !pair3)) {
         const uint64_t per_thread = (pair || pair3) ? 2 : 1;
         const uint32_t least = pair3s ? 96 : 64;             // 768 halves to 384, 192, 96: whole warps
         while (threads > least && (all_trials + threads * per_thread - 1) / (threads * per_thread) < (pair3s ? 1 : 4) * sms) threads >>= 1;

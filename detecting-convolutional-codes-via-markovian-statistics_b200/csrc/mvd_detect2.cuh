@@ -541,9 +541,10 @@ struct Fsm1Engine {
 // shared memory, e.g. m = 4 with S = 25 751 ... 232 567): nothing but the threshold masks and the
 // branch metrics is staged, LLS = 4 (no replicas).
 // NOUT = 3: rate-1/3 codes (NEXT-walk engines only).
-template <int LK, int M, int LLS, bool GT = false, int NOUT = 2>
-__global__ void __launch_bounds__(DET2_BLOCK, (LK == LK_FSM1 || LK == LK_FSM) ? 3 : 2) detect2_kernel(const __grid_constant__ Params P,
-                                                                const __grid_constant__ SegBatch B) {
+// BIG: blocks of DET2_BIG_BLOCK threads, two per SM (a shared-memory table that only fits twice; see plan_det2)
+template <int LK, int M, int LLS, bool GT = false, int NOUT = 2, bool BIG = false>
+__global__ void __launch_bounds__(BIG ? DET2_BIG_BLOCK : DET2_BLOCK, BIG ? 2 : ((LK == LK_FSM1 || LK == LK_FSM) ? 3 : 2))
+detect2_kernel(const __grid_constant__ Params P, const __grid_constant__ SegBatch B) {
     static_assert(NOUT == 2 || (NOUT == 3 && (LK == LK_FSM1 || LK == LK_FSM)), "n = 3 runs on the NEXT-walk engines");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int REP = 1 << (LLS - 4);

@@ -3,9 +3,9 @@
 #include "mvd_launch.h"
 
 namespace {
-template <int LK, int M, int LLS, bool GT, int NOUT = 2>
+template <int LK, int M, int LLS, bool GT, int NOUT = 2, bool BIG = false>
 cudaError_t launch_one(dim3 grid, unsigned threads, size_t smem, cudaStream_t st, const Params& P, const SegBatch& B) {
-    auto kern = detect2_kernel<LK, M, LLS, GT, NOUT>;
+    auto kern = detect2_kernel<LK, M, LLS, GT, NOUT, BIG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, threads, smem, st>>>(P, B);
@@ -39,7 +39,9 @@ cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned th
         switch (lls) {
             case 4: return launch_one<LK_FSM1, 1, 4, false>(grid, threads, smem, st, P, B);
             case 5: return launch_one<LK_FSM1, 1, 5, false>(grid, threads, smem, st, P, B);
-            case 6: return launch_one<LK_FSM1, 1, 6, false>(grid, threads, smem, st, P, B);
+            case 6:
+                if (threads > DET2_BLOCK) return launch_one<LK_FSM1, 1, 6, false, 2, true>(grid, threads, smem, st, P, B);
+                return launch_one<LK_FSM1, 1, 6, false>(grid, threads, smem, st, P, B);
             default: return launch_one<LK_FSM1, 1, 7, false>(grid, threads, smem, st, P, B);
         }
     }

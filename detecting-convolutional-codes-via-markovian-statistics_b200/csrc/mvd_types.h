@@ -78,6 +78,7 @@ struct Params {
 
 // ---- fast detection kernels (mvd_detect2.cuh)
 #define DET2_BLOCK 512
+#define DET2_BIG_BLOCK 768       // one-load NEXT walk whose 4-copy table fits twice per SM: two blocks of 768 threads keep the SM as full as three of 512
 #define DET2P_BLOCK 256
 #define DET2P_QUEUES ((DET2P_BLOCK / 32) * 1024)   // straggler queues of the pair kernel: 128 items x 8 bytes per warp
 #define DET3P_BLOCK 768         // m = 3 pair kernel: one block per SM shares conflict-poor table replicas (mvd_detect3p.cuh)
