@@ -521,14 +521,16 @@ bool plan_det2(const mvd_ctx* ctx, int engine, int* lk_out, int* lls_out, FastPl
         // (measured at S = 435: 8 / 4 / 2 / 1 copies = 7.06e11 / 8.46e11 / 8.44e11 / 8.17e11 steps/s)
         int lls = 7;
         const char* force = getenv("MVD_FSM1_LLS");                 // experiments only
-        // ... unless the launch is large enough for TWO blocks of 768 threads per SM around a 4-copy table (n = 2)
-        const bool big = !force && allow_big && big_out && ctx->n == 2 && 128 + (SR << 6) + 64 > 75 * 1024 &&
-                         128 + (SR << 6) + 64 <= 112 * 1024;
-        if (big) {
-            *big_out = true;
-            lls = 6;
-        } else if (force && *force >= '4' && *force <= '7') lls = *force - '0';
-        else while (lls > 4 && 128 + (SR << lls) + 64 > 75 * 1024) --lls;
+        if (force && *force >= '4' && *force <= '7') lls = *force - '0';
+        else {
+            while (lls > 4 && 128 + (SR << lls) + 64 > 75 * 1024) --lls;              // three blocks of 512 threads per SM
+            // ... unless the launch is large enough for TWO blocks of 768 threads per SM (as many threads) and a table with twice
+            // the copies fits twice: half the bank conflicts of the row reads (measured at S = 435: 8.5e11 -> 9.0e11 steps/s)
+            if (allow_big && big_out && ctx->n == 2 && lls < 7 && lls >= 4 && 128 + (SR << (lls + 1)) + 64 <= 112 * 1024) {
+                *big_out = true;
+                ++lls;
+            }
+        }
         while (lls > 4 && 128 + (SR << lls) + 64 > ctx->prop.sharedMemPerBlockOptin) --lls;
         fp->off_tb = 0;
         fp->off_bm = fp->off_st = 128;

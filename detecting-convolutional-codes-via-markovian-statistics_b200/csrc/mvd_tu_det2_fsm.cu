@@ -36,12 +36,17 @@ cudaError_t mvd_launch_det2_fsm(int lk, int lls, bool gt, dim3 grid, unsigned th
     }
     if (lk == LK_FSM1) {
         if (gt) return launch_one<LK_FSM1, 1, 4, true>(grid, threads, smem, st, P, B);
+        if (threads > DET2_BLOCK)                        // two blocks of DET2_BIG_BLOCK threads per SM (plan_det2)
+            switch (lls) {
+                case 5: return launch_one<LK_FSM1, 1, 5, false, 2, true>(grid, threads, smem, st, P, B);
+                case 6: return launch_one<LK_FSM1, 1, 6, false, 2, true>(grid, threads, smem, st, P, B);
+                case 7: return launch_one<LK_FSM1, 1, 7, false, 2, true>(grid, threads, smem, st, P, B);
+                default: return cudaErrorInvalidValue;
+            }
         switch (lls) {
             case 4: return launch_one<LK_FSM1, 1, 4, false>(grid, threads, smem, st, P, B);
             case 5: return launch_one<LK_FSM1, 1, 5, false>(grid, threads, smem, st, P, B);
-            case 6:
-                if (threads > DET2_BLOCK) return launch_one<LK_FSM1, 1, 6, false, 2, true>(grid, threads, smem, st, P, B);
-                return launch_one<LK_FSM1, 1, 6, false>(grid, threads, smem, st, P, B);
+            case 6: return launch_one<LK_FSM1, 1, 6, false>(grid, threads, smem, st, P, B);
             default: return launch_one<LK_FSM1, 1, 7, false>(grid, threads, smem, st, P, B);
         }
     }

@@ -327,6 +327,34 @@ def test_m3_pair_kernel_full_blocks_vs_oracle(codes_spec):
         assert int(t[0]) == want and np.array_equal(lp, wlp)
 
 
+@pytest.mark.parametrize("g0,g1,S,lls", [(11, 15, 435, 6), (12, 14, 165, 7), (9, 13, 665, 5)])
+def test_next_walk_two_big_blocks_vs_oracle(g0, g1, S, lls):
+    """The one-load NEXT walk at its large-launch geometry: two blocks of 768 threads per SM around a table with twice the
+    copies three blocks of 512 could hold (4, 8 and 2 copies for these three memory-3 decoders) -- enough trials that the
+    dispatcher takes it, last block ragged, N = 37; tallies and every per-trial float64 sum against the oracle."""
+    import c_oracle as co
+    from mvd import bitsource, codes
+    from mvd.engine import Detector, Seg
+    bits = lambda g: [(g >> 3) & 1, (g >> 2) & 1, (g >> 1) & 1, g & 1]
+    gen, enc_gen = [[bits(g0)], [bits(g1)]], [[[1, 1, 1, 1]], [[1, 0, 1, 1]]]
+    T, seed = bitsource.bsc_threshold(0.07), 5
+    with Detector(gen, 1, 2, 3) as det:
+        assert det.S == S
+        taps, etaps = det.taps_of(gen), det.taps_of(enc_gen)
+        tab = co.Table(det.table.metrics, 3)
+        edge, _ = co.learn_chain(taps, taps, 2, 3, 20000, 200, T, seed, bitsource.LEARN_STREAM, 0, tab)
+        P1 = codes.p1_from_edge_counts(det.table, edge, 1.0)
+        Tref = codes.tref_half_table(det.table)
+        det.set_models([P1])
+        ntr = 150 * 2 * 768 + 301
+        seg = Seg(N=37, threshold=T, stream=2, enc_taps=etaps, decide=1, trial_begin=9, trial_end=9 + ntr)
+        t, lp = det.detect([seg], seed=seed, engine="fsm", want_logp=True)
+        kind = det.last_kernel_kind()
+        assert (kind - 1) % 16 == 3 and (kind - 1) // 16 == lls, kind       # one-load walk, log2 of the row stride
+        want, wlp = co.run_trials(taps, etaps, 2, 3, 37, T, seed, 2, 9, 9 + ntr, tab, P1, Tref, 1, want_logp=True)
+        assert int(t[0]) == want and np.array_equal(lp, wlp)
+
+
 M3_DECODERS = [(g0, g1) for g0 in range(9, 16) for g1 in range(9, 16) if g0 != g1]
 
 
