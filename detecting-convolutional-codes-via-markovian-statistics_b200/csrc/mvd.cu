@@ -927,7 +927,17 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     if (plearn && maxL > 0) {
         // chunk-parallel learning chains (mvd_learn2.cuh): speculate, check, fix
         LearnParams LP{};
-        LP.nchunks = (maxL + LEARN_CH - 1) / LEARN_CH;
+        // steps per chunk: the longest of 128 / 256 / 512 / 1024 that still leaves every SM two rounds of 1 024 chunk-threads
+        // (the walk is bound by the latency of its dependent table reads; at S = 150 743 a 384-step warm-up in front of
+        // 128-step chunks quadruples the steps walked, in front of 512-step chunks it adds 75 %)
+        uint64_t sumL = 0;
+        for (uint32_t i = 0; i < nsegs; ++i) sumL += segs[i].N;
+        LP.chunk = LEARN_CH;
+        const char* fch = getenv("MVD_LEARN_CHUNK");               // tests / experiments: 128, 256, 512 or 1024 (identical counts)
+        const uint32_t forced = fch ? (uint32_t)atoi(fch) : 0u;
+        if (forced == 128u || forced == 256u || forced == 512u || forced == 1024u) LP.chunk = forced;
+        else while (LP.chunk < 1024u && sumL / (2ull * LP.chunk) >= 2ull * 1024ull * (uint64_t)ctx->prop.multiProcessorCount) LP.chunk *= 2u;
+        LP.nchunks = (maxL + LP.chunk - 1) / LP.chunk;
         LP.warm = ctx->learn_warm;
         const size_t cells = (size_t)nsegs * LP.nchunks;
         CK(ctx->d_lspec.reserve(cells * 4));

@@ -5,7 +5,7 @@
 // at the reference's own trial counts the learning chain, not the trial loop, is the GPU time.
 //
 // Because the MVD-PHILOX-2 stream is addressed by position, any 32-step block of the chain can be
-// generated independently.  The chain is cut into chunks of LEARN_CH steps:
+// generated independently.  The chain is cut into chunks of LP.chunk steps (128 .. 1024, chosen by the host):
 //   1. learn_spec_kernel: thread c walks chunk c.  It starts LEARN_WARM steps early from Markov state 0
 //      (the all-zero vector) -- the relative-metric recursion forgets its start as survivor paths
 //      merge -- records the state it has at the chunk start (spec_start[c]), counts the transitions of
@@ -116,14 +116,15 @@ __global__ void __launch_bounds__(LEARN_BLOCK) learn_spec_kernel(const __grid_co
     }
     unsigned long long* counts = P.counts + (size_t)seg * SR;
     const uint32_t c = blockIdx.x * LEARN_BLOCK + threadIdx.x;
-    // Every lane of a warp runs the same trip counts (warm / 32 + LEARN_CH / 32 blocks of 32 steps) with a per-lane
+    // Every lane of a warp runs the same trip counts (warm / 32 + chunk / 32 blocks of 32 steps) with a per-lane
     // `live` predicate: chunks whose warm-up reaches back past step 0, the ragged last chunk and lanes beyond the last
     // chunk idle through the iterations they do not have, so the full-mask votes below are reached by all 32 lanes
     // together (the programming model's requirement for __ballot_sync / __match_any_sync).
-    const bool have = c < (L + LEARN_CH - 1u) / LEARN_CH;
-    const uint32_t t_begin = have ? c * LEARN_CH : 0u;
-    const uint32_t t_end = have ? min(L, t_begin + LEARN_CH) : 0u;
-    const uint32_t nblk = (LP.warm + LEARN_CH) >> 5;              // warm is a multiple of 32 (mvd_set_option)
+    const uint32_t CH = LP.chunk;
+    const bool have = c < (L + CH - 1u) / CH;
+    const uint32_t t_begin = have ? c * CH : 0u;
+    const uint32_t t_end = have ? min(L, t_begin + CH) : 0u;
+    const uint32_t nblk = (LP.warm + CH) >> 5;              // warm is a multiple of 32 (mvd_set_option)
     const int b_first = (int)(t_begin >> 5) - (int)(LP.warm >> 5);
     uint32_t sx = 0;                                              // state 0 (exact when the walk starts at step 0)
     uint32_t Rw[MVD_MAX_N];
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(LEARN_BLOCK) learn_spec_kernel(const __grid_co
 __global__ void learn_check_kernel(const __grid_constant__ Params P, const __grid_constant__ LearnParams LP) {
     const uint32_t seg = blockIdx.y;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nch = (P.segs[seg].N + LEARN_CH - 1u) / LEARN_CH;
+    const uint32_t nch = (P.segs[seg].N + LP.chunk - 1u) / LP.chunk;
     bool dirty = false;
     if (c >= 1u && c < nch) {
         const size_t o = (size_t)seg * LP.nchunks;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(1024) learn_fix_kernel(const __grid_constant__
     __shared__ uint32_t s_first;
     const DevSeg sg = P.segs[seg];
     const uint32_t L = sg.N, SR = P.SR;
-    const uint32_t nch = (L + LEARN_CH - 1u) / LEARN_CH;
+    const uint32_t nch = (L + LP.chunk - 1u) / LP.chunk;
     const size_t o = (size_t)seg * LP.nchunks;
     volatile uint32_t* endv = LP.end + o;
     const uint32_t* spec = LP.spec_start + o;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(1024) learn_fix_kernel(const __grid_constant__
         if (found == 0xFFFFFFFFu) break;
         if (threadIdx.x == 0) {
             // walk chunk `found` from its true start beside the speculated trajectory
-            const uint32_t t_begin = found * LEARN_CH, t_end = min(L, t_begin + LEARN_CH);
+            const uint32_t t_begin = found * LP.chunk, t_end = min(L, t_begin + LP.chunk);
             uint32_t st = endv[found - 1u], ss = spec[found];
             uint32_t Rw[MVD_MAX_N];
             bool merged = false;

@@ -92,12 +92,14 @@ struct SegBatch {
 enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2, LK_FSM1 = 3 };
 
 // ---- chunk-parallel learning chains (mvd_learn2.cuh)
-#define LEARN_CH 128u       // steps per chunk (one info-word call)
+#define LEARN_CH 128u       // least steps per chunk (one info-word call); LearnParams.chunk = 128, 256, 512 or 1024
 #define LEARN_WARM 128u     // default warm-up steps (LearnParams.warm; multiples of 32)
 #define LEARN_BLOCK 128
 
 struct LearnParams {
     uint32_t nchunks;                 // per segment
+    uint32_t chunk;                   // steps per chunk (a multiple of LEARN_CH): long chains take longer chunks, the warm-up
+                                      // (walked for every chunk, counted for none) weighs less
     uint32_t warm;                    // warm-up steps before a chunk (multiple of 32)
     uint32_t* spec_start;             // [nsegs][nchunks]  state * R at the chunk start (speculated)
     uint32_t* end;                    // [nsegs][nchunks]  state * R at the chunk end

@@ -149,6 +149,33 @@ def test_learn_chunk_parallel_vs_oracle(codes_spec, dets, name, L, burn, p, warm
     assert np.array_equal(ser, want)
 
 
+@pytest.mark.parametrize("chunk", [256, 512, 1024])
+@pytest.mark.parametrize("name,L,burn,p,warm", [("c75", 6200, 200, 0.1, 128), ("m3a", 87000, 200, 0.05, 128), ("m3a", 20011, 33, 0.3, 32),
+                                                ("c75", 4097, 0, 0.5, 0)])
+def test_learn_chunk_lengths_vs_oracle(codes_spec, dets, monkeypatch, name, L, burn, p, warm, chunk):
+    """The longer chunks long chains are cut into (256 / 512 / 1 024 steps, forced here through MVD_LEARN_CHUNK; chosen per call
+    otherwise) give the sequential chain's counts bit for bit -- with the default warm-up, a short one and none (every chunk
+    repaired by the fix pass), ragged last chunks."""
+    import c_oracle as co
+    from mvd import bitsource
+    from mvd.engine import Seg
+    s = codes_spec[name]
+    det = dets(name)
+    tab = co.Table(det.table.metrics, s["m"])
+    taps = _taps(s)
+    T = bitsource.bsc_threshold(p)
+    seg = Seg(N=L, threshold=T, stream=bitsource.LEARN_STREAM, enc_taps=taps)
+    want, _ = co.learn_chain(taps, taps, s["n"], s["m"], L, burn, T, 77, bitsource.LEARN_STREAM, 0, tab)
+    monkeypatch.setenv("MVD_LEARN_CHUNK", str(chunk))
+    det.learn_warm(warm)
+    try:
+        got = det.learn_counts([seg, seg], burn=burn, seed=77, engine="fsm")
+        assert det.last_kernel_kind() == 1024
+    finally:
+        det.learn_warm(128)
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
+
+
 def test_learn_counts_many_chains(codes_spec, dets):
     """Several chains per segment aggregate into one histogram (shared-memory atomics)."""
     import c_oracle as co
