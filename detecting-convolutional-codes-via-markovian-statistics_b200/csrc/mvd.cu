@@ -659,10 +659,18 @@ int run(mvd_ctx* ctx, int mode, int engine, const mvd_src* src, const mvd_segmen
     uint64_t all_trials = 0;
     for (uint32_t i = 0; i < nsegs; ++i) all_trials += segs[i].trial_end >= segs[i].trial_begin ? segs[i].trial_end - segs[i].trial_begin : 0;
     const uint64_t sms = (uint64_t)ctx->prop.multiProcessorCount;
+    // blocks of 768 threads (one or two per SM around larger shared tables) pay off when the LONG segments of the launch fill the
+    // GPU by themselves: in an N sweep at few trials per point the tail is a handful of long blocks, and fewer, larger blocks
+    // lengthen it (m = 3 Pd-vs-N sweep at 10^4 trials per point: 10.5 ms with blocks of 512, 13.0 ms with blocks of 768)
+    uint32_t longest = 0;
+    for (uint32_t i = 0; i < nsegs; ++i) longest = std::max(longest, segs[i].N);
+    uint64_t long_trials = 0;
+    for (uint32_t i = 0; i < nsegs; ++i)
+        if (2ull * segs[i].N >= longest && segs[i].trial_end >= segs[i].trial_begin) long_trials += segs[i].trial_end - segs[i].trial_begin;
+    const bool big_ok = long_trials >= 2ull * DET2_BIG_BLOCK * sms && !getenv("MVD_NO_BIG_BLOCK");
     bool det2_big = false;
     const bool fast = mode == MODE_DETECT && !ctx->force_generic && !ctx->table_code &&
-                      plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt,
-                                all_trials >= 2ull * DET2_BIG_BLOCK * sms && !getenv("MVD_NO_BIG_BLOCK"), &det2_big);
+                      plan_det2(ctx, engine, &det2_lk, &det2_lls, &fplan, &det2_smem, &det2_gt, big_ok, &det2_big);
     // two trials per thread: ACS engine, m = 2, direct table, log rows replicated 8 x
     // (layout of detect2p_kernel: straggler queues, masks, branch metrics, log rows, then the state table at a 32 KB-aligned
     // absolute shared address; the dynamic window starts after the 1 KB the system reserves)
