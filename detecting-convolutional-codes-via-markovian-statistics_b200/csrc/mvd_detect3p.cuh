@@ -125,6 +125,7 @@ struct PairEngineN {
             a1B += vB.x;
             a0B += vB.y;
         }
+        const uint32_t one = P.fp.kq[4];
         uint32_t n[NS];
         if (ANTI) {
             // row r of the branch table: bytes x_g; the packed pair (n - x_g | r_A, n - x_g | r_B) = 0x00020002 - (x_g pair), one IMAD by -1
@@ -139,7 +140,6 @@ struct PairEngineN {
                 xa[0] = ra.x; xa[1] = ra.y;
                 xb[0] = rb.x; xb[1] = rb.y;
             }
-            const uint32_t one = P.fp.kq[4];
 #pragma unroll
             for (int g = 0; g < HALF; ++g) {
                 const uint32_t s4 = (uint32_t)(g & 3) | 0x80u | ((4u + (uint32_t)(g & 3)) << 8) | 0x8000u;
@@ -152,7 +152,7 @@ struct PairEngineN {
             const uint32_t VA = lds_u32(xadr(xA, kV)), VB = lds_u32(xadr(xB, kV));
 #pragma unroll
             for (int ns = 0; ns < NS; ++ns)             // new state ns from predecessors ns >> 1 and (ns >> 1) + HALF: Eq. 4, both trials
-                n[ns] = __viaddmin_u16x2(Q[ns >> 1], __byte_perm(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + __byte_perm(VA, VB, sel[2 * ns + 1]));
+                n[ns] = __viaddmin_u16x2(Q[ns >> 1], prmt_s(VA, VB, sel[2 * ns]), Q[(ns >> 1) + HALF] + prmt_s(VA, VB, sel[2 * ns + 1]));
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) Q[s] = n[s];
@@ -161,7 +161,7 @@ struct PairEngineN {
 #pragma unroll
         for (int q = 0; q < NS / 4; ++q) {
             uint32_t acc = madlo(Q[0], q == 0 ? P.fp.kq[5] : P.fp.kq[3], 0x88888888u);      // - 4369 D[0] (q = 0: - 4368 D[0]) + 8 per digit
-            if (q > 0) acc = madlo(Q[4 * q], one_(P), acc);
+            if (q > 0) acc = madlo(Q[4 * q], one, acc);
             acc = madlo(Q[4 * q + 1], P.fp.kq[0], acc);
             acc = madlo(Q[4 * q + 2], P.fp.kq[1], acc);
             k[q] = madlo(Q[4 * q + 3], P.fp.kq[2], acc);
@@ -169,7 +169,6 @@ struct PairEngineN {
         sxA = lookup(__byte_perm(k[0], k[1], 0x5410), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x5410) : 0u);
         sxB = lookup(__byte_perm(k[0], k[1], 0x7632), NS == 16 ? __byte_perm(k[NS / 4 - 2], k[NS / 4 - 1], 0x7632) : 0u);
     }
-    static __device__ __forceinline__ uint32_t one_(const Params& P) { return P.fp.kq[4]; }
 
     // Eq. 5 (keeps the lanes small; the key does not see it)
     __device__ __forceinline__ void normalise() {
