@@ -94,8 +94,11 @@ __device__ __forceinline__ uint32_t word_of_step(const uint32_t* Rw, int n, uint
 }
 
 // grid (ceil(nchunks / LEARN_BLOCK), nsegs)
+// (tables in global memory: the walk waits on dependent L2 reads -- long_scoreboard 17 per issued instruction at S = 25 751 --, so the
+// register budget is capped for 12 blocks of 128 threads per SM instead of the 7 that 72 registers allow: 1.55 -> 1.43 ms for 7 chains
+// of 5.2e6 steps.  Measured and rejected: per-thread run-length aggregation of the counts instead of the warp-level match: 1.95 ms)
 template <bool SMEM>
-__global__ void __launch_bounds__(LEARN_BLOCK) learn_spec_kernel(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(LEARN_BLOCK, SMEM ? 1 : 12) learn_spec_kernel(const __grid_constant__ Params P,
                                                                  const __grid_constant__ LearnParams LP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t seg = blockIdx.y;
