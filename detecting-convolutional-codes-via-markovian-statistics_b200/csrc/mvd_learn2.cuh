@@ -118,6 +118,19 @@ __global__ void __launch_bounds__(LEARN_BLOCK, SMEM ? 1 : 12) learn_spec_kernel(
         nxt = s_nx;
     }
     unsigned long long* counts = P.counts + (size_t)seg * SR;
+    // counts in global memory: a per-block table of LEARN_HOT slots (edge -> count) takes the additions first and is flushed at the
+    // end.  At low p a chain spends half its steps on 16 edges (S = 150 743, p = 0.001), and every block of the chain hammering
+    // the same few L2 addresses made those chains 3.4 x slower than the ones at p >= 0.3, whose edges are all different
+    // (one chain of 3.0e7 steps: 2.29 -> 0.45 ms at p = 0.001, 0.67 -> 0.75 ms at p = 0.5; seven chains 4.75 -> 2.2 ms).  Admitting
+    // an edge only when two lanes of a warp meet on it measured no better at high p and worse at p = 0.1.
+    __shared__ uint32_t hot_key[SMEM ? 1 : LEARN_HOT], hot_val[SMEM ? 1 : LEARN_HOT];
+    if (!SMEM) {
+        for (uint32_t i = threadIdx.x; i < LEARN_HOT; i += LEARN_BLOCK) {
+            hot_key[i] = 0xFFFFFFFFu;
+            hot_val[i] = 0u;
+        }
+        __syncthreads();
+    }
     const uint32_t c = blockIdx.x * LEARN_BLOCK + threadIdx.x;
     // Every lane of a warp runs the same trip counts (warm / 32 + chunk / 32 blocks of 32 steps) with a per-lane
     // `live` predicate: chunks whose warm-up reaches back past step 0, the ragged last chunk and lanes beyond the last
@@ -160,12 +173,22 @@ __global__ void __launch_bounds__(LEARN_BLOCK, SMEM ? 1 : 12) learn_spec_kernel(
                 // lanes that count the same edge elect one of them to add the group's size (one global atomic
                 // per distinct edge and step instead of up to 32 serialised ones on the same address)
                 const unsigned peers = __match_any_sync(0xFFFFFFFFu, tally ? e : 0xFFFFFFFFu);
-                if (tally && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + e, (unsigned long long)__popc(peers));
+                if (tally && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) {
+                    const uint32_t h = (e * 0x9E3779B1u) >> (32 - LEARN_HOT_LOG2);
+                    const uint32_t was = atomicCAS(hot_key + h, 0xFFFFFFFFu, e);          // claim the slot, or find it ours / taken
+                    if (was == 0xFFFFFFFFu || was == e) atomicAdd(hot_val + h, (uint32_t)__popc(peers));
+                    else atomicAdd(counts + e, (unsigned long long)__popc(peers));
+                }
                 if (step) sx = __ldg(nxt + e);
             }
         }
     }
     if (have) LP.end[(size_t)seg * LP.nchunks + c] = sx;
+    if (!SMEM) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < LEARN_HOT; i += LEARN_BLOCK)
+            if (hot_val[i]) atomicAdd(counts + hot_key[i], (unsigned long long)hot_val[i]);
+    }
     if (SMEM) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < SR; i += LEARN_BLOCK) {

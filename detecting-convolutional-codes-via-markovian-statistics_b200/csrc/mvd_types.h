@@ -95,6 +95,8 @@ enum { LK_DIRECT = 0, LK_HASH = 1, LK_FSM = 2, LK_FSM1 = 3 };
 #define LEARN_CH 128u       // least steps per chunk (one info-word call); LearnParams.chunk = 128, 256, 512 or 1024
 #define LEARN_WARM 128u     // default warm-up steps (LearnParams.warm; multiples of 32)
 #define LEARN_BLOCK 128
+#define LEARN_HOT_LOG2 10      // per-block table of hot edges in front of the global counts (mvd_learn2.cuh)
+#define LEARN_HOT (1u << LEARN_HOT_LOG2)
 
 struct LearnParams {
     uint32_t nchunks;                 // per segment
