@@ -1475,37 +1475,83 @@ int mvd_set_loglik(mvd_ctx* ctx, uint32_t ntables, const double* logP1, const do
     // log Tref[e] == c[e] * unit exactly, c = 0 or a power of two?  (unit = the non-zero value of least magnitude)
     bool large = false;
     {
-        double unit = 0.0;
-        for (size_t e = 0; e < SR; ++e)
-            if (logTref[e] != 0.0 && (unit == 0.0 || std::fabs(logTref[e]) < std::fabs(unit))) unit = logTref[e];
-        // the distinct non-zero values of log Tref, if there are at most three (class mode of the split path, mvd_split.cuh)
-        SplitClasses cls{};
-        for (size_t e = 0; e < SR && cls.n >= 0; ++e) {
+        // log Tref has a handful of distinct values (T(1/2) = mult / 2^n: at most 2^n of them), so the three scans below -- least
+        // magnitude, value classes, the packed multiple c of every entry -- go through a memo of the distinct values in order of first
+        // appearance instead of a division and a frexp per entry (S = 150 743: 603 000 entries per call); more than 16 distinct values
+        // (or NaNs, which never compare equal) take the entry-by-entry form
+        constexpr int MEMO = 16;
+        double mv[MEMO];
+        int nm = 0;
+        bool many = false;
+        for (size_t e = 0; e < SR && !many; ++e) {
             const double v = logTref[e];
-            if (v == 0.0) continue;
             int j = 0;
-            while (j < cls.n && cls.val[j] != v) ++j;
-            if (j == cls.n) {
-                if (cls.n == 3 || !(v < 0.0)) cls.n = -1;           // a fourth value, a positive one or a NaN: no class mode
-                else cls.val[cls.n++] = v;
+            while (j < nm && mv[j] != v) ++j;
+            if (j == nm) {
+                if (nm == MEMO) many = true;
+                else mv[nm++] = v;
             }
         }
-        if (cls.n < 0) cls = SplitClasses{};
-        ctx->split_cls = cls;
-        bool ok = true;
-        std::vector<uint32_t> code(SR, 0u);
-        for (size_t e = 0; e < SR && ok; ++e) {
+        auto code_of = [](double v, double unit, bool& ok) -> uint32_t {
             double c = 0.0;
-            if (logTref[e] != 0.0) {
-                c = logTref[e] / unit;
+            if (v != 0.0) {
+                c = v / unit;
                 int ex = 0;
-                ok = std::frexp(c, &ex) == 0.5 && c >= 1.0 && c <= 1048576.0 && c * unit == logTref[e];
+                ok = std::frexp(c, &ex) == 0.5 && c >= 1.0 && c <= 1048576.0 && c * unit == v;
             }
             uint64_t bits;
             memcpy(&bits, &c, 8);
             ok = ok && (uint32_t)bits == 0u;
-            code[e] = (uint32_t)(bits >> 32);
+            return (uint32_t)(bits >> 32);
+        };
+        double unit = 0.0;
+        SplitClasses cls{};
+        bool ok = true;
+        std::vector<uint32_t> code(SR, 0u);
+        if (!many) {
+            for (int j = 0; j < nm; ++j)
+                if (mv[j] != 0.0 && (unit == 0.0 || std::fabs(mv[j]) < std::fabs(unit))) unit = mv[j];
+            // the distinct non-zero values of log Tref, if there are at most three (class mode of the split path, mvd_split.cuh)
+            for (int j = 0; j < nm && cls.n >= 0; ++j) {
+                const double v = mv[j];
+                if (v == 0.0) continue;
+                if (cls.n == 3 || !(v < 0.0)) cls.n = -1;               // a fourth value, a positive one: no class mode
+                else cls.val[cls.n++] = v;
+            }
+            uint32_t mc[MEMO];
+            for (int j = 0; j < nm; ++j) {
+                bool okj = true;
+                mc[j] = code_of(mv[j], unit, okj);
+                ok = ok && okj;
+            }
+            if (ok)
+                for (size_t e = 0; e < SR; ++e) {
+                    const double v = logTref[e];
+                    int j = 0;
+                    while (mv[j] != v) ++j;                             // every value is in the memo
+                    code[e] = mc[j];
+                }
+        } else {
+            for (size_t e = 0; e < SR; ++e)
+                if (logTref[e] != 0.0 && (unit == 0.0 || std::fabs(logTref[e]) < std::fabs(unit))) unit = logTref[e];
+            for (size_t e = 0; e < SR && cls.n >= 0; ++e) {
+                const double v = logTref[e];
+                if (v == 0.0) continue;
+                int j = 0;
+                while (j < cls.n && cls.val[j] != v) ++j;
+                if (j == cls.n) {
+                    if (cls.n == 3 || !(v < 0.0)) cls.n = -1;           // a fourth value, a positive one or a NaN: no class mode
+                    else cls.val[cls.n++] = v;
+                }
+            }
+            for (size_t e = 0; e < SR && ok; ++e) {
+                bool oke = true;
+                code[e] = code_of(logTref[e], unit, oke);
+                ok = oke;
+            }
         }
+        if (cls.n < 0) cls = SplitClasses{};
+        ctx->split_cls = cls;
         ctx->tref_packed = ok;
         ctx->tref_unit = unit;
         ctx->have_gfsm1 = false;
